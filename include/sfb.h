@@ -1,0 +1,167 @@
+/*
+ * sfb.h -- C ABI of the B200-native batched QP / EKF engine (libsfb.so).
+ *
+ * This is the drop-in boundary for smooth_feedback's numerical hot path.  The reference has no FFI of
+ * its own (header-only C++20 templates), so each entry point cites the reference *call* it replaces;
+ * file:line are into the reference tree (pettni/smooth_feedback @ 9a08971).
+ *
+ *   sfb_qp_solve_dense_batch_f64/_f32   <- QPSolver<Pbm>::solve      include/smooth/feedback/qp_solver.hpp:343-568
+ *                                          solve_qp                   include/smooth/feedback/qp_solver.hpp:779-787
+ *                                          (call sites: mpc.hpp:491, asif.hpp:97)
+ *   sfb_qp_params / _default            <- QPSolverParams             qp_solver.hpp:29-68
+ *   sfb_qp_status                       <- QPSolutionStatus           qp.hpp:82-92
+ *   sfb_ekf_predict_batch_f64           <- EKF::predict (cov. ODE)    ekf.hpp:79-103
+ *   sfb_ekf_update_batch_f64            <- EKF::update                ekf.hpp:116-139
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every array is a contiguous batch of per-instance blocks laid out
+ *     exactly like the reference's Eigen members (column-major matrices):
+ *        P [batch][n*n]   P_ij at  i + n*j        q [batch][n]
+ *        A [batch][m*n]   A_ij at  i + m*j        l,u [batch][m]   (+-INFINITY allowed)
+ *   - every data pointer of one call must live in the same memory space: all device (resident on the
+ *     handle's device) or all host.  Host buffers are staged through the engine's own device workspace
+ *     in pipelined chunks (pinned host memory makes the copies asynchronous).
+ *   - functions return 0 (SFB_OK) or an sfb_error; per-instance outcomes are reported only through
+ *     out_status (never an error code), like the reference which never throws on the numeric path.
+ *   - there is NO CPU fallback: without a CUDA device sfb_create fails with SFB_ERR_NO_DEVICE.
+ *   - a handle is not re-entrant (like a QPSolver object, qp_solver.hpp:734-756); use one per host thread.
+ *     Work is enqueued on the handle's stream; calls with device pointers are asynchronous with respect
+ *     to the host unless stated otherwise, calls with host pointers return after the results are in place.
+ */
+#ifndef SFB_H
+#define SFB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFB_VERSION 100 /* 0.1.0 */
+
+typedef struct sfb_context* sfb_handle_t;
+
+typedef enum {
+  SFB_OK = 0,
+  SFB_ERR_INVALID_ARGUMENT = 1, /* null pointer, non-positive size, stop_check_iter == 0, ... */
+  SFB_ERR_NO_DEVICE = 2,        /* no CUDA device / wrong architecture: the engine has no CPU path */
+  SFB_ERR_CUDA = 3,             /* a CUDA runtime call failed; see sfb_last_error_message */
+  SFB_ERR_UNSUPPORTED_SIZE = 4, /* (n, m) does not fit the shared-memory resident kernels */
+  SFB_ERR_MIXED_MEMORY = 5,     /* host and device pointers mixed in one call */
+  SFB_ERR_OUT_OF_MEMORY = 6
+} sfb_error;
+
+/* QPSolutionStatus, qp.hpp:82-92 -- values and order are part of the contract */
+typedef enum {
+  SFB_QP_OPTIMAL = 0,
+  SFB_QP_POLISH_FAILED = 1, /* never produced, exactly like the reference (qp_solver.hpp:537 is overwritten at :544) */
+  SFB_QP_PRIMAL_INFEASIBLE = 2,
+  SFB_QP_DUAL_INFEASIBLE = 3,
+  SFB_QP_MAX_ITERATIONS = 4,
+  SFB_QP_MAX_TIME = 5,
+  SFB_QP_UNKNOWN = 6
+} sfb_qp_status;
+
+/*
+ * QPSolverParams, qp_solver.hpp:29-68, field for field.  The float members stay float: the reference
+ * casts them to Scalar (rho = (double)0.1f, not 0.1) and that is part of the algorithm.
+ */
+typedef struct {
+  int32_t verbose;          /* accepted, ignored on device */
+  float alpha;              /* 1.6f   relaxation */
+  float rho;                /* 0.1f   first dual step size */
+  float sigma;              /* 1e-6f  second dual step size */
+  int32_t scaling;          /* 1      Ruiz-style equilibration (qp_solver.hpp:673-730) */
+  float eps_abs;            /* 1e-3f */
+  float eps_rel;            /* 1e-3f */
+  float eps_primal_inf;     /* 1e-4f */
+  float eps_dual_inf;       /* 1e-4f */
+  int32_t has_max_iter;     /* 0      std::optional engaged? */
+  uint32_t max_iter;        /*        if !has_max_iter the device loop is still bounded by SFB_QP_DEVICE_ITER_CAP */
+  int32_t has_max_time;     /* 0 */
+  int64_t max_time_ns;      /*        per-instance budget measured with the device clock, checked at stop checks */
+  uint32_t stop_check_iter; /* 25     checks fire when iter % stop_check_iter == 1 (qp_solver.hpp:465,479) */
+  int32_t polish;           /* 1 */
+  uint32_t polish_iter;     /* 5 */
+  float delta;              /* 1e-6f  polish regularisation */
+} sfb_qp_params;
+
+/* an unbounded device loop would let one diverging instance hold a warp forever */
+#define SFB_QP_DEVICE_ITER_CAP 1000000u
+
+/* out_flags bits (optional diagnostics, not part of the reference's observable state) */
+#define SFB_QP_FLAG_POLISHED 1u       /* polish ran and its result was accepted */
+#define SFB_QP_FLAG_POLISH_SKIPPED 2u /* active set too large for the on-chip polish workspace: solution left unpolished,
+                                         which is also what the reference returns when its polish fails */
+#define SFB_QP_FLAG_POLISH_FAILED 4u  /* non-positive / non-finite pivot in the polish systems */
+
+int sfb_version(void);
+const char* sfb_error_string(int err);
+/* message of the last failing call on this handle (or of sfb_create when h == NULL); never NULL */
+const char* sfb_last_error_message(sfb_handle_t h);
+
+/* stream: a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) or NULL for the default stream */
+int sfb_create(int device, void* stream, sfb_handle_t* out);
+int sfb_destroy(sfb_handle_t h);
+int sfb_set_stream(sfb_handle_t h, void* stream);
+int sfb_synchronize(sfb_handle_t h);
+/* number of kernels of this library launched through the handle since creation */
+int sfb_kernel_launch_count(sfb_handle_t h, uint64_t* out);
+
+void sfb_qp_params_default(sfb_qp_params* p);
+
+/*
+ * Replaces QPSolver<QuadraticProgram<M,N,double>>::solve / solve_qp (qp_solver.hpp:343-568, :779-787) for a
+ * batch of independent dense problems of one shape.
+ *
+ *   warm_x [batch][n], warm_y [batch][m]  both NULL (cold) or both given      (qp_solver.hpp:436-445)
+ *   out_x [batch][n], out_y [batch][m], out_obj [batch]                        QPSolution::{primal,dual,objective}
+ *   out_status [batch] int32 (sfb_qp_status), out_iter [batch] uint32          QPSolution::{code,iter}
+ *   out_active [batch][m] int8, may be NULL: -1 lower-active, +1 upper-active, 0 inactive -- the sets
+ *       polish_qp builds (qp_solver.hpp:113-123) evaluated on the scaled dual when the ADMM loop ends
+ *   out_flags [batch] uint32, may be NULL: SFB_QP_FLAG_* diagnostics
+ */
+int sfb_qp_solve_dense_batch_f64(sfb_handle_t h, const sfb_qp_params* prm, int64_t batch, int n, int m,
+                                 const double* P, const double* q, const double* A, const double* l,
+                                 const double* u, const double* warm_x, const double* warm_y, double* out_x,
+                                 double* out_y, double* out_obj, int32_t* out_status, uint32_t* out_iter,
+                                 int8_t* out_active, uint32_t* out_flags);
+
+/* Same in single precision (new functionality: the reference has no float instantiation). */
+int sfb_qp_solve_dense_batch_f32(sfb_handle_t h, const sfb_qp_params* prm, int64_t batch, int n, int m,
+                                 const float* P, const float* q, const float* A, const float* l, const float* u,
+                                 const float* warm_x, const float* warm_y, float* out_x, float* out_y,
+                                 float* out_obj, int32_t* out_status, uint32_t* out_iter, int8_t* out_active,
+                                 uint32_t* out_flags);
+
+/* Largest m (for a given n) the shared-memory resident dense kernel accepts; 0 if n itself is too large. */
+int sfb_qp_dense_max_m(sfb_handle_t h, int n, int scalar_bytes);
+
+/* QPSolver::scale alone (qp_solver.hpp:673-730): out_c [batch], out_sx [batch][n], out_sy [batch][m]. Device pointers only. */
+int sfb_qp_scale_dense_batch_f64(sfb_handle_t h, int64_t batch, int n, int m, const double* P, const double* q,
+                                 const double* A, double* out_c, double* out_sx, double* out_sy);
+
+typedef enum { SFB_STEPPER_EULER = 0, SFB_STEPPER_RK4 = 1 } sfb_stepper;
+
+/*
+ * Replaces the covariance half of EKF::predict (ekf.hpp:79-103): integrates Pdot = symU(A P + P A^T + Q)
+ * over [0, tau] with the reference's step schedule (dt <= 0 -> one step of length tau, ekf.hpp:92-102).
+ * A = -ad(f) + d^r f/dx is evaluated by the caller at the pre-step estimate (user lambdas + autodiff stay
+ * on the host) and held constant over the call.  P, A, Q, out_P: [batch][d*d] column-major.  1 <= d <= 16.
+ */
+int sfb_ekf_predict_batch_f64(sfb_handle_t h, int64_t batch, int d, int stepper, const double* P,
+                              const double* A, const double* Q, double tau, double dt, double* out_P);
+
+/*
+ * Replaces the algebra of EKF::update (ekf.hpp:116-139): S = triu(H symU(P) H^T + R), K = (S^-1 H P)^T,
+ * out_delta = K * innov (the caller applies g_hat (+) delta), out_P = symU((I - K H) P).
+ * H [batch][ny*d] (H_ij at i + ny*j), R [batch][ny*ny], innov = y (-) h(g_hat) [batch][ny].  1 <= d, ny <= 16.
+ */
+int sfb_ekf_update_batch_f64(sfb_handle_t h, int64_t batch, int d, int ny, const double* P, const double* H,
+                             const double* R, const double* innov, double* out_delta, double* out_P);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFB_H */

@@ -1,0 +1,161 @@
+"""ctypes loader for libsfb.so, the C-ABI engine declared in include/sfb.h.
+
+There is deliberately no fallback: if the CUDA library is missing or no B200 is visible, importing works
+(so that CPU-only tooling can inspect the package) but every numerical entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import glob
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsfb.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+
+class SfbError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libsfb error {code}: {msg}")
+        self.code = code
+
+
+class SfbQpParams(C.Structure):
+    """sfb_qp_params == QPSolverParams (reference qp_solver.hpp:29-68), field for field."""
+
+    _fields_ = [
+        ("verbose", C.c_int32),
+        ("alpha", C.c_float),
+        ("rho", C.c_float),
+        ("sigma", C.c_float),
+        ("scaling", C.c_int32),
+        ("eps_abs", C.c_float),
+        ("eps_rel", C.c_float),
+        ("eps_primal_inf", C.c_float),
+        ("eps_dual_inf", C.c_float),
+        ("has_max_iter", C.c_int32),
+        ("max_iter", C.c_uint32),
+        ("has_max_time", C.c_int32),
+        ("max_time_ns", C.c_int64),
+        ("stop_check_iter", C.c_uint32),
+        ("polish", C.c_int32),
+        ("polish_iter", C.c_uint32),
+        ("delta", C.c_float),
+    ]
+
+
+# every symbol include/sfb.h declares (tests check the library exports exactly these)
+EXPORTED_SYMBOLS = [
+    "sfb_version", "sfb_error_string", "sfb_last_error_message", "sfb_create", "sfb_destroy", "sfb_set_stream",
+    "sfb_synchronize", "sfb_kernel_launch_count", "sfb_qp_params_default", "sfb_qp_solve_dense_batch_f64",
+    "sfb_qp_solve_dense_batch_f32", "sfb_qp_dense_max_m", "sfb_qp_scale_dense_batch_f64",
+    "sfb_ekf_predict_batch_f64", "sfb_ekf_update_batch_f64",
+]
+
+
+def build(verbose: bool = False) -> str:
+    """Compile csrc/ for sm_100a with nvcc (cross-compiles without a GPU). Returns the library path."""
+    out = None if verbose else subprocess.DEVNULL
+    subprocess.check_call(["make", "-C", CSRC], stdout=out)
+    return LIB_PATH
+
+
+def _preload_cudart() -> None:
+    # libsfb links libcudart.so.12 dynamically so that it shares one runtime with torch
+    try:
+        C.CDLL("libcudart.so.12", mode=C.RTLD_GLOBAL)
+        return
+    except OSError:
+        pass
+    import sysconfig
+
+    for base in {sysconfig.get_paths()["purelib"], sysconfig.get_paths()["platlib"]}:
+        for p in glob.glob(os.path.join(base, "nvidia", "cuda_runtime", "lib", "libcudart.so.12*")):
+            C.CDLL(p, mode=C.RTLD_GLOBAL)
+            return
+    for p in glob.glob("/usr/local/cuda/lib64/libcudart.so.12*"):
+        C.CDLL(p, mode=C.RTLD_GLOBAL)
+        return
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SfbError(-1, f"{LIB_PATH} not built; run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)")
+    _preload_cudart()
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, u64 = C.c_void_p, C.c_int, C.c_int64, C.c_uint64
+    L.sfb_version.restype = C.c_int
+    L.sfb_error_string.argtypes = [C.c_int]
+    L.sfb_error_string.restype = C.c_char_p
+    L.sfb_last_error_message.argtypes = [vp]
+    L.sfb_last_error_message.restype = C.c_char_p
+    L.sfb_create.argtypes = [i32, vp, C.POINTER(vp)]
+    L.sfb_destroy.argtypes = [vp]
+    L.sfb_set_stream.argtypes = [vp, vp]
+    L.sfb_synchronize.argtypes = [vp]
+    L.sfb_kernel_launch_count.argtypes = [vp, C.POINTER(u64)]
+    L.sfb_qp_params_default.argtypes = [C.POINTER(SfbQpParams)]
+    L.sfb_qp_params_default.restype = None
+    qp_sig = [vp, C.POINTER(SfbQpParams), i64, i32, i32] + [vp] * 14
+    L.sfb_qp_solve_dense_batch_f64.argtypes = qp_sig
+    L.sfb_qp_solve_dense_batch_f32.argtypes = qp_sig
+    L.sfb_qp_dense_max_m.argtypes = [vp, i32, i32]
+    L.sfb_qp_scale_dense_batch_f64.argtypes = [vp, i64, i32, i32] + [vp] * 6
+    L.sfb_ekf_predict_batch_f64.argtypes = [vp, i64, i32, i32, vp, vp, vp, C.c_double, C.c_double, vp]
+    L.sfb_ekf_update_batch_f64.argtypes = [vp, i64, i32, i32] + [vp] * 6
+    for name in EXPORTED_SYMBOLS:
+        fn = getattr(L, name)
+        if fn.restype is C.c_int and name not in ("sfb_version", "sfb_qp_dense_max_m"):
+            pass
+    _lib = L
+    return L
+
+
+class Handle:
+    """Owns one sfb_handle_t (one per host thread / stream, like a QPSolver object)."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self._h = C.c_void_p()
+        L = lib()
+        rc = L.sfb_create(int(device), C.c_void_p(stream or 0), C.byref(self._h))
+        if rc != 0:
+            raise SfbError(rc, L.sfb_last_error_message(None).decode())
+        self.device = int(device)
+
+    def check(self, rc: int) -> None:
+        if rc != 0:
+            raise SfbError(rc, lib().sfb_last_error_message(self._h).decode() or lib().sfb_error_string(rc).decode())
+
+    @property
+    def raw(self) -> C.c_void_p:
+        return self._h
+
+    def set_stream(self, stream: int | None) -> None:
+        self.check(lib().sfb_set_stream(self._h, C.c_void_p(stream or 0)))
+
+    def synchronize(self) -> None:
+        self.check(lib().sfb_synchronize(self._h))
+
+    def launch_count(self) -> int:
+        v = C.c_uint64()
+        self.check(lib().sfb_kernel_launch_count(self._h, C.byref(v)))
+        return int(v.value)
+
+    def close(self) -> None:
+        if self._h:
+            lib().sfb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

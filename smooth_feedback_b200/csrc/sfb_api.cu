@@ -1,0 +1,542 @@
+// sfb_api.cu -- host side of the C ABI declared in include/sfb.h.
+//
+// Thin by design: argument validation, launch geometry, and the host-buffer staging pipeline.  All numerics
+// live in the kernels (qp_dense_warp.cuh, ekf_kernels.cuh).  There is no CPU implementation of anything here:
+// without a CUDA device every entry point fails.
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sfb.h"
+#include "ekf_kernels.cuh"
+#include "qp_dense_warp.cuh"
+
+namespace {
+
+constexpr int kNumSlots = 3;  // staging slots of the host-buffer pipeline (H2D / compute / D2H overlap)
+
+std::string g_create_error;
+
+struct Slot
+{
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+  void* dev = nullptr;
+  size_t bytes = 0;
+};
+
+}  // namespace
+
+struct sfb_context
+{
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaDeviceProp prop{};
+  unsigned long long* counters = nullptr;  // work-queue heads, one per launch in flight
+  int num_counters = 64;
+  int next_counter = 0;
+  uint64_t launches = 0;
+  std::string last_error;
+  Slot slots[kNumSlots];
+  cudaEvent_t ev_start = nullptr;
+};
+
+namespace {
+
+int fail(sfb_context* h, int code, const char* fmt, ...)
+{
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->last_error = buf; else g_create_error = buf;
+  return code;
+}
+
+#define SFB_CUDA(h, call)                                                                              \
+  do {                                                                                                 \
+    cudaError_t e__ = (call);                                                                          \
+    if (e__ != cudaSuccess)                                                                            \
+      return fail(h, SFB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__,  \
+                  __LINE__);                                                                           \
+  } while (0)
+
+// 0 = host, 1 = device, -1 = unknown/error
+int mem_space(const void* p)
+{
+  cudaPointerAttributes at{};
+  cudaError_t e = cudaPointerGetAttributes(&at, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return 0;  // plain malloc'ed memory on older runtimes
+  }
+  if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) return 1;
+  return 0;
+}
+
+// classify a set of pointers (nullptr entries ignored): 0 all host, 1 all device, -1 mixed
+int classify(std::initializer_list<const void*> ps)
+{
+  int seen = -2;
+  for (const void* p : ps) {
+    if (!p) continue;
+    const int s = mem_space(p);
+    if (seen == -2) seen = s;
+    else if (seen != s) return -1;
+  }
+  return seen == -2 ? 1 : seen;
+}
+
+unsigned long long* next_counter(sfb_context* h)
+{
+  unsigned long long* c = h->counters + h->next_counter;
+  h->next_counter = (h->next_counter + 1) % h->num_counters;
+  return c;
+}
+
+int ensure_slot(sfb_context* h, Slot& s, size_t bytes)
+{
+  if (s.bytes >= bytes) return SFB_OK;
+  if (s.dev) {
+    SFB_CUDA(h, cudaStreamSynchronize(s.stream));
+    SFB_CUDA(h, cudaFree(s.dev));
+    s.dev = nullptr;
+    s.bytes = 0;
+  }
+  cudaError_t e = cudaMalloc(&s.dev, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(h, SFB_ERR_OUT_OF_MEMORY, "cudaMalloc(%zu) for staging failed: %s", bytes, cudaGetErrorString(e));
+  }
+  s.bytes = bytes;
+  return SFB_OK;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// -------------------------------------------------------------------------------------------------------
+// dense QP launch
+// -------------------------------------------------------------------------------------------------------
+struct QpGeom
+{
+  int warps_per_cta = 0;
+  int ctas_per_sm = 0;
+  size_t smem_per_cta = 0;
+};
+
+template <typename T> int qp_geometry(sfb_context* h, int n, int m, QpGeom* g)
+{
+  sfb::QpLayout L(n, m);
+  const size_t per_warp = (size_t)L.total * sizeof(T);
+  const size_t cap = h->prop.sharedMemPerBlockOptin;
+  int wpc = (int)std::min<size_t>(8, cap / per_warp);
+  if (wpc < 1) return SFB_ERR_UNSUPPORTED_SIZE;
+  // prefer several warps per SM: shrink the CTA until at least the per-SM shared memory is well used
+  const size_t per_sm = h->prop.sharedMemPerMultiprocessor;
+  int best_wpc = wpc, best_total = 0;
+  for (int w = wpc; w >= 1; --w) {
+    const size_t cta = per_warp * w + 1024;  // 1 KB per-CTA reservation
+    int ctas = (int)std::min<size_t>(per_sm / cta, (size_t)(64 / w));
+    ctas = std::min(ctas, 32);
+    const int total = ctas * w;
+    if (total > best_total) { best_total = total; best_wpc = w; }
+  }
+  g->warps_per_cta = best_wpc;
+  g->smem_per_cta = per_warp * best_wpc;
+  g->ctas_per_sm = std::max(1, std::min<int>((int)(per_sm / (g->smem_per_cta + 1024)), 64 / best_wpc));
+  return SFB_OK;
+}
+
+template <typename T>
+int qp_launch(sfb_context* h, cudaStream_t st, const sfb::QpArgs<T>& args_in)
+{
+  sfb::QpArgs<T> args = args_in;
+  QpGeom g;
+  if (qp_geometry<T>(h, args.n, args.m, &g) != SFB_OK)
+    return fail(h, SFB_ERR_UNSUPPORTED_SIZE, "dense QP n=%d m=%d (%zu-byte scalars) does not fit in shared memory",
+                args.n, args.m, sizeof(T));
+  auto kern = sfb::qp_dense_warp_kernel<T>;
+  SFB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_per_cta));
+  args.work_counter = next_counter(h);
+  SFB_CUDA(h, cudaMemsetAsync(args.work_counter, 0, sizeof(unsigned long long), st));
+  const long long want = (args.batch + g.warps_per_cta - 1) / g.warps_per_cta;
+  const long long persistent = (long long)h->prop.multiProcessorCount * g.ctas_per_sm;
+  const int grid = (int)std::max<long long>(1, std::min(want, persistent));
+  kern<<<grid, g.warps_per_cta * 32, g.smem_per_cta, st>>>(args);
+  SFB_CUDA(h, cudaGetLastError());
+  h->launches += 1;
+  return SFB_OK;
+}
+
+int check_params(sfb_context* h, const sfb_qp_params* prm, int64_t batch, int n, int m)
+{
+  if (!h) return SFB_ERR_INVALID_ARGUMENT;
+  if (!prm) return fail(h, SFB_ERR_INVALID_ARGUMENT, "prm is NULL");
+  if (batch < 0 || n <= 0 || m < 0) return fail(h, SFB_ERR_INVALID_ARGUMENT, "bad sizes batch=%lld n=%d m=%d", (long long)batch, n, m);
+  if (prm->stop_check_iter == 0) return fail(h, SFB_ERR_INVALID_ARGUMENT, "stop_check_iter must be > 0");
+  return SFB_OK;
+}
+
+template <typename T>
+int qp_solve_impl(sfb_context* h, const sfb_qp_params* prm, int64_t batch, int n, int m, const T* P, const T* q,
+                  const T* A, const T* l, const T* u, const T* warm_x, const T* warm_y, T* out_x, T* out_y,
+                  T* out_obj, int32_t* out_status, uint32_t* out_iter, int8_t* out_active, uint32_t* out_flags)
+{
+  int rc = check_params(h, prm, batch, n, m);
+  if (rc != SFB_OK) return rc;
+  if (!P || !q || !out_x || !out_y || !out_obj || !out_status || !out_iter || (m > 0 && (!A || !l || !u)))
+    return fail(h, SFB_ERR_INVALID_ARGUMENT, "required pointer is NULL");
+  if ((warm_x == nullptr) != (warm_y == nullptr))
+    return fail(h, SFB_ERR_INVALID_ARGUMENT, "warm_x and warm_y must both be given or both be NULL");
+  if (batch == 0) return SFB_OK;
+  SFB_CUDA(h, cudaSetDevice(h->device));
+  {
+    QpGeom g;
+    if (qp_geometry<T>(h, n, m, &g) != SFB_OK)
+      return fail(h, SFB_ERR_UNSUPPORTED_SIZE, "dense QP n=%d m=%d (%zu-byte scalars) does not fit in shared memory", n,
+                  m, sizeof(T));
+  }
+  const int space = classify({P, q, A, l, u, warm_x, warm_y, out_x, out_y, out_obj, out_status, out_iter, out_active, out_flags});
+  if (space < 0) return fail(h, SFB_ERR_MIXED_MEMORY, "host and device pointers mixed in one call");
+
+  sfb::QpArgs<T> a{};
+  a.batch = batch;
+  a.n = n;
+  a.m = m;
+  a.mode = 0;
+  a.prm = *prm;
+  a.max_iter_eff = prm->has_max_iter ? prm->max_iter : SFB_QP_DEVICE_ITER_CAP;
+
+  if (space == 1) {
+    a.P = P; a.q = q; a.A = A; a.l = l; a.u = u; a.warm_x = warm_x; a.warm_y = warm_y;
+    a.out_x = out_x; a.out_y = out_y; a.out_obj = out_obj; a.out_status = out_status; a.out_iter = out_iter;
+    a.out_active = out_active; a.out_flags = out_flags;
+    return qp_launch<T>(h, h->stream, a);
+  }
+
+  // ---- host buffers: pipelined staging (chunk k uses slot k % kNumSlots on its own stream) ----
+  const size_t sP = align_up(sizeof(T) * n * n, 16), sq = align_up(sizeof(T) * n, 16),
+               sA = align_up(sizeof(T) * m * n, 16), sm_ = align_up(sizeof(T) * m, 16);
+  (void)sP; (void)sq; (void)sA; (void)sm_;
+  const size_t in_per = sizeof(T) * ((size_t)n * n + n + (size_t)m * n + 2 * (size_t)m) +
+                        (warm_x ? sizeof(T) * ((size_t)n + m) : 0);
+  const size_t out_per = sizeof(T) * ((size_t)n + m + 1) + 8 + (size_t)m + 4;
+  const size_t per = in_per + out_per;
+  // chunk: ~64 MB of staging per slot, at least one instance, and at least ~4 chunks when the batch allows
+  long long chunk = std::max<long long>(1, (long long)((64ull << 20) / per));
+  chunk = std::min<long long>(chunk, std::max<long long>(1, (batch + 3) / 4));
+  chunk = std::min<long long>(chunk, batch);
+  // every per-field sub-buffer 256-byte aligned
+  auto fld = [&](size_t elems_bytes) { return align_up(elems_bytes * (size_t)chunk, 256); };
+  const size_t oP = 0, oq = oP + fld(sizeof(T) * n * n), oA = oq + fld(sizeof(T) * n), ol = oA + fld(sizeof(T) * m * n),
+               ou = ol + fld(sizeof(T) * m), owx = ou + fld(sizeof(T) * m), owy = owx + fld(sizeof(T) * n),
+               oox = owy + fld(sizeof(T) * m), ooy = oox + fld(sizeof(T) * n), oobj = ooy + fld(sizeof(T) * m),
+               ost = oobj + fld(sizeof(T)), oit = ost + fld(4), oact = oit + fld(4), ofl = oact + fld(m),
+               slot_bytes = ofl + fld(4);
+
+  SFB_CUDA(h, cudaEventRecord(h->ev_start, h->stream));
+  for (int s = 0; s < kNumSlots; ++s) SFB_CUDA(h, cudaStreamWaitEvent(h->slots[s].stream, h->ev_start, 0));
+  int k = 0;
+  for (long long b0 = 0; b0 < batch; b0 += chunk, ++k) {
+    Slot& s = h->slots[k % kNumSlots];
+    rc = ensure_slot(h, s, slot_bytes);
+    if (rc != SFB_OK) return rc;
+    const long long cnt = std::min<long long>(chunk, batch - b0);
+    char* d = static_cast<char*>(s.dev);
+    auto h2d = [&](size_t off, const T* src, size_t per_inst) -> cudaError_t {
+      return cudaMemcpyAsync(d + off, src + (size_t)b0 * per_inst, sizeof(T) * per_inst * (size_t)cnt,
+                             cudaMemcpyHostToDevice, s.stream);
+    };
+    SFB_CUDA(h, h2d(oP, P, (size_t)n * n));
+    SFB_CUDA(h, h2d(oq, q, n));
+    if (m > 0) {
+      SFB_CUDA(h, h2d(oA, A, (size_t)m * n));
+      SFB_CUDA(h, h2d(ol, l, m));
+      SFB_CUDA(h, h2d(ou, u, m));
+    }
+    if (warm_x) {
+      SFB_CUDA(h, h2d(owx, warm_x, n));
+      if (m > 0) SFB_CUDA(h, h2d(owy, warm_y, m));
+    }
+    sfb::QpArgs<T> c = a;
+    c.batch = cnt;
+    c.P = reinterpret_cast<const T*>(d + oP); c.q = reinterpret_cast<const T*>(d + oq);
+    c.A = reinterpret_cast<const T*>(d + oA); c.l = reinterpret_cast<const T*>(d + ol);
+    c.u = reinterpret_cast<const T*>(d + ou);
+    c.warm_x = warm_x ? reinterpret_cast<const T*>(d + owx) : nullptr;
+    c.warm_y = warm_x ? reinterpret_cast<const T*>(d + owy) : nullptr;
+    c.out_x = reinterpret_cast<T*>(d + oox); c.out_y = reinterpret_cast<T*>(d + ooy);
+    c.out_obj = reinterpret_cast<T*>(d + oobj); c.out_status = reinterpret_cast<int32_t*>(d + ost);
+    c.out_iter = reinterpret_cast<uint32_t*>(d + oit);
+    c.out_active = out_active ? reinterpret_cast<int8_t*>(d + oact) : nullptr;
+    c.out_flags = out_flags ? reinterpret_cast<uint32_t*>(d + ofl) : nullptr;
+    rc = qp_launch<T>(h, s.stream, c);
+    if (rc != SFB_OK) return rc;
+    auto d2h = [&](void* dst, size_t off, size_t bytes_per_inst) -> cudaError_t {
+      return cudaMemcpyAsync(static_cast<char*>(dst) + (size_t)b0 * bytes_per_inst, d + off,
+                             bytes_per_inst * (size_t)cnt, cudaMemcpyDeviceToHost, s.stream);
+    };
+    SFB_CUDA(h, d2h(out_x, oox, sizeof(T) * n));
+    if (m > 0) SFB_CUDA(h, d2h(out_y, ooy, sizeof(T) * m));
+    SFB_CUDA(h, d2h(out_obj, oobj, sizeof(T)));
+    SFB_CUDA(h, d2h(out_status, ost, 4));
+    SFB_CUDA(h, d2h(out_iter, oit, 4));
+    if (out_active && m > 0) SFB_CUDA(h, d2h(out_active, oact, m));
+    if (out_flags) SFB_CUDA(h, d2h(out_flags, ofl, 4));
+  }
+  for (int s = 0; s < kNumSlots; ++s) {
+    SFB_CUDA(h, cudaEventRecord(h->slots[s].done, h->slots[s].stream));
+    SFB_CUDA(h, cudaStreamWaitEvent(h->stream, h->slots[s].done, 0));
+  }
+  // host results must be in place when the call returns
+  for (int s = 0; s < kNumSlots; ++s) SFB_CUDA(h, cudaStreamSynchronize(h->slots[s].stream));
+  return SFB_OK;
+}
+
+// -------------------------------------------------------------------------------------------------------
+// EKF launches
+// -------------------------------------------------------------------------------------------------------
+int ekf_block_threads(sfb_context* h, size_t elems_per_thread, size_t scalar, size_t* smem)
+{
+  const size_t cap = h->prop.sharedMemPerBlockOptin;
+  for (int bd = 128; bd >= 32; bd -= 32) {
+    // target >= 2 CTAs per SM when possible
+    const size_t need = elems_per_thread * (size_t)(bd + 1) * scalar;
+    const size_t budget = (bd > 32) ? cap / 2 : cap;
+    if (need <= budget) { *smem = need; return bd; }
+  }
+  return 0;
+}
+
+}  // namespace
+
+// =======================================================================================================
+// C ABI
+// =======================================================================================================
+extern "C" {
+
+int sfb_version(void) { return SFB_VERSION; }
+
+const char* sfb_error_string(int err)
+{
+  switch (err) {
+    case SFB_OK: return "ok";
+    case SFB_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case SFB_ERR_NO_DEVICE: return "no usable CUDA device (this engine has no CPU path)";
+    case SFB_ERR_CUDA: return "CUDA runtime error";
+    case SFB_ERR_UNSUPPORTED_SIZE: return "problem size not supported by the shared-memory resident kernels";
+    case SFB_ERR_MIXED_MEMORY: return "host and device pointers mixed in one call";
+    case SFB_ERR_OUT_OF_MEMORY: return "out of device memory";
+    default: return "unknown error";
+  }
+}
+
+const char* sfb_last_error_message(sfb_handle_t h) { return h ? h->last_error.c_str() : g_create_error.c_str(); }
+
+int sfb_create(int device, void* stream, sfb_handle_t* out)
+{
+  if (!out) return fail(nullptr, SFB_ERR_INVALID_ARGUMENT, "out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return fail(nullptr, SFB_ERR_NO_DEVICE, "no CUDA device visible (%s); libsfb has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  }
+  if (device < 0 || device >= count) return fail(nullptr, SFB_ERR_INVALID_ARGUMENT, "device %d out of range [0,%d)", device, count);
+  sfb_context* h = new sfb_context();
+  h->device = device;
+  h->stream = static_cast<cudaStream_t>(stream);
+  if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&h->prop, device) != cudaSuccess) {
+    const char* msg = cudaGetErrorString(cudaGetLastError());
+    delete h;
+    return fail(nullptr, SFB_ERR_CUDA, "cannot open device %d: %s", device, msg);
+  }
+  if (h->prop.major != 10) {
+    const int mj = h->prop.major, mn = h->prop.minor;
+    delete h;
+    return fail(nullptr, SFB_ERR_NO_DEVICE, "device %d is sm_%d%d; libsfb is built for sm_100a only", device, mj, mn);
+  }
+  bool ok = cudaMalloc(&h->counters, sizeof(unsigned long long) * h->num_counters) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming) == cudaSuccess;
+  for (int s = 0; ok && s < kNumSlots; ++s) {
+    ok = ok && cudaStreamCreateWithFlags(&h->slots[s].stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->slots[s].done, cudaEventDisableTiming) == cudaSuccess;
+  }
+  if (!ok) {
+    const char* msg = cudaGetErrorString(cudaGetLastError());
+    sfb_destroy(h);
+    return fail(nullptr, SFB_ERR_CUDA, "handle setup failed: %s", msg);
+  }
+  *out = h;
+  return SFB_OK;
+}
+
+int sfb_destroy(sfb_handle_t h)
+{
+  if (!h) return SFB_OK;
+  cudaSetDevice(h->device);
+  for (int s = 0; s < kNumSlots; ++s) {
+    if (h->slots[s].stream) { cudaStreamSynchronize(h->slots[s].stream); cudaStreamDestroy(h->slots[s].stream); }
+    if (h->slots[s].done) cudaEventDestroy(h->slots[s].done);
+    if (h->slots[s].dev) cudaFree(h->slots[s].dev);
+  }
+  if (h->ev_start) cudaEventDestroy(h->ev_start);
+  if (h->counters) cudaFree(h->counters);
+  delete h;
+  return SFB_OK;
+}
+
+int sfb_set_stream(sfb_handle_t h, void* stream)
+{
+  if (!h) return SFB_ERR_INVALID_ARGUMENT;
+  h->stream = static_cast<cudaStream_t>(stream);
+  return SFB_OK;
+}
+
+int sfb_synchronize(sfb_handle_t h)
+{
+  if (!h) return SFB_ERR_INVALID_ARGUMENT;
+  SFB_CUDA(h, cudaSetDevice(h->device));
+  SFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return SFB_OK;
+}
+
+int sfb_kernel_launch_count(sfb_handle_t h, uint64_t* out)
+{
+  if (!h || !out) return SFB_ERR_INVALID_ARGUMENT;
+  *out = h->launches;
+  return SFB_OK;
+}
+
+void sfb_qp_params_default(sfb_qp_params* p)
+{
+  if (!p) return;
+  // qp_solver.hpp:29-68
+  p->verbose = 0;
+  p->alpha = 1.6f;
+  p->rho = 0.1f;
+  p->sigma = 1e-6f;
+  p->scaling = 1;
+  p->eps_abs = 1e-3f;
+  p->eps_rel = 1e-3f;
+  p->eps_primal_inf = 1e-4f;
+  p->eps_dual_inf = 1e-4f;
+  p->has_max_iter = 0;
+  p->max_iter = 0;
+  p->has_max_time = 0;
+  p->max_time_ns = 0;
+  p->stop_check_iter = 25;
+  p->polish = 1;
+  p->polish_iter = 5;
+  p->delta = 1e-6f;
+}
+
+int sfb_qp_solve_dense_batch_f64(sfb_handle_t h, const sfb_qp_params* prm, int64_t batch, int n, int m,
+                                 const double* P, const double* q, const double* A, const double* l,
+                                 const double* u, const double* warm_x, const double* warm_y, double* out_x,
+                                 double* out_y, double* out_obj, int32_t* out_status, uint32_t* out_iter,
+                                 int8_t* out_active, uint32_t* out_flags)
+{
+  return qp_solve_impl<double>(h, prm, batch, n, m, P, q, A, l, u, warm_x, warm_y, out_x, out_y, out_obj,
+                               out_status, out_iter, out_active, out_flags);
+}
+
+int sfb_qp_solve_dense_batch_f32(sfb_handle_t h, const sfb_qp_params* prm, int64_t batch, int n, int m,
+                                 const float* P, const float* q, const float* A, const float* l, const float* u,
+                                 const float* warm_x, const float* warm_y, float* out_x, float* out_y,
+                                 float* out_obj, int32_t* out_status, uint32_t* out_iter, int8_t* out_active,
+                                 uint32_t* out_flags)
+{
+  return qp_solve_impl<float>(h, prm, batch, n, m, P, q, A, l, u, warm_x, warm_y, out_x, out_y, out_obj, out_status,
+                              out_iter, out_active, out_flags);
+}
+
+int sfb_qp_dense_max_m(sfb_handle_t h, int n, int scalar_bytes)
+{
+  if (!h || n <= 0 || (scalar_bytes != 4 && scalar_bytes != 8)) return 0;
+  const size_t cap = h->prop.sharedMemPerBlockOptin;
+  int lo = 0, hi = 1 << 16;
+  if ((size_t)sfb::QpLayout(n, 1).total * scalar_bytes > cap) return 0;
+  while (lo + 1 < hi) {  // largest m that fits
+    const int mid = (lo + hi) / 2;
+    if ((size_t)sfb::QpLayout(n, mid).total * scalar_bytes <= cap) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+int sfb_qp_scale_dense_batch_f64(sfb_handle_t h, int64_t batch, int n, int m, const double* P, const double* q,
+                                 const double* A, double* out_c, double* out_sx, double* out_sy)
+{
+  sfb_qp_params prm;
+  sfb_qp_params_default(&prm);
+  int rc = check_params(h, &prm, batch, n, m);
+  if (rc != SFB_OK) return rc;
+  if (!P || !q || (m > 0 && !A) || !out_c || !out_sx || !out_sy) return fail(h, SFB_ERR_INVALID_ARGUMENT, "required pointer is NULL");
+  if (classify({P, q, A, out_c, out_sx, out_sy}) != 1) return fail(h, SFB_ERR_MIXED_MEMORY, "sfb_qp_scale_dense_batch_f64 takes device pointers only");
+  if (batch == 0) return SFB_OK;
+  SFB_CUDA(h, cudaSetDevice(h->device));
+  sfb::QpArgs<double> a{};
+  a.batch = batch; a.n = n; a.m = m; a.mode = 1; a.prm = prm; a.max_iter_eff = 0;
+  a.P = P; a.q = q; a.A = A; a.l = A; a.u = A;  // l/u are staged but unused in scale-only mode: point at valid memory
+  a.out_c = out_c; a.out_sx = out_sx; a.out_sy = out_sy;
+  return qp_launch<double>(h, h->stream, a);
+}
+
+int sfb_ekf_predict_batch_f64(sfb_handle_t h, int64_t batch, int d, int stepper, const double* P,
+                              const double* A, const double* Q, double tau, double dt, double* out_P)
+{
+  if (!h) return SFB_ERR_INVALID_ARGUMENT;
+  if (batch < 0 || d <= 0 || (stepper != SFB_STEPPER_EULER && stepper != SFB_STEPPER_RK4) || !P || !A || !Q || !out_P)
+    return fail(h, SFB_ERR_INVALID_ARGUMENT, "bad argument to sfb_ekf_predict_batch_f64");
+  if (classify({P, A, Q, out_P}) != 1) return fail(h, SFB_ERR_MIXED_MEMORY, "EKF entry points take device pointers only");
+  if (batch == 0) return SFB_OK;
+  SFB_CUDA(h, cudaSetDevice(h->device));
+  size_t smem = 0;
+  const int bd = ekf_block_threads(h, (size_t)6 * d * d, sizeof(double), &smem);
+  if (bd == 0) return fail(h, SFB_ERR_UNSUPPORTED_SIZE, "EKF predict d=%d does not fit in shared memory", d);
+  auto kern = sfb::ekf_predict_kernel<double>;
+  SFB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  sfb::EkfPredictArgs<double> a{P, A, Q, out_P, batch, d, stepper, tau, dt};
+  const long long tiles = (batch + bd - 1) / bd;
+  const int per_sm = (int)std::max<size_t>(1, h->prop.sharedMemPerMultiprocessor / (smem + 1024));
+  const int grid = (int)std::min<long long>(tiles, (long long)h->prop.multiProcessorCount * per_sm);
+  kern<<<grid, bd, smem, h->stream>>>(a);
+  SFB_CUDA(h, cudaGetLastError());
+  h->launches += 1;
+  return SFB_OK;
+}
+
+int sfb_ekf_update_batch_f64(sfb_handle_t h, int64_t batch, int d, int ny, const double* P, const double* H,
+                             const double* R, const double* innov, double* out_delta, double* out_P)
+{
+  if (!h) return SFB_ERR_INVALID_ARGUMENT;
+  if (batch < 0 || d <= 0 || ny <= 0 || ny > sfb::kEkfMaxNy || !P || !H || !R || !innov || !out_delta || !out_P)
+    return fail(h, SFB_ERR_INVALID_ARGUMENT, "bad argument to sfb_ekf_update_batch_f64");
+  if (classify({P, H, R, innov, out_delta, out_P}) != 1) return fail(h, SFB_ERR_MIXED_MEMORY, "EKF entry points take device pointers only");
+  if (batch == 0) return SFB_OK;
+  SFB_CUDA(h, cudaSetDevice(h->device));
+  size_t smem = 0;
+  const int bd = ekf_block_threads(h, sfb::ekf_update_elems<double>(d, ny), sizeof(double), &smem);
+  if (bd == 0) return fail(h, SFB_ERR_UNSUPPORTED_SIZE, "EKF update d=%d ny=%d does not fit in shared memory", d, ny);
+  auto kern = sfb::ekf_update_kernel<double>;
+  SFB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  sfb::EkfUpdateArgs<double> a{P, H, R, innov, out_delta, out_P, batch, d, ny};
+  const long long tiles = (batch + bd - 1) / bd;
+  const int per_sm = (int)std::max<size_t>(1, h->prop.sharedMemPerMultiprocessor / (smem + 1024));
+  const int grid = (int)std::min<long long>(tiles, (long long)h->prop.multiProcessorCount * per_sm);
+  kern<<<grid, bd, smem, h->stream>>>(a);
+  SFB_CUDA(h, cudaGetLastError());
+  h->launches += 1;
+  return SFB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,84 @@
+"""CPU-side checks of the C-ABI library: it builds for sm_100a, loads, exports every symbol include/sfb.h
+declares, and fails loudly (no fallback) without a device.  No compute calls."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from smooth_feedback_b200 import _lib
+
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build()
+    return _lib
+
+
+def test_header_symbols_are_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "sfb.h")).read()
+    declared = sorted(set(re.findall(r"\b(sfb_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared, "no declarations found"
+    L = lib.lib()
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/sfb.h but not exported by libsfb.so"
+    assert sorted(lib.EXPORTED_SYMBOLS) == declared
+
+
+def test_params_default_matches_reference(lib):
+    # QPSolverParams defaults, reference qp_solver.hpp:29-68
+    p = lib.SfbQpParams()
+    lib.lib().sfb_qp_params_default(C.byref(p))
+    import numpy as np
+
+    f32 = lambda v: float(np.float32(v))
+    assert (p.alpha, p.rho, p.sigma) == (f32(1.6), f32(0.1), f32(1e-6))
+    assert (p.eps_abs, p.eps_rel, p.eps_primal_inf, p.eps_dual_inf) == (f32(1e-3), f32(1e-3), f32(1e-4), f32(1e-4))
+    assert (p.scaling, p.polish, p.polish_iter, p.stop_check_iter, p.has_max_iter, p.has_max_time) == (1, 1, 5, 25, 0, 0)
+    assert p.delta == f32(1e-6)
+    from smooth_feedback_b200.qp import QPSolverParams
+
+    q = QPSolverParams().to_c()
+    for name, _ in lib.SfbQpParams._fields_:
+        assert getattr(p, name) == getattr(q, name), name
+
+
+def test_status_enum_order(lib):
+    from smooth_feedback_b200.qp import QPSolutionStatus as S
+
+    # qp.hpp:82-92
+    assert [s.name for s in S] == ["Optimal", "PolishFailed", "PrimalInfeasible", "DualInfeasible", "MaxIterations",
+                                   "MaxTime", "Unknown"]
+    assert [int(s) for s in S] == list(range(7))
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from smooth_feedback_b200 import Handle, SfbError
+
+    with pytest.raises(SfbError) as e:
+        Handle(0)
+    assert e.value.code == 2  # SFB_ERR_NO_DEVICE
+
+
+def test_only_sm100a_code_in_library(lib):
+    out = subprocess.run(["cuobjdump", "-lelf", lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "smooth_feedback_b200")
+    for dp, _, fns in os.walk(pkg):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                src = open(os.path.join(dp, fn)).read()
+                assert "oracle" not in src.replace("the oracle", "").replace("oracle's", "").replace("oracle/", "") or \
+                    not re.search(r"^\s*(from|import)\s+oracle|#include\s+\"[^\"]*oracle", src, re.M), fn

@@ -1,0 +1,259 @@
+"""GPU parity tests for the dense QP path: CUDA engine (through the C ABI) vs the CPU oracle.
+
+Bar (BASELINE.json north_star): status codes, iteration counts and active sets exact; primal/dual within
+1e-6 relative in fp64 (1e-3 in fp32).
+"""
+import numpy as np
+import pytest
+
+from qp_cases import CASES, OPTIMAL, as_batch, is_approx
+
+pytestmark = pytest.mark.gpu
+
+REL_F64 = 1e-6  # north_star tolerance, fp64
+REL_F32 = 1e-3  # north_star tolerance, fp32
+
+
+@pytest.fixture(scope="module")
+def sfb():
+    import smooth_feedback_b200 as s
+
+    return s
+
+
+def rel_err(a, ref):
+    a = np.asarray(a, dtype=np.float64); ref = np.asarray(ref, dtype=np.float64)
+    num = np.linalg.norm(a - ref, axis=-1)
+    den = np.maximum(np.linalg.norm(ref, axis=-1), 1e-9)
+    return num / den
+
+
+def gpu_solve(sfb, P, q, A, l, u, prm=None, warm=None, dtype=np.float64):
+    cm = sfb.to_colmajor
+    wx, wy = (None, None) if warm is None else warm
+    c = lambda t: None if t is None else np.ascontiguousarray(t, dtype=dtype)
+    return sfb.solve_dense_batch(c(cm(P)), c(q), c(cm(A)), c(l), c(u), prm, c(wx), c(wy))
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_known_answers_through_c_abi(sfb, case):
+    # the reference's own unit tests (tests/test_qp.cpp:54-336) run against the CUDA engine
+    P, q, A, l, u = as_batch(case)
+    r = gpu_solve(sfb, P, q, A, l, u)
+    assert r.status[0] == case["status"]
+    if case["x"] is not None:
+        assert is_approx(r.x[0], case["x"], case["x_rtol"])
+    if case["obj"] is not None:
+        assert abs(r.obj[0] - case["obj"]) <= case["obj_atol"]
+    if case["status"] == OPTIMAL:
+        r2 = gpu_solve(sfb, P, q, A, l, u, warm=(r.x, r.y))
+        assert r2.status[0] == OPTIMAL and r2.iter[0] == 2
+        assert is_approx(r2.x[0], case["x"], case["x_rtol"])
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_known_answers_match_oracle(sfb, oracle, case):
+    P, q, A, l, u = as_batch(case)
+    r = gpu_solve(sfb, P, q, A, l, u)
+    o = oracle.qp_solve_batch(P, q, A, l, u)
+    assert r.status[0] == o.status[0] and r.iter[0] == o.iter[0]
+    assert np.array_equal(r.active, o.active)
+    if case["status"] == OPTIMAL:
+        assert rel_err(r.x, o.x).max() <= REL_F64 and rel_err(r.y, o.y).max() <= REL_F64
+
+
+def _parity(sfb, oracle, B, n, m, seed, feasible=True, prm_kw=None, rel=REL_F64, max_iter=4000):
+    from smooth_feedback_b200.generators import random_qp_numpy
+
+    prm_kw = dict(prm_kw or {})
+    P, q, A, l, u = random_qp_numpy(B, n, m, seed=seed, feasible=feasible)
+    prm = sfb.QPSolverParams(max_iter=max_iter, **prm_kw)
+    r = gpu_solve(sfb, P, q, A, l, u, prm)
+    oprm = oracle.default_params(max_iter=max_iter, **{k: (int(v) if isinstance(v, bool) else v) for k, v in prm_kw.items()})
+    o = oracle.qp_solve_batch(P, q, A, l, u, params=oprm, nthreads=8)
+    return r, o
+
+
+def _assert_parity(r, o, rel, polish=True):
+    assert np.array_equal(r.status, o.status), f"status mismatches: {(r.status != o.status).sum()}"
+    assert np.array_equal(r.iter, o.iter), f"iteration-count mismatches: {(r.iter != o.iter).sum()} of {len(o.iter)}"
+    assert np.array_equal(r.active, o.active), f"active-set mismatches: {(r.active != o.active).any(1).sum()}"
+    ok = o.status == 0
+    assert rel_err(r.x[ok], o.x[ok]).max() <= rel
+    assert rel_err(r.y[ok], o.y[ok]).max() <= rel
+    assert np.abs(r.obj[ok] - o.obj[ok]).max() <= rel * np.maximum(1.0, np.abs(o.obj[ok])).max()
+
+
+def test_parity_cfg1_n10_m20(sfb, oracle):
+    # BASELINE.json configs[0] shape, batch 1024
+    r, o = _parity(sfb, oracle, 1024, 10, 20, seed=5)
+    assert (o.status == 0).all()
+    _assert_parity(r, o, REL_F64)
+
+
+def test_parity_cfg2_n50_m100(sfb, oracle):
+    # BASELINE.json configs[1] shape at a batch the oracle finishes in seconds
+    r, o = _parity(sfb, oracle, 512, 50, 100, seed=5)
+    assert (o.status == 0).all()
+    _assert_parity(r, o, REL_F64)
+
+
+def test_parity_tight_eps_no_polish(sfb, oracle):
+    # the reference benchmark protocol's tolerances (benchmarks/bench.cpp:149-150) with polish off:
+    # parity then rests on the ADMM iterates alone
+    r, o = _parity(sfb, oracle, 256, 10, 20, seed=7, prm_kw=dict(eps_abs=1e-6, eps_rel=1e-6, polish=False), max_iter=20000)
+    _assert_parity(r, o, 1e-5)
+
+
+def test_parity_no_scaling(sfb, oracle):
+    r, o = _parity(sfb, oracle, 256, 10, 20, seed=9, prm_kw=dict(scaling=False))
+    _assert_parity(r, o, REL_F64)
+
+
+def test_parity_infeasible_mix(sfb, oracle):
+    # literal bench_types.hpp recipe (delta ~ U(-1,1)): roughly half primal infeasible, heavy-tailed iteration counts
+    r, o = _parity(sfb, oracle, 256, 10, 20, seed=11, feasible=False, max_iter=5000)
+    assert (o.status == 2).any() and (o.status == 0).any()
+    assert np.array_equal(r.status, o.status)
+    assert (r.iter != o.iter).mean() <= 0.02
+    ok = (o.status == 0) & (r.iter == o.iter)
+    assert rel_err(r.x[ok], o.x[ok]).max() <= REL_F64
+
+
+@pytest.mark.parametrize("n,m", [(1, 1), (2, 1), (7, 13), (3, 203), (33, 31), (64, 64), (50, 1)])
+def test_parity_ragged_shapes(sfb, oracle, n, m):
+    r, o = _parity(sfb, oracle, 64, n, m, seed=n * 1000 + m)
+    assert np.array_equal(r.status, o.status)
+    assert np.array_equal(r.iter, o.iter)
+    ok = o.status == 0
+    assert rel_err(r.x[ok], o.x[ok]).max() <= REL_F64
+    assert rel_err(r.y[ok], o.y[ok]).max() <= 1e-5  # duals of tall problems are less well conditioned
+
+
+def test_scale_is_bit_exact(sfb, oracle):
+    # QPSolver::scale (qp_solver.hpp:673-730) uses only max/abs/mul/div/sqrt: the device result must equal the
+    # oracle's bit for bit
+    import torch
+
+    from smooth_feedback_b200.generators import random_qp_numpy
+    from smooth_feedback_b200.qp import qp_scale_batch
+
+    B, n, m = 64, 50, 100
+    P, q, A, l, u = random_qp_numpy(B, n, m, seed=3)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    c, sx, sy = qp_scale_batch(t(sfb.to_colmajor(P)), t(q), t(sfb.to_colmajor(A)))
+    torch.cuda.synchronize()
+    for b in range(B):
+        oc, osx, osy = oracle.qp_scale(P[b], q[b], A[b])
+        assert c[b].item() == oc
+        assert np.array_equal(sx[b].cpu().numpy(), osx) and np.array_equal(sy[b].cpu().numpy(), osy)
+
+
+def test_device_path_equals_host_path(sfb):
+    import torch
+
+    from smooth_feedback_b200.generators import random_qp_numpy
+
+    B, n, m = 300, 10, 20
+    P, q, A, l, u = random_qp_numpy(B, n, m, seed=21)
+    prm = sfb.QPSolverParams(max_iter=4000)
+    rh = gpu_solve(sfb, P, q, A, l, u, prm)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    rd = sfb.solve_dense_batch(t(sfb.to_colmajor(P)), t(q), t(sfb.to_colmajor(A)), t(l), t(u), prm)
+    torch.cuda.synchronize()
+    assert np.array_equal(rd.x.cpu().numpy(), rh.x) and np.array_equal(rd.y.cpu().numpy(), rh.y)
+    assert np.array_equal(rd.status.cpu().numpy(), rh.status)
+    assert np.array_equal(rd.iter.cpu().numpy().astype(np.uint32), rh.iter)
+
+
+def test_warm_start_batch(sfb, oracle):
+    from smooth_feedback_b200.generators import random_qp_numpy
+
+    P, q, A, l, u = random_qp_numpy(128, 10, 20, seed=31)
+    prm = sfb.QPSolverParams(max_iter=4000)
+    r = gpu_solve(sfb, P, q, A, l, u, prm)
+    r2 = gpu_solve(sfb, P, q, A, l, u, prm, warm=(r.x, r.y))
+    o2 = oracle.qp_solve_batch(P, q, A, l, u, params=oracle.default_params(max_iter=4000), warm_x=r.x, warm_y=r.y)
+    assert (r2.status == 0).all() and np.array_equal(r2.iter, o2.iter)
+    assert (r2.iter == 2).all()  # a solved problem exits at the first stop check
+    assert rel_err(r2.x, o2.x).max() <= REL_F64
+
+
+def test_max_iter_and_statuses(sfb, oracle):
+    P, q, A, l, u = as_batch(CASES[7])  # Portfolio needs 152 iterations
+    r = gpu_solve(sfb, P, q, A, l, u, sfb.QPSolverParams(max_iter=10))
+    assert r.status[0] == 4 and r.iter[0] == 10
+    r = gpu_solve(sfb, P, q, A, l, u, sfb.QPSolverParams(max_time=1e-9))
+    assert r.status[0] == 5 and r.iter[0] == 2  # MaxTime is tested at stop checks only (qp_solver.hpp:504-508)
+
+
+def test_fp32_against_fp64_oracle(sfb, oracle):
+    from smooth_feedback_b200.generators import random_qp_numpy
+
+    P, q, A, l, u = random_qp_numpy(256, 10, 20, seed=41)
+    prm = sfb.QPSolverParams(max_iter=4000)
+    r = gpu_solve(sfb, P, q, A, l, u, prm, dtype=np.float32)
+    o = oracle.qp_solve_batch(P, q, A, l, u, params=oracle.default_params(max_iter=4000), nthreads=8)
+    assert (r.status == 0).mean() >= 0.99
+    ok = (r.status == 0) & (o.status == 0)
+    assert np.quantile(rel_err(r.x[ok], o.x[ok]), 0.99) <= REL_F32
+
+
+def test_solver_object_api(sfb):
+    # tests/test_qp.cpp:338-372 SolverAPI: copies / fresh solvers give the same primal
+    import copy
+
+    pb = sfb.QuadraticProgram(P=np.eye(2), q=np.array([-4, 0.25]), A=np.eye(2), l=np.array([-1.0, -1]), u=np.array([1.0, 1]))
+    s1 = sfb.QPSolver(pb)
+    x1 = s1.solve(pb).primal
+    s2 = copy.deepcopy(s1)
+    x2 = s2.solve(pb).primal
+    x3 = sfb.solve_qp(pb, sfb.QPSolverParams()).primal
+    x4 = sfb.QPSolver(sfb.QPSolverParams()).solve(pb).primal
+    assert np.array_equal(x1, x2) and np.array_equal(x1, x3) and np.array_equal(x1, x4)
+    assert s1.sol().code == sfb.QPSolutionStatus.Optimal
+
+
+def test_api_errors(sfb):
+    from smooth_feedback_b200.generators import random_qp_numpy
+
+    P, q, A, l, u = random_qp_numpy(2, 4, 6, seed=1)
+    with pytest.raises(sfb.SfbError) as e:
+        gpu_solve(sfb, P, q, A, l, u, sfb.QPSolverParams(stop_check_iter=0))
+    assert e.value.code == 1
+    Pb, qb, Ab, lb, ub = random_qp_numpy(1, 300, 300, seed=1)
+    with pytest.raises(sfb.SfbError) as e:
+        gpu_solve(sfb, Pb, qb, Ab, lb, ub)
+    assert e.value.code == 4  # does not fit the shared-memory resident kernel: loud, not a fallback
+
+
+def test_full_size_properties(sfb):
+    """BASELINE.json configs[1] at full size (n=50, m=100, batch 65536, fp64): size-independent properties."""
+    import torch
+
+    from smooth_feedback_b200.generators import random_qp_torch
+
+    B, n, m = 65536, 50, 100
+    P_cm, q, A_cm, l, u = random_qp_torch(B, n, m, seed=5)
+    r = sfb.solve_dense_batch(P_cm, q, A_cm, l, u, sfb.QPSolverParams(max_iter=4000))
+    torch.cuda.synchronize()
+    assert (r.status == 0).all()
+    it = r.iter.to(torch.int64)
+    assert ((it % 25) == 2).all()
+    A = A_cm.transpose(1, 2)
+    Ax = torch.einsum("bij,bj->bi", A, r.x)
+    assert (Ax <= u + 1e-7).all()                                   # primal feasibility
+    stat = torch.einsum("bij,bj->bi", P_cm, r.x) + q + torch.einsum("bij,bi->bj", A, r.y)
+    assert stat.abs().max().item() < 1e-6                           # stationarity (P symmetric)
+    assert (r.y >= -1e-9).all()                                     # dual feasibility (l = -inf)
+    assert (r.y * (Ax - u)).abs().max().item() < 1e-6               # complementary slackness
+    obj = 0.5 * torch.einsum("bi,bij,bj->b", r.x, P_cm, r.x) + (q * r.x).sum(1)
+    assert torch.allclose(obj, r.obj, rtol=1e-10, atol=1e-10)
+    act = (r.y > 100 * 2.220446049250313e-16)
+    assert ((r.active != 0) == act).float().mean().item() > 0.999   # polished duals reproduce the active set
+    # idempotence: the solution warm-starts itself out at the first check
+    r2 = sfb.solve_dense_batch(P_cm, q, A_cm, l, u, sfb.QPSolverParams(max_iter=4000), warm_x=r.x, warm_y=r.y)
+    torch.cuda.synchronize()
+    assert (r2.status == 0).all() and (r2.iter == 2).all()
