@@ -117,7 +117,7 @@ def cpu_baseline(sample_target_s: float = 12.0):
         r = orc.qp_solve_batch(P, q, A, l, u, params=prm, nthreads=cores, fast=True)
         best = max(best, count / (time.perf_counter() - t0))
     return {"value": best, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"first {count} of the {BATCH} G+ instances (seed {SEED}), best of 2, oracle -O3 -march=native, "
+            "sample": f"first {count} of the {BATCH} G+ instances (seed {SEED}), best of 2, oracle -O3 -march=x86-64-v3 (AVX2+FMA), "
                       f"OpenMP dynamic over {cores} threads, one reusable workspace per thread",
             "mean_iter": float(r.iter.mean()), "optimal_frac": float((r.status == 0).mean())}
 

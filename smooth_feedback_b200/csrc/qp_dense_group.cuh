@@ -1,0 +1,1262 @@
+// qp_dense_group.cuh -- batched dense operator-splitting QP solver for sm_100a.
+// One group of G warps (G = 1, 2 or 4; one CTA per group) owns one QP instance at a time and keeps its whole
+// working set in shared memory for the lifetime of the solve.
+//
+// Replaces (reference paths relative to pettni/smooth_feedback @ 9a08971):
+//   QPSolver::scale           include/smooth/feedback/qp_solver.hpp:673-730
+//   QPSolver::solve           include/smooth/feedback/qp_solver.hpp:343-568
+//   QPSolver::check_stopping  include/smooth/feedback/qp_solver.hpp:574-644
+//   detail::polish_qp         include/smooth/feedback/qp_solver.hpp:92-204
+//
+// Design (details and measurements in DESIGN.md):
+//   * HBM sees the problem data once (coalesced load) and the solution once; everything else is on chip.
+//   * The reference factorises the (n+m)x(n+m) quasi-definite KKT matrix with a pivoted LDL^T and runs two
+//     triangular sweeps per ADMM iteration -- a serial dependency chain on a GPU.  This kernel eliminates the
+//     diagonal (2,2) block -1/rho analytically,
+//         (Pbar + sigma I + Abar^T R Abar) xt = sigma x - qbar + Abar^T (R z - y),   nu = R (Abar xt - z) + y,
+//     and keeps the explicit n x n inverse Minv on chip, so that an iteration is three conflict-free GEMV
+//     passes (Abar^T w, Minv rhs, Abar xt).  Mathematically identical to the KKT solve (Eigen's pivoting
+//     eliminates the large |-1/rho| diagonal first as well).
+//   * Abar (m x n) and Minv (n x n) are column-major with an ODD leading dimension: thread-per-row accesses are
+//     consecutive, thread-per-column accesses have an odd stride -- both shared-memory bank-conflict free.
+//   * G is chosen on the host so that an SM holds >= ~12 warps: the first version (one warp per QP, profiles/)
+//     was shared-memory-capacity limited to 3 warps per SM and stalled 65% of the time on its own latencies.
+//   * polish solves the reference's regularised KKT system by block elimination in the order Eigen's diagonal
+//     pivoting takes (primal block first): Kinv = (Pbar + delta I)^-1, Sinv = (delta I + Aa Kinv Aa^T)^-1; when
+//     there are more active rows than variables the equivalent Woodbury form (n x n) is used instead.
+
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "../../include/sfb.h"
+
+namespace sfb {
+
+constexpr unsigned kFullMask = 0xffffffffu;
+constexpr int kStatusUnset = -1;
+constexpr int kRedSlots = 12;  // scalars per batched group reduction
+constexpr int kGjPad = 64;    // padded length of the pivot row / column buffers of the register-blocked inverse
+
+__device__ __forceinline__ double rcp(double x) { return __drcp_rn(x); }
+__device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
+
+template <typename T> struct Num;
+template <> struct Num<double>
+{
+  __device__ static double inf() { return CUDART_INF; }
+  __device__ static double eps() { return 2.220446049250313e-16; }
+};
+template <> struct Num<float>
+{
+  __device__ static float inf() { return CUDART_INF_F; }
+  __device__ static float eps() { return 1.1920928955078125e-07f; }
+};
+
+template <typename T> __device__ __forceinline__ T warp_max(T v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(kFullMask, v, o));
+  return v;
+}
+template <typename T> __device__ __forceinline__ T warp_sum(T v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+  return v;
+}
+
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+template <typename T> struct QpArgs
+{
+  const T* P;
+  const T* q;
+  const T* A;
+  const T* l;
+  const T* u;
+  const T* warm_x;
+  const T* warm_y;
+  T* out_x;
+  T* out_y;
+  T* out_obj;
+  int32_t* out_status;
+  uint32_t* out_iter;
+  int8_t* out_active;
+  uint32_t* out_flags;
+  // scale-only mode outputs (mode == 1)
+  T* out_c;
+  T* out_sx;
+  T* out_sy;
+  T* scratch;            // global polish workspace, scratch_per_cta scalars per CTA (may be null if 0)
+  long long scratch_per_cta;
+  long long batch;
+  int n, m;
+  int mode;  // 0 = solve, 1 = scale only
+  sfb_qp_params prm;
+  unsigned max_iter_eff;
+  unsigned long long* work_counter;
+};
+
+// per-CTA shared-memory layout (units of T)
+struct QpLayout
+{
+  int ldA, ldN, npart;
+  int offAs, offMs, offN, offM, offPart, offRed, offGj, offSlot, total;
+  __host__ __device__ static int odd(int v) { return v | 1; }
+  __host__ __device__ QpLayout(int n, int m, int nthreads)
+  {
+    const int mm = m > 0 ? m : 1;
+    ldA = odd(mm);
+    ldN = odd(n);
+    npart = nthreads > n ? nthreads : n;
+    offAs = 0;
+    offMs = offAs + ldA * n;
+    offN = offMs + ldN * n;
+    offM = offN + 8 * n;
+    offPart = offM + 10 * mm;
+    offRed = offPart + npart;
+    offGj = offRed + 2 * 4 * kRedSlots;
+    offSlot = (offGj + 4 * kGjPad + 1) & ~1;  // 8-byte aligned work-queue slot
+    total = offSlot + 2;
+  }
+};
+
+// out-of-line stages (defined below the struct).  They re-derive every pointer from the dynamic shared-memory
+// symbol, so the compiler still knows the address space (LDS/STS, not generic LD/ST) while the kernel keeps ONE
+// copy of each cold stage: the fully inlined version was 430 KB of SASS and spent half its time on instruction
+// fetch (profiles/).
+template <typename T, int G> __device__ __noinline__ bool qp_stage_gj(int n, int m, int where, int sz);
+template <typename T, int G> __device__ __noinline__ bool qp_stage_gj_generic(int n, int m, T* Mx, int ld, int sz);
+template <typename T, int G> __device__ __noinline__ T qp_stage_load_scale(const QpArgs<T>* a, long long b);
+template <typename T, int G> __device__ __noinline__ int qp_stage_setup(const QpArgs<T>* a, T c);
+template <typename T, int G> __device__ __noinline__ int qp_stage_check(const QpArgs<T>* a, long long b, T c);
+template <typename T, int G> __device__ __noinline__ unsigned qp_stage_polish(const QpArgs<T>* a, long long b, T c, int na, T* gscratch);
+
+template <typename T, int G> struct QpGroup
+{
+  static constexpr int NT = 32 * G;
+  int n, m, ldA, ldN, tid, lane, warp;
+  // column-pass geometry: cw threads side by side own consecutive columns, csegs such bands split the rows
+  int cw, csegs, cseg, c0;
+  T* As;  // m x n   raw A, then Abar = Sy A Sx  (polish: active rows compacted on top, Sinv below when it fits)
+  T* Ms;  // n x n   raw P, then M, then Minv    (polish: Kinv or the Woodbury inverse)
+  T *sx, *q, *qb, *x, *xt, *xold, *nv1, *nv2;           // n-vectors
+  T *sy, *l, *u, *rho, *rinv, *z, *y, *w, *yold, *mv1;  // m-vectors
+  T* part;  // max(NT, n) scalars: partial results of column passes
+  T* red;   // reduction scratch, double buffered
+  T* gjbuf; // 4 * kGjPad scalars for the register-blocked inverse
+  int rsel;
+  T c;
+
+  __device__ QpGroup(T* base, int n_, int m_) : n(n_), m(m_)
+  {
+    tid = threadIdx.x;
+    lane = tid & 31;
+    warp = tid >> 5;
+    QpLayout L(n_, m_, NT);
+    ldA = L.ldA;
+    ldN = L.ldN;
+    As = base + L.offAs;
+    Ms = base + L.offMs;
+    T* nv = base + L.offN;
+    sx = nv; q = nv + n; qb = nv + 2 * n; x = nv + 3 * n; xt = nv + 4 * n; xold = nv + 5 * n; nv1 = nv + 6 * n;
+    nv2 = nv + 7 * n;
+    T* mv = base + L.offM;
+    const int mm = m > 0 ? m : 1;
+    sy = mv; l = mv + mm; u = mv + 2 * mm; rho = mv + 3 * mm; rinv = mv + 4 * mm; z = mv + 5 * mm; y = mv + 6 * mm;
+    w = mv + 7 * mm; yold = mv + 8 * mm; mv1 = mv + 9 * mm;
+    part = base + L.offPart;
+    red = base + L.offRed;
+    gjbuf = base + L.offGj;
+    rsel = 0;
+    c = T(1);
+    const int ru = ((n + 31) / 32) * 32;
+    cw = ru < NT ? ru : NT;
+    csegs = NT / cw;
+    cseg = tid / cw;
+    c0 = tid - cseg * cw;
+    if (cseg >= csegs) { cseg = csegs; c0 = n; }  // NT not a multiple of cw: leftover threads own no column
+  }
+
+  // ---------------------------------------------------------------- group primitives
+  __device__ __forceinline__ void gsync()
+  {
+    if (G == 1) __syncwarp(); else __syncthreads();
+  }
+  __device__ __forceinline__ bool gany(bool p)
+  {
+    if (G == 1) return __any_sync(kFullMask, p);
+    return __syncthreads_or(p) != 0;
+  }
+  __device__ __forceinline__ bool gall(bool p)
+  {
+    if (G == 1) return __all_sync(kFullMask, p);
+    return __syncthreads_and(p) != 0;
+  }
+  // batched reductions: K maxima and K2 sums in one barrier
+  template <int KM, int KS> __device__ __forceinline__ void greduce(T (&mx)[KM], T (&sm)[KS])
+  {
+#pragma unroll
+    for (int k = 0; k < KM; ++k) mx[k] = warp_max(mx[k]);
+#pragma unroll
+    for (int k = 0; k < KS; ++k) sm[k] = warp_sum(sm[k]);
+    if (G > 1) {
+      T* r = red + rsel * (4 * kRedSlots);
+      rsel ^= 1;
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < KM; ++k) r[warp * kRedSlots + k] = mx[k];
+#pragma unroll
+        for (int k = 0; k < KS; ++k) r[warp * kRedSlots + KM + k] = sm[k];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < KM; ++k) {
+        T v = r[k];
+#pragma unroll 1
+        for (int wv = 1; wv < G; ++wv) v = fmax(v, r[wv * kRedSlots + k]);
+        mx[k] = v;
+      }
+#pragma unroll
+      for (int k = 0; k < KS; ++k) {
+        T v = r[KM + k];
+#pragma unroll 1
+        for (int wv = 1; wv < G; ++wv) v += r[wv * kRedSlots + KM + k];
+        sm[k] = v;
+      }
+    }
+  }
+  __device__ __forceinline__ T gmax(T v)
+  {
+    T a[1] = {v}, b[1] = {T(0)};
+    greduce<1, 0 + 1>(a, b);
+    return a[0];
+  }
+  __device__ __forceinline__ T gsum(T v)
+  {
+    T a[1] = {T(0)}, b[1] = {v};
+    greduce<1, 1>(a, b);
+    return b[0];
+  }
+  __device__ __forceinline__ T part_sum(int idx, int len) const
+  {
+    T v = part[idx];
+#pragma unroll 1
+    for (int s = 1; s < csegs; ++s) v += part[s * len + idx];
+    return v;
+  }
+  __device__ __forceinline__ T part_max(int idx, int len) const
+  {
+    T v = part[idx];
+#pragma unroll 1
+    for (int s = 1; s < csegs; ++s) v = fmax(v, part[s * len + idx]);
+    return v;
+  }
+
+  // ---------------------------------------------------------------- stage one instance HBM -> shared memory
+  __device__ void load(const QpArgs<T>& a, long long b)
+  {
+    const T* gA = a.A + b * (long long)m * n;
+    const T* gP = a.P + b * (long long)n * n;
+    if (m > 0) {
+      int i = tid % m, j = tid / m;
+      const int di = NT % m, dj = NT / m;
+#pragma unroll 1
+      for (int e = tid; e < m * n; e += NT) {
+        As[i + ldA * j] = __ldg(gA + e);
+        i += di; j += dj;
+        if (i >= m) { i -= m; ++j; }
+      }
+    }
+    {
+      int i = tid % n, j = tid / n;
+      const int di = NT % n, dj = NT / n;
+#pragma unroll 1
+      for (int e = tid; e < n * n; e += NT) {
+        Ms[i + ldN * j] = __ldg(gP + e);
+        i += di; j += dj;
+        if (i >= n) { i -= n; ++j; }
+      }
+    }
+#pragma unroll 1
+    for (int j = tid; j < n; j += NT) q[j] = __ldg(a.q + b * (long long)n + j);
+#pragma unroll 1
+    for (int i = tid; i < m; i += NT) {
+      l[i] = __ldg(a.l + b * (long long)m + i);
+      u[i] = __ldg(a.u + b * (long long)m + i);
+    }
+    gsync();
+  }
+
+  // ---------------------------------------------------------------- QPSolver::scale, qp_solver.hpp:673-730
+  // Products are formed in the reference's order and max() is exact, so c, sx, sy agree with the CPU
+  // restatement bit for bit whatever the thread decomposition.
+  __device__ void scale()
+  {
+#pragma unroll 1
+    for (int j = tid; j < n; j += NT) sx[j] = T(1);
+#pragma unroll 1
+    for (int i = tid; i < m; i += NT) sy[i] = T(1);
+    const int rpsP = (n + csegs - 1) / csegs, rpsA = (m + csegs - 1) / csegs;
+#pragma unroll 1
+    for (int j = c0; j < n; j += cw) {
+      const int i0 = cseg * rpsP, i1 = min(n, i0 + rpsP);
+      T g = T(0);
+#pragma unroll 1
+      for (int i = i0; i < i1; ++i) g = fmax(g, fabs(Ms[i + ldN * j]));  // :681-685
+      part[cseg * n + j] = g;
+    }
+    gsync();
+    T qn = T(0);
+#pragma unroll 1
+    for (int j = tid; j < n; j += NT) {
+      T g = part_max(j, n);
+      if (g == T(0)) g = T(1);  // :688-690
+      nv1[j] = g;
+      qn = fmax(qn, fabs(q[j]));
+    }
+    qn = gmax(qn);
+    gsync();
+    if (tid == 0) {
+      T mean = T(0);
+#pragma unroll 1
+      for (int j = 0; j < n; ++j) mean += nv1[j];  // sequential on purpose: same rounding as the CPU restatement
+      mean /= T(n);
+      nv2[0] = mean;
+    }
+    gsync();
+    c = T(1) / fmax(fmax(T(1e-6), nv2[0]), qn);  // :693
+    gsync();
+
+    int it = 0;
+    bool again;
+#pragma unroll 1
+    do {
+      // column norms of [Ps As'; As 0]  :701-716
+#pragma unroll 1
+      for (int j = c0; j < n; j += cw) {
+        const T sxj = sx[j];
+        T g = T(0);
+        {
+          const int i0 = cseg * rpsP, i1 = min(n, i0 + rpsP);
+#pragma unroll 1
+          for (int i = i0; i < i1; ++i) g = fmax(g, fabs(((c * sx[i]) * sxj) * Ms[i + ldN * j]));
+        }
+        {
+          const int i0 = cseg * rpsA, i1 = min(m, i0 + rpsA);
+#pragma unroll 1
+          for (int i = i0; i < i1; ++i) g = fmax(g, fabs((sy[i] * sxj) * As[i + ldA * j]));
+        }
+        part[cseg * n + j] = g;
+      }
+#pragma unroll 1
+      for (int i = tid; i < m; i += NT) {
+        const T syi = sy[i];
+        T g = T(0);
+#pragma unroll 1
+        for (int j = 0; j < n; ++j) g = fmax(g, fabs((syi * sx[j]) * As[i + ldA * j]));
+        if (g == T(0)) g = T(1);
+        mv1[i] = g;
+      }
+      gsync();
+      T dev = T(0);
+#pragma unroll 1
+      for (int j = tid; j < n; j += NT) {
+        T g = part_max(j, n);
+        if (g == T(0)) g = T(1);
+        sx[j] = sqrt(T(1) / fmax(g, T(1e-8))) * sx[j];  // :726
+        dev = fmax(dev, fabs(g - T(1)));
+      }
+#pragma unroll 1
+      for (int i = tid; i < m; i += NT) {
+        const T g = mv1[i];
+        sy[i] = sqrt(T(1) / fmax(g, T(1e-8))) * sy[i];  // :727
+        dev = fmax(dev, fabs(g - T(1)));
+      }
+      dev = gmax(dev);
+      gsync();
+      again = (it++ < 10) && (dev > T(0.1));  // :728-729
+    } while (again);
+  }
+
+  // ---------------------------------------------------------------- SPD inverse, register-blocked Gauss-Jordan
+  // Thread (ti, tj) of a TR x TC grid owns the cyclic block {(ti + TR a, tj + TC b)} (a < RB, b < CB) in registers for
+  // the whole elimination; per step only the pivot row and column travel through shared memory (double buffered:
+  // one barrier per step).  Needs sz <= TR*RB and sz <= TC*CB; buf: 4*sz scalars of shared scratch.
+  static constexpr int TR = (G == 4) ? 16 : 8;
+  static constexpr int TC = NT / TR;
+  static constexpr int RB = 4, CB = 8;
+  __device__ __forceinline__ bool gj_fits_regs(int sz) const { return sz <= TR * RB && sz <= TC * CB; }
+  __device__ bool gj_invert_reg(T* Mx, int ld, int sz, T* buf)
+  {
+    // buf: 4 * kGjPad scalars (two {row, column} buffer pairs, padded so that no bounds checks are needed)
+    const int ti = tid % TR, tj = tid / TR;
+    T v[RB][CB];
+#pragma unroll
+    for (int a = 0; a < RB; ++a)
+#pragma unroll
+      for (int b2 = 0; b2 < CB; ++b2) {
+        const int i = ti + TR * a, j = tj + TC * b2;
+        v[a][b2] = (i < sz && j < sz) ? Mx[i + ld * j] : T(0);
+      }
+    bool ok = true;
+    // The pivot index runs as k = ak*TR + h*TC + t2 so that the register slots (ak, bk) holding row k and
+    // column k are compile-time constants: no dynamic register indexing, no branches in the step body.
+#pragma unroll
+    for (int ak = 0; ak < RB; ++ak) {
+#pragma unroll
+      for (int h = 0; h < TR / TC; ++h) {
+        constexpr int Q = TR / TC;
+        const int bk = ak * Q + h;
+#pragma unroll 1
+        for (int t2 = 0; t2 < TC; ++t2) {
+          const int t = h * TC + t2;
+          const int k = ak * TR + t;
+          if (k >= sz || !ok) break;
+          T* rowk = buf + (k & 1) * (2 * kGjPad);
+          T* colk = rowk + kGjPad;
+          if (ti == t) {
+#pragma unroll
+            for (int b2 = 0; b2 < CB; ++b2) rowk[tj + TC * b2] = v[ak][b2];
+          }
+          if (tj == t2) {
+#pragma unroll
+            for (int a = 0; a < RB; ++a) colk[ti + TR * a] = v[a][bk];
+          }
+          gsync();
+          const T p = rowk[k];
+          if (!(p > T(0)) || !(p < Num<T>::inf())) { ok = false; break; }
+          const T pinv = rcp(p);
+          T ck[RB], rk[CB];
+#pragma unroll
+          for (int a = 0; a < RB; ++a) ck[a] = colk[ti + TR * a];
+#pragma unroll
+          for (int b2 = 0; b2 < CB; ++b2) rk[b2] = rowk[tj + TC * b2] * pinv;
+          // pivot column (j == k): result -c_i * pinv  ==  0 - c_i * rk'  with rk' = pinv
+          if (tj == t2) {
+            rk[bk] = pinv;
+#pragma unroll
+            for (int a = 0; a < RB; ++a) v[a][bk] = T(0);
+          }
+          // pivot row (i == k): result rk_j (pinv at the pivot)  ==  rk_j - 0 * rk_j
+          if (ti == t) {
+            ck[ak] = T(0);
+#pragma unroll
+            for (int b2 = 0; b2 < CB; ++b2) v[ak][b2] = rk[b2];
+          }
+#pragma unroll
+          for (int a = 0; a < RB; ++a)
+#pragma unroll
+            for (int b2 = 0; b2 < CB; ++b2) v[a][b2] -= ck[a] * rk[b2];
+        }
+      }
+    }
+    gsync();
+    if (!ok) return false;
+#pragma unroll
+    for (int a = 0; a < RB; ++a)
+#pragma unroll
+      for (int b2 = 0; b2 < CB; ++b2) {
+        const int i = ti + TR * a, j = tj + TC * b2;
+        if (i < sz && j < sz) Mx[i + ld * j] = v[a][b2];
+      }
+    gsync();
+    return true;
+  }
+
+  // ---------------------------------------------------------------- SPD inverse in place (Gauss-Jordan, no pivoting)
+  // Mx may live in shared or global memory.  rowk / colk: >= sz scalars of shared scratch.
+  // Returns false (group-uniform) on a non-positive or non-finite pivot.
+  // where = 0: Ms (n x n, ldN);  where = 1: the Schur block kept below the compacted rows, As + sz (sz x sz, ldA)
+  __device__ __forceinline__ bool gj_invert_at(int where, int sz)
+  {
+    if (gj_fits_regs(sz)) return qp_stage_gj<T, G>(n, m, where, sz);
+    return qp_stage_gj_generic<T, G>(n, m, where == 0 ? Ms : As + sz, where == 0 ? ldN : ldA, sz);
+  }
+  __device__ bool gj_invert_smem(T* Mx, int ld, int sz, T* rowk, T* colk)
+  {
+#pragma unroll 1
+    for (int k = 0; k < sz; ++k) {
+      const T p = Mx[k + ld * k];
+      if (!(p > T(0)) || !(p < Num<T>::inf())) return false;
+      const T pinv = T(1) / p;
+#pragma unroll 1
+      for (int j = tid; j < sz; j += NT) {
+        rowk[j] = Mx[k + ld * j] * pinv;
+        colk[j] = Mx[j + ld * k];
+      }
+      gsync();
+      int i = tid % sz, j = tid / sz;
+      const int di = NT % sz, dj = NT / sz;
+#pragma unroll 1
+      for (int e = tid; e < sz * sz; e += NT) {
+        T v;
+        if (i == k) v = (j == k) ? pinv : rowk[j];
+        else if (j == k) v = -colk[i] * pinv;
+        else v = Mx[i + ld * j] - colk[i] * rowk[j];
+        Mx[i + ld * j] = v;
+        i += di; j += dj;
+        if (i >= sz) { i -= sz; ++j; }
+      }
+      gsync();
+    }
+    return true;
+  }
+
+  // ---------------------------------------------------------------- transposed product, partials into part[]
+  // part[seg * n + j] = sum_{i in seg} As[i, j] * v[i]   (and a second vector into part2 if given)
+  __device__ __forceinline__ void colpass(const T* v, int rows)
+  {
+    const int rps = (rows + csegs - 1) / csegs;
+    const int i0 = cseg * rps, i1 = min(rows, i0 + rps);
+#pragma unroll 1
+    for (int j = c0; j < n; j += cw) {
+      const T* col = As + ldA * j;
+      T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0);
+      int i = i0;
+#pragma unroll 1
+      for (; i + 3 < i1; i += 4) {
+        a0 += col[i] * v[i];
+        a1 += col[i + 1] * v[i + 1];
+        a2 += col[i + 2] * v[i + 2];
+        a3 += col[i + 3] * v[i + 3];
+      }
+#pragma unroll 1
+      for (; i < i1; ++i) a0 += col[i] * v[i];
+      part[cseg * n + j] = (a0 + a1) + (a2 + a3);
+    }
+  }
+  // tall-skinny variant (n <= 8): every thread strides over rows, one group reduction per column; result in o[]
+  __device__ void colpass_skinny(const T* v, int rows, T* o)
+  {
+    T acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = T(0);
+#pragma unroll 1
+    for (int i = tid; i < rows; i += NT) {
+      const T vi = v[i];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < n) acc[j] += As[i + ldA * j] * vi;
+    }
+    T dummy[1] = {T(0)};
+    greduce<1, 8>(dummy, acc);
+    if (tid < n) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j == tid) o[j] = acc[j];
+    }
+  }
+  // o[j] = (Abar^T v)_j  for all j, visible to the whole group on return
+  __device__ void At_vec(const T* v, int rows, T* o)
+  {
+    if (n <= 8) {
+      colpass_skinny(v, rows, o);
+      gsync();
+    } else {
+      colpass(v, rows);
+      gsync();
+#pragma unroll 1
+      for (int j = tid; j < n; j += NT) o[j] = part_sum(j, n);
+      gsync();
+    }
+  }
+  // dot of row i of a column-major matrix with v (4 accumulators for ILP)
+  __device__ __forceinline__ T rowdot(const T* Mx, int ld, int i, int cols, const T* v) const
+  {
+    const T* p = Mx + i;
+    T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0);
+    int j = 0;
+#pragma unroll 1
+    for (; j + 3 < cols; j += 4) {
+      a0 += p[ld * j] * v[j];
+      a1 += p[ld * (j + 1)] * v[j + 1];
+      a2 += p[ld * (j + 2)] * v[j + 2];
+      a3 += p[ld * (j + 3)] * v[j + 3];
+    }
+#pragma unroll 1
+    for (; j < cols; ++j) a0 += p[ld * j] * v[j];
+    return (a0 + a1) + (a2 + a3);
+  }
+
+  // ---------------------------------------------------------------- check_stopping, qp_solver.hpp:574-644
+  // Called right after the iterate update of a check iteration; xold / yold hold the pre-update iterates.
+  // A x_us is evaluated as Sy^-1 (Abar x) and A^T y_us as Sx^-1 Abar^T y / c (the same quantities).
+  __device__ int check_stopping(const QpArgs<T>& a, const T* gP)
+  {
+    const T eps_abs = T(a.prm.eps_abs), eps_rel = T(a.prm.eps_rel);
+    const T eps_pinf = T(a.prm.eps_primal_inf), eps_dinf = T(a.prm.eps_dual_inf);
+    const T inf = Num<T>::inf();
+
+    // n-space: x_us -> nv1, dx (scaled) -> nv2, dx_us -> xold ; m-space: dy (scaled) -> w
+    T qn = T(0), dxn = T(0), qdx = T(0), Edy = T(0);
+#pragma unroll 1
+    for (int j = tid; j < n; j += NT) {
+      const T xj = x[j];
+      const T d = xj - xold[j];
+      nv1[j] = sx[j] * xj;      // :481
+      nv2[j] = d;
+      const T dus = sx[j] * d;  // :484
+      xold[j] = dus;
+      qn = fmax(qn, fabs(q[j]));
+      dxn = fmax(dxn, fabs(dus));
+      qdx += q[j] * dus;
+    }
+#pragma unroll 1
+    for (int i = tid; i < m; i += NT) {
+      const T d = y[i] - yold[i];
+      w[i] = d;
+      Edy = fmax(Edy, fabs(sy[i] * d / c));  // :485
+    }
+    {
+      T mx[3] = {qn, dxn, Edy}, sm[1] = {qdx};
+      greduce<3, 1>(mx, sm);
+      qn = mx[0]; dxn = mx[1]; Edy = mx[2]; qdx = sm[0];
+    }
+    gsync();
+
+    // row pass: A x_us, A dx_us
+    T n_Ax = T(0), n_r = T(0), n_z = T(0), s_pinf = T(0);
+    bool pinf_blocked = false, dinf_rows_ok = true;
+#pragma unroll 1
+    for (int i = tid; i < m; i += NT) {
+      T ax = T(0), adx = T(0);
+      const T* p = As + i;
+#pragma unroll 1
+      for (int j = 0; j < n; ++j) {
+        const T aij = p[ldA * j];
+        ax += aij * x[j];
+        adx += aij * nv2[j];
+      }
+      const T syinv = T(1) / sy[i];
+      ax *= syinv;
+      adx *= syinv;
+      const T zus = syinv * z[i];  // :483
+      n_Ax = fmax(n_Ax, fabs(ax));
+      n_r = fmax(n_r, fabs(ax - zus));
+      n_z = fmax(n_z, fabs(zus));
+      const T dyus = sy[i] * w[i] / c;
+      const T li = l[i], ui = u[i];
+      // :602-617 (the reference's early break only matters through "any trigger -> +inf")
+      if (ui != inf) s_pinf += ui * fmax(T(0), dyus);
+      else if (dyus > eps_pinf * Edy) pinf_blocked = true;
+      if (li != -inf) s_pinf += li * fmin(T(0), dyus);
+      else if (dyus < -eps_pinf * Edy) pinf_blocked = true;
+      // :631-639
+      if (ui == inf) dinf_rows_ok = dinf_rows_ok && (adx >= -eps_dinf * dxn);
+      else if (li == -inf) dinf_rows_ok = dinf_rows_ok && (adx <= eps_dinf * dxn);
+      else dinf_rows_ok = dinf_rows_ok && (fabs(adx) < eps_dinf * dxn);
+    }
+    {
+      T mx[3] = {n_Ax, n_r, n_z}, sm[1] = {s_pinf};
+      greduce<3, 1>(mx, sm);
+      n_Ax = mx[0]; n_r = mx[1]; n_z = mx[2]; s_pinf = sm[0];
+    }
+    pinf_blocked = gany(pinf_blocked);
+    dinf_rows_ok = gall(dinf_rows_ok);
+    if (pinf_blocked) s_pinf = inf;
+
+    // column passes: Abar^T y -> xt, Abar^T dy -> nv2 (scaled dx is dead after the row pass)
+    gsync();
+    At_vec(y, m, xt);
+    At_vec(w, m, nv2);
+    T n_Px = T(0), n_Aty = T(0), n_res = T(0), n_Atdy = T(0), n_Pdx = T(0);
+#pragma unroll 1
+    for (int j = tid; j < n; j += NT) {
+      const T sc = T(1) / (sx[j] * c);
+      const T aty = xt[j] * sc;
+      const T atdy = nv2[j] * sc;
+      T px = T(0), pdx = T(0);
+#pragma unroll 1
+      for (int k = 0; k < n; ++k) {
+        const T pjk = __ldg(gP + j + (long long)n * k);  // row j of the unscaled P (coalesced across threads)
+        px += pjk * nv1[k];
+        pdx += pjk * xold[k];
+      }
+      n_Px = fmax(n_Px, fabs(px));
+      n_Aty = fmax(n_Aty, fabs(aty));
+      n_res = fmax(n_res, fabs(px + q[j] + aty));
+      n_Atdy = fmax(n_Atdy, fabs(atdy));
+      n_Pdx = fmax(n_Pdx, fabs(pdx));
+    }
+    {
+      T mx[5] = {n_Px, n_Aty, n_res, n_Atdy, n_Pdx}, sm[1] = {T(0)};
+      greduce<5, 1>(mx, sm);
+      n_Px = mx[0]; n_Aty = mx[1]; n_res = mx[2]; n_Atdy = mx[3]; n_Pdx = mx[4];
+    }
+    gsync();
+
+    // OPTIMALITY :584-594
+    if (n_r <= eps_abs + eps_rel * fmax(n_Ax, n_z)) {
+      const T dual_scale = fmax(fmax(n_Px, qn), n_Aty);
+      if (n_res <= eps_abs + eps_rel * dual_scale) return SFB_QP_OPTIMAL;
+    }
+    // PRIMAL INFEASIBILITY :619
+    if (fmax(n_Atdy, s_pinf) < eps_pinf * Edy) return SFB_QP_PRIMAL_INFEASIBLE;
+    // DUAL INFEASIBILITY :629-641
+    if ((n_Pdx <= eps_dinf * dxn) && (qdx <= eps_dinf * dxn) && dinf_rows_ok) return SFB_QP_DUAL_INFEASIBLE;
+    return kStatusUnset;
+  }
+
+  // Pbar(i, j): upper triangle of c Sx P Sx mirrored (selfadjointView<Upper>), from the unscaled global P
+  __device__ __forceinline__ T pbar(const T* gP, int i, int j) const
+  {
+    const int r = i <= j ? i : j, cc = i <= j ? j : i;
+    return ((c * sx[r]) * __ldg(gP + r + (long long)n * cc)) * sx[cc];
+  }
+
+  // ---------------------------------------------------------------- detail::polish_qp, qp_solver.hpp:92-204
+  // `na` active rows (ascending) are listed in idx[], their scaled bounds in bnd[].  Returns SFB_QP_FLAG_* bits.
+  __device__ unsigned polish(const QpArgs<T>& a, const T* gP, int na, const int* idx, const T* bnd, T* gscratch)
+  {
+    const T delta = T(a.prm.delta);
+    const bool woodbury = na > n;  // more active rows than variables: S would be na x na and singular-ish
+    T* S = nullptr;
+    int ldS = 0;
+    if (!woodbury && na > 0) {
+      if (2 * na <= ldA) { S = As + na; ldS = ldA; }                       // below the compacted rows
+      else if (gscratch != nullptr && (long long)na * na <= a.scratch_per_cta) { S = gscratch; ldS = na; }
+      else return SFB_QP_FLAG_POLISH_SKIPPED;
+    }
+
+    // compact the active rows of Abar to the top of every column (idx ascending => in-place safe)
+#pragma unroll 1
+    for (int j = tid; j < n; j += NT) {
+      T* col = As + ldA * j;
+#pragma unroll 1
+      for (int r = 0; r < na; ++r) col[r] = col[idx[r]];
+    }
+    gsync();
+
+    // K = Pbar + delta I  (+ Aa^T Aa / delta in the Woodbury form)   :161,175
+    {
+      const T dinv = T(1) / delta;
+      int i = tid % n, j = tid / n;
+      const int di = NT % n, dj = NT / n;
+#pragma unroll 1
+      for (int e = tid; e < n * n; e += NT) {
+        T h = pbar(gP, i, j);
+        if (i == j) h += delta;
+        if (woodbury) {
+          const T* ci = As + ldA * i;
+          const T* cj = As + ldA * j;
+          T acc = T(0);
+#pragma unroll 1
+          for (int r = 0; r < na; ++r) acc += ci[r] * cj[r];
+          h += dinv * acc;
+        }
+        Ms[i + ldN * j] = h;
+        i += di; j += dj;
+        if (i >= n) { i -= n; ++j; }
+      }
+    }
+    gsync();
+    if (!gj_invert_at(0, n)) return SFB_QP_FLAG_POLISH_FAILED;
+
+    if (S != nullptr) {
+      // S = delta I + Aa Kinv Aa^T, four columns at a time: T4 = Kinv Aa[s0..s0+3,:]^T (n x 4 in xt,xold,nv1,nv2),
+      // then S[:, s0..s0+3] = Aa T4
+#pragma unroll 1
+      for (int s0 = 0; s0 < na; s0 += 4) {
+        const int ns = min(4, na - s0);
+#pragma unroll 1
+        for (int e = tid; e < n * ns; e += NT) {
+          const int i = e % n, sc = e / n;
+          const T* p = Ms + i;
+          const T* arow = As + (s0 + sc);
+          T a0 = T(0), a1 = T(0);
+          int j = 0;
+#pragma unroll 1
+          for (; j + 1 < n; j += 2) {
+            a0 += p[ldN * j] * arow[ldA * j];
+            a1 += p[ldN * (j + 1)] * arow[ldA * (j + 1)];
+          }
+          if (j < n) a0 += p[ldN * j] * arow[ldA * j];
+          xt[sc * n + i] = a0 + a1;
+        }
+        gsync();
+#pragma unroll 1
+        for (int e = tid; e < na * ns; e += NT) {
+          const int r = e % na, sc = e / na;
+          T acc = rowdot(As, ldA, r, n, xt + sc * n);
+          if (r == s0 + sc) acc += delta;
+          S[r + ldS * (s0 + sc)] = acc;
+        }
+        gsync();
+      }
+      const bool s_ok = (S == As + na) ? gj_invert_at(1, na) : qp_stage_gj_generic<T, G>(n, m, S, ldS, na);
+      if (!s_ok) return SFB_QP_FLAG_POLISH_FAILED;
+    }
+
+    // iterative refinement  t += Hp^-1 (h - H t)   :192-195
+    T* tx = xt;    // n
+    T* ty = z;     // na
+    T* rx = nv1;   // n
+    T* ux = nv2;   // n
+    T* ry = yold;  // na
+    T* sv = rho;   // na
+    T* dy = rinv;  // na
+    const T dinv = T(1) / delta;
+#pragma unroll 1
+    for (int j = tid; j < n; j += NT) tx[j] = T(0);
+#pragma unroll 1
+    for (int r = tid; r < na; r += NT) ty[r] = T(0);
+    gsync();
+#pragma unroll 1
+    for (uint32_t it = 0; it != a.prm.polish_iter; ++it) {
+      // residual r = h - sym(H) t,  H = [Pbar Aa^T; Aa 0]
+#pragma unroll 1
+      for (int i = tid; i < n; i += NT) {
+        T acc = T(0);
+#pragma unroll 1
+        for (int j = 0; j < n; ++j) acc += pbar(gP, i, j) * tx[j];
+        const T* col = As + ldA * i;
+#pragma unroll 1
+        for (int r = 0; r < na; ++r) acc += col[r] * ty[r];
+        rx[i] = -c * (sx[i] * q[i]) - acc;  // :180
+      }
+#pragma unroll 1
+      for (int r = tid; r < na; r += NT) ry[r] = bnd[r] - rowdot(As, ldA, r, n, tx);  // :181-182
+      gsync();
+      if (!woodbury) {
+        // [K Aa^T; Aa -delta I] [dx; dy] = [rx; ry]:  dy = Sinv (Aa Kinv rx - ry),  dx = Kinv (rx - Aa^T dy)
+#pragma unroll 1
+        for (int i = tid; i < n; i += NT) ux[i] = rowdot(Ms, ldN, i, n, rx);
+        gsync();
+#pragma unroll 1
+        for (int r = tid; r < na; r += NT) sv[r] = rowdot(As, ldA, r, n, ux) - ry[r];
+        gsync();
+#pragma unroll 1
+        for (int r = tid; r < na; r += NT) {
+          T acc = T(0);
+#pragma unroll 1
+          for (int s = 0; s < na; ++s) acc += S[r + ldS * s] * sv[s];
+          dy[r] = acc;
+        }
+        gsync();
+#pragma unroll 1
+        for (int i = tid; i < n; i += NT) {
+          const T* col = As + ldA * i;
+          T acc = rx[i];
+#pragma unroll 1
+          for (int r = 0; r < na; ++r) acc -= col[r] * dy[r];
+          ux[i] = acc;
+        }
+        gsync();
+#pragma unroll 1
+        for (int i = tid; i < n; i += NT) tx[i] += rowdot(Ms, ldN, i, n, ux);
+#pragma unroll 1
+        for (int r = tid; r < na; r += NT) ty[r] += dy[r];
+      } else {
+        // same system, duals eliminated first:  (K + Aa^T Aa / delta) dx = rx + Aa^T ry / delta,  dy = (Aa dx - ry) / delta
+#pragma unroll 1
+        for (int i = tid; i < n; i += NT) {
+          const T* col = As + ldA * i;
+          T acc = T(0);
+#pragma unroll 1
+          for (int r = 0; r < na; ++r) acc += col[r] * ry[r];
+          ux[i] = rx[i] + dinv * acc;
+        }
+        gsync();
+#pragma unroll 1
+        for (int i = tid; i < n; i += NT) rx[i] = rowdot(Ms, ldN, i, n, ux);  // rx now holds dx
+        gsync();
+#pragma unroll 1
+        for (int r = tid; r < na; r += NT) ty[r] += (rowdot(As, ldA, r, n, rx) - ry[r]) * dinv;
+#pragma unroll 1
+        for (int i = tid; i < n; i += NT) tx[i] += rx[i];
+      }
+      gsync();
+    }
+    // :199-201
+#pragma unroll 1
+    for (int j = tid; j < n; j += NT) x[j] = tx[j];
+    gsync();  // ty aliases z, y is a distinct vector: scatter after everyone is done reading
+#pragma unroll 1
+    for (int r = tid; r < na; r += NT) y[idx[r]] = ty[r];
+    gsync();
+    return SFB_QP_FLAG_POLISHED;
+  }
+
+  // ---------------------------------------------------------------- M = Pbar + sigma I + Abar^T R Abar
+  // 4x4 register tiles over the upper triangle; each thread walks the m rows in a rotated order so that the
+  // threads of a warp hit different shared-memory banks.
+  __device__ void form_reduced_kkt(T sigma)
+  {
+    const int nb = (n + 3) / 4;
+    const int ntiles = nb * (nb + 1) / 2;
+#pragma unroll 1
+    for (int t = tid; t < ntiles; t += NT) {
+      int J = 0, rem = t;
+#pragma unroll 1
+      while (rem > J) { rem -= (J + 1); ++J; }
+      const int I = rem;  // I <= J
+      int ci[4], cj[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        ci[k] = min(4 * I + k, n - 1) * ldA;
+        cj[k] = min(4 * J + k, n - 1) * ldA;
+      }
+      T acc[4][4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int s = 0; s < 4; ++s) acc[p][s] = T(0);
+      int r = (m > 0) ? (tid % m) : 0;
+#pragma unroll 1
+      for (int k = 0; k < m; ++k) {
+        const T rr = rho[r];
+        T av[4], bv[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          av[p] = As[r + ci[p]];
+          bv[p] = rr * As[r + cj[p]];
+        }
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+          for (int s = 0; s < 4; ++s) acc[p][s] += av[p] * bv[s];
+        if (++r == m) r = 0;
+      }
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          const int gi = 4 * I + p, gj = 4 * J + s;
+          if (gi < n && gj < n && gi <= gj) {
+            T v = Ms[gi + ldN * gj] + acc[p][s];
+            if (gi == gj) v += sigma;
+            Ms[gi + ldN * gj] = v;
+            Ms[gj + ldN * gi] = v;
+          }
+        }
+    }
+    gsync();
+  }
+
+  // rho classes, trivially empty feasible set, in-place data scaling, reduced KKT matrix and its inverse
+  __device__ int setup(const QpArgs<T>& a)
+  {
+    const T inf = Num<T>::inf();
+    const T rho_bar = T(a.prm.rho), sigma = T(a.prm.sigma);
+    int code = kStatusUnset;
+
+    // rho per constraint class + trivially empty feasible set  :361-374
+    bool triv = false;
+#pragma unroll 1
+    for (int i = tid; i < m; i += NT) {
+      const T li = l[i], ui = u[i];
+      if (li == inf || ui == -inf || ui - li < T(0)) triv = true;
+      T r;
+      if (li == -inf && ui == inf) r = T(1e-6);
+      else if (sy[i] * fabs(li - ui) < T(1e-5)) r = T(1e3) * rho_bar;
+      else r = rho_bar;
+      rho[i] = r;
+      rinv[i] = T(1) / r;
+    }
+    if (gany(triv)) code = SFB_QP_PRIMAL_INFEASIBLE;
+
+    // scale the data in place:  qb = c Sx q,  Abar = Sy A Sx,  upper(Pbar) = c Sx P Sx   :401-403,:450
+#pragma unroll 1
+    for (int j = tid; j < n; j += NT) qb[j] = (c * sx[j]) * q[j];
+#pragma unroll 1
+    for (int i = tid; i < m; i += NT) {
+      const T syi = sy[i];
+      T* p = As + i;
+#pragma unroll 1
+      for (int j = 0; j < n; ++j) p[ldA * j] = (syi * p[ldA * j]) * sx[j];
+    }
+#pragma unroll 1
+    for (int i = tid; i < n; i += NT) {
+      const T csxi = c * sx[i];
+#pragma unroll 1
+      for (int j = i; j < n; ++j) Ms[i + ldN * j] = (csxi * Ms[i + ldN * j]) * sx[j];
+    }
+    gsync();
+
+    form_reduced_kkt(sigma);
+    if (!gj_invert_at(0, n)) code = SFB_QP_UNKNOWN;  // :433
+    return code;
+  }
+
+  // ---------------------------------------------------------------- QPSolver::solve, qp_solver.hpp:343-568
+  __device__ void solve(const QpArgs<T>& a, long long b, T* gscratch)
+  {
+    const T inf = Num<T>::inf();
+    const T* gP = a.P + b * (long long)n * n;
+    const unsigned long long t0 = a.prm.has_max_time ? global_timer_ns() : 0ull;
+
+    c = qp_stage_load_scale<T, G>(&a, b);  // :347
+    if (a.mode == 1) {
+      if (tid == 0) a.out_c[b] = c;
+#pragma unroll 1
+      for (int j = tid; j < n; j += NT) a.out_sx[b * (long long)n + j] = sx[j];
+#pragma unroll 1
+      for (int i = tid; i < m; i += NT) a.out_sy[b * (long long)m + i] = sy[i];
+      gsync();
+      return;
+    }
+
+    const T alpha = T(a.prm.alpha), alpha_comp = T(1) - alpha, sigma = T(a.prm.sigma);
+    int code = qp_stage_setup<T, G>(&a, c);  // rho classes, trivial infeasibility, in-place scaling, M, Minv
+
+    // initial iterate  :436-445
+    if (a.warm_x != nullptr) {
+#pragma unroll 1
+      for (int j = tid; j < n; j += NT) x[j] = (T(1) / sx[j]) * __ldg(a.warm_x + b * (long long)n + j);
+#pragma unroll 1
+      for (int i = tid; i < m; i += NT) y[i] = c * ((T(1) / sy[i]) * __ldg(a.warm_y + b * (long long)m + i));
+      gsync();
+#pragma unroll 1
+      for (int i = tid; i < m; i += NT) z[i] = rowdot(As, ldA, i, n, x);
+    } else {
+#pragma unroll 1
+      for (int j = tid; j < n; j += NT) x[j] = T(0);
+#pragma unroll 1
+      for (int i = tid; i < m; i += NT) {
+        y[i] = T(0);
+        z[i] = T(0);
+      }
+    }
+    gsync();
+#pragma unroll 1
+    for (int i = tid; i < m; i += NT) w[i] = rho[i] * z[i] - y[i];
+    gsync();
+
+    // main ADMM loop  :449-510
+    const unsigned sci = a.prm.stop_check_iter;
+    unsigned iter = 0;
+#pragma unroll 1
+    for (; iter != a.max_iter_eff && code == kStatusUnset; ++iter) {
+      // rhs_x = sigma x - qb + Abar^T w,  w = R z - y
+      if (n <= 8) {
+        colpass_skinny(w, m, nv2);
+        gsync();
+#pragma unroll 1
+        for (int j = tid; j < n; j += NT) xt[j] = sigma * x[j] - qb[j] + nv2[j];
+      } else {
+        colpass(w, m);
+        gsync();
+#pragma unroll 1
+        for (int j = tid; j < n; j += NT) xt[j] = sigma * x[j] - qb[j] + part_sum(j, n);
+      }
+      gsync();
+      // xtilde = Minv rhs_x ; x <- alpha xtilde + (1 - alpha) x   :470
+      const bool chk = (iter % sci == 1u);
+#pragma unroll 1
+      for (int i = tid; i < n; i += NT) {
+        const T xti = rowdot(Ms, ldN, i, n, xt);
+        nv1[i] = xti;
+        const T xi = x[i];
+        if (chk) xold[i] = xi;  // :465-468
+        x[i] = alpha * xti + alpha_comp * xi;
+      }
+      gsync();
+      // nu = R (Abar xtilde - z) + y ; z, y updates  :471-477 ; next w
+#pragma unroll 1
+      for (int i = tid; i < m; i += NT) {
+        const T zt = rowdot(As, ldA, i, n, nv1);
+        const T zi = z[i], yi = y[i], ri = rho[i], rinvi = rinv[i];
+        if (chk) yold[i] = yi;
+        const T nu = ri * (zt - zi) + yi;
+        T v = alpha * (rinvi * nu) + alpha_comp * (rinvi * yi) + zi;
+        v = fmax(v, sy[i] * l[i]);
+        v = fmin(v, sy[i] * u[i]);
+        const T yn = alpha_comp * yi + alpha * nu + ri * zi - ri * v;
+        y[i] = yn;
+        z[i] = v;
+        w[i] = ri * v - yn;
+      }
+      gsync();
+      if (chk) {
+        code = qp_stage_check<T, G>(&a, b, c);  // :488  (clobbers w)
+        if (code == kStatusUnset && a.prm.has_max_time) {
+          // :504-508 ; one thread reads the clock so that the decision is group-uniform
+          const bool late = (tid == 0) && ((long long)(global_timer_ns() - t0) > a.prm.max_time_ns);
+          if (gany(late)) code = SFB_QP_MAX_TIME;
+        }
+#pragma unroll 1
+        for (int i = tid; i < m; i += NT) w[i] = rho[i] * z[i] - y[i];
+        gsync();
+      }
+    }
+
+    // active sets as polish_qp builds them (:113-123), ascending order, on the scaled dual
+    int na = 0;
+    int* idx = reinterpret_cast<int*>(mv1);
+    T* bnd = w;
+    {
+      const T thr = T(100) * Num<T>::eps();
+      int* wcnt = reinterpret_cast<int*>(part);
+#pragma unroll 1
+      for (int base = 0; base < m; base += NT) {
+        const int i = base + tid;
+        int act = 0;
+        T bv = T(0);
+        if (i < m) {
+          if (y[i] < -thr && l[i] != -inf) { act = -1; bv = sy[i] * l[i]; }
+          if (y[i] > thr && u[i] != inf) { act = 1; bv = sy[i] * u[i]; }
+          if (a.out_active) a.out_active[b * (long long)m + i] = (int8_t)act;
+        }
+        const unsigned bal = __ballot_sync(kFullMask, act != 0);
+        int before = 0, total = __popc(bal);
+        if (G > 1) {
+          if (lane == 0) wcnt[warp] = total;
+          __syncthreads();
+          total = 0;
+#pragma unroll 1
+          for (int wv = 0; wv < G; ++wv) {
+            if (wv < warp) before += wcnt[wv];
+            total += wcnt[wv];
+          }
+        }
+        if (act != 0) {
+          const int pos = na + before + __popc(bal & ((1u << lane) - 1u));
+          idx[pos] = i;
+          bnd[pos] = bv;
+        }
+        na += total;
+        gsync();
+      }
+    }
+
+    unsigned flags = 0;
+    if (code == SFB_QP_OPTIMAL && a.prm.polish) flags = qp_stage_polish<T, G>(&a, b, c, na, gscratch);  // :515-539
+
+    // unscale + objective  :544-548
+#pragma unroll 1
+    for (int j = tid; j < n; j += NT) {
+      const T v = sx[j] * x[j];
+      nv1[j] = v;
+      a.out_x[b * (long long)n + j] = v;
+    }
+#pragma unroll 1
+    for (int i = tid; i < m; i += NT) a.out_y[b * (long long)m + i] = sy[i] * y[i] / c;
+    gsync();
+    T obj = T(0);
+#pragma unroll 1
+    for (int i = tid; i < n; i += NT) {
+      T acc = T(0);
+#pragma unroll 1
+      for (int j = 0; j < n; ++j) acc += T(0.5) * __ldg(gP + i + (long long)n * j) * nv1[j];
+      obj += nv1[i] * (acc + q[i]);
+    }
+    obj = gsum(obj);
+    if (tid == 0) {
+      a.out_obj[b] = obj;
+      a.out_status[b] = (code == kStatusUnset) ? (int32_t)SFB_QP_MAX_ITERATIONS : (int32_t)code;
+      a.out_iter[b] = iter;
+      if (a.out_flags) a.out_flags[b] = flags;
+    }
+    gsync();
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------
+// out-of-line stages
+// ------------------------------------------------------------------------------------------------------
+template <typename T, int G> __device__ __forceinline__ QpGroup<T, G> qp_view(int n, int m, T c)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  QpGroup<T, G> s(reinterpret_cast<T*>(smem_raw), n, m);
+  s.c = c;
+  s.gsync();  // every thread is out of the caller's last reduction: the scratch parity may restart at 0
+  return s;
+}
+
+template <typename T, int G> __device__ __noinline__ T qp_stage_load_scale(const QpArgs<T>* a, long long b)
+{
+  QpGroup<T, G> s = qp_view<T, G>(a->n, a->m, T(1));
+  s.load(*a, b);
+  if (a->prm.scaling) {
+    s.scale();
+  } else {
+#pragma unroll 1
+    for (int j = s.tid; j < s.n; j += 32 * G) s.sx[j] = T(1);
+#pragma unroll 1
+    for (int i = s.tid; i < s.m; i += 32 * G) s.sy[i] = T(1);
+    s.c = T(1);
+  }
+  s.gsync();
+  return s.c;
+}
+
+template <typename T, int G> __device__ __noinline__ int qp_stage_setup(const QpArgs<T>* a, T c)
+{
+  QpGroup<T, G> s = qp_view<T, G>(a->n, a->m, c);
+  const int code = s.setup(*a);
+  s.gsync();
+  return code;
+}
+
+template <typename T, int G> __device__ __noinline__ bool qp_stage_gj(int n, int m, int where, int sz)
+{
+  QpGroup<T, G> s = qp_view<T, G>(n, m, T(1));
+  const bool ok = s.gj_invert_reg(where == 0 ? s.Ms : s.As + sz, where == 0 ? s.ldN : s.ldA, sz, s.gjbuf);
+  s.gsync();
+  return ok;
+}
+
+// generic-pointer variant (matrix may live in global memory; shared scratch): sizes beyond the register blocking
+template <typename T, int G> __device__ __noinline__ bool qp_stage_gj_generic(int n, int m, T* Mx, int ld, int sz)
+{
+  QpGroup<T, G> s = qp_view<T, G>(n, m, T(1));
+  // row / column buffers: xt..nv2 hold 4n scalars; a Schur block has sz <= n, Ms itself has sz == n
+  const bool ok = s.gj_invert_smem(Mx, ld, sz, s.xt, s.xt + sz);
+  s.gsync();
+  return ok;
+}
+
+template <typename T, int G> __device__ __noinline__ int qp_stage_check(const QpArgs<T>* a, long long b, T c)
+{
+  QpGroup<T, G> s = qp_view<T, G>(a->n, a->m, c);
+  const int code = s.check_stopping(*a, a->P + b * (long long)a->n * a->n);
+  s.gsync();
+  return code;
+}
+
+template <typename T, int G>
+__device__ __noinline__ unsigned qp_stage_polish(const QpArgs<T>* a, long long b, T c, int na, T* gscratch)
+{
+  QpGroup<T, G> s = qp_view<T, G>(a->n, a->m, c);
+  const unsigned fl = s.polish(*a, a->P + b * (long long)a->n * a->n, na, reinterpret_cast<const int*>(s.mv1), s.w, gscratch);
+  s.gsync();
+  return fl;
+}
+
+// One CTA of G warps per instance; CTAs pull instances from a global work counter (iteration counts are
+// heavy-tailed), so a slow instance never idles the rest of the grid.
+template <typename T, int G, int MINB>
+__global__ void __launch_bounds__(32 * G, MINB) qp_dense_group_kernel(const __grid_constant__ QpArgs<T> a)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* base = reinterpret_cast<T*>(smem_raw);
+  QpGroup<T, G> s(base, a.n, a.m);
+  T* gscratch = a.scratch ? a.scratch + (long long)blockIdx.x * a.scratch_per_cta : nullptr;
+  unsigned long long* slot = reinterpret_cast<unsigned long long*>(base + QpLayout(a.n, a.m, 32 * G).offSlot);
+#pragma unroll 1
+  for (;;) {
+    unsigned long long b = 0;
+    if (G == 1) {
+      if (s.lane == 0) b = atomicAdd(a.work_counter, 1ull);
+      b = __shfl_sync(kFullMask, b, 0);
+    } else {
+      if (threadIdx.x == 0) *slot = atomicAdd(a.work_counter, 1ull);
+      __syncthreads();
+      b = *slot;
+      __syncthreads();
+    }
+    if ((long long)b >= a.batch) break;
+    s.solve(a, (long long)b, gscratch);
+  }
+}
+
+}  // namespace sfb

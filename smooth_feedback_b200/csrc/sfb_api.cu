@@ -15,7 +15,7 @@
 
 #include "../../include/sfb.h"
 #include "ekf_kernels.cuh"
-#include "qp_dense_warp.cuh"
+#include "qp_dense_group.cuh"
 
 namespace {
 
@@ -27,6 +27,13 @@ struct Slot
 {
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
+  void* dev = nullptr;
+  size_t bytes = 0;
+};
+
+// global polish workspace (only touched when an instance's Schur block does not fit in shared memory)
+struct Scratch
+{
   void* dev = nullptr;
   size_t bytes = 0;
 };
@@ -44,6 +51,7 @@ struct sfb_context
   uint64_t launches = 0;
   std::string last_error;
   Slot slots[kNumSlots];
+  Scratch scratch[kNumSlots + 1];  // [kNumSlots] belongs to the handle's own stream
   cudaEvent_t ev_start = nullptr;
 };
 
@@ -126,51 +134,109 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // -------------------------------------------------------------------------------------------------------
 struct QpGeom
 {
-  int warps_per_cta = 0;
+  int G = 0;            // warps cooperating on one instance (= warps per CTA)
   int ctas_per_sm = 0;
   size_t smem_per_cta = 0;
 };
 
+template <typename T, int G> constexpr int qp_minb() { return G == 4 ? 3 : (G == 2 ? 8 : 16); }
+
+template <typename T, int G> int qp_occupancy(sfb_context* h, int n, int m, QpGeom* g)
+{
+  sfb::QpLayout L(n, m, 32 * G);
+  const size_t bytes = (size_t)L.total * sizeof(T);
+  if (bytes > h->prop.sharedMemPerBlockOptin) return 0;
+  auto kern = sfb::qp_dense_group_kernel<T, G, qp_minb<T, G>()>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 32 * G, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  g->G = G;
+  g->ctas_per_sm = nb;
+  g->smem_per_cta = bytes;
+  return nb * G;  // resident warps per SM
+}
+
+// Smallest group size that still puts >= 16 warps on an SM; otherwise the one with the most resident warps.
 template <typename T> int qp_geometry(sfb_context* h, int n, int m, QpGeom* g)
 {
-  sfb::QpLayout L(n, m);
-  const size_t per_warp = (size_t)L.total * sizeof(T);
-  const size_t cap = h->prop.sharedMemPerBlockOptin;
-  int wpc = (int)std::min<size_t>(8, cap / per_warp);
-  if (wpc < 1) return SFB_ERR_UNSUPPORTED_SIZE;
-  // prefer several warps per SM: shrink the CTA until at least the per-SM shared memory is well used
-  const size_t per_sm = h->prop.sharedMemPerMultiprocessor;
-  int best_wpc = wpc, best_total = 0;
-  for (int w = wpc; w >= 1; --w) {
-    const size_t cta = per_warp * w + 1024;  // 1 KB per-CTA reservation
-    int ctas = (int)std::min<size_t>(per_sm / cta, (size_t)(64 / w));
-    ctas = std::min(ctas, 32);
-    const int total = ctas * w;
-    if (total > best_total) { best_total = total; best_wpc = w; }
+  QpGeom c1, c2, c4;
+  const int w1 = qp_occupancy<T, 1>(h, n, m, &c1);
+  const int w2 = qp_occupancy<T, 2>(h, n, m, &c2);
+  const int w4 = qp_occupancy<T, 4>(h, n, m, &c4);
+  if (w1 == 0 && w2 == 0 && w4 == 0) return SFB_ERR_UNSUPPORTED_SIZE;
+  if (w1 >= 16) *g = c1;
+  else if (w2 >= 16) *g = c2;
+  else if (w4 >= w2 && w4 >= w1) *g = c4;
+  else if (w2 >= w1) *g = c2;
+  else *g = c1;
+  return SFB_OK;
+}
+
+int ensure_scratch(sfb_context* h, Scratch& s, size_t bytes, cudaStream_t st)
+{
+  if (s.bytes >= bytes) return SFB_OK;
+  if (s.dev) {
+    SFB_CUDA(h, cudaStreamSynchronize(st));
+    SFB_CUDA(h, cudaFree(s.dev));
+    s.dev = nullptr;
+    s.bytes = 0;
   }
-  g->warps_per_cta = best_wpc;
-  g->smem_per_cta = per_warp * best_wpc;
-  g->ctas_per_sm = std::max(1, std::min<int>((int)(per_sm / (g->smem_per_cta + 1024)), 64 / best_wpc));
+  cudaError_t e = cudaMalloc(&s.dev, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(h, SFB_ERR_OUT_OF_MEMORY, "cudaMalloc(%zu) for the polish workspace failed: %s", bytes, cudaGetErrorString(e));
+  }
+  s.bytes = bytes;
+  return SFB_OK;
+}
+
+template <typename T, int G>
+int qp_launch_g(sfb_context* h, cudaStream_t st, sfb::QpArgs<T>& args, const QpGeom& g, int grid)
+{
+  auto kern = sfb::qp_dense_group_kernel<T, G, qp_minb<T, G>()>;
+  SFB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_per_cta));
+  kern<<<grid, 32 * G, g.smem_per_cta, st>>>(args);
+  SFB_CUDA(h, cudaGetLastError());
   return SFB_OK;
 }
 
 template <typename T>
-int qp_launch(sfb_context* h, cudaStream_t st, const sfb::QpArgs<T>& args_in)
+int qp_launch(sfb_context* h, cudaStream_t st, int scratch_slot, const sfb::QpArgs<T>& args_in)
 {
   sfb::QpArgs<T> args = args_in;
   QpGeom g;
   if (qp_geometry<T>(h, args.n, args.m, &g) != SFB_OK)
     return fail(h, SFB_ERR_UNSUPPORTED_SIZE, "dense QP n=%d m=%d (%zu-byte scalars) does not fit in shared memory",
                 args.n, args.m, sizeof(T));
-  auto kern = sfb::qp_dense_warp_kernel<T>;
-  SFB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_per_cta));
+  const long long persistent = (long long)h->prop.multiProcessorCount * g.ctas_per_sm;
+  const int grid = (int)std::max<long long>(1, std::min<long long>(args.batch, persistent));
+  // polish workspace: the Schur block S (na x na, na <= min(n, m)) lives in shared memory when 2 na <= ldA
+  args.scratch = nullptr;
+  args.scratch_per_cta = 0;
+  if (args.mode == 0 && args.prm.polish) {
+    const long long k = std::min(args.n, args.m);
+    const sfb::QpLayout L(args.n, args.m, 32 * g.G);
+    if (2 * k > L.ldA) {
+      const size_t bytes = sizeof(T) * (size_t)(k * k) * (size_t)grid;
+      int rc = ensure_scratch(h, h->scratch[scratch_slot], bytes, st);
+      if (rc != SFB_OK) return rc;
+      args.scratch = static_cast<T*>(h->scratch[scratch_slot].dev);
+      args.scratch_per_cta = k * k;
+    }
+  }
   args.work_counter = next_counter(h);
   SFB_CUDA(h, cudaMemsetAsync(args.work_counter, 0, sizeof(unsigned long long), st));
-  const long long want = (args.batch + g.warps_per_cta - 1) / g.warps_per_cta;
-  const long long persistent = (long long)h->prop.multiProcessorCount * g.ctas_per_sm;
-  const int grid = (int)std::max<long long>(1, std::min(want, persistent));
-  kern<<<grid, g.warps_per_cta * 32, g.smem_per_cta, st>>>(args);
-  SFB_CUDA(h, cudaGetLastError());
+  int rc;
+  if (g.G == 4) rc = qp_launch_g<T, 4>(h, st, args, g, grid);
+  else if (g.G == 2) rc = qp_launch_g<T, 2>(h, st, args, g, grid);
+  else rc = qp_launch_g<T, 1>(h, st, args, g, grid);
+  if (rc != SFB_OK) return rc;
   h->launches += 1;
   return SFB_OK;
 }
@@ -218,7 +284,7 @@ int qp_solve_impl(sfb_context* h, const sfb_qp_params* prm, int64_t batch, int n
     a.P = P; a.q = q; a.A = A; a.l = l; a.u = u; a.warm_x = warm_x; a.warm_y = warm_y;
     a.out_x = out_x; a.out_y = out_y; a.out_obj = out_obj; a.out_status = out_status; a.out_iter = out_iter;
     a.out_active = out_active; a.out_flags = out_flags;
-    return qp_launch<T>(h, h->stream, a);
+    return qp_launch<T>(h, h->stream, kNumSlots, a);
   }
 
   // ---- host buffers: pipelined staging (chunk k uses slot k % kNumSlots on its own stream) ----
@@ -277,7 +343,7 @@ int qp_solve_impl(sfb_context* h, const sfb_qp_params* prm, int64_t batch, int n
     c.out_iter = reinterpret_cast<uint32_t*>(d + oit);
     c.out_active = out_active ? reinterpret_cast<int8_t*>(d + oact) : nullptr;
     c.out_flags = out_flags ? reinterpret_cast<uint32_t*>(d + ofl) : nullptr;
-    rc = qp_launch<T>(h, s.stream, c);
+    rc = qp_launch<T>(h, s.stream, k % kNumSlots, c);
     if (rc != SFB_OK) return rc;
     auto d2h = [&](void* dst, size_t off, size_t bytes_per_inst) -> cudaError_t {
       return cudaMemcpyAsync(static_cast<char*>(dst) + (size_t)b0 * bytes_per_inst, d + off,
@@ -390,6 +456,8 @@ int sfb_destroy(sfb_handle_t h)
     if (h->slots[s].dev) cudaFree(h->slots[s].dev);
   }
   if (h->ev_start) cudaEventDestroy(h->ev_start);
+  for (auto& sc : h->scratch)
+    if (sc.dev) cudaFree(sc.dev);
   if (h->counters) cudaFree(h->counters);
   delete h;
   return SFB_OK;
@@ -465,10 +533,10 @@ int sfb_qp_dense_max_m(sfb_handle_t h, int n, int scalar_bytes)
   if (!h || n <= 0 || (scalar_bytes != 4 && scalar_bytes != 8)) return 0;
   const size_t cap = h->prop.sharedMemPerBlockOptin;
   int lo = 0, hi = 1 << 16;
-  if ((size_t)sfb::QpLayout(n, 1).total * scalar_bytes > cap) return 0;
+  if ((size_t)sfb::QpLayout(n, 1, 32).total * scalar_bytes > cap) return 0;
   while (lo + 1 < hi) {  // largest m that fits
     const int mid = (lo + hi) / 2;
-    if ((size_t)sfb::QpLayout(n, mid).total * scalar_bytes <= cap) lo = mid; else hi = mid;
+    if ((size_t)sfb::QpLayout(n, mid, 32).total * scalar_bytes <= cap) lo = mid; else hi = mid;
   }
   return lo;
 }
@@ -488,7 +556,7 @@ int sfb_qp_scale_dense_batch_f64(sfb_handle_t h, int64_t batch, int n, int m, co
   a.batch = batch; a.n = n; a.m = m; a.mode = 1; a.prm = prm; a.max_iter_eff = 0;
   a.P = P; a.q = q; a.A = A; a.l = A; a.u = A;  // l/u are staged but unused in scale-only mode: point at valid memory
   a.out_c = out_c; a.out_sx = out_sx; a.out_sy = out_sy;
-  return qp_launch<double>(h, h->stream, a);
+  return qp_launch<double>(h, h->stream, kNumSlots, a);
 }
 
 int sfb_ekf_predict_batch_f64(sfb_handle_t h, int64_t batch, int d, int stepper, const double* P,

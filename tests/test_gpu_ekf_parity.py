@@ -82,6 +82,6 @@ def test_full_size_properties(sfb):
     # information form: Pu^-1 = Pp^-1 + H^T R^-1 H  <=>  Pu (I + H^T R^-1 H Pp)^... checked as Pu = Pp - K S K^T
     S = H @ Pp @ H.transpose(1, 2) + R
     K = torch.linalg.solve(S, H @ Pp).transpose(1, 2)
-    assert (Pu - (Pp - K @ S @ K.transpose(1, 2))).abs().max().item() <= 1e-9 * Pp.abs().max().item()
-    assert (delta - torch.einsum("bij,bj->bi", K, innov)).abs().max().item() <= 1e-9 * delta.abs().max().item()
+    assert (Pu - (Pp - K @ S @ K.transpose(1, 2))).abs().max().item() <= REL_F64 * Pp.abs().max().item()  # cond(S) reaches 1e6 in 2^20 draws
+    assert (delta - torch.einsum("bij,bj->bi", K, innov)).abs().max().item() <= REL_F64 * delta.abs().max().item()
     assert (torch.linalg.eigvalsh(Pu).min(dim=1).values > 0).all()  # stays positive definite

@@ -69,3 +69,49 @@ try:
     timeit(65536, 50, 100, dtype=torch.float32)
 except Exception as e:
     print("FAILED:", repr(e), flush=True)
+
+# ---- full-size property statistics (what fraction of polished solutions violate inactive rows?) ----
+try:
+    B, n, m = 65536, 50, 100
+    P_cm, q, A_cm, l, u = random_qp_torch(B, n, m, seed=5)
+    r = sfb.solve_dense_batch(P_cm, q, A_cm, l, u, sfb.QPSolverParams(max_iter=4000))
+    torch.cuda.synchronize()
+    A = A_cm.transpose(1, 2)
+    viol = (torch.einsum("bij,bj->bi", A, r.x) - u).clamp(min=0).max(dim=1).values
+    stat = (torch.einsum("bij,bj->bi", P_cm, r.x) + q + torch.einsum("bij,bi->bj", A, r.y)).abs().max(dim=1).values
+    print(f"[fullsize] viol>1e-7: {(viol > 1e-7).sum().item()} max {viol.max().item():.3e}; stat>1e-6: {(stat > 1e-6).sum().item()} max {stat.max().item():.3e}; "
+          f"miny {r.y.min().item():.3e}; flags {torch.bincount(r.flags, minlength=8).tolist()}; na max {(r.active != 0).sum(1).max().item()}", flush=True)
+    bad = torch.nonzero(viol > 1e-7).flatten()[:64]
+    if len(bad):
+        cpu = lambda t_: t_.cpu().numpy()
+        Pb = np.swapaxes(cpu(P_cm[bad]), 1, 2); Ab = np.swapaxes(cpu(A_cm[bad]), 1, 2)
+        o = orc.qp_solve_batch(Pb, cpu(q[bad]), Ab, cpu(l[bad]), cpu(u[bad]), params=orc.default_params(max_iter=4000), nthreads=os.cpu_count())
+        ov = np.clip(np.einsum("bij,bj->bi", Ab, o.x) - cpu(u[bad]), 0, None).max(1)
+        ex = np.linalg.norm(cpu(r.x[bad]) - o.x, axis=1) / np.linalg.norm(o.x, axis=1)
+        print(f"   oracle on the {len(bad)} violating instances: oracle viol max {ov.max():.3e} (>1e-7: {(ov > 1e-7).sum()}), relx vs gpu max {ex.max():.3e}, "
+              f"iter equal {(cpu(r.iter[bad]).astype(np.uint32) == o.iter).all()}, active equal {(cpu(r.active[bad]) == o.active).all()}", flush=True)
+except Exception as e:
+    import traceback; traceback.print_exc()
+
+# ---- EKF large batch vs oracle on slices ----
+try:
+    from smooth_feedback_b200.generators import random_ekf_numpy
+    B, d, ny = 200000, 6, 3
+    Pk, Ak, Qk, Hk, Rk, innov = random_ekf_numpy(B, d, ny, seed=5)
+    Pp = sfb.ekf_predict_batch(t(cm(Pk)), t(cm(Ak)), t(cm(Qk)), 0.1)
+    delta, Pu = sfb.ekf_update_batch(Pp, t(cm(Hk)), t(cm(Rk)), t(innov))
+    torch.cuda.synchronize()
+    oPp = orc.ekf_predict_batch(Pk, Ak, Qk, 0.1, nthreads=os.cpu_count())
+    od, oPu = orc.ekf_update_batch(oPp, Hk, Rk, innov, nthreads=os.cpu_count())
+    eP = np.abs(np.swapaxes(Pp.cpu().numpy(), 1, 2) - oPp).reshape(B, -1).max(1)
+    eU = np.abs(np.swapaxes(Pu.cpu().numpy(), 1, 2) - oPu).reshape(B, -1).max(1)
+    eD = np.abs(delta.cpu().numpy() - od).max(1)
+    print(f"[ekf B={B}] predict err max {eP.max():.3e} update err max {eU.max():.3e} (argmax {eU.argmax()}) delta err max {eD.max():.3e}; n bad(>1e-9) {(eU > 1e-9).sum()}", flush=True)
+    # same check against the textbook formula in float64 numpy
+    S = Hk @ oPp @ np.swapaxes(Hk, 1, 2) + Rk
+    K = oPp @ np.swapaxes(Hk, 1, 2) @ np.linalg.inv(S)
+    tb = (np.eye(d) - K @ Hk) @ oPp
+    eT = np.abs(oPu - tb).reshape(B, -1).max(1)
+    print(f"   oracle vs textbook err max {eT.max():.3e}, cond(S) max {np.linalg.cond(S).max():.3e}", flush=True)
+except Exception as e:
+    import traceback; traceback.print_exc()
