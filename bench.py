@@ -10,7 +10,7 @@ smooth_feedback_b200/generators.py).  Prints ONE JSON line (rank 0).
   value     whole-job solves/s, inputs resident in HBM, CUDA-event timed, max over ranks
   e2e       same metric through the C ABI with pinned HOST buffers (H2D of the problems and D2H of the solutions
             inside the timed region, pipelined in chunks by the engine)
-  roofline  dominant kernel (qp_dense_warp_kernel<double>) against the measured HBM peak, using SURVEY 8(d)'s
+  roofline  dominant kernel (qp_dense_group_kernel<double,4,3>) against the measured HBM peak, using SURVEY 8(d)'s
             algorithmic bytes per solve:  B_comp + iters * B_iter  (the north star's per-iteration model), with the
             compulsory-only figure beside it
   cpu_baseline  the CPU oracle (reference-algorithm restatement; Eigen is unavailable) on all host cores, bounded sample
@@ -290,7 +290,7 @@ def main():
                        "sharding": "independent shards per rank; one all-gather of packed results per step" if world > 1 else "single GPU",
                        "mean_iter": mean_iter, "optimal_frac": optimal_frac},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "qp_dense_warp_kernel<double>",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "qp_dense_group_kernel<double,4,3>",
                          "kernel_ms": kern_ms,
                          "model": "SURVEY 8(d) per-iteration bytes: B_comp + mean_iter*B_iter per solve "
                                   f"({bc} + {mean_iter:.1f}*{bi}); the factor stays in shared memory, so true DRAM traffic is ~B_comp",
