@@ -40,6 +40,15 @@ constexpr int kStatusUnset = -1;
 constexpr int kRedSlots = 12;  // scalars per batched group reduction
 constexpr int kGjPad = 64;    // padded length of the pivot row / column buffers of the register-blocked inverse
 
+template <typename T> struct Vec2T;
+template <> struct Vec2T<double> { using type = double2; };
+template <> struct Vec2T<float> { using type = float2; };
+// two consecutive scalars in one shared-memory transaction (address must be 2-scalar aligned)
+template <typename T> __device__ __forceinline__ typename Vec2T<T>::type ld2(const T* p)
+{
+  return *reinterpret_cast<const typename Vec2T<T>::type*>(p);
+}
+
 __device__ __forceinline__ double rcp(double x) { return __drcp_rn(x); }
 __device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
 
@@ -108,21 +117,25 @@ template <typename T> struct QpArgs
 // per-CTA shared-memory layout (units of T)
 struct QpLayout
 {
-  int ldA, ldN, npart;
+  int ldA, ldN, npad, mpad, npart;
   int offAs, offMs, offN, offM, offPart, offRed, offGj, offSlot, total;
   __host__ __device__ static int odd(int v) { return v | 1; }
   __host__ __device__ QpLayout(int n, int m, int nthreads)
   {
     const int mm = m > 0 ? m : 1;
-    ldA = odd(mm);
-    ldN = odd(n);
+    // Abar: leading dimension == 2 (mod 4).  Thread-per-row accesses are consecutive; thread-per-column accesses
+    // fetch two rows per 2-scalar load and the column stride ldA/2 is odd: both patterns are bank-conflict free.
+    ldA = mm + ((2 - mm % 4) + 4) % 4;
+    ldN = odd(n);  // Minv / P: only row-wise and scalar column accesses -> odd stride
+    npad = (n + 1) & ~1;
+    mpad = (mm + 1) & ~1;
     npart = nthreads > n ? nthreads : n;
     offAs = 0;
     offMs = offAs + ldA * n;
-    offN = offMs + ldN * n;
-    offM = offN + 8 * n;
-    offPart = offM + 10 * mm;
-    offRed = offPart + npart;
+    offN = (offMs + ldN * n + 1) & ~1;  // every vector starts on a 2-scalar boundary (vector loads)
+    offM = offN + 8 * npad;
+    offPart = offM + 10 * mpad;
+    offRed = (offPart + npart + 1) & ~1;
     offGj = offRed + 2 * 4 * kRedSlots;
     offSlot = (offGj + 4 * kGjPad + 1) & ~1;  // 8-byte aligned work-queue slot
     total = offSlot + 2;
@@ -143,7 +156,7 @@ template <typename T, int G> __device__ __noinline__ unsigned qp_stage_polish(co
 template <typename T, int G> struct QpGroup
 {
   static constexpr int NT = 32 * G;
-  int n, m, ldA, ldN, tid, lane, warp;
+  int n, m, ldA, ldN, npad, mpad, tid, lane, warp;
   // column-pass geometry: cw threads side by side own consecutive columns, csegs such bands split the rows
   int cw, csegs, cseg, c0;
   T* As;  // m x n   raw A, then Abar = Sy A Sx  (polish: active rows compacted on top, Sinv below when it fits)
@@ -166,13 +179,14 @@ template <typename T, int G> struct QpGroup
     ldN = L.ldN;
     As = base + L.offAs;
     Ms = base + L.offMs;
+    npad = L.npad;
+    mpad = L.mpad;
     T* nv = base + L.offN;
-    sx = nv; q = nv + n; qb = nv + 2 * n; x = nv + 3 * n; xt = nv + 4 * n; xold = nv + 5 * n; nv1 = nv + 6 * n;
-    nv2 = nv + 7 * n;
+    sx = nv; q = nv + npad; qb = nv + 2 * npad; x = nv + 3 * npad; xt = nv + 4 * npad; xold = nv + 5 * npad;
+    nv1 = nv + 6 * npad; nv2 = nv + 7 * npad;
     T* mv = base + L.offM;
-    const int mm = m > 0 ? m : 1;
-    sy = mv; l = mv + mm; u = mv + 2 * mm; rho = mv + 3 * mm; rinv = mv + 4 * mm; z = mv + 5 * mm; y = mv + 6 * mm;
-    w = mv + 7 * mm; yold = mv + 8 * mm; mv1 = mv + 9 * mm;
+    sy = mv; l = mv + mpad; u = mv + 2 * mpad; rho = mv + 3 * mpad; rinv = mv + 4 * mpad; z = mv + 5 * mpad;
+    y = mv + 6 * mpad; w = mv + 7 * mpad; yold = mv + 8 * mpad; mv1 = mv + 9 * mpad;
     part = base + L.offPart;
     red = base + L.offRed;
     gjbuf = base + L.offGj;
@@ -515,19 +529,22 @@ template <typename T, int G> struct QpGroup
   // part[seg * n + j] = sum_{i in seg} As[i, j] * v[i]   (and a second vector into part2 if given)
   __device__ __forceinline__ void colpass(const T* v, int rows)
   {
-    const int rps = (rows + csegs - 1) / csegs;
-    const int i0 = cseg * rps, i1 = min(rows, i0 + rps);
+    int rps = (rows + csegs - 1) / csegs;
+    rps = (rps + 1) & ~1;  // segments start on even rows: 2-scalar loads stay aligned
+    const int i0 = min(rows, cseg * rps), i1 = min(rows, i0 + rps);
 #pragma unroll 1
     for (int j = c0; j < n; j += cw) {
       const T* col = As + ldA * j;
       T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0);
       int i = i0;
-#pragma unroll 1
+#pragma unroll 2
       for (; i + 3 < i1; i += 4) {
-        a0 += col[i] * v[i];
-        a1 += col[i + 1] * v[i + 1];
-        a2 += col[i + 2] * v[i + 2];
-        a3 += col[i + 3] * v[i + 3];
+        const auto c01 = ld2(col + i), c23 = ld2(col + i + 2);
+        const auto v01 = ld2(v + i), v23 = ld2(v + i + 2);
+        a0 += c01.x * v01.x;
+        a1 += c01.y * v01.y;
+        a2 += c23.x * v23.x;
+        a3 += c23.y * v23.y;
       }
 #pragma unroll 1
       for (; i < i1; ++i) a0 += col[i] * v[i];
@@ -575,12 +592,13 @@ template <typename T, int G> struct QpGroup
     const T* p = Mx + i;
     T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0);
     int j = 0;
-#pragma unroll 1
+#pragma unroll 2
     for (; j + 3 < cols; j += 4) {
-      a0 += p[ld * j] * v[j];
-      a1 += p[ld * (j + 1)] * v[j + 1];
-      a2 += p[ld * (j + 2)] * v[j + 2];
-      a3 += p[ld * (j + 3)] * v[j + 3];
+      const auto v01 = ld2(v + j), v23 = ld2(v + j + 2);  // v is 2-scalar aligned (vector strides are padded)
+      a0 += p[ld * j] * v01.x;
+      a1 += p[ld * (j + 1)] * v01.y;
+      a2 += p[ld * (j + 2)] * v23.x;
+      a3 += p[ld * (j + 3)] * v23.y;
     }
 #pragma unroll 1
     for (; j < cols; ++j) a0 += p[ld * j] * v[j];
@@ -744,32 +762,44 @@ template <typename T, int G> struct QpGroup
     gsync();
 
     // K = Pbar + delta I  (+ Aa^T Aa / delta in the Woodbury form)   :161,175
+    // one coalesced sweep over the unscaled P: every upper-triangle entry is scaled and written to both (i,j), (j,i)
     {
-      const T dinv = T(1) / delta;
       int i = tid % n, j = tid / n;
       const int di = NT % n, dj = NT / n;
 #pragma unroll 1
       for (int e = tid; e < n * n; e += NT) {
-        T h = pbar(gP, i, j);
-        if (i == j) h += delta;
-        if (woodbury) {
-          const T* ci = As + ldA * i;
-          const T* cj = As + ldA * j;
-          T acc = T(0);
-#pragma unroll 1
-          for (int r = 0; r < na; ++r) acc += ci[r] * cj[r];
-          h += dinv * acc;
+        if (i <= j) {
+          T h = ((c * sx[i]) * __ldg(gP + e)) * sx[j];
+          if (i == j) h += delta;
+          Ms[i + ldN * j] = h;
+          Ms[j + ldN * i] = h;
         }
-        Ms[i + ldN * j] = h;
         i += di; j += dj;
         if (i >= n) { i -= n; ++j; }
       }
     }
     gsync();
+    if (woodbury) {
+      const T dinv = T(1) / delta;
+      int i = tid % n, j = tid / n;
+      const int di = NT % n, dj = NT / n;
+#pragma unroll 1
+      for (int e = tid; e < n * n; e += NT) {
+        const T* ci = As + ldA * i;
+        const T* cj = As + ldA * j;
+        T acc = T(0);
+#pragma unroll 1
+        for (int r = 0; r < na; ++r) acc += ci[r] * cj[r];
+        Ms[i + ldN * j] += dinv * acc;
+        i += di; j += dj;
+        if (i >= n) { i -= n; ++j; }
+      }
+      gsync();
+    }
     if (!gj_invert_at(0, n)) return SFB_QP_FLAG_POLISH_FAILED;
 
     if (S != nullptr) {
-      // S = delta I + Aa Kinv Aa^T, four columns at a time: T4 = Kinv Aa[s0..s0+3,:]^T (n x 4 in xt,xold,nv1,nv2),
+      // S = delta I + Aa Kinv Aa^T, four columns at a time: T4 = Kinv Aa[s0..s0+3,:]^T (n x 4 in xt,xold,nv1,nv2; stride npad),
       // then S[:, s0..s0+3] = Aa T4
 #pragma unroll 1
       for (int s0 = 0; s0 < na; s0 += 4) {
@@ -787,13 +817,13 @@ template <typename T, int G> struct QpGroup
             a1 += p[ldN * (j + 1)] * arow[ldA * (j + 1)];
           }
           if (j < n) a0 += p[ldN * j] * arow[ldA * j];
-          xt[sc * n + i] = a0 + a1;
+          xt[sc * npad + i] = a0 + a1;
         }
         gsync();
 #pragma unroll 1
         for (int e = tid; e < na * ns; e += NT) {
           const int r = e % na, sc = e / na;
-          T acc = rowdot(As, ldA, r, n, xt + sc * n);
+          T acc = rowdot(As, ldA, r, n, xt + sc * npad);
           if (r == s0 + sc) acc += delta;
           S[r + ldS * (s0 + sc)] = acc;
         }
@@ -817,22 +847,43 @@ template <typename T, int G> struct QpGroup
 #pragma unroll 1
     for (int r = tid; r < na; r += NT) ty[r] = T(0);
     gsync();
+    // The reference iterates t <- t + Hp^-1 (h - H t) with H = Hp - D, D = diag(delta I_n, -delta I_na).  Since
+    // h - H t = (h + D t) - Hp t, the same sequence is t <- Hp^-1 (h + D t): no product with H (whose Pbar block lives
+    // in HBM) is needed.  Only the last sweep uses the literal residual form, so that rounding errors of the explicit
+    // inverses are corrected once, exactly like iterative refinement does.
 #pragma unroll 1
     for (uint32_t it = 0; it != a.prm.polish_iter; ++it) {
-      // residual r = h - sym(H) t,  H = [Pbar Aa^T; Aa 0]
+      const bool literal = (it + 1 == a.prm.polish_iter) && (it > 0);
+      if (literal) {
+        // residual r = h - sym(H) t,  H = [Pbar Aa^T; Aa 0]
 #pragma unroll 1
-      for (int i = tid; i < n; i += NT) {
-        T acc = T(0);
+        for (int i = tid; i < n; i += NT) {
+          T acc = T(0);
 #pragma unroll 1
-        for (int j = 0; j < n; ++j) acc += pbar(gP, i, j) * tx[j];
-        const T* col = As + ldA * i;
+          for (int j = 0; j < n; ++j) acc += pbar(gP, i, j) * tx[j];
+          const T* col = As + ldA * i;
 #pragma unroll 1
-        for (int r = 0; r < na; ++r) acc += col[r] * ty[r];
-        rx[i] = -c * (sx[i] * q[i]) - acc;  // :180
+          for (int r = 0; r < na; ++r) acc += col[r] * ty[r];
+          rx[i] = -c * (sx[i] * q[i]) - acc;  // :180
+        }
+#pragma unroll 1
+        for (int r = tid; r < na; r += NT) ry[r] = bnd[r] - rowdot(As, ldA, r, n, tx);  // :181-182
+      } else {
+        // rhs = h + D t ; the solve below then yields the new t directly (accumulated as t += (t_new - t))
+#pragma unroll 1
+        for (int i = tid; i < n; i += NT) rx[i] = -c * (sx[i] * q[i]) + delta * tx[i];
+#pragma unroll 1
+        for (int r = tid; r < na; r += NT) ry[r] = bnd[r] - delta * ty[r];
       }
-#pragma unroll 1
-      for (int r = tid; r < na; r += NT) ry[r] = bnd[r] - rowdot(As, ldA, r, n, tx);  // :181-182
       gsync();
+      if (!literal) {
+        // the solve returns t_new, and the common update below adds the solve result to t: start from zero
+#pragma unroll 1
+        for (int i = tid; i < n; i += NT) tx[i] = T(0);
+#pragma unroll 1
+        for (int r = tid; r < na; r += NT) ty[r] = T(0);
+        gsync();
+      }
       if (!woodbury) {
         // [K Aa^T; Aa -delta I] [dx; dy] = [rx; ry]:  dy = Sinv (Aa Kinv rx - ry),  dx = Kinv (rx - Aa^T dy)
 #pragma unroll 1
