@@ -280,26 +280,31 @@ template <typename T, int G> struct QpGroup
   {
     const T* gA = a.A + b * (long long)m * n;
     const T* gP = a.P + b * (long long)n * n;
-    if (m > 0) {
-      int i = tid % m, j = tid / m;
-      const int di = NT % m, dj = NT / m;
+    // Coalesced streaming loads, 8 independent requests in flight per thread (the copy is pure DRAM latency:
+    // with one request in flight it cost ~40k cycles per instance, profiles/r01_ncu_v5_summary.txt).
+    auto copy = [&](const T* g, T* sm, int rows, int ld, int total) {
+      constexpr int U = 8;
+      int e = tid;
 #pragma unroll 1
-      for (int e = tid; e < m * n; e += NT) {
-        As[i + ldA * j] = __ldg(gA + e);
-        i += di; j += dj;
-        if (i >= m) { i -= m; ++j; }
+      for (; e + (U - 1) * NT < total; e += U * NT) {
+        T v[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) v[k] = __ldg(g + e + k * NT);
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+          const int ee = e + k * NT;
+          const int j = ee / rows, i = ee - j * rows;
+          sm[i + ld * j] = v[k];
+        }
       }
-    }
-    {
-      int i = tid % n, j = tid / n;
-      const int di = NT % n, dj = NT / n;
 #pragma unroll 1
-      for (int e = tid; e < n * n; e += NT) {
-        Ms[i + ldN * j] = __ldg(gP + e);
-        i += di; j += dj;
-        if (i >= n) { i -= n; ++j; }
+      for (; e < total; e += NT) {
+        const int j = e / rows, i = e - j * rows;
+        sm[i + ld * j] = __ldg(g + e);
       }
-    }
+    };
+    if (m > 0) copy(gA, As, m, ldA, m * n);
+    copy(gP, Ms, n, ldN, n * n);
 #pragma unroll 1
     for (int j = tid; j < n; j += NT) q[j] = __ldg(a.q + b * (long long)n + j);
 #pragma unroll 1

@@ -1,0 +1,54 @@
+// The reference's own BasicDynamic / Portfolio / SolverAPI unit tests (tests/test_qp.cpp:75-98, :244-272, :338-372) written
+// against the overlay header, with mock matrices instead of Eigen.  Needs a GPU to run; compiles anywhere.
+#include <cmath>
+#include <cstdio>
+#include <limits>
+#include "../../include/smooth_feedback_b200/qp_solver_b200.hpp"
+#include "mock_eigen.hpp"
+
+#define CHECK(c) do { if (!(c)) { std::printf("FAILED %s:%d %s\n", __FILE__, __LINE__, #c); return 1; } } while (0)
+
+int main()
+{
+  using namespace smooth::feedback;
+  using Pbm = mock::QuadraticProgram<double>;
+  constexpr double inf = std::numeric_limits<double>::infinity();
+  const QPSolverParams test_prm{.verbose = false, .polish = true};
+
+  Pbm basic;
+  basic.P.resize(2, 2); basic.P(0, 0) = 1; basic.P(1, 1) = 1;
+  basic.q.resize(2); basic.q(0) = -4; basic.q(1) = 0.25;
+  basic.A.resize(2, 2); basic.A(0, 0) = 1; basic.A(1, 1) = 1;
+  basic.l.resize(2); basic.l(0) = -1; basic.l(1) = -1;
+  basic.u.resize(2); basic.u(0) = 1; basic.u(1) = 1;
+
+  auto sol = solve_qp(basic, test_prm);
+  CHECK(sol.code == QPSolutionStatus::Optimal);
+  CHECK(std::fabs(sol.primal(0) - 1) < 1e-4 && std::fabs(sol.primal(1) + 0.25) < 1e-4);
+  CHECK(std::fabs(sol.objective - (0.5 - 4 - 1. / 32)) < 1e-4);
+  auto sol_hs = solve_qp(basic, test_prm, sol);  // warm start with own solution
+  CHECK(sol_hs.code == QPSolutionStatus::Optimal && sol_hs.iter == 2);
+
+  // SolverAPI: copies and moved-from solvers give the same primal
+  QPSolver<Pbm> s1(basic, test_prm);
+  const auto x1 = s1.solve(basic).primal;
+  QPSolver<Pbm> s2 = s1;
+  const auto x2 = s2.solve(basic).primal;
+  QPSolver<Pbm> s3(std::move(s2));
+  const auto x3 = s3.solve(basic).primal;
+  CHECK(x1(0) == x2(0) && x1(1) == x2(1) && x1(0) == x3(0) && x1(1) == x3(1));
+
+  // trivially infeasible -> status only, never an exception
+  Pbm bad = basic; bad.l(1) = 1; bad.u(1) = -1;
+  CHECK(solve_qp(bad, test_prm).code == QPSolutionStatus::PrimalInfeasible);
+
+  // extension: a batch
+  std::vector<Pbm> batch(100, basic);
+  for (int i = 0; i < 100; ++i) { batch[i].q(0) = -4 + 0.01 * i; }
+  std::vector<QPSolver<Pbm>::Solution> sols(100);
+  s1.solve_batch(batch, sols);
+  for (int i = 0; i < 100; ++i) { CHECK(sols[i].code == QPSolutionStatus::Optimal && std::fabs(sols[i].primal(0) - 1) < 1e-4); }
+  (void)inf;
+  std::printf("overlay ok\n");
+  return 0;
+}
