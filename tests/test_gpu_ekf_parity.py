@@ -82,16 +82,17 @@ def test_full_size_properties(sfb, oracle):
     torch.cuda.synchronize()
     assert torch.equal(Pu, Pu.transpose(1, 2))                                   # selfadjointView<Upper>: exactly symmetric
     # NB: (I - K H) P is the reference's update (ekf.hpp:138), not the Joseph form: it does not guarantee a positive
-    # definite result when S is ill conditioned, and neither does the reference.  Checked on the well-conditioned bulk.
-    # innovation covariance identity on the well-conditioned bulk: Pu = Pp - K S K^T   (cond(S) reaches 1e6 in 2^20 draws)
-    S = H @ Pp @ H.transpose(1, 2) + R
-    good = torch.cat([torch.linalg.cond(S[b0:b0 + (1 << 16)]) for b0 in range(0, B, 1 << 16)]) < 1e3
-    K = torch.linalg.solve(S, H @ Pp).transpose(1, 2)
-    err = (Pu - (Pp - K @ S @ K.transpose(1, 2))).abs().amax(dim=(1, 2))
-    assert err[good].max().item() <= 1e-9 * Pp.abs().max().item() and good.float().mean().item() > 0.5
-    assert (torch.linalg.cholesky_ex(Pu[good][: 1 << 16]).info == 0).all()        # positive definite there
+    # definite result when S is ill conditioned (cond(S) reaches 1e6 in 2^20 draws), and neither does the reference.
+    # Size-independent identity on a well-conditioned strided sample: Pu = Pp - K S K^T, PD, trace never grows.
+    sl = slice(0, B, 64)
+    S = H[sl] @ Pp[sl] @ H[sl].transpose(1, 2) + R[sl]
+    good = torch.linalg.cond(S) < 1e3
+    K = torch.linalg.solve(S, H[sl] @ Pp[sl]).transpose(1, 2)
+    err = (Pu[sl] - (Pp[sl] - K @ S @ K.transpose(1, 2))).abs().amax(dim=(1, 2))
+    assert good.float().mean().item() > 0.5 and err[good].max().item() <= 1e-9 * Pp.abs().max().item()
+    assert (torch.linalg.cholesky_ex(Pu[sl][good]).info == 0).all()
     tr = lambda M: M.diagonal(dim1=1, dim2=2).sum(1)
-    assert (tr(Pu)[good] <= tr(Pp)[good]).all()                                  # a measurement never adds uncertainty
+    assert (tr(Pu[sl])[good] <= tr(Pp[sl])[good]).all()
     # parity with the oracle on a strided sample
     pick = torch.arange(0, B, 257, device="cuda")
     c = lambda t: t[pick].cpu().numpy()
