@@ -146,14 +146,18 @@ struct QpLayout
 // symbol, so the compiler still knows the address space (LDS/STS, not generic LD/ST) while the kernel keeps ONE
 // copy of each cold stage: the fully inlined version was 430 KB of SASS and spent half its time on instruction
 // fetch (profiles/).
-template <typename T, int G> __device__ __noinline__ bool qp_stage_gj(int n, int m, int where, int sz);
-template <typename T, int G> __device__ __noinline__ bool qp_stage_gj_generic(int n, int m, T* Mx, int ld, int sz);
-template <typename T, int G> __device__ __noinline__ T qp_stage_load_scale(const QpArgs<T>* a, long long b);
-template <typename T, int G> __device__ __noinline__ int qp_stage_setup(const QpArgs<T>* a, T c);
-template <typename T, int G> __device__ __noinline__ int qp_stage_check(const QpArgs<T>* a, long long b, T c);
-template <typename T, int G> __device__ __noinline__ unsigned qp_stage_polish(const QpArgs<T>* a, long long b, T c, int na, T* gscratch);
+template <typename T, int G, int NS, int MS> __device__ __noinline__ bool qp_stage_gj(int n, int m, int where, int sz);
+template <typename T, int G, int NS, int MS> __device__ __noinline__ bool qp_stage_gj_generic(int n, int m, T* Mx, int ld, int sz);
+template <typename T, int G, int NS, int MS> __device__ __noinline__ T qp_stage_load_scale(const QpArgs<T>* a, long long b);
+template <typename T, int G, int NS, int MS> __device__ __noinline__ int qp_stage_setup(const QpArgs<T>* a, T c);
+template <typename T, int G, int NS, int MS> __device__ __noinline__ int qp_stage_check(const QpArgs<T>* a, long long b, T c);
+template <typename T, int G, int NS, int MS> __device__ __noinline__ unsigned qp_stage_polish(const QpArgs<T>* a, long long b, T c, int na, T* gscratch);
+template <typename T, int G, int NS, int MS>
+__device__ __noinline__ int qp_stage_loop(const QpArgs<T>* a, long long b, T c, unsigned long long t0, int code, unsigned* iter_out);
 
-template <typename T, int G> struct QpGroup
+// NS, MS: compile-time problem shape (0 = runtime).  A shape-specialised instantiation lets the compiler fold every
+// leading dimension / trip count into immediates, which removes most of the integer overhead of the GEMV passes.
+template <typename T, int G, int NS, int MS> struct QpGroup
 {
   static constexpr int NT = 32 * G;
   int n, m, ldA, ldN, npad, mpad, tid, lane, warp;
@@ -497,8 +501,8 @@ template <typename T, int G> struct QpGroup
   // where = 0: Ms (n x n, ldN);  where = 1: the Schur block kept below the compacted rows, As + sz (sz x sz, ldA)
   __device__ __forceinline__ bool gj_invert_at(int where, int sz)
   {
-    if (gj_fits_regs(sz)) return qp_stage_gj<T, G>(n, m, where, sz);
-    return qp_stage_gj_generic<T, G>(n, m, where == 0 ? Ms : As + sz, where == 0 ? ldN : ldA, sz);
+    if (gj_fits_regs(sz)) return qp_stage_gj<T, G, NS, MS>(n, m, where, sz);
+    return qp_stage_gj_generic<T, G, NS, MS>(n, m, where == 0 ? Ms : As + sz, where == 0 ? ldN : ldA, sz);
   }
   __device__ bool gj_invert_smem(T* Mx, int ld, int sz, T* rowk, T* colk)
   {
@@ -542,7 +546,7 @@ template <typename T, int G> struct QpGroup
       const T* col = As + ldA * j;
       T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0);
       int i = i0;
-#pragma unroll 2
+#pragma unroll(NS > 0 ? 4 : 2)
       for (; i + 3 < i1; i += 4) {
         const auto c01 = ld2(col + i), c23 = ld2(col + i + 2);
         const auto v01 = ld2(v + i), v23 = ld2(v + i + 2);
@@ -597,7 +601,7 @@ template <typename T, int G> struct QpGroup
     const T* p = Mx + i;
     T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0);
     int j = 0;
-#pragma unroll 2
+#pragma unroll(NS > 0 ? 4 : 2)
     for (; j + 3 < cols; j += 4) {
       const auto v01 = ld2(v + j), v23 = ld2(v + j + 2);  // v is 2-scalar aligned (vector strides are padded)
       a0 += p[ld * j] * v01.x;
@@ -834,7 +838,7 @@ template <typename T, int G> struct QpGroup
         }
         gsync();
       }
-      const bool s_ok = (S == As + na) ? gj_invert_at(1, na) : qp_stage_gj_generic<T, G>(n, m, S, ldS, na);
+      const bool s_ok = (S == As + na) ? gj_invert_at(1, na) : qp_stage_gj_generic<T, G, NS, MS>(n, m, S, ldS, na);
       if (!s_ok) return SFB_QP_FLAG_POLISH_FAILED;
     }
 
@@ -1050,51 +1054,11 @@ template <typename T, int G> struct QpGroup
     return code;
   }
 
-  // ---------------------------------------------------------------- QPSolver::solve, qp_solver.hpp:343-568
-  __device__ void solve(const QpArgs<T>& a, long long b, T* gscratch)
+  // ---------------------------------------------------------------- main ADMM loop  qp_solver.hpp:449-510
+  // Outlined as its own stage (qp_stage_loop).  Returns the status code (kStatusUnset when the iteration budget ran out).
+  __device__ int admm_loop(const QpArgs<T>& a, long long b, unsigned long long t0, int code, unsigned* iter_out)
   {
-    const T inf = Num<T>::inf();
-    const T* gP = a.P + b * (long long)n * n;
-    const unsigned long long t0 = a.prm.has_max_time ? global_timer_ns() : 0ull;
-
-    c = qp_stage_load_scale<T, G>(&a, b);  // :347
-    if (a.mode == 1) {
-      if (tid == 0) a.out_c[b] = c;
-#pragma unroll 1
-      for (int j = tid; j < n; j += NT) a.out_sx[b * (long long)n + j] = sx[j];
-#pragma unroll 1
-      for (int i = tid; i < m; i += NT) a.out_sy[b * (long long)m + i] = sy[i];
-      gsync();
-      return;
-    }
-
     const T alpha = T(a.prm.alpha), alpha_comp = T(1) - alpha, sigma = T(a.prm.sigma);
-    int code = qp_stage_setup<T, G>(&a, c);  // rho classes, trivial infeasibility, in-place scaling, M, Minv
-
-    // initial iterate  :436-445
-    if (a.warm_x != nullptr) {
-#pragma unroll 1
-      for (int j = tid; j < n; j += NT) x[j] = (T(1) / sx[j]) * __ldg(a.warm_x + b * (long long)n + j);
-#pragma unroll 1
-      for (int i = tid; i < m; i += NT) y[i] = c * ((T(1) / sy[i]) * __ldg(a.warm_y + b * (long long)m + i));
-      gsync();
-#pragma unroll 1
-      for (int i = tid; i < m; i += NT) z[i] = rowdot(As, ldA, i, n, x);
-    } else {
-#pragma unroll 1
-      for (int j = tid; j < n; j += NT) x[j] = T(0);
-#pragma unroll 1
-      for (int i = tid; i < m; i += NT) {
-        y[i] = T(0);
-        z[i] = T(0);
-      }
-    }
-    gsync();
-#pragma unroll 1
-    for (int i = tid; i < m; i += NT) w[i] = rho[i] * z[i] - y[i];
-    gsync();
-
-    // main ADMM loop  :449-510
     const unsigned sci = a.prm.stop_check_iter;
     unsigned iter = 0;
 #pragma unroll 1
@@ -1140,7 +1104,7 @@ template <typename T, int G> struct QpGroup
       }
       gsync();
       if (chk) {
-        code = qp_stage_check<T, G>(&a, b, c);  // :488  (clobbers w)
+        code = qp_stage_check<T, G, NS, MS>(&a, b, c);  // :488  (clobbers w)
         if (code == kStatusUnset && a.prm.has_max_time) {
           // :504-508 ; one thread reads the clock so that the decision is group-uniform
           const bool late = (tid == 0) && ((long long)(global_timer_ns() - t0) > a.prm.max_time_ns);
@@ -1151,6 +1115,56 @@ template <typename T, int G> struct QpGroup
         gsync();
       }
     }
+
+    *iter_out = iter;
+    return code;
+  }
+
+  // ---------------------------------------------------------------- QPSolver::solve, qp_solver.hpp:343-568
+  __device__ void solve(const QpArgs<T>& a, long long b, T* gscratch)
+  {
+    const T inf = Num<T>::inf();
+    const T* gP = a.P + b * (long long)n * n;
+    const unsigned long long t0 = a.prm.has_max_time ? global_timer_ns() : 0ull;
+
+    c = qp_stage_load_scale<T, G, NS, MS>(&a, b);  // :347
+    if (a.mode == 1) {
+      if (tid == 0) a.out_c[b] = c;
+#pragma unroll 1
+      for (int j = tid; j < n; j += NT) a.out_sx[b * (long long)n + j] = sx[j];
+#pragma unroll 1
+      for (int i = tid; i < m; i += NT) a.out_sy[b * (long long)m + i] = sy[i];
+      gsync();
+      return;
+    }
+
+    int code = qp_stage_setup<T, G, NS, MS>(&a, c);  // rho classes, trivial infeasibility, in-place scaling, M, Minv
+
+    // initial iterate  :436-445
+    if (a.warm_x != nullptr) {
+#pragma unroll 1
+      for (int j = tid; j < n; j += NT) x[j] = (T(1) / sx[j]) * __ldg(a.warm_x + b * (long long)n + j);
+#pragma unroll 1
+      for (int i = tid; i < m; i += NT) y[i] = c * ((T(1) / sy[i]) * __ldg(a.warm_y + b * (long long)m + i));
+      gsync();
+#pragma unroll 1
+      for (int i = tid; i < m; i += NT) z[i] = rowdot(As, ldA, i, n, x);
+    } else {
+#pragma unroll 1
+      for (int j = tid; j < n; j += NT) x[j] = T(0);
+#pragma unroll 1
+      for (int i = tid; i < m; i += NT) {
+        y[i] = T(0);
+        z[i] = T(0);
+      }
+    }
+    gsync();
+#pragma unroll 1
+    for (int i = tid; i < m; i += NT) w[i] = rho[i] * z[i] - y[i];
+    gsync();
+
+    unsigned iter = 0;
+    code = qp_stage_loop<T, G, NS, MS>(&a, b, c, t0, code, &iter);
 
     // active sets as polish_qp builds them (:113-123), ascending order, on the scaled dual
     int na = 0;
@@ -1192,7 +1206,7 @@ template <typename T, int G> struct QpGroup
     }
 
     unsigned flags = 0;
-    if (code == SFB_QP_OPTIMAL && a.prm.polish) flags = qp_stage_polish<T, G>(&a, b, c, na, gscratch);  // :515-539
+    if (code == SFB_QP_OPTIMAL && a.prm.polish) flags = qp_stage_polish<T, G, NS, MS>(&a, b, c, na, gscratch);  // :515-539
 
     // unscale + objective  :544-548
 #pragma unroll 1
@@ -1226,18 +1240,18 @@ template <typename T, int G> struct QpGroup
 // ------------------------------------------------------------------------------------------------------
 // out-of-line stages
 // ------------------------------------------------------------------------------------------------------
-template <typename T, int G> __device__ __forceinline__ QpGroup<T, G> qp_view(int n, int m, T c)
+template <typename T, int G, int NS, int MS> __device__ __forceinline__ QpGroup<T, G, NS, MS> qp_view(int n, int m, T c)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  QpGroup<T, G> s(reinterpret_cast<T*>(smem_raw), n, m);
+  QpGroup<T, G, NS, MS> s(reinterpret_cast<T*>(smem_raw), NS > 0 ? NS : n, MS > 0 ? MS : m);
   s.c = c;
   s.gsync();  // every thread is out of the caller's last reduction: the scratch parity may restart at 0
   return s;
 }
 
-template <typename T, int G> __device__ __noinline__ T qp_stage_load_scale(const QpArgs<T>* a, long long b)
+template <typename T, int G, int NS, int MS> __device__ __noinline__ T qp_stage_load_scale(const QpArgs<T>* a, long long b)
 {
-  QpGroup<T, G> s = qp_view<T, G>(a->n, a->m, T(1));
+  QpGroup<T, G, NS, MS> s = qp_view<T, G, NS, MS>(a->n, a->m, T(1));
   s.load(*a, b);
   if (a->prm.scaling) {
     s.scale();
@@ -1252,59 +1266,68 @@ template <typename T, int G> __device__ __noinline__ T qp_stage_load_scale(const
   return s.c;
 }
 
-template <typename T, int G> __device__ __noinline__ int qp_stage_setup(const QpArgs<T>* a, T c)
+template <typename T, int G, int NS, int MS> __device__ __noinline__ int qp_stage_setup(const QpArgs<T>* a, T c)
 {
-  QpGroup<T, G> s = qp_view<T, G>(a->n, a->m, c);
+  QpGroup<T, G, NS, MS> s = qp_view<T, G, NS, MS>(a->n, a->m, c);
   const int code = s.setup(*a);
   s.gsync();
   return code;
 }
 
-template <typename T, int G> __device__ __noinline__ bool qp_stage_gj(int n, int m, int where, int sz)
+template <typename T, int G, int NS, int MS> __device__ __noinline__ bool qp_stage_gj(int n, int m, int where, int sz)
 {
-  QpGroup<T, G> s = qp_view<T, G>(n, m, T(1));
+  QpGroup<T, G, NS, MS> s = qp_view<T, G, NS, MS>(n, m, T(1));
   const bool ok = s.gj_invert_reg(where == 0 ? s.Ms : s.As + sz, where == 0 ? s.ldN : s.ldA, sz, s.gjbuf);
   s.gsync();
   return ok;
 }
 
 // generic-pointer variant (matrix may live in global memory; shared scratch): sizes beyond the register blocking
-template <typename T, int G> __device__ __noinline__ bool qp_stage_gj_generic(int n, int m, T* Mx, int ld, int sz)
+template <typename T, int G, int NS, int MS> __device__ __noinline__ bool qp_stage_gj_generic(int n, int m, T* Mx, int ld, int sz)
 {
-  QpGroup<T, G> s = qp_view<T, G>(n, m, T(1));
+  QpGroup<T, G, NS, MS> s = qp_view<T, G, NS, MS>(n, m, T(1));
   // row / column buffers: xt..nv2 hold 4n scalars; a Schur block has sz <= n, Ms itself has sz == n
   const bool ok = s.gj_invert_smem(Mx, ld, sz, s.xt, s.xt + sz);
   s.gsync();
   return ok;
 }
 
-template <typename T, int G> __device__ __noinline__ int qp_stage_check(const QpArgs<T>* a, long long b, T c)
+template <typename T, int G, int NS, int MS> __device__ __noinline__ int qp_stage_check(const QpArgs<T>* a, long long b, T c)
 {
-  QpGroup<T, G> s = qp_view<T, G>(a->n, a->m, c);
+  QpGroup<T, G, NS, MS> s = qp_view<T, G, NS, MS>(a->n, a->m, c);
   const int code = s.check_stopping(*a, a->P + b * (long long)a->n * a->n);
   s.gsync();
   return code;
 }
 
-template <typename T, int G>
+template <typename T, int G, int NS, int MS>
 __device__ __noinline__ unsigned qp_stage_polish(const QpArgs<T>* a, long long b, T c, int na, T* gscratch)
 {
-  QpGroup<T, G> s = qp_view<T, G>(a->n, a->m, c);
+  QpGroup<T, G, NS, MS> s = qp_view<T, G, NS, MS>(a->n, a->m, c);
   const unsigned fl = s.polish(*a, a->P + b * (long long)a->n * a->n, na, reinterpret_cast<const int*>(s.mv1), s.w, gscratch);
   s.gsync();
   return fl;
 }
 
+template <typename T, int G, int NS, int MS>
+__device__ __noinline__ int qp_stage_loop(const QpArgs<T>* a, long long b, T c, unsigned long long t0, int code, unsigned* iter_out)
+{
+  QpGroup<T, G, NS, MS> s = qp_view<T, G, NS, MS>(a->n, a->m, c);
+  const int r = s.admm_loop(*a, b, t0, code, iter_out);
+  s.gsync();
+  return r;
+}
+
 // One CTA of G warps per instance; CTAs pull instances from a global work counter (iteration counts are
 // heavy-tailed), so a slow instance never idles the rest of the grid.
-template <typename T, int G, int MINB>
+template <typename T, int G, int MINB, int NS, int MS>
 __global__ void __launch_bounds__(32 * G, MINB) qp_dense_group_kernel(const __grid_constant__ QpArgs<T> a)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* base = reinterpret_cast<T*>(smem_raw);
-  QpGroup<T, G> s(base, a.n, a.m);
+  QpGroup<T, G, NS, MS> s(base, NS > 0 ? NS : a.n, MS > 0 ? MS : a.m);
   T* gscratch = a.scratch ? a.scratch + (long long)blockIdx.x * a.scratch_per_cta : nullptr;
-  unsigned long long* slot = reinterpret_cast<unsigned long long*>(base + QpLayout(a.n, a.m, 32 * G).offSlot);
+  unsigned long long* slot = reinterpret_cast<unsigned long long*>(base + QpLayout(NS > 0 ? NS : a.n, MS > 0 ? MS : a.m, 32 * G).offSlot);
 #pragma unroll 1
   for (;;) {
     unsigned long long b = 0;

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/sfb.h"
@@ -146,7 +147,7 @@ template <typename T, int G> int qp_occupancy(sfb_context* h, int n, int m, QpGe
   sfb::QpLayout L(n, m, 32 * G);
   const size_t bytes = (size_t)L.total * sizeof(T);
   if (bytes > h->prop.sharedMemPerBlockOptin) return 0;
-  auto kern = sfb::qp_dense_group_kernel<T, G, qp_minb<T, G>()>;
+  auto kern = sfb::qp_dense_group_kernel<T, G, qp_minb<T, G>(), 0, 0>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
     cudaGetLastError();
     return 0;
@@ -196,10 +197,10 @@ int ensure_scratch(sfb_context* h, Scratch& s, size_t bytes, cudaStream_t st)
   return SFB_OK;
 }
 
-template <typename T, int G>
+template <typename T, int G, int NS, int MS>
 int qp_launch_g(sfb_context* h, cudaStream_t st, sfb::QpArgs<T>& args, const QpGeom& g, int grid)
 {
-  auto kern = sfb::qp_dense_group_kernel<T, G, qp_minb<T, G>()>;
+  auto kern = sfb::qp_dense_group_kernel<T, G, qp_minb<T, G>(), NS, MS>;
   SFB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_per_cta));
   kern<<<grid, 32 * G, g.smem_per_cta, st>>>(args);
   SFB_CUDA(h, cudaGetLastError());
@@ -233,9 +234,15 @@ int qp_launch(sfb_context* h, cudaStream_t st, int scratch_slot, const sfb::QpAr
   args.work_counter = next_counter(h);
   SFB_CUDA(h, cudaMemsetAsync(args.work_counter, 0, sizeof(unsigned long long), st));
   int rc;
-  if (g.G == 4) rc = qp_launch_g<T, 4>(h, st, args, g, grid);
-  else if (g.G == 2) rc = qp_launch_g<T, 2>(h, st, args, g, grid);
-  else rc = qp_launch_g<T, 1>(h, st, args, g, grid);
+  // shape-specialised instantiations (compile-time n, m) for the headline shapes, generic kernels otherwise
+  if (g.G == 4) {
+    if (std::is_same<T, double>::value && args.n == 50 && args.m == 100) rc = qp_launch_g<T, 4, 50, 100>(h, st, args, g, grid);
+    else rc = qp_launch_g<T, 4, 0, 0>(h, st, args, g, grid);
+  } else if (g.G == 2) {
+    rc = qp_launch_g<T, 2, 0, 0>(h, st, args, g, grid);
+  } else {
+    rc = qp_launch_g<T, 1, 0, 0>(h, st, args, g, grid);
+  }
   if (rc != SFB_OK) return rc;
   h->launches += 1;
   return SFB_OK;
