@@ -595,6 +595,24 @@ template <typename T, int G, int NS, int MS> struct QpGroup
       gsync();
     }
   }
+  // dot of two contiguous, 2-scalar aligned shared-memory vectors (4 accumulators)
+  __device__ __forceinline__ T vecdot(const T* a, const T* v, int len) const
+  {
+    T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0);
+    int i = 0;
+#pragma unroll 1
+    for (; i + 3 < len; i += 4) {
+      const auto c01 = ld2(a + i), c23 = ld2(a + i + 2);
+      const auto v01 = ld2(v + i), v23 = ld2(v + i + 2);
+      a0 += c01.x * v01.x;
+      a1 += c01.y * v01.y;
+      a2 += c23.x * v23.x;
+      a3 += c23.y * v23.y;
+    }
+#pragma unroll 1
+    for (; i < len; ++i) a0 += a[i] * v[i];
+    return (a0 + a1) + (a2 + a3);
+  }
   // dot of row i of a column-major matrix with v (4 accumulators for ILP)
   __device__ __forceinline__ T rowdot(const T* Mx, int ld, int i, int cols, const T* v) const
   {
@@ -761,6 +779,7 @@ template <typename T, int G, int NS, int MS> struct QpGroup
       else return SFB_QP_FLAG_POLISH_SKIPPED;
     }
 
+    const bool s_shared = (S != nullptr) && (ldS == ldA);
     // compact the active rows of Abar to the top of every column (idx ascending => in-place safe)
 #pragma unroll 1
     for (int j = tid; j < n; j += NT) {
@@ -834,11 +853,11 @@ template <typename T, int G, int NS, int MS> struct QpGroup
           const int r = e % na, sc = e / na;
           T acc = rowdot(As, ldA, r, n, xt + sc * npad);
           if (r == s0 + sc) acc += delta;
-          S[r + ldS * (s0 + sc)] = acc;
+          if (s_shared) As[na + r + ldA * (s0 + sc)] = acc; else S[r + ldS * (s0 + sc)] = acc;
         }
         gsync();
       }
-      const bool s_ok = (S == As + na) ? gj_invert_at(1, na) : qp_stage_gj_generic<T, G, NS, MS>(n, m, S, ldS, na);
+      const bool s_ok = s_shared ? gj_invert_at(1, na) : qp_stage_gj_generic<T, G, NS, MS>(n, m, S, ldS, na);
       if (!s_ok) return SFB_QP_FLAG_POLISH_FAILED;
     }
 
@@ -860,9 +879,12 @@ template <typename T, int G, int NS, int MS> struct QpGroup
     // h - H t = (h + D t) - Hp t, the same sequence is t <- Hp^-1 (h + D t): no product with H (whose Pbar block lives
     // in HBM) is needed.  Only the last sweep uses the literal residual form, so that rounding errors of the explicit
     // inverses are corrected once, exactly like iterative refinement does.
+    bool converged = false;
 #pragma unroll 1
     for (uint32_t it = 0; it != a.prm.polish_iter; ++it) {
-      const bool literal = (it + 1 == a.prm.polish_iter) && (it > 0);
+      // Once t stops changing (to a few ulp) further sweeps of the fixed-point form are no-ops up to rounding: jump to
+      // the closing literal sweep.  Well-conditioned systems contract by delta / lambda_min ~ 1e-6 per sweep.
+      const bool literal = ((it + 1 == a.prm.polish_iter) || converged) && (it > 0);
       if (literal) {
         // residual r = h - sym(H) t,  H = [Pbar Aa^T; Aa 0]
 #pragma unroll 1
@@ -870,29 +892,19 @@ template <typename T, int G, int NS, int MS> struct QpGroup
           T acc = T(0);
 #pragma unroll 1
           for (int j = 0; j < n; ++j) acc += pbar(gP, i, j) * tx[j];
-          const T* col = As + ldA * i;
-#pragma unroll 1
-          for (int r = 0; r < na; ++r) acc += col[r] * ty[r];
-          rx[i] = -c * (sx[i] * q[i]) - acc;  // :180
+          rx[i] = -c * (sx[i] * q[i]) - (acc + vecdot(As + ldA * i, ty, na));  // :180
         }
 #pragma unroll 1
         for (int r = tid; r < na; r += NT) ry[r] = bnd[r] - rowdot(As, ldA, r, n, tx);  // :181-182
       } else {
-        // rhs = h + D t ; the solve below then yields the new t directly (accumulated as t += (t_new - t))
+        // rhs = h + D t ; the solve below then yields the new t directly
 #pragma unroll 1
         for (int i = tid; i < n; i += NT) rx[i] = -c * (sx[i] * q[i]) + delta * tx[i];
 #pragma unroll 1
         for (int r = tid; r < na; r += NT) ry[r] = bnd[r] - delta * ty[r];
       }
       gsync();
-      if (!literal) {
-        // the solve returns t_new, and the common update below adds the solve result to t: start from zero
-#pragma unroll 1
-        for (int i = tid; i < n; i += NT) tx[i] = T(0);
-#pragma unroll 1
-        for (int r = tid; r < na; r += NT) ty[r] = T(0);
-        gsync();
-      }
+      T diff = T(0), mag = T(0);
       if (!woodbury) {
         // [K Aa^T; Aa -delta I] [dx; dy] = [rx; ry]:  dy = Sinv (Aa Kinv rx - ry),  dx = Kinv (rx - Aa^T dy)
 #pragma unroll 1
@@ -902,44 +914,73 @@ template <typename T, int G, int NS, int MS> struct QpGroup
         for (int r = tid; r < na; r += NT) sv[r] = rowdot(As, ldA, r, n, ux) - ry[r];
         gsync();
 #pragma unroll 1
-        for (int r = tid; r < na; r += NT) {
-          T acc = T(0);
+        for (int r = tid; r < na; r += NT)
+          dy[r] = s_shared ? rowdot(As + na, ldA, r, na, sv) : rowdot(S, ldS, r, na, sv);  // keep LDS on the common path
+        gsync();
 #pragma unroll 1
-          for (int s = 0; s < na; ++s) acc += S[r + ldS * s] * sv[s];
-          dy[r] = acc;
-        }
+        for (int i = tid; i < n; i += NT) ux[i] = rx[i] - vecdot(As + ldA * i, dy, na);
         gsync();
 #pragma unroll 1
         for (int i = tid; i < n; i += NT) {
-          const T* col = As + ldA * i;
-          T acc = rx[i];
-#pragma unroll 1
-          for (int r = 0; r < na; ++r) acc -= col[r] * dy[r];
-          ux[i] = acc;
+          const T d = rowdot(Ms, ldN, i, n, ux);
+          if (literal) {
+            tx[i] += d;
+          } else {
+            diff = fmax(diff, fabs(d - tx[i]));
+            mag = fmax(mag, fabs(d));
+            tx[i] = d;
+          }
         }
-        gsync();
 #pragma unroll 1
-        for (int i = tid; i < n; i += NT) tx[i] += rowdot(Ms, ldN, i, n, ux);
-#pragma unroll 1
-        for (int r = tid; r < na; r += NT) ty[r] += dy[r];
+        for (int r = tid; r < na; r += NT) {
+          const T d = dy[r];
+          if (literal) {
+            ty[r] += d;
+          } else {
+            diff = fmax(diff, fabs(d - ty[r]));
+            mag = fmax(mag, fabs(d));
+            ty[r] = d;
+          }
+        }
       } else {
         // same system, duals eliminated first:  (K + Aa^T Aa / delta) dx = rx + Aa^T ry / delta,  dy = (Aa dx - ry) / delta
 #pragma unroll 1
-        for (int i = tid; i < n; i += NT) {
-          const T* col = As + ldA * i;
-          T acc = T(0);
-#pragma unroll 1
-          for (int r = 0; r < na; ++r) acc += col[r] * ry[r];
-          ux[i] = rx[i] + dinv * acc;
-        }
+        for (int i = tid; i < n; i += NT) ux[i] = rx[i] + dinv * vecdot(As + ldA * i, ry, na);
         gsync();
 #pragma unroll 1
         for (int i = tid; i < n; i += NT) rx[i] = rowdot(Ms, ldN, i, n, ux);  // rx now holds dx
         gsync();
 #pragma unroll 1
-        for (int r = tid; r < na; r += NT) ty[r] += (rowdot(As, ldA, r, n, rx) - ry[r]) * dinv;
+        for (int r = tid; r < na; r += NT) {
+          const T d = (rowdot(As, ldA, r, n, rx) - ry[r]) * dinv;
+          if (literal) {
+            ty[r] += d;
+          } else {
+            diff = fmax(diff, fabs(d - ty[r]));
+            mag = fmax(mag, fabs(d));
+            ty[r] = d;
+          }
+        }
 #pragma unroll 1
-        for (int i = tid; i < n; i += NT) tx[i] += rx[i];
+        for (int i = tid; i < n; i += NT) {
+          const T d = rx[i];
+          if (literal) {
+            tx[i] += d;
+          } else {
+            diff = fmax(diff, fabs(d - tx[i]));
+            mag = fmax(mag, fabs(d));
+            tx[i] = d;
+          }
+        }
+      }
+      if (literal) {
+        gsync();
+        break;
+      }
+      {
+        T mx[2] = {diff, mag}, sm[1] = {T(0)};
+        greduce<2, 1>(mx, sm);
+        converged = mx[0] <= T(8) * Num<T>::eps() * mx[1];
       }
       gsync();
     }
