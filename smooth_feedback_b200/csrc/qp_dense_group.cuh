@@ -370,13 +370,27 @@ template <typename T, int G, int NS, int MS> struct QpGroup
         T g = T(0);
         {
           const int i0 = cseg * rpsP, i1 = min(n, i0 + rpsP);
-#pragma unroll 1
-          for (int i = i0; i < i1; ++i) g = fmax(g, fabs(((c * sx[i]) * sxj) * Ms[i + ldN * j]));
+          T g1 = T(0);
+          int i = i0;
+#pragma unroll 2
+          for (; i + 1 < i1; i += 2) {  // two independent maxima: max is exact, the split does not change the result
+            g = fmax(g, fabs(((c * sx[i]) * sxj) * Ms[i + ldN * j]));
+            g1 = fmax(g1, fabs(((c * sx[i + 1]) * sxj) * Ms[i + 1 + ldN * j]));
+          }
+          if (i < i1) g = fmax(g, fabs(((c * sx[i]) * sxj) * Ms[i + ldN * j]));
+          g = fmax(g, g1);
         }
         {
           const int i0 = cseg * rpsA, i1 = min(m, i0 + rpsA);
-#pragma unroll 1
-          for (int i = i0; i < i1; ++i) g = fmax(g, fabs((sy[i] * sxj) * As[i + ldA * j]));
+          T g1 = T(0);
+          int i = i0;
+#pragma unroll 2
+          for (; i + 1 < i1; i += 2) {
+            g = fmax(g, fabs((sy[i] * sxj) * As[i + ldA * j]));
+            g1 = fmax(g1, fabs((sy[i + 1] * sxj) * As[i + 1 + ldA * j]));
+          }
+          if (i < i1) g = fmax(g, fabs((sy[i] * sxj) * As[i + ldA * j]));
+          g = fmax(g, g1);
         }
         part[cseg * n + j] = g;
       }
@@ -384,8 +398,15 @@ template <typename T, int G, int NS, int MS> struct QpGroup
       for (int i = tid; i < m; i += NT) {
         const T syi = sy[i];
         T g = T(0);
-#pragma unroll 1
-        for (int j = 0; j < n; ++j) g = fmax(g, fabs((syi * sx[j]) * As[i + ldA * j]));
+        T g1 = T(0);
+        int j = 0;
+#pragma unroll 2
+        for (; j + 1 < n; j += 2) {
+          g = fmax(g, fabs((syi * sx[j]) * As[i + ldA * j]));
+          g1 = fmax(g1, fabs((syi * sx[j + 1]) * As[i + ldA * (j + 1)]));
+        }
+        if (j < n) g = fmax(g, fabs((syi * sx[j]) * As[i + ldA * j]));
+        g = fmax(g, g1);
         if (g == T(0)) g = T(1);
         mv1[i] = g;
       }
@@ -720,8 +741,8 @@ template <typename T, int G, int NS, int MS> struct QpGroup
       const T aty = xt[j] * sc;
       const T atdy = nv2[j] * sc;
       T px = T(0), pdx = T(0);
-#pragma unroll 1
-      for (int k = 0; k < n; ++k) {
+#pragma unroll 10
+      for (int k = 0; k < n; ++k) {  // unrolled: the L2 loads are independent, keep ~10 in flight
         const T pjk = __ldg(gP + j + (long long)n * k);  // row j of the unscaled P (coalesced across threads)
         px += pjk * nv1[k];
         pdx += pjk * xold[k];
@@ -837,15 +858,18 @@ template <typename T, int G, int NS, int MS> struct QpGroup
           const int i = e % n, sc = e / n;
           const T* p = Ms + i;
           const T* arow = As + (s0 + sc);
-          T a0 = T(0), a1 = T(0);
+          T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0);
           int j = 0;
-#pragma unroll 1
-          for (; j + 1 < n; j += 2) {
+#pragma unroll 2
+          for (; j + 3 < n; j += 4) {
             a0 += p[ldN * j] * arow[ldA * j];
             a1 += p[ldN * (j + 1)] * arow[ldA * (j + 1)];
+            a2 += p[ldN * (j + 2)] * arow[ldA * (j + 2)];
+            a3 += p[ldN * (j + 3)] * arow[ldA * (j + 3)];
           }
-          if (j < n) a0 += p[ldN * j] * arow[ldA * j];
-          xt[sc * npad + i] = a0 + a1;
+#pragma unroll 1
+          for (; j < n; ++j) a0 += p[ldN * j] * arow[ldA * j];
+          xt[sc * npad + i] = (a0 + a1) + (a2 + a3);
         }
         gsync();
 #pragma unroll 1
@@ -890,7 +914,7 @@ template <typename T, int G, int NS, int MS> struct QpGroup
 #pragma unroll 1
         for (int i = tid; i < n; i += NT) {
           T acc = T(0);
-#pragma unroll 1
+#pragma unroll 10
           for (int j = 0; j < n; ++j) acc += pbar(gP, i, j) * tx[j];
           rx[i] = -c * (sx[i] * q[i]) - (acc + vecdot(As + ldA * i, ty, na));  // :180
         }
@@ -1263,7 +1287,7 @@ template <typename T, int G, int NS, int MS> struct QpGroup
 #pragma unroll 1
     for (int i = tid; i < n; i += NT) {
       T acc = T(0);
-#pragma unroll 1
+#pragma unroll 10
       for (int j = 0; j < n; ++j) acc += T(0.5) * __ldg(gP + i + (long long)n * j) * nv1[j];
       obj += nv1[i] * (acc + q[i]);
     }
