@@ -12,6 +12,7 @@
  *   sfb_qp_status                       <- QPSolutionStatus           qp.hpp:82-92
  *   sfb_ekf_predict_batch_f64           <- EKF::predict (cov. ODE)    ekf.hpp:79-103
  *   sfb_ekf_update_batch_f64            <- EKF::update                ekf.hpp:116-139
+ *   sfb_ekf_step_batch_f64              <- EKF::predict + EKF::update ekf.hpp:79-139 (fused, one HBM pass)
  *
  * Conventions
  *   - plain pointers and sizes only; every array is a contiguous batch of per-instance blocks laid out
@@ -160,6 +161,18 @@ int sfb_ekf_predict_batch_f64(sfb_handle_t h, int64_t batch, int d, int stepper,
  */
 int sfb_ekf_update_batch_f64(sfb_handle_t h, int64_t batch, int d, int ny, const double* P, const double* H,
                              const double* R, const double* innov, double* out_delta, double* out_P);
+
+/*
+ * One EKF cycle of the covariance in a single pass over HBM: predict (euler stepper, the reference default,
+ * ekf.hpp:147) followed by update, i.e. sfb_ekf_predict_batch_f64 + sfb_ekf_update_batch_f64 without the round
+ * trip of the predicted covariance through memory.  H and innov are evaluated by the caller at the PREDICTED
+ * estimate g_hat (+) tau f (ekf.hpp:96,119 -- they do not depend on P).  Arguments as in the two calls above;
+ * stepper must be SFB_STEPPER_EULER or SFB_STEPPER_RK4 (RK4 runs the two generic kernels back to back).
+ * out_P may alias P.
+ */
+int sfb_ekf_step_batch_f64(sfb_handle_t h, int64_t batch, int d, int ny, int stepper, const double* P,
+                           const double* A, const double* Q, double tau, double dt, const double* H,
+                           const double* R, const double* innov, double* out_delta, double* out_P);
 
 #ifdef __cplusplus
 }

@@ -50,7 +50,7 @@ EXPORTED_SYMBOLS = [
     "sfb_version", "sfb_error_string", "sfb_last_error_message", "sfb_create", "sfb_destroy", "sfb_set_stream",
     "sfb_synchronize", "sfb_kernel_launch_count", "sfb_qp_params_default", "sfb_qp_solve_dense_batch_f64",
     "sfb_qp_solve_dense_batch_f32", "sfb_qp_dense_max_m", "sfb_qp_scale_dense_batch_f64",
-    "sfb_ekf_predict_batch_f64", "sfb_ekf_update_batch_f64",
+    "sfb_ekf_predict_batch_f64", "sfb_ekf_update_batch_f64", "sfb_ekf_step_batch_f64",
 ]
 
 
@@ -111,6 +111,7 @@ def lib() -> C.CDLL:
     L.sfb_qp_scale_dense_batch_f64.argtypes = [vp, i64, i32, i32] + [vp] * 6
     L.sfb_ekf_predict_batch_f64.argtypes = [vp, i64, i32, i32, vp, vp, vp, C.c_double, C.c_double, vp]
     L.sfb_ekf_update_batch_f64.argtypes = [vp, i64, i32, i32] + [vp] * 6
+    L.sfb_ekf_step_batch_f64.argtypes = [vp, i64, i32, i32, i32, vp, vp, vp, C.c_double, C.c_double] + [vp] * 5
     for name in EXPORTED_SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("sfb_version", "sfb_qp_dense_max_m"):

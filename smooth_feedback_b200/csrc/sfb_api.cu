@@ -9,12 +9,14 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <type_traits>
 #include <vector>
 
 #include "../../include/sfb.h"
+#include "ekf_fused_tma.cuh"
 #include "ekf_kernels.cuh"
 #include "qp_dense_group.cuh"
 
@@ -54,6 +56,7 @@ struct sfb_context
   Slot slots[kNumSlots];
   Scratch scratch[kNumSlots + 1];  // [kNumSlots] belongs to the handle's own stream
   cudaEvent_t ev_start = nullptr;
+  bool ekf_force_generic = false;
 };
 
 namespace {
@@ -389,6 +392,84 @@ int ekf_block_threads(sfb_context* h, size_t elems_per_thread, size_t scalar, si
   return 0;
 }
 
+// ---- fused, size-specialised TMA path (ekf_fused_tma.cuh) -----------------------------------------------
+constexpr int kEkfTile = 64;
+
+bool aligned16(std::initializer_list<const void*> ps)
+{
+  for (const void* p : ps)
+    if (p && (reinterpret_cast<uintptr_t>(p) & 15u)) return false;
+  return true;
+}
+
+template <int D, int NY, bool PRED, bool UPD>
+int ekf_fused_launch(sfb_context* h, const sfb::EkfStepArgs& a)
+{
+  using L = sfb::EkfFusedLayout<D, NY, PRED, UPD, kEkfTile>;
+  auto kern = sfb::ekf_fused_tma_kernel<D, NY, PRED, UPD, kEkfTile>;
+  SFB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes));
+  int nb = 0;
+  SFB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kEkfTile, L::bytes));
+  if (nb < 1) return fail(h, SFB_ERR_UNSUPPORTED_SIZE, "fused EKF kernel does not fit on this device");
+  const long long tiles = (a.batch + kEkfTile - 1) / kEkfTile;
+  const int grid = (int)std::min<long long>(tiles, (long long)h->prop.multiProcessorCount * nb);
+  kern<<<grid, kEkfTile, L::bytes, h->stream>>>(a);
+  SFB_CUDA(h, cudaGetLastError());
+  h->launches += 1;
+  return SFB_OK;
+}
+
+// returns -1 when no specialisation exists for (d, ny, mode): the caller takes the generic kernels
+template <bool PRED, bool UPD> int ekf_fused_dispatch(sfb_context* h, int d, int ny, const sfb::EkfStepArgs& a)
+{
+  if (h->ekf_force_generic) return -1;  // SFB_EKF_FORCE_GENERIC=1: A/B measurements against the generic kernels
+  if (!UPD) {
+    if (d == 3) return ekf_fused_launch<3, 1, PRED, false>(h, a);
+    if (d == 6) return ekf_fused_launch<6, 1, PRED, false>(h, a);
+    return -1;
+  }
+  if (d == 6 && ny == 3) return ekf_fused_launch<6, 3, PRED, true>(h, a);
+  if (d == 6 && ny == 6) return ekf_fused_launch<6, 6, PRED, true>(h, a);
+  if (d == 3 && ny == 3) return ekf_fused_launch<3, 3, PRED, true>(h, a);
+  return -1;
+}
+
+int ekf_predict_generic(sfb_context* h, int64_t batch, int d, int stepper, const double* P, const double* A,
+                        const double* Q, double tau, double dt, double* out_P)
+{
+  size_t smem = 0;
+  const int bd = ekf_block_threads(h, (size_t)6 * d * d, sizeof(double), &smem);
+  if (bd == 0) return fail(h, SFB_ERR_UNSUPPORTED_SIZE, "EKF predict d=%d does not fit in shared memory", d);
+  auto kern = sfb::ekf_predict_kernel<double>;
+  SFB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  sfb::EkfPredictArgs<double> a{P, A, Q, out_P, batch, d, stepper, tau, dt};
+  const long long tiles = (batch + bd - 1) / bd;
+  const int per_sm = (int)std::max<size_t>(1, h->prop.sharedMemPerMultiprocessor / (smem + 1024));
+  const int grid = (int)std::min<long long>(tiles, (long long)h->prop.multiProcessorCount * per_sm);
+  kern<<<grid, bd, smem, h->stream>>>(a);
+  SFB_CUDA(h, cudaGetLastError());
+  h->launches += 1;
+  return SFB_OK;
+}
+
+int ekf_update_generic(sfb_context* h, int64_t batch, int d, int ny, const double* P, const double* H,
+                       const double* R, const double* innov, double* out_delta, double* out_P)
+{
+  size_t smem = 0;
+  const int bd = ekf_block_threads(h, sfb::ekf_update_elems<double>(d, ny), sizeof(double), &smem);
+  if (bd == 0) return fail(h, SFB_ERR_UNSUPPORTED_SIZE, "EKF update d=%d ny=%d does not fit in shared memory", d, ny);
+  auto kern = sfb::ekf_update_kernel<double>;
+  SFB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  sfb::EkfUpdateArgs<double> a{P, H, R, innov, out_delta, out_P, batch, d, ny};
+  const long long tiles = (batch + bd - 1) / bd;
+  const int per_sm = (int)std::max<size_t>(1, h->prop.sharedMemPerMultiprocessor / (smem + 1024));
+  const int grid = (int)std::min<long long>(tiles, (long long)h->prop.multiProcessorCount * per_sm);
+  kern<<<grid, bd, smem, h->stream>>>(a);
+  SFB_CUDA(h, cudaGetLastError());
+  h->launches += 1;
+  return SFB_OK;
+}
+
 }  // namespace
 
 // =======================================================================================================
@@ -428,6 +509,7 @@ int sfb_create(int device, void* stream, sfb_handle_t* out)
   if (device < 0 || device >= count) return fail(nullptr, SFB_ERR_INVALID_ARGUMENT, "device %d out of range [0,%d)", device, count);
   sfb_context* h = new sfb_context();
   h->device = device;
+  { const char* e = getenv("SFB_EKF_FORCE_GENERIC"); h->ekf_force_generic = e && e[0] == '1'; }
   h->stream = static_cast<cudaStream_t>(stream);
   if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&h->prop, device) != cudaSuccess) {
     const char* msg = cudaGetErrorString(cudaGetLastError());
@@ -576,19 +658,12 @@ int sfb_ekf_predict_batch_f64(sfb_handle_t h, int64_t batch, int d, int stepper,
   if (classify({P, A, Q, out_P}) != 1) return fail(h, SFB_ERR_MIXED_MEMORY, "EKF entry points take device pointers only");
   if (batch == 0) return SFB_OK;
   SFB_CUDA(h, cudaSetDevice(h->device));
-  size_t smem = 0;
-  const int bd = ekf_block_threads(h, (size_t)6 * d * d, sizeof(double), &smem);
-  if (bd == 0) return fail(h, SFB_ERR_UNSUPPORTED_SIZE, "EKF predict d=%d does not fit in shared memory", d);
-  auto kern = sfb::ekf_predict_kernel<double>;
-  SFB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  sfb::EkfPredictArgs<double> a{P, A, Q, out_P, batch, d, stepper, tau, dt};
-  const long long tiles = (batch + bd - 1) / bd;
-  const int per_sm = (int)std::max<size_t>(1, h->prop.sharedMemPerMultiprocessor / (smem + 1024));
-  const int grid = (int)std::min<long long>(tiles, (long long)h->prop.multiProcessorCount * per_sm);
-  kern<<<grid, bd, smem, h->stream>>>(a);
-  SFB_CUDA(h, cudaGetLastError());
-  h->launches += 1;
-  return SFB_OK;
+  if (stepper == SFB_STEPPER_EULER && aligned16({P, A, Q, out_P})) {
+    sfb::EkfStepArgs a{P, A, Q, nullptr, nullptr, nullptr, nullptr, out_P, batch, tau, dt};
+    const int rc = ekf_fused_dispatch<true, false>(h, d, 1, a);
+    if (rc >= 0) return rc;
+  }
+  return ekf_predict_generic(h, batch, d, stepper, P, A, Q, tau, dt, out_P);
 }
 
 int sfb_ekf_update_batch_f64(sfb_handle_t h, int64_t batch, int d, int ny, const double* P, const double* H,
@@ -600,19 +675,36 @@ int sfb_ekf_update_batch_f64(sfb_handle_t h, int64_t batch, int d, int ny, const
   if (classify({P, H, R, innov, out_delta, out_P}) != 1) return fail(h, SFB_ERR_MIXED_MEMORY, "EKF entry points take device pointers only");
   if (batch == 0) return SFB_OK;
   SFB_CUDA(h, cudaSetDevice(h->device));
-  size_t smem = 0;
-  const int bd = ekf_block_threads(h, sfb::ekf_update_elems<double>(d, ny), sizeof(double), &smem);
-  if (bd == 0) return fail(h, SFB_ERR_UNSUPPORTED_SIZE, "EKF update d=%d ny=%d does not fit in shared memory", d, ny);
-  auto kern = sfb::ekf_update_kernel<double>;
-  SFB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  sfb::EkfUpdateArgs<double> a{P, H, R, innov, out_delta, out_P, batch, d, ny};
-  const long long tiles = (batch + bd - 1) / bd;
-  const int per_sm = (int)std::max<size_t>(1, h->prop.sharedMemPerMultiprocessor / (smem + 1024));
-  const int grid = (int)std::min<long long>(tiles, (long long)h->prop.multiProcessorCount * per_sm);
-  kern<<<grid, bd, smem, h->stream>>>(a);
-  SFB_CUDA(h, cudaGetLastError());
-  h->launches += 1;
-  return SFB_OK;
+  if (aligned16({P, H, R, innov, out_delta, out_P})) {
+    sfb::EkfStepArgs a{P, nullptr, nullptr, H, R, innov, out_delta, out_P, batch, 0.0, 0.0};
+    const int rc = ekf_fused_dispatch<false, true>(h, d, ny, a);
+    if (rc >= 0) return rc;
+  }
+  return ekf_update_generic(h, batch, d, ny, P, H, R, innov, out_delta, out_P);
+}
+
+int sfb_ekf_step_batch_f64(sfb_handle_t h, int64_t batch, int d, int ny, int stepper, const double* P,
+                           const double* A, const double* Q, double tau, double dt, const double* H,
+                           const double* R, const double* innov, double* out_delta, double* out_P)
+{
+  if (!h) return SFB_ERR_INVALID_ARGUMENT;
+  if (batch < 0 || d <= 0 || ny <= 0 || ny > sfb::kEkfMaxNy || (stepper != SFB_STEPPER_EULER && stepper != SFB_STEPPER_RK4) ||
+      !P || !A || !Q || !H || !R || !innov || !out_delta || !out_P)
+    return fail(h, SFB_ERR_INVALID_ARGUMENT, "bad argument to sfb_ekf_step_batch_f64");
+  if (classify({P, A, Q, H, R, innov, out_delta, out_P}) != 1)
+    return fail(h, SFB_ERR_MIXED_MEMORY, "EKF entry points take device pointers only");
+  if (batch == 0) return SFB_OK;
+  SFB_CUDA(h, cudaSetDevice(h->device));
+  if (stepper == SFB_STEPPER_EULER && aligned16({P, A, Q, H, R, innov, out_delta, out_P})) {
+    sfb::EkfStepArgs a{P, A, Q, H, R, innov, out_delta, out_P, batch, tau, dt};
+    const int rc = ekf_fused_dispatch<true, true>(h, d, ny, a);
+    if (rc >= 0) return rc;
+  }
+  // generic sizes / RK4: the two generic kernels back to back; the update works in place on out_P (each CTA stages its
+  // tile of P completely before it stores)
+  int rc = ekf_predict_generic(h, batch, d, stepper, P, A, Q, tau, dt, out_P);
+  if (rc != SFB_OK) return rc;
+  return ekf_update_generic(h, batch, d, ny, out_P, H, R, innov, out_delta, out_P);
 }
 
 }  // extern "C"

@@ -60,3 +60,31 @@ def ekf_update_batch(P_cm, H_cm, R_cm, innov, handle: Handle | None = None, out_
     h.check(_lib.lib().sfb_ekf_update_batch_f64(h.raw, B, d, ny, _ptr(P_cm), _ptr(H_cm), _ptr(R_cm), _ptr(innov),
                                                 _ptr(out_delta), _ptr(out_P)))
     return out_delta, out_P
+
+
+def ekf_step_batch(P_cm, A_cm, Q_cm, tau: float, H_cm, R_cm, innov, dt: float | None = None, stepper: str = "euler",
+                   handle: Handle | None = None, out_delta=None, out_P=None):
+    """One predict + update cycle of the covariance (ekf.hpp:79-139) in a single pass over HBM.
+
+    Same arguments as ekf_predict_batch followed by ekf_update_batch; H_cm and innov are evaluated by the caller at
+    the predicted estimate.  Returns (delta [B,d], P_new_cm [B,d,d]).
+    """
+    import torch
+
+    B, d, _ = P_cm.shape
+    ny = innov.shape[1]
+    dev = P_cm.device
+    assert tuple(A_cm.shape) == (B, d, d) and tuple(Q_cm.shape) == (B, d, d)
+    assert tuple(H_cm.shape) == (B, d, ny) and tuple(R_cm.shape) == (B, ny, ny)
+    for t in (P_cm, A_cm, Q_cm, H_cm, R_cm, innov):
+        assert t.is_cuda and t.is_contiguous() and t.dtype == torch.float64
+    h = handle or default_handle(dev.index or 0)
+    h.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    if out_delta is None:
+        out_delta = torch.empty((B, d), dtype=torch.float64, device=dev)
+    if out_P is None:
+        out_P = torch.empty_like(P_cm)
+    h.check(_lib.lib().sfb_ekf_step_batch_f64(h.raw, B, d, ny, STEPPERS[stepper], _ptr(P_cm), _ptr(A_cm), _ptr(Q_cm),
+                                              float(tau), -1.0 if dt is None else float(dt), _ptr(H_cm), _ptr(R_cm),
+                                              _ptr(innov), _ptr(out_delta), _ptr(out_P)))
+    return out_delta, out_P
