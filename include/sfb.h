@@ -10,6 +10,8 @@
  *                                          (call sites: mpc.hpp:491, asif.hpp:97)
  *   sfb_qp_params / _default            <- QPSolverParams             qp_solver.hpp:29-68
  *   sfb_qp_status                       <- QPSolutionStatus           qp.hpp:82-92
+ *   sfb_qp_sparse_analyze               <- SimplicialLDLT::analyzePattern, call site qp_solver.hpp:424 (mpc.hpp:424)
+ *   sfb_qp_solve_sparse_batch_f64/_f32  <- QPSolver<QuadraticProgramSparse>::solve   qp_solver.hpp:343-568 (mpc.hpp:491)
  *   sfb_ekf_predict_batch_f64           <- EKF::predict (cov. ODE)    ekf.hpp:79-103
  *   sfb_ekf_update_batch_f64            <- EKF::update                ekf.hpp:116-139
  *   sfb_ekf_step_batch_f64              <- EKF::predict + EKF::update ekf.hpp:79-139 (fused, one HBM pass)
@@ -173,6 +175,44 @@ int sfb_ekf_update_batch_f64(sfb_handle_t h, int64_t batch, int d, int ny, const
 int sfb_ekf_step_batch_f64(sfb_handle_t h, int64_t batch, int d, int ny, int stepper, const double* P,
                            const double* A, const double* Q, double tau, double dt, const double* H,
                            const double* R, const double* innov, double* out_delta, double* out_P);
+
+/*
+ * ---- sparse problems with a SHARED sparsity pattern (QuadraticProgramSparse, qp.hpp:60-79) ---------------------
+ *
+ * sfb_qp_sparse_analyze replaces SimplicialLDLT::analyzePattern (call site qp_solver.hpp:424, done once per solver
+ * object -- MPC does it in its constructor, mpc.hpp:424): fill-reducing ordering, symbolic factor and assembly
+ * schedules of the reduced KKT matrix, uploaded to the handle's device.  The pattern arrays are HOST pointers in
+ * Eigen's compressed storage:  P column-major (SparseMatrix<double>: outerIndexPtr = P_colptr [n+1], innerIndexPtr
+ * = P_rowidx), A row-major (SparseMatrix<double, RowMajor>: A_rowptr [m+1], A_colidx).  Explicit zeros are part of the
+ * pattern.  Like the reference, only entries of P with col >= row enter the factorisation (qp_solver.hpp:384) while
+ * scaling, residuals and the objective use the entries as stored.
+ */
+typedef struct sfb_qp_sparse_pattern* sfb_qp_sparse_pattern_t;
+
+int sfb_qp_sparse_analyze(sfb_handle_t h, int n, int m, const int32_t* P_colptr, const int32_t* P_rowidx,
+                          const int32_t* A_rowptr, const int32_t* A_colidx, sfb_qp_sparse_pattern_t* out);
+int sfb_qp_sparse_pattern_destroy(sfb_qp_sparse_pattern_t p);
+/* nnz of the strictly lower factor L, multiply-adds of one numeric factorisation, ordering (perm_out [n], may be NULL) */
+int sfb_qp_sparse_pattern_info(sfb_qp_sparse_pattern_t p, int64_t* nnz_L, int64_t* factor_flops, int32_t* perm_out);
+
+/*
+ * Replaces QPSolver<QuadraticProgramSparse<double>>::solve (qp_solver.hpp:343-568, sparse branches; call site
+ * mpc.hpp:491) for a batch of problems sharing `pattern`:
+ *   P_vals [batch][nnzP], A_vals [batch][nnzA]  the valuePtr() arrays of each instance, in pattern order
+ *   q [batch][n], l,u [batch][m]; warm starts and outputs exactly as in sfb_qp_solve_dense_batch_f64.
+ * All-host or all-device pointers.
+ */
+int sfb_qp_solve_sparse_batch_f64(sfb_handle_t h, sfb_qp_sparse_pattern_t pattern, const sfb_qp_params* prm,
+                                  int64_t batch, const double* P_vals, const double* q, const double* A_vals,
+                                  const double* l, const double* u, const double* warm_x, const double* warm_y,
+                                  double* out_x, double* out_y, double* out_obj, int32_t* out_status,
+                                  uint32_t* out_iter, int8_t* out_active, uint32_t* out_flags);
+/* single precision (new functionality; polish is reported as skipped, as in the dense f32 entry point) */
+int sfb_qp_solve_sparse_batch_f32(sfb_handle_t h, sfb_qp_sparse_pattern_t pattern, const sfb_qp_params* prm,
+                                  int64_t batch, const float* P_vals, const float* q, const float* A_vals,
+                                  const float* l, const float* u, const float* warm_x, const float* warm_y, float* out_x,
+                                  float* out_y, float* out_obj, int32_t* out_status, uint32_t* out_iter,
+                                  int8_t* out_active, uint32_t* out_flags);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,189 @@
+// qp_sparse_host.hpp -- host-side symbolic analysis for the batched sparse QP path (shared sparsity pattern).
+//
+// Replaces what the reference gets from Eigen for QuadraticProgramSparse problems
+// (pettni/smooth_feedback @ 9a08971):
+//   SimplicialLDLT::analyzePattern   call site include/smooth/feedback/qp_solver.hpp:424   (ordering + symbolic factor)
+//   sparse KKT fill                  include/smooth/feedback/qp_solver.hpp:380-397
+// The engine does not factorise the (n+m) x (n+m) quasi-definite KKT matrix: the diagonal (2,2) block -1/rho is
+// eliminated analytically (as in the dense kernel) and the n x n matrix
+//      M = c Sx triu(P) Sx (mirrored) + sigma I + Abar^T R Abar
+// is factorised as L D L^T.  Its pattern depends only on the patterns of P and A, which every instance of a batch
+// shares (MPC: one OCP structure, many agents / time steps), so ordering, fill, assembly targets and the
+// right-looking update schedule are computed ONCE here and uploaded as flat index arrays.
+//
+// Ordering: greedy minimum degree on the elimination graph (exact degrees; n is a few hundred to a few thousand).
+
+#pragma once
+
+#include <algorithm>
+#include <cstdint>
+#include <map>
+#include <set>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace sfb {
+
+struct SparseSymbolic
+{
+  int n = 0, m = 0, nnzP = 0, nnzA = 0, nnzL = 0;
+  std::vector<int> perm, iperm;       // perm[new] = old, iperm[old] = new
+  std::vector<int> P_colptr, P_row;   // as given (original indices)
+  std::vector<int> P_rowp, P_colp;    // per stored entry: permuted row / column
+  std::vector<int> P_tgt;             // per stored entry: slot in W (L slots, then nnzL + i for D_i), -1 if below the diagonal
+  std::vector<int> A_rowptr, A_col;   // CSR, column index permuted
+  std::vector<int> A_pair_ptr, A_pair_tgt;  // per row: targets of the pairs (a <= b) of its entries, a-major
+  std::vector<int> L_colptr, L_row;   // strictly lower triangle of L, CSC, permuted indices, rows ascending
+  std::vector<int> F_ptr, F_tgt;      // per column k: targets of the pairs (a <= b) of struct(k), a-major
+  long long flops = 0;                // multiply-adds of the numeric factorisation
+  std::string error;
+};
+
+inline bool sparse_analyze(int n, int m, const int32_t* P_colptr, const int32_t* P_rowidx, const int32_t* A_rowptr,
+                           const int32_t* A_colidx, SparseSymbolic& S)
+{
+  S = SparseSymbolic();
+  S.n = n;
+  S.m = m;
+  if (n <= 0 || m < 0 || !P_colptr || (m > 0 && !A_rowptr)) { S.error = "bad sizes or null pattern"; return false; }
+  S.nnzP = P_colptr[n];
+  S.nnzA = m > 0 ? A_rowptr[m] : 0;
+  if (P_colptr[0] != 0 || (m > 0 && A_rowptr[0] != 0)) { S.error = "pattern pointers must start at 0"; return false; }
+  S.P_colptr.assign(P_colptr, P_colptr + n + 1);
+  S.P_row.assign(P_rowidx, P_rowidx + S.nnzP);
+  S.A_rowptr.assign(m + 1, 0);
+  if (m > 0) S.A_rowptr.assign(A_rowptr, A_rowptr + m + 1);
+  std::vector<int> A_col_orig(A_colidx, A_colidx + S.nnzA);
+  for (int j = 0; j < n; ++j)
+    if (P_colptr[j + 1] < P_colptr[j]) { S.error = "P_colptr not monotone"; return false; }
+  for (int e = 0; e < S.nnzP; ++e)
+    if (P_rowidx[e] < 0 || P_rowidx[e] >= n) { S.error = "P row index out of range"; return false; }
+  for (int i = 0; i < m; ++i)
+    if (A_rowptr[i + 1] < A_rowptr[i]) { S.error = "A_rowptr not monotone"; return false; }
+  for (int e = 0; e < S.nnzA; ++e)
+    if (A_colidx[e] < 0 || A_colidx[e] >= n) { S.error = "A column index out of range"; return false; }
+
+  // ---- pattern of M (original indices) ----
+  std::vector<std::set<int>> adj(n);
+  for (int j = 0; j < n; ++j)
+    for (int e = P_colptr[j]; e < P_colptr[j + 1]; ++e) {
+      const int r = P_rowidx[e];
+      if (j >= r && j != r) { adj[r].insert(j); adj[j].insert(r); }  // only col >= row enters the KKT (qp_solver.hpp:384)
+    }
+  for (int i = 0; i < m; ++i)
+    for (int e1 = A_rowptr[i]; e1 < A_rowptr[i + 1]; ++e1)
+      for (int e2 = e1 + 1; e2 < A_rowptr[i + 1]; ++e2) {
+        const int a = A_colidx[e1], b = A_colidx[e2];
+        if (a == b) { S.error = "duplicate column index in a row of A (pattern must be compressed)"; return false; }
+        adj[a].insert(b);
+        adj[b].insert(a);
+      }
+
+  // ---- greedy minimum-degree ordering + symbolic elimination ----
+  S.perm.assign(n, -1);
+  S.iperm.assign(n, -1);
+  std::vector<std::vector<int>> struct_old(n);  // per elimination step: higher neighbours (original indices)
+  {
+    std::vector<std::set<int>> g = adj;
+    std::vector<char> alive(n, 1);
+    std::set<std::pair<int, int>> queue;  // (degree, vertex)
+    for (int v = 0; v < n; ++v) queue.insert({(int)g[v].size(), v});
+    for (int step = 0; step < n; ++step) {
+      const auto it = queue.begin();
+      const int v = it->second;
+      queue.erase(it);
+      alive[v] = 0;
+      S.perm[step] = v;
+      S.iperm[v] = step;
+      struct_old[step].assign(g[v].begin(), g[v].end());
+      const std::vector<int>& nb = struct_old[step];
+      for (int a : nb) {
+        queue.erase({(int)g[a].size(), a});
+        g[a].erase(v);
+        for (int b : nb)
+          if (b != a) g[a].insert(b);
+        queue.insert({(int)g[a].size(), a});
+      }
+      g[v].clear();
+    }
+  }
+  // L in CSC over permuted indices
+  S.L_colptr.assign(n + 1, 0);
+  std::vector<std::vector<int>> st(n);
+  for (int k = 0; k < n; ++k) {
+    st[k].reserve(struct_old[k].size());
+    for (int v : struct_old[k]) st[k].push_back(S.iperm[v]);
+    std::sort(st[k].begin(), st[k].end());
+    S.L_colptr[k + 1] = S.L_colptr[k] + (int)st[k].size();
+  }
+  S.nnzL = S.L_colptr[n];
+  S.L_row.resize(S.nnzL);
+  std::vector<std::unordered_map<int, int>> slot(n);  // slot[col][row] -> index into L values
+  for (int k = 0; k < n; ++k) {
+    slot[k].reserve(st[k].size() * 2 + 1);
+    for (size_t t = 0; t < st[k].size(); ++t) {
+      S.L_row[S.L_colptr[k] + t] = st[k][t];
+      slot[k][st[k][t]] = S.L_colptr[k] + (int)t;
+    }
+  }
+  auto target = [&](int pr, int pc) -> int {  // permuted indices, any order
+    if (pr == pc) return S.nnzL + pr;
+    const int lo = std::min(pr, pc), hi = std::max(pr, pc);
+    const auto f = slot[lo].find(hi);
+    return f == slot[lo].end() ? -2 : f->second;
+  };
+
+  // ---- assembly targets ----
+  S.P_tgt.assign(S.nnzP, -1);
+  S.P_rowp.resize(S.nnzP);
+  S.P_colp.resize(S.nnzP);
+  for (int j = 0; j < n; ++j)
+    for (int e = P_colptr[j]; e < P_colptr[j + 1]; ++e) {
+      const int r = P_rowidx[e];
+      S.P_rowp[e] = S.iperm[r];
+      S.P_colp[e] = S.iperm[j];
+      if (j >= r) {
+        S.P_tgt[e] = target(S.iperm[r], S.iperm[j]);
+        if (S.P_tgt[e] == -2) { S.error = "internal: P entry outside the symbolic factor"; return false; }
+      }
+    }
+  S.A_col.resize(S.nnzA);
+  for (int e = 0; e < S.nnzA; ++e) S.A_col[e] = S.iperm[A_col_orig[e]];
+  S.A_pair_ptr.assign(m + 1, 0);
+  for (int i = 0; i < m; ++i) {
+    const int k = S.A_rowptr[i + 1] - S.A_rowptr[i];
+    S.A_pair_ptr[i + 1] = S.A_pair_ptr[i] + k * (k + 1) / 2;
+  }
+  S.A_pair_tgt.resize(S.A_pair_ptr[m]);
+  for (int i = 0; i < m; ++i) {
+    int p = S.A_pair_ptr[i];
+    for (int e1 = S.A_rowptr[i]; e1 < S.A_rowptr[i + 1]; ++e1)
+      for (int e2 = e1; e2 < S.A_rowptr[i + 1]; ++e2) {
+        const int t = target(S.A_col[e1], S.A_col[e2]);
+        if (t == -2) { S.error = "internal: A^T A entry outside the symbolic factor"; return false; }
+        S.A_pair_tgt[p++] = t;
+      }
+  }
+
+  // ---- right-looking update schedule ----
+  S.F_ptr.assign(n + 1, 0);
+  for (int k = 0; k < n; ++k) {
+    const long long s = (long long)st[k].size();
+    S.F_ptr[k + 1] = S.F_ptr[k] + (int)(s * (s + 1) / 2);
+    S.flops += s * (s + 1) / 2;
+  }
+  S.F_tgt.resize(S.F_ptr[n]);
+  for (int k = 0; k < n; ++k) {
+    int p = S.F_ptr[k];
+    for (size_t a = 0; a < st[k].size(); ++a)
+      for (size_t b = a; b < st[k].size(); ++b) {
+        const int t = target(st[k][b], st[k][a]);
+        if (t == -2) { S.error = "internal: fill entry outside the symbolic factor"; return false; }
+        S.F_tgt[p++] = t;
+      }
+  }
+  return true;
+}
+
+}  // namespace sfb
