@@ -16,6 +16,7 @@
 #pragma once
 
 #include <algorithm>
+#include <array>
 #include <cstdint>
 #include <map>
 #include <set>
@@ -34,8 +35,18 @@ struct SparseSymbolic
   std::vector<int> P_tgt;             // per stored entry: slot in W (L slots, then nnzL + i for D_i), -1 if below the diagonal
   std::vector<int> A_rowptr, A_col;   // CSR, column index permuted
   std::vector<int> A_pair_ptr, A_pair_tgt;  // per row: targets of the pairs (a <= b) of its entries, a-major
+  std::vector<int> A_pair_ab, F_ab;         // the pair itself, (a << 16) | b, offsets relative to the row / column start
   std::vector<int> L_colptr, L_row;   // strictly lower triangle of L, CSC, permuted indices, rows ascending
   std::vector<int> F_ptr, F_tgt;      // per column k: targets of the pairs (a <= b) of struct(k), a-major
+  // gather-form mirrors (no read-modify-write in the hot loops): each lists, per output element, the (input index, value
+  // slot) pairs it sums over
+  std::vector<int> LR_ptr, LR_col, LR_slot;   // rows of L:           v[k] -= sum W[slot] v[col]        (forward solve)
+  std::vector<int> AT_ptr, AT_row, AT_slot;   // columns of A:        out[j] = sum A[slot] in[row]      (Abar^T w)
+  std::vector<int> PR_ptr, PR_col, PR_slot;   // rows of P as stored: out[r] = sum P[slot] in[col]      (P x)
+  std::vector<int> PS_ptr, PS_col, PS_slot;   // rows of sym(triu P): out[r] = sum Pbar[slot] in[col]   (polish)
+  std::vector<int> LB_ptr, LB_row, LB_slot;   // columns of L in REVERSE column order (backward solve as one forward stream)
+  std::vector<int> PC_ptr;                    // P_colptr re-indexed by PERMUTED column (entries regrouped in PC_slot)
+  std::vector<int> PC_slot;
   long long flops = 0;                // multiply-adds of the numeric factorisation
   std::string error;
 };
@@ -162,8 +173,54 @@ inline bool sparse_analyze(int n, int m, const int32_t* P_colptr, const int32_t*
       for (int e2 = e1; e2 < S.A_rowptr[i + 1]; ++e2) {
         const int t = target(S.A_col[e1], S.A_col[e2]);
         if (t == -2) { S.error = "internal: A^T A entry outside the symbolic factor"; return false; }
+        S.A_pair_ab.push_back(((e1 - S.A_rowptr[i]) << 16) | (e2 - S.A_rowptr[i]));
         S.A_pair_tgt[p++] = t;
       }
+    if (S.A_rowptr[i + 1] - S.A_rowptr[i] > 0xffff) { S.error = "more than 65535 entries in a row of A"; return false; }
+  }
+
+  // ---- gather-form mirrors ----
+  auto build_rows = [&](int nrows, const std::vector<std::array<int, 3>>& trip, std::vector<int>& ptr, std::vector<int>& col,
+                        std::vector<int>& slt) {  // trip = (row, col, slot), stable order within a row
+    ptr.assign(nrows + 1, 0);
+    for (const auto& t : trip) ptr[t[0] + 1]++;
+    for (int r = 0; r < nrows; ++r) ptr[r + 1] += ptr[r];
+    col.resize(trip.size());
+    slt.resize(trip.size());
+    std::vector<int> fill(ptr.begin(), ptr.end() - 1);
+    for (const auto& t : trip) {
+      const int p = fill[t[0]]++;
+      col[p] = t[1];
+      slt[p] = t[2];
+    }
+  };
+  {
+    std::vector<std::array<int, 3>> trip;
+    for (int k = 0; k < n; ++k)
+      for (int e = S.L_colptr[k]; e < S.L_colptr[k + 1]; ++e) trip.push_back({S.L_row[e], k, e});
+    build_rows(n, trip, S.LR_ptr, S.LR_col, S.LR_slot);
+    trip.clear();
+    for (int k = n - 1; k >= 0; --k)
+      for (int e = S.L_colptr[k]; e < S.L_colptr[k + 1]; ++e) trip.push_back({n - 1 - k, S.L_row[e], e});
+    build_rows(n, trip, S.LB_ptr, S.LB_row, S.LB_slot);
+    trip.clear();
+    for (int i = 0; i < m; ++i)
+      for (int e = S.A_rowptr[i]; e < S.A_rowptr[i + 1]; ++e) trip.push_back({S.A_col[e], i, e});
+    build_rows(n, trip, S.AT_ptr, S.AT_row, S.AT_slot);
+    trip.clear();
+    for (int e = 0; e < S.nnzP; ++e) trip.push_back({S.P_rowp[e], S.P_colp[e], e});
+    build_rows(n, trip, S.PR_ptr, S.PR_col, S.PR_slot);
+    trip.clear();
+    for (int e = 0; e < S.nnzP; ++e) {
+      if (S.P_tgt[e] < 0) continue;
+      trip.push_back({S.P_rowp[e], S.P_colp[e], e});
+      if (S.P_rowp[e] != S.P_colp[e]) trip.push_back({S.P_colp[e], S.P_rowp[e], e});
+    }
+    build_rows(n, trip, S.PS_ptr, S.PS_col, S.PS_slot);
+    trip.clear();
+    for (int e = 0; e < S.nnzP; ++e) trip.push_back({S.P_colp[e], S.P_rowp[e], e});
+    std::vector<int> dummy;
+    build_rows(n, trip, S.PC_ptr, dummy, S.PC_slot);
   }
 
   // ---- right-looking update schedule ----
@@ -180,8 +237,10 @@ inline bool sparse_analyze(int n, int m, const int32_t* P_colptr, const int32_t*
       for (size_t b = a; b < st[k].size(); ++b) {
         const int t = target(st[k][b], st[k][a]);
         if (t == -2) { S.error = "internal: fill entry outside the symbolic factor"; return false; }
+        S.F_ab.push_back((int)((a << 16) | b));
         S.F_tgt[p++] = t;
       }
+    if (st[k].size() > 0xffff) { S.error = "more than 65535 entries in a column of L"; return false; }
   }
   return true;
 }

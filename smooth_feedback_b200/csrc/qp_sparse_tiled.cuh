@@ -4,18 +4,23 @@
 //   QPSolver<QuadraticProgramSparse>::solve   include/smooth/feedback/qp_solver.hpp:343-568 (fill :380-397,
 //                                             SimplicialLDLT factorize :424-426, permuted solve :456-460)
 //   QPSolver::scale / check_stopping          :673-730 / :574-644 (InnerIterator walks only stored entries)
+//   detail::polish_qp                         :92-204
 // i.e. the call MPC::operator() makes at mpc.hpp:491.
 //
-// Layout: thread-per-instance.  A warp owns a TILE of 32 instances; every per-instance array of the working set
-// lives in global memory as [tile][element][32], so that the 32 lanes of a warp -- which all execute the same
-// pattern-driven program (the index arrays are shared by the whole batch and broadcast) -- touch 32 consecutive
-// scalars per access: every load and store of the solve is a fully coalesced 256-byte (fp64) line.  The per-iteration
-// traffic is therefore exactly the north star's model: one pass over Abar twice and over the L D L^T factor twice,
-// streamed from HBM/L2 (B_iter), plus the vectors.
+// Layout.  A warp owns a TILE of TW instances (TW = 32 or 8); every per-instance array of the working set lives in
+// global memory as [tile][element][TW].  All lanes of a warp execute the same pattern-driven program (the index arrays
+// are shared by the whole batch and broadcast), lane -> (instance = lane % TW, row-lane r = lane / TW): an access to
+// element e touches TW consecutive scalars, so every load and store of the solve is a full, coalesced line and the
+// per-iteration traffic is exactly the north star's model (Abar twice, the L D L^T factor twice, the iterate vectors;
+// B_iter).  With TW = 8 the RL = 4 lanes of an instance split the entries of a row between them (small
+// batches: 4x more warps to hide the memory latency, which is what bounds this kernel); with TW = 32 a lane owns its
+// instance alone and the code is free of shuffles and barriers.
 //
 // The KKT system is reduced as in the dense kernel:  (Pbar + sigma I + Abar^T R Abar) xt = sigma x - qbar + Abar^T (R z - y),
 // nu = R (Abar xt - z) + y; the n x n matrix is factorised L D L^T without pivoting (it is SPD) in the fill-reducing
-// order computed on the host (qp_sparse_host.hpp).  Variables are kept in the permuted order throughout.
+// order computed on the host (qp_sparse_host.hpp).  Variables are kept in the permuted order throughout.  Every hot
+// loop is in GATHER form (index mirrors built on the host) or updates provably distinct targets, so that a batch of
+// kSpU independent loads is in flight per lane before the first one is consumed.
 //
 // P is used exactly as the reference uses it: only entries with col >= row enter the factorised matrix
 // (qp_solver.hpp:384), while scale(), the dual residual, the dual-infeasibility test and the objective multiply
@@ -34,12 +39,16 @@ namespace sfb {
 
 constexpr int kSpNV = 10;  // n-vectors of the working set
 constexpr int kSpMV = 9;   // m-vectors
+constexpr int kSpU = 8;    // independent loads kept in flight per lane in the gather / update loops
 
 struct SpPattern
 {
   int n, m, nnzP, nnzA, nnzL;
   const int *perm, *iperm, *P_rowp, *P_colp, *P_tgt, *A_rowptr, *A_col, *A_pair_ptr, *A_pair_tgt, *L_colptr, *L_row,
     *F_ptr, *F_tgt;
+  // gather-form mirrors and packed pair lists (qp_sparse_host.hpp)
+  const int *LR_ptr, *LR_col, *LR_slot, *AT_ptr, *AT_row, *AT_slot, *PR_ptr, *PR_col, *PR_slot, *PS_ptr, *PS_col, *PS_slot,
+    *PC_ptr, *PC_slot, *LB_ptr, *LB_row, *LB_slot, *A_pair_ab, *F_ab;
 };
 
 template <typename T> struct SpArgs
@@ -52,52 +61,139 @@ template <typename T> struct SpArgs
   uint32_t* out_iter;
   int8_t* out_active;
   uint32_t* out_flags;
-  // tiled workspace: [tile][len][32]
+  // tiled workspace: [tile][len][TW]
   T *wsA, *wsP, *wsW, *wsN, *wsM;
   long long batch;
   sfb_qp_params prm;
   unsigned max_iter_eff;
 };
 
-// element e of this lane's instance inside a [len][32] tile block
-template <typename T> struct TV
+// element e of this lane's instance inside a [len][TW] tile block
+template <typename T, int TW> struct TV
 {
   T* p;
-  __device__ __forceinline__ T& operator[](int e) const { return p[(size_t)e * 32]; }
+  __device__ __forceinline__ T& operator[](int e) const { return p[(size_t)e * TW]; }
 };
 
-template <typename T> struct SpSolver
+template <typename T, int TW> struct SpSolver
 {
+  static constexpr int RL = 32 / TW;  // lanes cooperating on one instance
+  using V = TV<T, TW>;
   const SpPattern& S;
-  int n, m;
-  TV<T> A, P, W;
-  TV<T> q, qb, x, xold, v, sx, t1, t2, t3, t4;      // n-vectors (permuted order)
-  TV<T> l, u, sy, rho, rinv, z, y, yold, w;        // m-vectors
+  int n, m, r;
+  unsigned gmask;
+  V A, P, W;
+  V q, qb, x, xold, v, sx, t1, t2, t3, t4;  // n-vectors (permuted order)
+  V l, u, sy, rho, rinv, z, y, yold, w;    // m-vectors
   T c;
 
   __device__ SpSolver(const SpArgs<T>& a, long long tile, int lane) : S(a.pat), n(a.pat.n), m(a.pat.m)
   {
-    A.p = a.wsA + (size_t)tile * S.nnzA * 32 + lane;
-    P.p = a.wsP + (size_t)tile * S.nnzP * 32 + lane;
-    W.p = a.wsW + (size_t)tile * (S.nnzL + n) * 32 + lane;
-    T* nv = a.wsN + (size_t)tile * kSpNV * n * 32 + lane;
-    T* mv = a.wsM + (size_t)tile * kSpMV * m * 32 + lane;
-    auto N = [&](int k) { return TV<T>{nv + (size_t)k * n * 32}; };
-    auto M = [&](int k) { return TV<T>{mv + (size_t)k * m * 32}; };
+    const int inst = lane & (TW - 1);
+    r = lane / TW;
+    gmask = (RL == 1) ? (1u << lane) : (0x01010101u << inst);
+    A.p = a.wsA + (size_t)tile * S.nnzA * TW + inst;
+    P.p = a.wsP + (size_t)tile * S.nnzP * TW + inst;
+    W.p = a.wsW + (size_t)tile * (S.nnzL + n) * TW + inst;
+    T* nv = a.wsN + (size_t)tile * kSpNV * n * TW + inst;
+    T* mv = a.wsM + (size_t)tile * kSpMV * m * TW + inst;
+    auto N = [&](int k) { return V{nv + (size_t)k * n * TW}; };
+    auto M = [&](int k) { return V{mv + (size_t)k * m * TW}; };
     q = N(0); qb = N(1); x = N(2); xold = N(3); v = N(4); sx = N(5); t1 = N(6); t2 = N(7); t3 = N(8); t4 = N(9);
     l = M(0); u = M(1); sy = M(2); rho = M(3); rinv = M(4); z = M(5); y = M(6); yold = M(7); w = M(8);
     c = T(1);
   }
 
+  // ---------------------------------------------------------------- group primitives (the RL lanes of one instance)
+  __device__ __forceinline__ void gsync() const
+  {
+    if (RL > 1) __syncwarp(gmask);
+  }
+  __device__ __forceinline__ T gsum(T val) const
+  {
+#pragma unroll
+    for (int o = TW; o < 32; o <<= 1) val += __shfl_xor_sync(gmask, val, o);
+    return val;
+  }
+  __device__ __forceinline__ T gmax(T val) const
+  {
+#pragma unroll
+    for (int o = TW; o < 32; o <<= 1) val = fmax(val, __shfl_xor_sync(gmask, val, o));
+    return val;
+  }
+  __device__ __forceinline__ bool gany(bool pr) const
+  {
+    int val = pr ? 1 : 0;
+#pragma unroll
+    for (int o = TW; o < 32; o <<= 1) val |= __shfl_xor_sync(gmask, val, o);
+    return val != 0;
+  }
+
+  // sum over e = e0 + first, e0 + first + step, ... < e1 of val(e) * vec(idx[e]); a batch of kSpU entries is loaded
+  // before any of them is used
+  template <class VAL, class VEC>
+  __device__ __forceinline__ T gather_sum(int e0, int e1, int first, int step, const int* __restrict__ idx, VAL val, VEC vec) const
+  {
+    T acc = T(0);
+    for (int e = e0 + first; e < e1; e += kSpU * step) {
+      int j[kSpU];
+      T a[kSpU], b[kSpU];
+#pragma unroll
+      for (int k = 0; k < kSpU; ++k) j[k] = (e + k * step < e1) ? idx[e + k * step] : 0;
+#pragma unroll
+      for (int k = 0; k < kSpU; ++k) a[k] = (e + k * step < e1) ? val(e + k * step) : T(0);
+#pragma unroll
+      for (int k = 0; k < kSpU; ++k) b[k] = (e + k * step < e1) ? vec(j[k]) : T(0);
+#pragma unroll
+      for (int k = 0; k < kSpU; ++k)
+        if (e + k * step < e1) acc += a[k] * b[k];
+    }
+    return acc;
+  }
+  // max over e in [e0, e1) of f(e), batched the same way
+  template <class F> __device__ __forceinline__ T gather_max(T g, int e0, int e1, F f) const
+  {
+    for (int e = e0; e < e1; e += kSpU) {
+      T a[kSpU];
+#pragma unroll
+      for (int k = 0; k < kSpU; ++k) a[k] = (e + k < e1) ? f(e + k) : T(0);
+#pragma unroll
+      for (int k = 0; k < kSpU; ++k) g = fmax(g, a[k]);
+    }
+    return g;
+  }
+  // W[tgt[p]] += delta(p) for p = p0 + r, p0 + r + RL, ... < p1.  The targets of one call are DISTINCT (pairs of one
+  // row of A / one column of L), so a batch is loaded, updated and stored without intermediate dependencies.
+  template <class F> __device__ __forceinline__ void rmw_flat(int p0, int p1, const int* __restrict__ tgt, F delta) const
+  {
+    const V Wl = W;
+    for (int p = p0 + r; p < p1; p += kSpU * RL) {
+      int t[kSpU];
+      T d[kSpU], o[kSpU];
+#pragma unroll
+      for (int k = 0; k < kSpU; ++k) t[k] = (p + k * RL < p1) ? tgt[p + k * RL] : 0;
+#pragma unroll
+      for (int k = 0; k < kSpU; ++k) d[k] = (p + k * RL < p1) ? delta(p + k * RL) : T(0);
+#pragma unroll
+      for (int k = 0; k < kSpU; ++k) o[k] = (p + k * RL < p1) ? Wl[t[k]] : T(0);
+#pragma unroll
+      for (int k = 0; k < kSpU; ++k)
+        if (p + k * RL < p1) Wl[t[k]] = o[k] + d[k];
+    }
+  }
+
   // ---------------------------------------------------------------- QPSolver::scale, qp_solver.hpp:673-730
+  // Column / row maxima in gather form (PC_*, AT_* mirrors, CSR rows): max() is exact and order independent and the
+  // products are formed in the reference's order, so sx, sy agree with the CPU restatement bit for bit (c too: every
+  // lane sums the column maxima in the original column order).
   __device__ void scale()
   {
-    for (int j = 0; j < n; ++j) { sx[j] = T(1); t1[j] = T(0); }
-    for (int i = 0; i < m; ++i) sy[i] = T(1);
-    for (int e = 0; e < S.nnzP; ++e) {
-      const int cj = S.P_colp[e];
-      t1[cj] = fmax(t1[cj], fabs(P[e]));
-    }
+    const V Pl = P, Al = A, sxl = sx, syl = sy;
+    for (int j = r; j < n; j += RL) sx[j] = T(1);
+    for (int i = r; i < m; i += RL) sy[i] = T(1);
+    for (int pj = r; pj < n; pj += RL)
+      t1[pj] = gather_max(T(0), S.PC_ptr[pj], S.PC_ptr[pj + 1], [&](int e) { return fabs(Pl[S.PC_slot[e]]); });
+    gsync();
     T mean = T(0), qn = T(0);
     for (int j = 0; j < n; ++j) {  // original column order: the mean is summed as the reference sums it
       const int pj = S.iperm[j];
@@ -108,63 +204,78 @@ template <typename T> struct SpSolver
     }
     mean /= T(n);
     c = T(1) / fmax(fmax(T(1e-6), mean), qn);
+    const T cc = c;
     int it = 0;
     T dev;
     do {
-      for (int j = 0; j < n; ++j) t1[j] = T(0);
-      for (int e = 0; e < S.nnzP; ++e) {
-        const int rj = S.P_rowp[e], cj = S.P_colp[e];
-        t1[cj] = fmax(t1[cj], fabs(((c * sx[rj]) * sx[cj]) * P[e]));
+      gsync();
+      for (int pj = r; pj < n; pj += RL) {
+        const T sxj = sxl[pj];
+        T g = gather_max(T(0), S.PC_ptr[pj], S.PC_ptr[pj + 1], [&](int e) {
+          const int sl = S.PC_slot[e];
+          return fabs(((cc * sxl[S.P_rowp[sl]]) * sxj) * Pl[sl]);
+        });
+        g = gather_max(g, S.AT_ptr[pj], S.AT_ptr[pj + 1], [&](int e) { return fabs((syl[S.AT_row[e]] * sxj) * Al[S.AT_slot[e]]); });
+        t1[pj] = g;
       }
-      for (int i = 0; i < m; ++i) {
-        const T syi = sy[i];
-        T g = T(0);
-        for (int e = S.A_rowptr[i]; e < S.A_rowptr[i + 1]; ++e) {
-          const int cj = S.A_col[e];
-          const T aij = fabs((syi * sx[cj]) * A[e]);
-          t1[cj] = fmax(t1[cj], aij);
-          g = fmax(g, aij);
-        }
-        w[i] = g;
+      for (int i = r; i < m; i += RL) {
+        const T syi = syl[i];
+        w[i] = gather_max(T(0), S.A_rowptr[i], S.A_rowptr[i + 1], [&](int e) { return fabs((syi * sxl[S.A_col[e]]) * Al[e]); });
       }
+      gsync();  // every maximum is formed before any scale factor changes
       dev = T(0);
-      for (int j = 0; j < n; ++j) {
+      for (int j = r; j < n; j += RL) {
         T g = t1[j];
         if (g == T(0)) g = T(1);
         sx[j] = sqrt(T(1) / fmax(g, T(1e-8))) * sx[j];
         dev = fmax(dev, fabs(g - T(1)));
       }
-      for (int i = 0; i < m; ++i) {
+      for (int i = r; i < m; i += RL) {
         T g = w[i];
         if (g == T(0)) g = T(1);
         sy[i] = sqrt(T(1) / fmax(g, T(1e-8))) * sy[i];
         dev = fmax(dev, fabs(g - T(1)));
       }
+      dev = gmax(dev);
     } while (it++ < 10 && dev > T(0.1));
+    gsync();
   }
 
   // ---------------------------------------------------------------- W <- shift I + c Sx triu(P) Sx + Abar^T diag(wt) Abar
   // (lower triangle in the factor's slots, diagonal in W[nnzL + i]); wt = rho for the ADMM system
-  __device__ void assemble(T shift, const TV<T>& wt)
+  __device__ void assemble(T shift, const V& wt)
   {
     const int nW = S.nnzL + n;
-    for (int e = 0; e < S.nnzL; ++e) W[e] = T(0);
-    for (int e = S.nnzL; e < nW; ++e) W[e] = shift;
-    for (int e = 0; e < S.nnzP; ++e) {
-      const int t = S.P_tgt[e];
-      if (t >= 0) W[t] += ((c * sx[S.P_rowp[e]]) * sx[S.P_colp[e]]) * P[e];  // qp_solver.hpp:386
+    const V Al = A;
+    for (int e = r; e < S.nnzL; e += RL) W[e] = T(0);
+    for (int e = S.nnzL + r; e < nW; e += RL) W[e] = shift;
+    gsync();
+    if (r == 0) {  // compressed P: distinct targets; kept on one lane, nnzP is small
+      for (int e = 0; e < S.nnzP; e += kSpU) {
+        int t[kSpU];
+        T d[kSpU], o[kSpU];
+#pragma unroll
+        for (int k = 0; k < kSpU; ++k) t[k] = (e + k < S.nnzP) ? S.P_tgt[e + k] : -1;
+#pragma unroll
+        for (int k = 0; k < kSpU; ++k)
+          d[k] = (t[k] >= 0) ? ((c * sx[S.P_rowp[e + k]]) * sx[S.P_colp[e + k]]) * P[e + k] : T(0);  // qp_solver.hpp:386
+#pragma unroll
+        for (int k = 0; k < kSpU; ++k) o[k] = (t[k] >= 0) ? W[t[k]] : T(0);
+#pragma unroll
+        for (int k = 0; k < kSpU; ++k)
+          if (t[k] >= 0) W[t[k]] = o[k] + d[k];
+      }
     }
+    gsync();
     for (int i = 0; i < m; ++i) {
       const T ri = wt[i];
-      const int e0 = S.A_rowptr[i], e1 = S.A_rowptr[i + 1];
-      int p = S.A_pair_ptr[i];
-      if (ri == T(0)) continue;
-      for (int ea = e0; ea < e1; ++ea) {
-        const T ra = ri * A[ea];
-        for (int eb = ea; eb < e1; ++eb) {
-          const int t = S.A_pair_tgt[p++];
-          W[t] += ra * A[eb];
-        }
+      if (ri != T(0)) {  // group-uniform
+        const int e0 = S.A_rowptr[i];
+        rmw_flat(S.A_pair_ptr[i], S.A_pair_ptr[i + 1], S.A_pair_tgt, [&](int p) {
+          const int ab = S.A_pair_ab[p];
+          return (ri * Al[e0 + (ab >> 16)]) * Al[e0 + (ab & 0xffff)];
+        });
+        gsync();
       }
     }
   }
@@ -174,59 +285,80 @@ template <typename T> struct SpSolver
   {
     bool ok = true;
     const int nL = S.nnzL;
+    const V Wl = W;
     for (int k = 0; k < n; ++k) {
       const T dk = W[nL + k];
       if (!(dk > T(0)) || !(dk < Num<T>::inf())) ok = false;
       const T dinv = T(1) / dk;
       const int c0 = S.L_colptr[k], c1 = S.L_colptr[k + 1];
-      int p = S.F_ptr[k];
-      for (int a = c0; a < c1; ++a) {
-        const T la = W[a] * dinv;
-#pragma unroll 4
-        for (int b = a; b < c1; ++b) {
-          const int t = S.F_tgt[p++];
-          W[t] -= W[b] * la;
-        }
-      }
-      for (int a = c0; a < c1; ++a) W[a] *= dinv;
-      W[nL + k] = dinv;
+      rmw_flat(S.F_ptr[k], S.F_ptr[k + 1], S.F_tgt, [&](int p) {
+        const int ab = S.F_ab[p];
+        return -(Wl[c0 + (ab & 0xffff)] * (Wl[c0 + (ab >> 16)] * dinv));
+      });
+      gsync();
+      for (int a = c0 + r; a < c1; a += RL) W[a] *= dinv;
+      if (r == 0) W[nL + k] = dinv;
+      gsync();
     }
     return ok;
   }
 
-  // v <- (L D L^T)^-1 v
+  // v <- (L D L^T)^-1 v.  Both sweeps in gather form: forward over the rows of L (LR_* mirror), backward over its
+  // columns in reverse order (LB_* mirror); the RL lanes of an instance split the entries of a row.
   __device__ void solve()
   {
     const int nL = S.nnzL;
+    const V Wl = W, vv = v;
     for (int k = 0; k < n; ++k) {
-      const T vk = v[k];
-      const int c0 = S.L_colptr[k], c1 = S.L_colptr[k + 1];
-#pragma unroll 4
-      for (int e = c0; e < c1; ++e) {
-        const int r = S.L_row[e];
-        v[r] -= W[e] * vk;
-      }
+      const int e0 = S.LR_ptr[k], e1 = S.LR_ptr[k + 1];
+      if (e0 == e1) continue;
+      const T s = gsum(gather_sum(e0, e1, r, RL, S.LR_col, [&](int e) { return Wl[S.LR_slot[e]]; }, [&](int j) { return vv[j]; }));
+      if (r == 0) v[k] = v[k] - s;
+      gsync();
     }
-    for (int k = n - 1; k >= 0; --k) {
-      T acc = v[k] * W[nL + k];
-      const int c0 = S.L_colptr[k], c1 = S.L_colptr[k + 1];
-#pragma unroll 4
-      for (int e = c0; e < c1; ++e) acc -= W[e] * v[S.L_row[e]];
-      v[k] = acc;
+    for (int kk = 0; kk < n; ++kk) {
+      const int k = n - 1 - kk;
+      const T s = gsum(gather_sum(S.LB_ptr[kk], S.LB_ptr[kk + 1], r, RL, S.LB_row, [&](int e) { return Wl[S.LB_slot[e]]; },
+                                  [&](int j) { return vv[j]; }));
+      if (r == 0) v[k] = v[k] * W[nL + k] - s;
+      gsync();
     }
   }
 
-  // out[col] (+)= sum_i Abar_ij in_i   (row-wise scatter; out must be zeroed by the caller)
-  __device__ void At_acc(const TV<T>& in, const TV<T>& out)
+  // out[j] = fin(j, sum_i Abar_ij in_i)  (column gather through the AT_* mirror; columns are dealt to the row-lanes)
+  template <class FIN> __device__ void At_gather(const V& in, const V& out, FIN fin)
   {
-    for (int i = 0; i < m; ++i) {
-      const T wi = in[i];
-#pragma unroll 4
-      for (int e = S.A_rowptr[i]; e < S.A_rowptr[i + 1]; ++e) {
-        const int cj = S.A_col[e];
-        out[cj] += A[e] * wi;
-      }
-    }
+    const V Al = A;
+    for (int j = r; j < n; j += RL)
+      out[j] = fin(j, gather_sum(S.AT_ptr[j], S.AT_ptr[j + 1], 0, 1, S.AT_row, [&](int e) { return Al[S.AT_slot[e]]; },
+                                 [&](int i) { return in[i]; }));
+    gsync();
+  }
+  // out[j] = fin(j, sum_k sym(Pbar)_jk in_k)  (upper triangle of c Sx P Sx mirrored, PS_* mirror)
+  template <class FIN> __device__ void Psym_gather(const V& in, const V& out, FIN fin)
+  {
+    const V Pl = P, sxl = sx;
+    const T cc = c;
+    for (int j = r; j < n; j += RL)
+      out[j] = fin(j, gather_sum(S.PS_ptr[j], S.PS_ptr[j + 1], 0, 1, S.PS_col,
+                                 [&](int e) { const int sl = S.PS_slot[e]; return ((cc * sxl[S.P_rowp[sl]]) * sxl[S.P_colp[sl]]) * Pl[sl]; },
+                                 [&](int k) { return in[k]; }));
+    gsync();
+  }
+  // out[j] = sum_k (sc P_jk) in_k with the entries as stored (PR_* mirror)
+  __device__ void P_gather(const V& in, const V& out, T sc)
+  {
+    const V Pl = P;
+    for (int j = r; j < n; j += RL)
+      out[j] = gather_sum(S.PR_ptr[j], S.PR_ptr[j + 1], 0, 1, S.PR_col, [&](int e) { return sc * Pl[S.PR_slot[e]]; },
+                          [&](int k) { return in[k]; });
+    gsync();
+  }
+  // sum_j Abar_ij vec_j for row i (whole row on the calling lane)
+  __device__ __forceinline__ T A_row_dot(int i, const V& vec) const
+  {
+    const V Al = A;
+    return gather_sum(S.A_rowptr[i], S.A_rowptr[i + 1], 0, 1, S.A_col, [&](int e) { return Al[e]; }, [&](int j) { return vec[j]; });
   }
 
   // ---------------------------------------------------------------- check_stopping, qp_solver.hpp:574-644
@@ -237,7 +369,7 @@ template <typename T> struct SpSolver
     const T eps_pinf = T(prm.eps_primal_inf), eps_dinf = T(prm.eps_dual_inf);
     const T inf = Num<T>::inf();
     T qn = T(0), dxn = T(0), qdx = T(0), Edy = T(0);
-    for (int j = 0; j < n; ++j) {
+    for (int j = r; j < n; j += RL) {
       const T xj = x[j];
       const T d = xj - xold[j];
       t1[j] = sx[j] * xj;       // x_us   :481
@@ -246,29 +378,23 @@ template <typename T> struct SpSolver
       xold[j] = dus;
       qn = fmax(qn, fabs(q[j]));
       dxn = fmax(dxn, fabs(dus));
-      t3[j] = T(0);
-      t4[j] = T(0);
     }
-    for (int jo = 0; jo < n; ++jo) {  // q . dx_us summed in the original variable order
+    gsync();
+    for (int jo = r; jo < n; jo += RL) {  // q . dx_us in the original variable order (exactly so when RL == 1)
       const int j = S.iperm[jo];
       qdx += q[j] * xold[j];
     }
-    for (int i = 0; i < m; ++i) {
+    for (int i = r; i < m; i += RL) {
       const T d = y[i] - yold[i];
       w[i] = d;
       Edy = fmax(Edy, fabs(sy[i] * d / c));  // :485
     }
+    qn = gmax(qn); dxn = gmax(dxn); Edy = gmax(Edy); qdx = gsum(qdx);
+    gsync();
     T n_Ax = T(0), n_r = T(0), n_z = T(0), s_pinf = T(0);
     bool pinf_blocked = false, dinf_rows_ok = true;
-    for (int i = 0; i < m; ++i) {
-      T ax = T(0), adx = T(0);
-#pragma unroll 4
-      for (int e = S.A_rowptr[i]; e < S.A_rowptr[i + 1]; ++e) {
-        const int cj = S.A_col[e];
-        const T aij = A[e];
-        ax += aij * x[cj];
-        adx += aij * t2[cj];
-      }
+    for (int i = r; i < m; i += RL) {
+      T ax = A_row_dot(i, x), adx = A_row_dot(i, t2);
       const T syinv = T(1) / sy[i];
       ax *= syinv;
       adx *= syinv;
@@ -286,20 +412,18 @@ template <typename T> struct SpSolver
       else if (li == -inf) dinf_rows_ok = dinf_rows_ok && (adx <= eps_dinf * dxn);
       else dinf_rows_ok = dinf_rows_ok && (fabs(adx) < eps_dinf * dxn);
     }
+    n_Ax = gmax(n_Ax); n_r = gmax(n_r); n_z = gmax(n_z); s_pinf = gsum(s_pinf);
+    pinf_blocked = gany(pinf_blocked);
+    dinf_rows_ok = !gany(!dinf_rows_ok);
     if (pinf_blocked) s_pinf = inf;
-    // Abar^T y -> v, Abar^T dy -> t2 (scaled dx is dead)
-    for (int j = 0; j < n; ++j) { v[j] = T(0); t2[j] = T(0); }
-    At_acc(y, v);
-    At_acc(w, t2);
-    // P x_us -> t3, P dx_us -> t4 with the entries as stored
-    for (int e = 0; e < S.nnzP; ++e) {
-      const int rj = S.P_rowp[e], cj = S.P_colp[e];
-      const T pv = P[e];
-      t3[rj] += pv * t1[cj];
-      t4[rj] += pv * xold[cj];
-    }
+    gsync();
+    // Abar^T y -> v, Abar^T dy -> t2 (scaled dx is dead); P x_us -> t3, P dx_us -> t4 with the entries as stored
+    At_gather(y, v, [](int, T sum) { return sum; });
+    At_gather(w, t2, [](int, T sum) { return sum; });
+    P_gather(t1, t3, T(1));
+    P_gather(xold, t4, T(1));
     T n_Px = T(0), n_Aty = T(0), n_res = T(0), n_Atdy = T(0), n_Pdx = T(0);
-    for (int j = 0; j < n; ++j) {
+    for (int j = r; j < n; j += RL) {
       const T sc = T(1) / (sx[j] * c);
       const T aty = v[j] * sc;
       const T atdy = t2[j] * sc;
@@ -310,6 +434,8 @@ template <typename T> struct SpSolver
       n_Atdy = fmax(n_Atdy, fabs(atdy));
       n_Pdx = fmax(n_Pdx, fabs(pdx));
     }
+    n_Px = gmax(n_Px); n_Aty = gmax(n_Aty); n_res = gmax(n_res); n_Atdy = gmax(n_Atdy); n_Pdx = gmax(n_Pdx);
+    gsync();
     if (n_r <= eps_abs + eps_rel * fmax(n_Ax, n_z)) {  // :584-594
       const T dual_scale = fmax(fmax(n_Px, qn), n_Aty);
       if (n_res <= eps_abs + eps_rel * dual_scale) return SFB_QP_OPTIMAL;
@@ -326,111 +452,76 @@ template <typename T> struct SpSolver
   // s2 = (Aa s1 - r2) / delta, whose pattern is a subset of M's.  That reduced matrix is ill conditioned (1/delta = 1e6
   // against delta), so every application of Hp^-1 is followed by two steps of iterative refinement on Hp itself; the
   // outer iteration t += Hp^-1 (h - H t) then follows the reference's sequence to ~1e-9.
-  // On entry: w[i] = 1 for active rows else 0, yold = scaled active bound.  Uses rho, rinv, z, l, u and t1..t3, v as scratch.
+  // On entry: w[i] = 1 for active rows else 0, yold = scaled active bound.  Uses rho, rinv, z, l, u, xold, t1..t3, v as
+  // scratch.  Every row-space vector of the polish is kept EXACTLY zero on inactive rows, so the gathers need no mask.
 
-  // in: r1 in v, r2 in R2 (active rows) -> out: s1 in v, s2 in R2 (in place)
-  __device__ void polish_reduced_solve(const TV<T>& R2, T dinv)
+  // in: r1 in v, r2 in R2 -> out: s1 in v, s2 in R2 (in place)
+  __device__ void polish_reduced_solve(const V& R2, T dinv)
   {
-    for (int i = 0; i < m; ++i) {
-      if (w[i] == T(0)) continue;
-      const T sc = R2[i] * dinv;
-      for (int e = S.A_rowptr[i]; e < S.A_rowptr[i + 1]; ++e) v[S.A_col[e]] += A[e] * sc;
-    }
+    const V vv = v;
+    At_gather(R2, v, [&](int j, T sum) { return vv[j] + dinv * sum; });
     solve();
-    for (int i = 0; i < m; ++i) {
-      if (w[i] == T(0)) continue;
-      T as = T(0);
-      for (int e = S.A_rowptr[i]; e < S.A_rowptr[i + 1]; ++e) as += A[e] * v[S.A_col[e]];
-      R2[i] = (as - R2[i]) * dinv;
+    for (int i = r; i < m; i += RL) {
+      const T as = A_row_dot(i, v);
+      R2[i] = (w[i] != T(0)) ? (as - R2[i]) * dinv : T(0);
     }
+    gsync();
   }
 
-  // out1 (n) = r1 - (sym(Pbar) X + shift X + Aa^T Y),  out2 (m, active rows) = r2 - (Aa X - shift Y)
-  __device__ void polish_residual(const TV<T>& r1, const TV<T>& r2, const TV<T>& X, const TV<T>& Y, T shift,
-                                  const TV<T>& out1, const TV<T>& out2)
+  // out1 (n) = r1 - (sym(Pbar) X + shift1 X + Aa^T Y),  out2 (m) = r2 - (Aa X + shift2 Y) on active rows, 0 elsewhere
+  __device__ void polish_residual(const V& r1, const V& r2, const V& X, const V& Y, T shift1, T shift2, const V& out1,
+                                  const V& out2)
   {
-    for (int j = 0; j < n; ++j) out1[j] = r1[j] - shift * X[j];
-    for (int e = 0; e < S.nnzP; ++e) {
-      if (S.P_tgt[e] < 0) continue;
-      const int rj = S.P_rowp[e], cj = S.P_colp[e];
-      const T pb = ((c * sx[rj]) * sx[cj]) * P[e];
-      out1[rj] -= pb * X[cj];
-      if (rj != cj) out1[cj] -= pb * X[rj];
+    Psym_gather(X, out1, [&](int j, T sum) { return r1[j] - shift1 * X[j] - sum; });
+    const V o1 = out1;
+    At_gather(Y, out1, [&](int j, T sum) { return o1[j] - sum; });
+    for (int i = r; i < m; i += RL) {
+      const T at = A_row_dot(i, X);
+      out2[i] = (w[i] != T(0)) ? r2[i] - (at + shift2 * Y[i]) : T(0);
     }
-    for (int i = 0; i < m; ++i) {
-      if (w[i] == T(0)) continue;
-      T at = T(0);
-      const T yi = Y[i];
-      for (int e = S.A_rowptr[i]; e < S.A_rowptr[i + 1]; ++e) {
-        const int cj = S.A_col[e];
-        at += A[e] * X[cj];
-        out1[cj] -= A[e] * yi;
-      }
-      out2[i] = r2[i] - (at - shift * yi);
-    }
+    gsync();
   }
 
   __device__ unsigned polish(const sfb_qp_params& prm)
   {
     const T delta = T(prm.delta), dinv = T(1) / delta;
-    for (int i = 0; i < m; ++i) rho[i] = (w[i] != T(0)) ? dinv : T(0);
+    for (int i = r; i < m; i += RL) rho[i] = (w[i] != T(0)) ? dinv : T(0);
+    gsync();
     assemble(delta, rho);
     if (!factor()) return SFB_QP_FLAG_POLISH_FAILED;
-    // t = (t1 [n], rinv [m]);  h = (-qb, bnd)
-    for (int j = 0; j < n; ++j) { t1[j] = T(0); xold[j] = -qb[j]; }
-    for (int i = 0; i < m; ++i) rinv[i] = T(0);
+    // t = (t1 [n], rinv [m]);  h = (-qb, bnd) in (xold, yold)
+    for (int j = r; j < n; j += RL) { t1[j] = T(0); xold[j] = -qb[j]; }
+    for (int i = r; i < m; i += RL) rinv[i] = T(0);
+    gsync();
     for (unsigned it = 0; it < prm.polish_iter; ++it) {
-      // r = h - H t  -> (t2, z)        (H = Hp without the delta blocks: shift 0)
-      polish_residual(xold, yold, t1, rinv, T(0), t2, z);
-      // s = Hp^-1 r -> (t3, l), refined twice against Hp
-      for (int j = 0; j < n; ++j) v[j] = t2[j];
-      for (int i = 0; i < m; ++i) l[i] = z[i];
+      // r = h - H t -> (t2, z)     (H = Hp without the delta blocks)
+      polish_residual(xold, yold, t1, rinv, T(0), T(0), t2, z);
+      // s = Hp^-1 r -> (t3, l), refined twice against Hp = H + diag(delta I, -delta I)
+      for (int j = r; j < n; j += RL) v[j] = t2[j];
+      for (int i = r; i < m; i += RL) l[i] = z[i];
+      gsync();
       polish_reduced_solve(l, dinv);
-      for (int j = 0; j < n; ++j) t3[j] = v[j];
+      for (int j = r; j < n; j += RL) t3[j] = v[j];
+      gsync();
       for (int rf = 0; rf < 2; ++rf) {
-        // Hp s = [ (Pbar + delta I) s1 + Aa^T s2 ; Aa s1 - delta s2 ]
-        for (int i = 0; i < m; ++i) u[i] = T(0);
-        polish_residual_hp(delta);
+        polish_residual(t2, z, t3, l, delta, -delta, v, u);
         polish_reduced_solve(u, dinv);
-        for (int j = 0; j < n; ++j) t3[j] += v[j];
-        for (int i = 0; i < m; ++i)
-          if (w[i] != T(0)) l[i] += u[i];
+        for (int j = r; j < n; j += RL) t3[j] += v[j];
+        for (int i = r; i < m; i += RL) l[i] += u[i];
+        gsync();
       }
-      for (int j = 0; j < n; ++j) t1[j] += t3[j];
-      for (int i = 0; i < m; ++i)
-        if (w[i] != T(0)) rinv[i] += l[i];
+      for (int j = r; j < n; j += RL) t1[j] += t3[j];
+      for (int i = r; i < m; i += RL) rinv[i] += l[i];
+      gsync();
     }
-    bool finite = true;
-    for (int j = 0; j < n; ++j) finite = finite && (fabs(t1[j]) < Num<T>::inf());
-    if (!finite) return SFB_QP_FLAG_POLISH_FAILED;
-    for (int j = 0; j < n; ++j) x[j] = t1[j];  // :199
-    for (int i = 0; i < m; ++i)
+    bool bad = false;
+    for (int j = r; j < n; j += RL) bad = bad || !(fabs(t1[j]) < Num<T>::inf());
+    if (gany(bad)) return SFB_QP_FLAG_POLISH_FAILED;
+    for (int j = r; j < n; j += RL) x[j] = t1[j];  // :199
+    for (int i = r; i < m; i += RL)
       if (w[i] != T(0)) y[i] = rinv[i];  // :200-201 (other duals unchanged)
+    gsync();
     return SFB_QP_FLAG_POLISHED;
-  }
-
-  // (v, u) <- (t2, z) - Hp (t3, l):  first block has +delta on the diagonal, second block -delta
-  __device__ void polish_residual_hp(T delta)
-  {
-    for (int j = 0; j < n; ++j) v[j] = t2[j] - delta * t3[j];
-    for (int e = 0; e < S.nnzP; ++e) {
-      if (S.P_tgt[e] < 0) continue;
-      const int rj = S.P_rowp[e], cj = S.P_colp[e];
-      const T pb = ((c * sx[rj]) * sx[cj]) * P[e];
-      v[rj] -= pb * t3[cj];
-      if (rj != cj) v[cj] -= pb * t3[rj];
-    }
-    for (int i = 0; i < m; ++i) {
-      if (w[i] == T(0)) continue;
-      T at = T(0);
-      const T yi = l[i];
-      for (int e = S.A_rowptr[i]; e < S.A_rowptr[i + 1]; ++e) {
-        const int cj = S.A_col[e];
-        at += A[e] * t3[cj];
-        v[cj] -= A[e] * yi;
-      }
-      u[i] = z[i] - (at - delta * yi);
-    }
   }
 
   // ---------------------------------------------------------------- QPSolver::solve, qp_solver.hpp:343-568
@@ -443,100 +534,118 @@ template <typename T> struct SpSolver
     {
       const T* gA = a.A + b * (long long)S.nnzA;
       const T* gP = a.P + b * (long long)S.nnzP;
-      for (int e = 0; e < S.nnzA; ++e) A[e] = __ldg(gA + e);
-      for (int e = 0; e < S.nnzP; ++e) P[e] = __ldg(gP + e);
-      for (int j = 0; j < n; ++j) q[S.iperm[j]] = __ldg(a.q + b * (long long)n + j);
-      for (int i = 0; i < m; ++i) {
+      for (int e = r; e < S.nnzA; e += RL) A[e] = __ldg(gA + e);
+      for (int e = r; e < S.nnzP; e += RL) P[e] = __ldg(gP + e);
+      for (int j = r; j < n; j += RL) q[S.iperm[j]] = __ldg(a.q + b * (long long)n + j);
+      for (int i = r; i < m; i += RL) {
         l[i] = __ldg(a.l + b * (long long)m + i);
         u[i] = __ldg(a.u + b * (long long)m + i);
       }
+      gsync();
     }
     if (prm.scaling) scale();  // :347
     else {
       c = T(1);
-      for (int j = 0; j < n; ++j) sx[j] = T(1);
-      for (int i = 0; i < m; ++i) sy[i] = T(1);
+      for (int j = r; j < n; j += RL) sx[j] = T(1);
+      for (int i = r; i < m; i += RL) sy[i] = T(1);
+      gsync();
     }
     // ---- rho classes + trivially empty feasible set  :361-374
     int code = kStatusUnset;
     const T rho_bar = T(prm.rho), sigma = T(prm.sigma), alpha = T(prm.alpha), alpha_comp = T(1) - alpha;
-    for (int i = 0; i < m; ++i) {
+    bool triv = false;
+    for (int i = r; i < m; i += RL) {
       const T li = l[i], ui = u[i];
-      if (li == inf || ui == -inf || ui - li < T(0)) code = SFB_QP_PRIMAL_INFEASIBLE;
-      T r;
-      if (li == -inf && ui == inf) r = T(1e-6);
-      else if (sy[i] * fabs(li - ui) < T(1e-5)) r = T(1e3) * rho_bar;
-      else r = rho_bar;
-      rho[i] = r;
-      rinv[i] = T(1) / r;
+      if (li == inf || ui == -inf || ui - li < T(0)) triv = true;
+      T rr;
+      if (li == -inf && ui == inf) rr = T(1e-6);
+      else if (sy[i] * fabs(li - ui) < T(1e-5)) rr = T(1e3) * rho_bar;
+      else rr = rho_bar;
+      rho[i] = rr;
+      rinv[i] = T(1) / rr;
     }
+    if (gany(triv)) code = SFB_QP_PRIMAL_INFEASIBLE;
     // ---- scaled data: qb = c Sx q, Abar = Sy A Sx  (:401-403, :450)
-    for (int j = 0; j < n; ++j) qb[j] = (c * sx[j]) * q[j];
-    for (int i = 0; i < m; ++i) {
-      const T syi = sy[i];
-      for (int e = S.A_rowptr[i]; e < S.A_rowptr[i + 1]; ++e) A[e] = (syi * sx[S.A_col[e]]) * A[e];
+    for (int j = r; j < n; j += RL) qb[j] = (c * sx[j]) * q[j];
+    {
+      const V Al = A, sxl = sx;
+      for (int i = r; i < m; i += RL) {
+        const T syi = sy[i];
+        const int e1 = S.A_rowptr[i + 1];
+        for (int e = S.A_rowptr[i]; e < e1; e += kSpU) {
+          T a0[kSpU], s0[kSpU];
+#pragma unroll
+          for (int k = 0; k < kSpU; ++k) a0[k] = (e + k < e1) ? Al[e + k] : T(0);
+#pragma unroll
+          for (int k = 0; k < kSpU; ++k) s0[k] = (e + k < e1) ? sxl[S.A_col[e + k]] : T(0);
+#pragma unroll
+          for (int k = 0; k < kSpU; ++k)
+            if (e + k < e1) Al[e + k] = (syi * s0[k]) * a0[k];
+        }
+      }
     }
+    gsync();
     assemble(sigma, rho);
     if (!factor()) code = SFB_QP_UNKNOWN;  // :433
     // ---- initial iterate  :436-445
     if (a.warm_x != nullptr) {
-      for (int j = 0; j < n; ++j) {
+      for (int j = r; j < n; j += RL) {
         const int pj = S.iperm[j];
         x[pj] = (T(1) / sx[pj]) * __ldg(a.warm_x + b * (long long)n + j);
       }
-      for (int i = 0; i < m; ++i) {
+      gsync();
+      for (int i = r; i < m; i += RL) {
         y[i] = c * ((T(1) / sy[i]) * __ldg(a.warm_y + b * (long long)m + i));
-        T zt = T(0);
-        for (int e = S.A_rowptr[i]; e < S.A_rowptr[i + 1]; ++e) zt += A[e] * x[S.A_col[e]];
-        z[i] = zt;
+        z[i] = A_row_dot(i, x);
       }
     } else {
-      for (int j = 0; j < n; ++j) x[j] = T(0);
-      for (int i = 0; i < m; ++i) { y[i] = T(0); z[i] = T(0); }
+      for (int j = r; j < n; j += RL) x[j] = T(0);
+      for (int i = r; i < m; i += RL) { y[i] = T(0); z[i] = T(0); }
     }
-    for (int i = 0; i < m; ++i) w[i] = rho[i] * z[i] - y[i];
+    for (int i = r; i < m; i += RL) w[i] = rho[i] * z[i] - y[i];
+    gsync();
 
     // ---- main loop  :449-510
     const unsigned sci = prm.stop_check_iter;
     unsigned iter = 0;
     for (; iter != a.max_iter_eff && code == kStatusUnset; ++iter) {
-      for (int j = 0; j < n; ++j) v[j] = T(0);
-      At_acc(w, v);
-      for (int j = 0; j < n; ++j) v[j] = sigma * x[j] - qb[j] + v[j];
+      At_gather(w, v, [&](int j, T sum) { return sigma * x[j] - qb[j] + sum; });  // rhs = sigma x - qb + Abar^T w
       solve();
       const bool chk = (iter % sci == 1u);
-      for (int j = 0; j < n; ++j) {
+      for (int j = r; j < n; j += RL) {
         const T xi = x[j];
         if (chk) xold[j] = xi;  // :465-468
         x[j] = alpha * v[j] + alpha_comp * xi;  // :470
       }
-      for (int i = 0; i < m; ++i) {
-        T zt = T(0);
-#pragma unroll 4
-        for (int e = S.A_rowptr[i]; e < S.A_rowptr[i + 1]; ++e) zt += A[e] * v[S.A_col[e]];
-        const T zi = z[i], yi = y[i], ri = rho[i], rinvi = rinv[i];
+      for (int i = r; i < m; i += RL) {
+        const T zi = z[i], yi = y[i], ri = rho[i], rinvi = rinv[i];  // issued before the dot: their latency overlaps it
+        const T lo = sy[i] * l[i], hi = sy[i] * u[i];
+        const T zt = A_row_dot(i, v);
         if (chk) yold[i] = yi;
         const T nu = ri * (zt - zi) + yi;
-        T vv = alpha * (rinvi * nu) + alpha_comp * (rinvi * yi) + zi;  // :471-474
-        vv = fmax(vv, sy[i] * l[i]);
-        vv = fmin(vv, sy[i] * u[i]);
-        const T yn = alpha_comp * yi + alpha * nu + ri * zi - ri * vv;  // :475-477
+        T zn = alpha * (rinvi * nu) + alpha_comp * (rinvi * yi) + zi;  // :471-474
+        zn = fmax(zn, lo);
+        zn = fmin(zn, hi);
+        const T yn = alpha_comp * yi + alpha * nu + ri * zi - ri * zn;  // :475-477
         y[i] = yn;
-        z[i] = vv;
-        w[i] = ri * vv - yn;
+        z[i] = zn;
+        w[i] = ri * zn - yn;
       }
+      gsync();
       if (chk) {
         code = check_stopping(prm);  // :488 (clobbers w, v, t1..t4, xold)
-        if (code == kStatusUnset && prm.has_max_time && (long long)(global_timer_ns() - t0) > prm.max_time_ns)
-          code = SFB_QP_MAX_TIME;  // :504-508
-        for (int i = 0; i < m; ++i) w[i] = rho[i] * z[i] - y[i];
+        if (code == kStatusUnset && prm.has_max_time) {
+          const bool late = (long long)(global_timer_ns() - t0) > prm.max_time_ns;  // :504-508
+          if (gany(late)) code = SFB_QP_MAX_TIME;
+        }
+        for (int i = r; i < m; i += RL) w[i] = rho[i] * z[i] - y[i];
+        gsync();
       }
     }
 
     // ---- active sets as polish_qp builds them (:113-123) on the scaled dual
     const T thr = T(100) * Num<T>::eps();
-    int na = 0;
-    for (int i = 0; i < m; ++i) {
+    for (int i = r; i < m; i += RL) {
       int act = 0;
       T bv = T(0);
       if (y[i] < -thr && l[i] != -inf) { act = -1; bv = sy[i] * l[i]; }
@@ -544,44 +653,44 @@ template <typename T> struct SpSolver
       if (a.out_active) a.out_active[b * (long long)m + i] = (int8_t)act;
       w[i] = (act != 0) ? T(1) : T(0);
       yold[i] = bv;
-      na += (act != 0);
     }
+    gsync();
     unsigned flags = 0;
     if (code == SFB_QP_OPTIMAL && prm.polish) {
       if (sizeof(T) == 4) flags = SFB_QP_FLAG_POLISH_SKIPPED;  // delta = 1e-6 is not resolvable in fp32 (as in the dense kernel)
       else flags = polish(prm);
     }
     // ---- unscale + objective  :544-548
-    for (int j = 0; j < n; ++j) {
-      t1[j] = sx[j] * x[j];
-      t3[j] = T(0);
-    }
-    for (int e = 0; e < S.nnzP; ++e) t3[S.P_rowp[e]] += (T(0.5) * P[e]) * t1[S.P_colp[e]];
+    for (int j = r; j < n; j += RL) t1[j] = sx[j] * x[j];
+    gsync();
+    P_gather(t1, t3, T(0.5));
     T obj = T(0);
-    for (int jo = 0; jo < n; ++jo) {
+    for (int jo = r; jo < n; jo += RL) {
       const int j = S.iperm[jo];
       const T xv = t1[j];
       a.out_x[b * (long long)n + jo] = xv;
       obj += xv * (t3[j] + q[j]);
     }
-    for (int i = 0; i < m; ++i) a.out_y[b * (long long)m + i] = sy[i] * y[i] / c;
-    a.out_obj[b] = obj;
-    a.out_status[b] = (code == kStatusUnset) ? (int32_t)SFB_QP_MAX_ITERATIONS : (int32_t)code;
-    a.out_iter[b] = iter;
-    if (a.out_flags) a.out_flags[b] = flags;
-    (void)na;
+    obj = gsum(obj);
+    for (int i = r; i < m; i += RL) a.out_y[b * (long long)m + i] = sy[i] * y[i] / c;
+    if (r == 0) {
+      a.out_obj[b] = obj;
+      a.out_status[b] = (code == kStatusUnset) ? (int32_t)SFB_QP_MAX_ITERATIONS : (int32_t)code;
+      a.out_iter[b] = iter;
+      if (a.out_flags) a.out_flags[b] = flags;
+    }
   }
 };
 
-// One warp per tile of 32 instances, one warp per CTA (small batches still spread over all SMs).
-template <typename T> __global__ void __launch_bounds__(32) qp_sparse_tiled_kernel(const SpArgs<T> a)
+// One warp per tile of TW instances, one warp per CTA (small batches still spread over all SMs).
+template <typename T, int TW> __global__ void __launch_bounds__(32) qp_sparse_tiled_kernel(const SpArgs<T> a)
 {
   const int lane = threadIdx.x;
-  const long long ntiles = (a.batch + 31) / 32;
+  const long long ntiles = (a.batch + TW - 1) / TW;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const long long b = tile * 32 + lane;
+    const long long b = tile * TW + (lane & (TW - 1));
     if (b < a.batch) {
-      SpSolver<T> s(a, tile, lane);
+      SpSolver<T, TW> s(a, tile, lane);
       s.run(a, b);
     }
   }

@@ -59,6 +59,7 @@ struct sfb_context
   Scratch scratch[kNumSlots + 1];  // [kNumSlots] belongs to the handle's own stream
   cudaEvent_t ev_start = nullptr;
   bool ekf_force_generic = false;
+  int sparse_tw = 0;     // SFB_SPARSE_TW=8|32 overrides the tile-width heuristic of the sparse QP path (A/B measurements)
   Scratch sparse_ws;     // tiled working set of the sparse QP path
   Scratch sparse_stage;  // device copies of host buffers (sparse path)
 };
@@ -508,8 +509,12 @@ int qp_sparse_solve_impl(sfb_context* h, const sfb_qp_sparse_pattern* pt, const 
   if (space < 0) return fail(h, SFB_ERR_MIXED_MEMORY, "host and device pointers mixed in one call");
 
   const sfb::SparseSymbolic& S = pt->sym;
-  const long long tiles = (batch + 31) / 32;
-  const size_t per_tile = ((size_t)S.nnzA + S.nnzP + S.nnzL + n + (size_t)sfb::kSpNV * n + (size_t)sfb::kSpMV * m) * 32 * sizeof(T);
+  // tile width: 8 instances per warp (4 lanes cooperate on one instance) while the batch is too small to fill the GPU
+  // with one-lane-per-instance warps; the kernel is latency-bound, so resident warps are what buys throughput
+  int tw = (batch < 4ll * 32 * 8 * h->prop.multiProcessorCount) ? 8 : 32;
+  if (h->sparse_tw == 8 || h->sparse_tw == 32) tw = h->sparse_tw;
+  const long long tiles = (batch + tw - 1) / tw;
+  const size_t per_tile = ((size_t)S.nnzA + S.nnzP + S.nnzL + n + (size_t)sfb::kSpNV * n + (size_t)sfb::kSpMV * m) * tw * sizeof(T);
   rc = ensure_scratch(h, h->sparse_ws, per_tile * (size_t)tiles, h->stream);
   if (rc != SFB_OK) return rc;
 
@@ -520,14 +525,16 @@ int qp_sparse_solve_impl(sfb_context* h, const sfb_qp_sparse_pattern* pt, const 
   a.max_iter_eff = prm->has_max_iter ? prm->max_iter : SFB_QP_DEVICE_ITER_CAP;
   {
     T* w = static_cast<T*>(h->sparse_ws.dev);
-    a.wsA = w; w += (size_t)tiles * S.nnzA * 32;
-    a.wsP = w; w += (size_t)tiles * S.nnzP * 32;
-    a.wsW = w; w += (size_t)tiles * (S.nnzL + n) * 32;
-    a.wsN = w; w += (size_t)tiles * sfb::kSpNV * n * 32;
+    a.wsA = w; w += (size_t)tiles * S.nnzA * tw;
+    a.wsP = w; w += (size_t)tiles * S.nnzP * tw;
+    a.wsW = w; w += (size_t)tiles * (S.nnzL + n) * tw;
+    a.wsN = w; w += (size_t)tiles * sfb::kSpNV * n * tw;
     a.wsM = w;
   }
   auto launch = [&]() -> int {
-    sfb::qp_sparse_tiled_kernel<T><<<(unsigned)std::min<long long>(tiles, 1 << 30), 32, 0, h->stream>>>(a);
+    const unsigned grid = (unsigned)std::min<long long>(tiles, 1 << 30);
+    if (tw == 8) sfb::qp_sparse_tiled_kernel<T, 8><<<grid, 32, 0, h->stream>>>(a);
+    else sfb::qp_sparse_tiled_kernel<T, 32><<<grid, 32, 0, h->stream>>>(a);
     SFB_CUDA(h, cudaGetLastError());
     h->launches += 1;
     return SFB_OK;
@@ -620,6 +627,7 @@ int sfb_create(int device, void* stream, sfb_handle_t* out)
   sfb_context* h = new sfb_context();
   h->device = device;
   { const char* e = getenv("SFB_EKF_FORCE_GENERIC"); h->ekf_force_generic = e && e[0] == '1'; }
+  { const char* e = getenv("SFB_SPARSE_TW"); h->sparse_tw = e ? atoi(e) : 0; }
   h->stream = static_cast<cudaStream_t>(stream);
   if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&h->prop, device) != cudaSuccess) {
     const char* msg = cudaGetErrorString(cudaGetLastError());
@@ -836,7 +844,9 @@ int sfb_qp_sparse_analyze(sfb_handle_t h, int n, int m, const int32_t* P_colptr,
   }
   const sfb::SparseSymbolic& S = p->sym;
   const std::vector<int>* arrs[] = {&S.perm, &S.iperm, &S.P_rowp, &S.P_colp, &S.P_tgt, &S.A_rowptr, &S.A_col, &S.A_pair_ptr,
-                                    &S.A_pair_tgt, &S.L_colptr, &S.L_row, &S.F_ptr, &S.F_tgt};
+                                    &S.A_pair_tgt, &S.L_colptr, &S.L_row, &S.F_ptr, &S.F_tgt, &S.LR_ptr, &S.LR_col, &S.LR_slot,
+                                    &S.AT_ptr, &S.AT_row, &S.AT_slot, &S.PR_ptr, &S.PR_col, &S.PR_slot, &S.PS_ptr, &S.PS_col,
+                                    &S.PS_slot, &S.PC_ptr, &S.PC_slot, &S.LB_ptr, &S.LB_row, &S.LB_slot, &S.A_pair_ab, &S.F_ab};
   size_t total = 0;
   std::vector<size_t> off;
   for (auto* v : arrs) { off.push_back(total); total += (v->size() + 31) / 32 * 32; }
@@ -855,6 +865,13 @@ int sfb_qp_sparse_analyze(sfb_handle_t h, int n, int m, const int32_t* P_colptr,
   d.perm = base + off[0]; d.iperm = base + off[1]; d.P_rowp = base + off[2]; d.P_colp = base + off[3]; d.P_tgt = base + off[4];
   d.A_rowptr = base + off[5]; d.A_col = base + off[6]; d.A_pair_ptr = base + off[7]; d.A_pair_tgt = base + off[8];
   d.L_colptr = base + off[9]; d.L_row = base + off[10]; d.F_ptr = base + off[11]; d.F_tgt = base + off[12];
+  d.LR_ptr = base + off[13]; d.LR_col = base + off[14]; d.LR_slot = base + off[15];
+  d.AT_ptr = base + off[16]; d.AT_row = base + off[17]; d.AT_slot = base + off[18];
+  d.PR_ptr = base + off[19]; d.PR_col = base + off[20]; d.PR_slot = base + off[21];
+  d.PS_ptr = base + off[22]; d.PS_col = base + off[23]; d.PS_slot = base + off[24];
+  d.PC_ptr = base + off[25]; d.PC_slot = base + off[26];
+  d.LB_ptr = base + off[27]; d.LB_row = base + off[28]; d.LB_slot = base + off[29];
+  d.A_pair_ab = base + off[30]; d.F_ab = base + off[31];
   *out = p;
   return SFB_OK;
 }

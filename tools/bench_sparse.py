@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--small", action="store_true", help="n = m = 63 (tests/test_mpc.cpp size)")
+    ap.add_argument("--tw", type=int, default=0, help="force the tile width (8 or 32); 0 = library heuristic")
     a = ap.parse_args()
     import numpy as np
     import torch
@@ -42,7 +43,10 @@ def main():
     t = lambda x: torch.from_numpy(np.tile(x, (rep, 1))[: a.batch]).to("cuda:0", dtype=dt).contiguous()
     Pv, q, Av, l, u = t(Pv), t(q), t(Av), t(l), t(u)
     t0 = time.perf_counter()
-    sp = sfb.SparsePattern(pat["n"], pat["m"], pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], pat["A_colidx"])
+    if a.tw:
+        os.environ["SFB_SPARSE_TW"] = str(a.tw)
+    handle = sfb.Handle(0)
+    sp = sfb.SparsePattern(pat["n"], pat["m"], pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], pat["A_colidx"], handle=handle)
     t_analyze = time.perf_counter() - t0
     prm = sfb.QPSolverParams(max_iter=4000)
     out = None
@@ -64,7 +68,7 @@ def main():
         peak = float(json.load(open(pk))["hbm_gbs"])
     ach = a.batch * (bcomp + it * biter) / (mean_ms * 1e-3) / 1e9
     print(json.dumps({
-        "workload": f"sparse QP (MPC structure) n={pat['n']} m={pat['m']} nnzA={sp.nnzA} nnzP={sp.nnzP} nnzL={sp.nnzL} batch={a.batch} {a.dtype}",
+        "workload": f"sparse QP (MPC structure) n={pat['n']} m={pat['m']} nnzA={sp.nnzA} nnzP={sp.nnzP} nnzL={sp.nnzL} batch={a.batch} {a.dtype} tw={a.tw or 'auto'}",
         "solves_per_s": a.batch / (mean_ms * 1e-3), "ms": mean_ms, "ms_all": ms, "mean_iter": it,
         "status_hist": torch.bincount(out.status, minlength=7).tolist(), "polished_frac": float((out.flags & 1).double().mean().item()),
         "analyze_s": t_analyze, "factor_flops": sp.factor_flops, "bytes_compulsory": bcomp, "bytes_per_iteration": biter,
