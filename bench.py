@@ -122,6 +122,49 @@ def cpu_baseline(sample_target_s: float = 12.0):
             "mean_iter": float(r.iter.mean()), "optimal_frac": float((r.status == 0).mean())}
 
 
+def secondary_configs(dev):
+    """The other BASELINE.json configs the engine covers, each as one short measured line (single GPU, data resident,
+    CUDA events).  They ride along in the JSON under "secondary"; the headline stays configs[1]."""
+    import torch
+
+    import smooth_feedback_b200 as sfb
+    from smooth_feedback_b200.generators import random_qp_torch
+    from tools import bench_ekf, bench_sparse
+
+    out = {}
+
+    def dense(name, B, n, m, dtype, **kw):
+        P, q, A, l, u = random_qp_torch(B, n, m, seed=SEED, device=dev, dtype=dtype)
+        prm = sfb.QPSolverParams(max_iter=MAX_ITER, **kw)
+        r = None
+        for _ in range(2):
+            r = sfb.solve_dense_batch(P, q, A, l, u, prm, out=r)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            r = sfb.solve_dense_batch(P, q, A, l, u, prm, out=r)
+        e1.record(); e1.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        out[name] = {"workload": f"dense QP n={n} m={m} batch={B} {'f64' if dtype == torch.float64 else 'f32'} G+", "solves_per_s": B / (ms * 1e-3),
+                     "ms": ms, "mean_iter": float(r.iter.double().mean().item()), "optimal_frac": float((r.status == 0).double().mean().item())}
+
+    steps = [
+        ("cfg1_dense_n10_m20_f64", lambda: dense("cfg1_dense_n10_m20_f64", 65536, 10, 20, torch.float64)),
+        ("cfg5_shape_dense_n3_m203_f32", lambda: dense("cfg5_shape_dense_n3_m203_f32", 32768, 3, 203, torch.float32, polish=False)),
+        ("cfg4_ekf_d6_ny3_f64", lambda: out.__setitem__("cfg4_ekf_d6_ny3_f64", bench_ekf.run(1 << 20, 6, 3, 10))),
+        ("cfg3_mpc_sparse_n422_f32", lambda: out.__setitem__("cfg3_mpc_sparse_n422_f32", bench_sparse.run(8192, "f32", 2))),
+        ("cfg3_mpc_sparse_n422_f64", lambda: out.__setitem__("cfg3_mpc_sparse_n422_f64", bench_sparse.run(8192, "f64", 2))),
+    ]
+    for name, fn in steps:
+        try:
+            fn()
+        except Exception as e:  # a secondary line must never take the headline down; the error is reported, not hidden
+            out[name] = {"error": f"{type(e).__name__}: {e}"}
+        torch.cuda.empty_cache()
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -154,6 +197,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH, help="per-GPU batch (default = BASELINE configs[1])")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the short lines for the other BASELINE configs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -302,6 +346,10 @@ def main():
             line["e2e"] = e2e
         if not args.no_cpu and world == 1:
             line["cpu_baseline"] = cpu_baseline()
+        if not args.no_secondary and world == 1:
+            del P_cm, A_cm, q, l, u, out
+            torch.cuda.empty_cache()
+            line["secondary"] = secondary_configs(dev)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -45,6 +45,11 @@ struct SparseSymbolic
   std::vector<int> PR_ptr, PR_col, PR_slot;   // rows of P as stored: out[r] = sum P[slot] in[col]      (P x)
   std::vector<int> PS_ptr, PS_col, PS_slot;   // rows of sym(triu P): out[r] = sum Pbar[slot] in[col]   (polish)
   std::vector<int> LB_ptr, LB_row, LB_slot;   // columns of L in REVERSE column order (backward solve as one forward stream)
+  // padded sweep schedules (TW == 8 kernel): a sweep is a list of STEPS of exactly kStepWidth entries; a row of L takes
+  // ceil(len / kStepWidth) consecutive steps.  meta = (row << 1) | last_step_of_row; col / slot are padded with 0 / -1.
+  static constexpr int kStepWidth = 32;
+  std::vector<int> FS_meta, FS_col, FS_slot;  // forward:  rows ascending, rows without entries skipped
+  std::vector<int> BS_meta, BS_col, BS_slot;  // backward: rows descending, every row present (1 / D scaling)
   std::vector<int> PC_ptr;                    // P_colptr re-indexed by PERMUTED column (entries regrouped in PC_slot)
   std::vector<int> PC_slot;
   long long flops = 0;                // multiply-adds of the numeric factorisation
@@ -221,6 +226,34 @@ inline bool sparse_analyze(int n, int m, const int32_t* P_colptr, const int32_t*
     for (int e = 0; e < S.nnzP; ++e) trip.push_back({S.P_colp[e], S.P_rowp[e], e});
     std::vector<int> dummy;
     build_rows(n, trip, S.PC_ptr, dummy, S.PC_slot);
+  }
+
+  // ---- padded sweep schedules ----
+  {
+    auto emit = [&](int k, const std::vector<std::pair<int, int>>& ent, bool keep_empty, std::vector<int>& meta,
+                    std::vector<int>& col, std::vector<int>& slt) {
+      const int W = SparseSymbolic::kStepWidth;
+      const int steps = ent.empty() ? (keep_empty ? 1 : 0) : (int)((ent.size() + W - 1) / W);
+      for (int st = 0; st < steps; ++st) {
+        meta.push_back((k << 1) | (st == steps - 1 ? 1 : 0));
+        for (int i = 0; i < W; ++i) {
+          const size_t idx = (size_t)st * W + i;
+          col.push_back(idx < ent.size() ? ent[idx].first : 0);
+          slt.push_back(idx < ent.size() ? ent[idx].second : -1);
+        }
+      }
+    };
+    std::vector<std::pair<int, int>> ent;
+    for (int k = 0; k < n; ++k) {
+      ent.clear();
+      for (int e = S.LR_ptr[k]; e < S.LR_ptr[k + 1]; ++e) ent.push_back({S.LR_col[e], S.LR_slot[e]});
+      emit(k, ent, false, S.FS_meta, S.FS_col, S.FS_slot);
+    }
+    for (int k = n - 1; k >= 0; --k) {
+      ent.clear();
+      for (int e = S.L_colptr[k]; e < S.L_colptr[k + 1]; ++e) ent.push_back({S.L_row[e], e});
+      emit(k, ent, true, S.BS_meta, S.BS_col, S.BS_slot);
+    }
   }
 
   // ---- right-looking update schedule ----

@@ -7,14 +7,15 @@
 //   detail::polish_qp                         :92-204
 // i.e. the call MPC::operator() makes at mpc.hpp:491.
 //
-// Layout.  A warp owns a TILE of TW instances (TW = 32 or 8); every per-instance array of the working set lives in
+// Layout.  A warp owns a TILE of TW instances (TW = 32, 8 or 4); every per-instance array of the working set lives in
 // global memory as [tile][element][TW].  All lanes of a warp execute the same pattern-driven program (the index arrays
 // are shared by the whole batch and broadcast), lane -> (instance = lane % TW, row-lane r = lane / TW): an access to
 // element e touches TW consecutive scalars, so every load and store of the solve is a full, coalesced line and the
 // per-iteration traffic is exactly the north star's model (Abar twice, the L D L^T factor twice, the iterate vectors;
-// B_iter).  With TW = 8 the RL = 4 lanes of an instance split the entries of a row between them (small
-// batches: 4x more warps to hide the memory latency, which is what bounds this kernel); with TW = 32 a lane owns its
-// instance alone and the code is free of shuffles and barriers.
+// B_iter).  With TW < 32 the RL = 32 / TW lanes of an instance split the entries of a row between them
+// (small batches: RL times more warps to hide the memory latency, which is what bounds this kernel), the solve vector
+// lives in shared memory and the triangular sweeps run as a register-pipelined list of fixed-width steps; with TW = 32
+// a lane owns its instance alone and the code is free of shuffles and barriers.
 //
 // The KKT system is reduced as in the dense kernel:  (Pbar + sigma I + Abar^T R Abar) xt = sigma x - qbar + Abar^T (R z - y),
 // nu = R (Abar xt - z) + y; the n x n matrix is factorised L D L^T without pivoting (it is SPD) in the fill-reducing
@@ -49,7 +50,21 @@ struct SpPattern
   // gather-form mirrors and packed pair lists (qp_sparse_host.hpp)
   const int *LR_ptr, *LR_col, *LR_slot, *AT_ptr, *AT_row, *AT_slot, *PR_ptr, *PR_col, *PR_slot, *PS_ptr, *PS_col, *PS_slot,
     *PC_ptr, *PC_slot, *LB_ptr, *LB_row, *LB_slot, *A_pair_ab, *F_ab;
+  // padded sweep schedules (TW == 8): nFS / nBS steps of kSpStep entries each
+  const int *FS_meta, *FS_col, *FS_slot, *BS_meta, *BS_col, *BS_slot;
+  int nFS, nBS;
 };
+
+constexpr int kSpStep = 32;  // == SparseSymbolic::kStepWidth
+constexpr int kSpDepth = 4;  // sweep steps in flight per lane
+
+// scalars per instance of the W block: factor (nnzL + n) followed by its two stream-ordered copies
+__host__ __device__ inline size_t sp_w_len(const SpPattern& p, int tw)
+{
+  const size_t copies = (tw < 32) ? (size_t)(p.nFS + p.nBS) * kSpStep : 2 * (size_t)p.nnzL;
+  return (size_t)p.nnzL + p.n + copies;
+}
+__host__ __device__ inline size_t sp_fwd_len(const SpPattern& p, int tw) { return (tw < 32) ? (size_t)p.nFS * kSpStep : (size_t)p.nnzL; }
 
 template <typename T> struct SpArgs
 {
@@ -82,25 +97,31 @@ template <typename T, int TW> struct SpSolver
   const SpPattern& S;
   int n, m, r;
   unsigned gmask;
-  V A, P, W;
+  V A, P, W, LRW, LBW;  // LRW / LBW: the factor's values again, in the forward / backward sweep's stream order
   V q, qb, x, xold, v, sx, t1, t2, t3, t4;  // n-vectors (permuted order)
   V l, u, sy, rho, rinv, z, y, yold, w;    // m-vectors
   T c;
 
-  __device__ SpSolver(const SpArgs<T>& a, long long tile, int lane) : S(a.pat), n(a.pat.n), m(a.pat.m)
+  // smem_v: [n][TW] scalars of shared memory for the solve vector (TW == 8 only, nullptr otherwise)
+  __device__ SpSolver(const SpArgs<T>& a, long long tile, int lane, T* smem_v) : S(a.pat), n(a.pat.n), m(a.pat.m)
   {
     const int inst = lane & (TW - 1);
     r = lane / TW;
-    gmask = (RL == 1) ? (1u << lane) : (0x01010101u << inst);
+    gmask = 0u;
+#pragma unroll
+    for (int k = 0; k < RL; ++k) gmask |= 1u << (inst + k * TW);
     A.p = a.wsA + (size_t)tile * S.nnzA * TW + inst;
     P.p = a.wsP + (size_t)tile * S.nnzP * TW + inst;
-    W.p = a.wsW + (size_t)tile * (S.nnzL + n) * TW + inst;
+    W.p = a.wsW + (size_t)tile * sp_w_len(S, TW) * TW + inst;
+    LRW.p = W.p + (size_t)(S.nnzL + n) * TW;
+    LBW.p = LRW.p + sp_fwd_len(S, TW) * TW;
     T* nv = a.wsN + (size_t)tile * kSpNV * n * TW + inst;
     T* mv = a.wsM + (size_t)tile * kSpMV * m * TW + inst;
     auto N = [&](int k) { return V{nv + (size_t)k * n * TW}; };
     auto M = [&](int k) { return V{mv + (size_t)k * m * TW}; };
     q = N(0); qb = N(1); x = N(2); xold = N(3); v = N(4); sx = N(5); t1 = N(6); t2 = N(7); t3 = N(8); t4 = N(9);
     l = M(0); u = M(1); sy = M(2); rho = M(3); rinv = M(4); z = M(5); y = M(6); yold = M(7); w = M(8);
+    if (smem_v != nullptr) v.p = smem_v + inst;  // the solve vector is gathered from ~40 times per row sweep: keep it on chip
     c = T(1);
   }
 
@@ -300,28 +321,113 @@ template <typename T, int TW> struct SpSolver
       if (r == 0) W[nL + k] = dinv;
       gsync();
     }
+    // stream-order copies for the sweeps (contiguous, no slot indirection, prefetchable); TW == 8: padded step layout
+    auto copy_stream = [&](const V& dst, const int* __restrict__ slot, int len) {
+      for (int e = r; e < len; e += kSpU * RL) {
+        int sl[kSpU];
+        T a0[kSpU];
+#pragma unroll
+        for (int k = 0; k < kSpU; ++k) sl[k] = (e + k * RL < len) ? slot[e + k * RL] : -1;
+#pragma unroll
+        for (int k = 0; k < kSpU; ++k) a0[k] = (sl[k] >= 0) ? Wl[sl[k]] : T(0);
+#pragma unroll
+        for (int k = 0; k < kSpU; ++k)
+          if (e + k * RL < len) dst[e + k * RL] = a0[k];
+      }
+    };
+    if (RL > 1) {
+      copy_stream(LRW, S.FS_slot, S.nFS * kSpStep);
+      copy_stream(LBW, S.BS_slot, S.nBS * kSpStep);
+    } else {
+      copy_stream(LRW, S.LR_slot, nL);
+      copy_stream(LBW, S.LB_slot, nL);
+    }
+    gsync();
     return ok;
   }
 
-  // v <- (L D L^T)^-1 v.  Both sweeps in gather form: forward over the rows of L (LR_* mirror), backward over its
-  // columns in reverse order (LB_* mirror); the RL lanes of an instance split the entries of a row.
-  __device__ void solve()
+  // One sweep of the triangular solve in gather form over the stream-ordered factor copy LW:
+  //   forward:  v[k] <- v[k] - sum_e LW[e] v[col[e]]          backward:  v[k] <- v[k] / D_k - sum_e LW[e] v[col[e]]
+  // TW == 8: the sweep is a list of fixed-width STEPS (kSpStep padded entries, RL lanes x kSpU each); a row of L spans one
+  // or more consecutive steps.  Factor entries and column indices do not depend on the solve's dependency chain, so they
+  // are fetched TWO steps ahead into registers: what is left on the chain per step is the gather from v (shared memory),
+  // the RL-lane shuffles and one store.
+  static constexpr int SU = (RL > 1) ? kSpStep / RL : kSpU;  // entries of a step per lane
+  struct StepBuf
   {
-    const int nL = S.nnzL;
-    const V Wl = W, vv = v;
-    for (int k = 0; k < n; ++k) {
-      const int e0 = S.LR_ptr[k], e1 = S.LR_ptr[k + 1];
-      if (e0 == e1) continue;
-      const T s = gsum(gather_sum(e0, e1, r, RL, S.LR_col, [&](int e) { return Wl[S.LR_slot[e]]; }, [&](int j) { return vv[j]; }));
-      if (r == 0) v[k] = v[k] - s;
+    int meta;
+    int j[SU];
+    T a[SU];
+    T vk, dk;
+  };
+  template <bool FWD> __device__ __forceinline__ void step_load(StepBuf& B, int st, const int* __restrict__ meta,
+                                                                const int* __restrict__ col, const V& LW) const
+  {
+    B.meta = meta[st];
+    const int base = st * kSpStep + r;
+#pragma unroll
+    for (int t = 0; t < SU; ++t) {
+      B.j[t] = col[base + t * RL];
+      B.a[t] = LW[base + t * RL];
+    }
+    const int k = B.meta >> 1;
+    B.vk = v[k];  // row k of the right-hand side is only written at its own (last) step
+    B.dk = FWD ? T(1) : W[S.nnzL + k];
+  }
+  template <bool FWD> __device__ __forceinline__ void step_apply(const StepBuf& B, T& acc)
+  {
+    const V vv = v;
+#pragma unroll
+    for (int t = 0; t < SU; ++t) acc += B.a[t] * vv[B.j[t]];  // padding carries a = 0, j = 0
+    if (B.meta & 1) {  // last step of the row (warp-uniform)
+      const T s = gsum(acc);
+      if (r == 0) v[B.meta >> 1] = FWD ? B.vk - s : B.vk * B.dk - s;
+      acc = T(0);
       gsync();
     }
+  }
+  // kSpDepth step buffers rotate through a loop unrolled kSpDepth times (static register indexing, no moves): a step's
+  // operands are requested kSpDepth steps (~ kSpDepth x 300 cycles) before they are used
+  template <bool FWD> __device__ void sweep_steps(int nsteps, const int* __restrict__ meta, const int* __restrict__ col, const V& LW)
+  {
+    if (nsteps == 0) return;
+    StepBuf b[kSpDepth];
+#pragma unroll
+    for (int d = 0; d < kSpDepth; ++d) step_load<FWD>(b[d], d < nsteps ? d : nsteps - 1, meta, col, LW);
+    T acc = T(0);
+    for (int st = 0; st < nsteps; st += kSpDepth) {
+#pragma unroll
+      for (int d = 0; d < kSpDepth; ++d) {
+        if (st + d < nsteps) {
+          step_apply<FWD>(b[d], acc);
+          if (st + d + kSpDepth < nsteps) step_load<FWD>(b[d], st + d + kSpDepth, meta, col, LW);
+        }
+      }
+    }
+  }
+  // TW == 32: one lane per instance, rows walked with batched gathers over the contiguous copies
+  template <bool FWD> __device__ void sweep_rows(const int* __restrict__ ptr, const int* __restrict__ col, const V& LW)
+  {
+    const V vv = v;
     for (int kk = 0; kk < n; ++kk) {
-      const int k = n - 1 - kk;
-      const T s = gsum(gather_sum(S.LB_ptr[kk], S.LB_ptr[kk + 1], r, RL, S.LB_row, [&](int e) { return Wl[S.LB_slot[e]]; },
-                                  [&](int j) { return vv[j]; }));
-      if (r == 0) v[k] = v[k] * W[nL + k] - s;
-      gsync();
+      const int k = FWD ? kk : n - 1 - kk;
+      const int e0 = ptr[kk], e1 = ptr[kk + 1];
+      if (FWD && e0 == e1) continue;
+      const T vk = v[k], dk = FWD ? T(1) : W[S.nnzL + k];
+      const T s = gather_sum(e0, e1, 0, 1, col, [&](int e) { return LW[e]; }, [&](int j) { return vv[j]; });
+      v[k] = FWD ? vk - s : vk * dk - s;
+    }
+  }
+
+  // v <- (L D L^T)^-1 v
+  __device__ void solve()
+  {
+    if (RL > 1) {
+      sweep_steps<true>(S.nFS, S.FS_meta, S.FS_col, LRW);
+      sweep_steps<false>(S.nBS, S.BS_meta, S.BS_col, LBW);
+    } else {
+      sweep_rows<true>(S.LR_ptr, S.LR_col, LRW);
+      sweep_rows<false>(S.LB_ptr, S.LB_row, LBW);
     }
   }
 
@@ -683,16 +789,19 @@ template <typename T, int TW> struct SpSolver
 };
 
 // One warp per tile of TW instances, one warp per CTA (small batches still spread over all SMs).
-template <typename T, int TW> __global__ void __launch_bounds__(32) qp_sparse_tiled_kernel(const SpArgs<T> a)
+template <typename T, int TW> __global__ void __launch_bounds__(32, TW == 8 ? 8 : 16) qp_sparse_tiled_kernel(const SpArgs<T> a)
 {
+  extern __shared__ __align__(16) unsigned char sp_smem_raw[];
   const int lane = threadIdx.x;
+  T* smem_v = (TW < 32) ? reinterpret_cast<T*>(sp_smem_raw) : nullptr;
   const long long ntiles = (a.batch + TW - 1) / TW;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long b = tile * TW + (lane & (TW - 1));
     if (b < a.batch) {
-      SpSolver<T, TW> s(a, tile, lane);
+      SpSolver<T, TW> s(a, tile, lane, smem_v);
       s.run(a, b);
     }
+    __syncwarp();
   }
 }
 

@@ -59,7 +59,7 @@ struct sfb_context
   Scratch scratch[kNumSlots + 1];  // [kNumSlots] belongs to the handle's own stream
   cudaEvent_t ev_start = nullptr;
   bool ekf_force_generic = false;
-  int sparse_tw = 0;     // SFB_SPARSE_TW=8|32 overrides the tile-width heuristic of the sparse QP path (A/B measurements)
+  int sparse_tw = 0;     // SFB_SPARSE_TW=4|8|32 overrides the tile-width heuristic of the sparse QP path (A/B measurements)
   Scratch sparse_ws;     // tiled working set of the sparse QP path
   Scratch sparse_stage;  // device copies of host buffers (sparse path)
 };
@@ -509,12 +509,15 @@ int qp_sparse_solve_impl(sfb_context* h, const sfb_qp_sparse_pattern* pt, const 
   if (space < 0) return fail(h, SFB_ERR_MIXED_MEMORY, "host and device pointers mixed in one call");
 
   const sfb::SparseSymbolic& S = pt->sym;
-  // tile width: 8 instances per warp (4 lanes cooperate on one instance) while the batch is too small to fill the GPU
-  // with one-lane-per-instance warps; the kernel is latency-bound, so resident warps are what buys throughput
-  int tw = (batch < 4ll * 32 * 8 * h->prop.multiProcessorCount) ? 8 : 32;
-  if (h->sparse_tw == 8 || h->sparse_tw == 32) tw = h->sparse_tw;
+  // tile width: the kernel is bound by memory latency, so resident warps are what buys throughput.  Large batches take
+  // one lane per instance (32 instances per warp, no shuffles); below ~8 warps per SM of those, 4 instances per warp with
+  // 8 lanes cooperating on each (measured at n = m = 422: batch 8192 -> 71k solves/s with 4, 49k with 8, 14k with 32;
+  // batch 65536 -> 84k with 4, 95k with 32; profiles/README.md)
+  int tw = (batch < 8ll * 32 * h->prop.multiProcessorCount) ? 4 : 32;
+  if (h->sparse_tw == 4 || h->sparse_tw == 8 || h->sparse_tw == 32) tw = h->sparse_tw;
   const long long tiles = (batch + tw - 1) / tw;
-  const size_t per_tile = ((size_t)S.nnzA + S.nnzP + S.nnzL + n + (size_t)sfb::kSpNV * n + (size_t)sfb::kSpMV * m) * tw * sizeof(T);
+  const size_t wlen = sfb::sp_w_len(pt->pat, tw);  // factor + its stream-ordered copies
+  const size_t per_tile = ((size_t)S.nnzA + S.nnzP + wlen + (size_t)sfb::kSpNV * n + (size_t)sfb::kSpMV * m) * tw * sizeof(T);
   rc = ensure_scratch(h, h->sparse_ws, per_tile * (size_t)tiles, h->stream);
   if (rc != SFB_OK) return rc;
 
@@ -527,14 +530,25 @@ int qp_sparse_solve_impl(sfb_context* h, const sfb_qp_sparse_pattern* pt, const 
     T* w = static_cast<T*>(h->sparse_ws.dev);
     a.wsA = w; w += (size_t)tiles * S.nnzA * tw;
     a.wsP = w; w += (size_t)tiles * S.nnzP * tw;
-    a.wsW = w; w += (size_t)tiles * (S.nnzL + n) * tw;
+    a.wsW = w; w += (size_t)tiles * wlen * tw;
     a.wsN = w; w += (size_t)tiles * sfb::kSpNV * n * tw;
     a.wsM = w;
   }
   auto launch = [&]() -> int {
     const unsigned grid = (unsigned)std::min<long long>(tiles, 1 << 30);
-    if (tw == 8) sfb::qp_sparse_tiled_kernel<T, 8><<<grid, 32, 0, h->stream>>>(a);
-    else sfb::qp_sparse_tiled_kernel<T, 32><<<grid, 32, 0, h->stream>>>(a);
+    if (tw < 32) {
+      const size_t smem = (size_t)n * tw * sizeof(T);  // the solve vector of the tile
+      if (smem > h->prop.sharedMemPerBlockOptin) return fail(h, SFB_ERR_UNSUPPORTED_SIZE, "sparse QP n=%d: solve vector does not fit in shared memory", n);
+      if (tw == 8) {
+        SFB_CUDA(h, cudaFuncSetAttribute(sfb::qp_sparse_tiled_kernel<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sfb::qp_sparse_tiled_kernel<T, 8><<<grid, 32, smem, h->stream>>>(a);
+      } else {
+        SFB_CUDA(h, cudaFuncSetAttribute(sfb::qp_sparse_tiled_kernel<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sfb::qp_sparse_tiled_kernel<T, 4><<<grid, 32, smem, h->stream>>>(a);
+      }
+    } else {
+      sfb::qp_sparse_tiled_kernel<T, 32><<<grid, 32, 0, h->stream>>>(a);
+    }
     SFB_CUDA(h, cudaGetLastError());
     h->launches += 1;
     return SFB_OK;
@@ -846,7 +860,8 @@ int sfb_qp_sparse_analyze(sfb_handle_t h, int n, int m, const int32_t* P_colptr,
   const std::vector<int>* arrs[] = {&S.perm, &S.iperm, &S.P_rowp, &S.P_colp, &S.P_tgt, &S.A_rowptr, &S.A_col, &S.A_pair_ptr,
                                     &S.A_pair_tgt, &S.L_colptr, &S.L_row, &S.F_ptr, &S.F_tgt, &S.LR_ptr, &S.LR_col, &S.LR_slot,
                                     &S.AT_ptr, &S.AT_row, &S.AT_slot, &S.PR_ptr, &S.PR_col, &S.PR_slot, &S.PS_ptr, &S.PS_col,
-                                    &S.PS_slot, &S.PC_ptr, &S.PC_slot, &S.LB_ptr, &S.LB_row, &S.LB_slot, &S.A_pair_ab, &S.F_ab};
+                                    &S.PS_slot, &S.PC_ptr, &S.PC_slot, &S.LB_ptr, &S.LB_row, &S.LB_slot, &S.A_pair_ab, &S.F_ab, &S.FS_meta, &S.FS_col, &S.FS_slot,
+                                    &S.BS_meta, &S.BS_col, &S.BS_slot};
   size_t total = 0;
   std::vector<size_t> off;
   for (auto* v : arrs) { off.push_back(total); total += (v->size() + 31) / 32 * 32; }
@@ -872,6 +887,9 @@ int sfb_qp_sparse_analyze(sfb_handle_t h, int n, int m, const int32_t* P_colptr,
   d.PC_ptr = base + off[25]; d.PC_slot = base + off[26];
   d.LB_ptr = base + off[27]; d.LB_row = base + off[28]; d.LB_slot = base + off[29];
   d.A_pair_ab = base + off[30]; d.F_ab = base + off[31];
+  d.FS_meta = base + off[32]; d.FS_col = base + off[33]; d.FS_slot = base + off[34];
+  d.BS_meta = base + off[35]; d.BS_col = base + off[36]; d.BS_slot = base + off[37];
+  d.nFS = (int)S.FS_meta.size(); d.nBS = (int)S.BS_meta.size();
   *out = p;
   return SFB_OK;
 }

@@ -21,31 +21,25 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--batch", type=int, default=8192)
-    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
-    ap.add_argument("--steps", type=int, default=3)
-    ap.add_argument("--small", action="store_true", help="n = m = 63 (tests/test_mpc.cpp size)")
-    ap.add_argument("--tw", type=int, default=0, help="force the tile width (8 or 32); 0 = library heuristic")
-    a = ap.parse_args()
+def run(batch=8192, dtype="f64", steps=3, small=False, tw=0):
     import numpy as np
     import torch
 
     import smooth_feedback_b200 as sfb
     from smooth_feedback_b200.generators import mpc_structured_batch, mpc_structured_pattern
 
-    pat = mpc_structured_pattern(Nx=3, Nu=2, nivals=3, Ki=4) if a.small else mpc_structured_pattern()
+    pat = mpc_structured_pattern(Nx=3, Nu=2, nivals=3, Ki=4) if small else mpc_structured_pattern()
     base = 512  # distinct agents generated on the host, tiled to the batch (keeps host generation to seconds)
-    Pv, q, Av, l, u = mpc_structured_batch(pat, min(base, a.batch), seed=5)
-    rep = (a.batch + Pv.shape[0] - 1) // Pv.shape[0]
-    dt = torch.float64 if a.dtype == "f64" else torch.float32
-    t = lambda x: torch.from_numpy(np.tile(x, (rep, 1))[: a.batch]).to("cuda:0", dtype=dt).contiguous()
+    Pv, q, Av, l, u = mpc_structured_batch(pat, min(base, batch), seed=5)
+    rep = (batch + Pv.shape[0] - 1) // Pv.shape[0]
+    dt = torch.float64 if dtype == "f64" else torch.float32
+    t = lambda x: torch.from_numpy(np.tile(x, (rep, 1))[:batch]).to("cuda:0", dtype=dt).contiguous()
     Pv, q, Av, l, u = t(Pv), t(q), t(Av), t(l), t(u)
-    t0 = time.perf_counter()
-    if a.tw:
-        os.environ["SFB_SPARSE_TW"] = str(a.tw)
+    if tw:
+        os.environ["SFB_SPARSE_TW"] = str(tw)
     handle = sfb.Handle(0)
+    os.environ.pop("SFB_SPARSE_TW", None)
+    t0 = time.perf_counter()
     sp = sfb.SparsePattern(pat["n"], pat["m"], pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], pat["A_colidx"], handle=handle)
     t_analyze = time.perf_counter() - t0
     prm = sfb.QPSolverParams(max_iter=4000)
@@ -54,25 +48,36 @@ def main():
         out = sfb.solve_sparse_batch(sp, Pv, q, Av, l, u, prm, out=out)
     torch.cuda.synchronize()
     ms = []
-    for _ in range(a.steps):
+    for _ in range(steps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); out = sfb.solve_sparse_batch(sp, Pv, q, Av, l, u, prm, out=out); e1.record(); e1.synchronize()
         ms.append(e0.elapsed_time(e1))
     mean_ms = sum(ms) / len(ms)
-    s = 8 if a.dtype == "f64" else 4
+    s = 8 if dtype == "f64" else 4
     it = out.iter.double().mean().item()
     bcomp, biter = sp.bytes_compulsory(s), sp.bytes_per_iteration(s)
     peak = 6650.0
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
         peak = float(json.load(open(pk))["hbm_gbs"])
-    ach = a.batch * (bcomp + it * biter) / (mean_ms * 1e-3) / 1e9
-    print(json.dumps({
-        "workload": f"sparse QP (MPC structure) n={pat['n']} m={pat['m']} nnzA={sp.nnzA} nnzP={sp.nnzP} nnzL={sp.nnzL} batch={a.batch} {a.dtype} tw={a.tw or 'auto'}",
-        "solves_per_s": a.batch / (mean_ms * 1e-3), "ms": mean_ms, "ms_all": ms, "mean_iter": it,
+    ach = batch * (bcomp + it * biter) / (mean_ms * 1e-3) / 1e9
+    return {
+        "workload": f"sparse QP (MPC structure) n={pat['n']} m={pat['m']} nnzA={sp.nnzA} nnzP={sp.nnzP} nnzL={sp.nnzL} batch={batch} {dtype} tw={tw or 'auto'}",
+        "solves_per_s": batch / (mean_ms * 1e-3), "ms": mean_ms, "ms_all": ms, "mean_iter": it,
         "status_hist": torch.bincount(out.status, minlength=7).tolist(), "polished_frac": float((out.flags & 1).double().mean().item()),
         "analyze_s": t_analyze, "factor_flops": sp.factor_flops, "bytes_compulsory": bcomp, "bytes_per_iteration": biter,
-        "achieved_gbs": ach, "hbm_peak_gbs": peak, "frac_hbm": ach / peak}), flush=True)
+        "achieved_gbs": ach, "hbm_peak_gbs": peak, "frac_hbm": ach / peak}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=8192)
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--small", action="store_true", help="n = m = 63 (tests/test_mpc.cpp size)")
+    ap.add_argument("--tw", type=int, default=0, help="force the tile width (8 or 32); 0 = library heuristic")
+    a = ap.parse_args()
+    print(json.dumps(run(a.batch, a.dtype, a.steps, a.small, a.tw)), flush=True)
 
 
 if __name__ == "__main__":

@@ -22,8 +22,9 @@ src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-so
 rows = list(csv.reader(io.StringIO(src)))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Line No")
 h = rows[hi]
-ci_smp = h.index("# Samples"); ci_ins = h.index("Instructions Executed"); ci_wf = h.index("L1 Wavefronts Shared")
-ci_wfi = h.index("L1 Wavefronts Shared Ideal")
+ci_smp = h.index("# Samples"); ci_ins = h.index("Instructions Executed")
+ci_wf = h.index("L1 Wavefronts Shared") if "L1 Wavefronts Shared" in h else ci_ins  # kernels without shared memory
+ci_wfi = h.index("L1 Wavefronts Shared Ideal") if "L1 Wavefronts Shared Ideal" in h else ci_ins
 lines = []
 for r in rows[hi + 1:]:
     if len(r) <= ci_wf or not r[0].strip(): continue
