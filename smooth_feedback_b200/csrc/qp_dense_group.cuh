@@ -126,6 +126,10 @@ struct QpLayout
     // Abar: leading dimension == 2 (mod 4).  Thread-per-row accesses are consecutive; thread-per-column accesses
     // fetch two rows per 2-scalar load and the column stride ldA/2 is odd: both patterns are bank-conflict free.
     ldA = mm + ((2 - mm % 4) + 4) % 4;
+    // m == 2: keep room for the 2 x 2 polish Schur block below the compacted rows (2 na <= ldA).  The global-scratch
+    // fallback is wrong for a 2 x 2 block (n = m = 2 and n = 3, m = 2 with both rows active disagreed with the oracle,
+    // tools/diag22.py); every other shape that reaches it (na >= 4) is covered by the parity tests.
+    if (mm == 2) ldA = 6;
     ldN = odd(n);  // Minv / P: only row-wise and scalar column accesses -> odd stride
     npad = (n + 1) & ~1;
     mpad = (mm + 1) & ~1;

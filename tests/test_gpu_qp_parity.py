@@ -81,6 +81,7 @@ def _parity(sfb, oracle, B, n, m, seed, feasible=True, prm_kw=None, rel=REL_F64,
     o = oracle.qp_solve_batch(P, q, A, l, u, params=oracle.default_params(max_iter=max_iter, **okw), nthreads=8)
     o2 = oracle.qp_solve_batch(P, q, A, l, u, params=oracle.default_params(max_iter=max_iter, **okw), nthreads=8, fast=True)
     well_posed = (o.status == o2.status) & (o.iter == o2.iter) & (o.active == o2.active).all(axis=1)
+    _parity.last_fast = o2
     return r, o, well_posed
 
 
@@ -133,7 +134,20 @@ def test_parity_infeasible_mix(sfb, oracle):
 def test_parity_ragged_shapes(sfb, oracle, n, m):
     # odd sizes, m < n, tall-skinny (ASIF-like n=3, m=203), sizes beyond the register-blocked inverse (70)
     r, o, wp = _parity(sfb, oracle, 64, n, m, seed=n * 1000 + m)
-    _assert_parity(r, o, wp, 1e-4, min_well_posed=0.9)  # tiny / tall / degenerate problems: the polish systems are ill conditioned
+    # tiny / tall / degenerate problems: some polish systems are singular to working precision (n = m = 2 with both rows
+    # active: the duals are then determined by rounding alone and the oracle disagrees with ITSELF, FMA vs no FMA, by
+    # orders of magnitude).  Discrete outputs exact; continuous outputs within 1e-4 or 10x the oracle's own disagreement.
+    o2 = _parity.last_fast
+    assert wp.mean() >= 0.9
+    assert np.array_equal(r.status[wp], o.status[wp]) and np.array_equal(r.iter[wp], o.iter[wp])
+    assert np.array_equal(r.active[wp], o.active[wp])
+    ok = (o.status == 0) & wp
+    if ok.any():
+        tol_x = np.maximum(1e-4, 10 * rel_err(o2.x[ok], o.x[ok]))
+        tol_y = np.maximum(1e-4, 10 * rel_err(o2.y[ok], o.y[ok]))
+        ex, ey = rel_err(r.x[ok], o.x[ok]), rel_err(r.y[ok], o.y[ok])
+        assert (ex <= tol_x).all() and (ey <= tol_y).all(), (ex.max(), ey.max())
+        assert (ex <= 1e-4).mean() >= 0.9 and (ey <= 1e-4).mean() >= 0.9
 
 
 def test_scale_is_bit_exact(sfb, oracle):
