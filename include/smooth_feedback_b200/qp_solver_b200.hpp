@@ -8,14 +8,20 @@
 // so that `qp_solver_.solve(qp_, warmstart_)` (mpc.hpp:491) and `solve_qp(qp_, prm_.qp, warmstart_)` (asif.hpp:97)
 // compile unchanged; plus the one extension the GPU engine exists for: QPSolver::solve_batch.
 //
-// `Pbm` is any type with public dense members P, q, A, l, u that offer rows(), cols(), operator()(i,j) / operator()(i)
-// (Eigen matrices do; tests/cpp/mock_eigen.hpp is the stand-in used where Eigen is not installed).  Dense problems only:
-// the sparse MPC-sized path is not part of this engine yet.
+// `Pbm` is any type with public members P, q, A, l, u, exactly as in the reference (qp_solver.hpp:245-251 only looks at
+// decltype(Pbm::A)):
+//   dense  (QuadraticProgram<M,N,Scalar>, qp.hpp:31-45): P, A offer rows(), cols(), operator()(i,j)  -> sfb_qp_solve_dense_batch_*
+//   sparse (QuadraticProgramSparse<Scalar>, qp.hpp:60-79): P column-major, A row-major compressed matrices offering
+//          outerIndexPtr(), innerIndexPtr(), valuePtr(), nonZeros()                                  -> sfb_qp_solve_sparse_batch_*
+// (Eigen matrices do; tests/cpp/mock_eigen.hpp is the stand-in used where Eigen is not installed).  For sparse problems
+// the pattern is analysed on the first solve after construction or copy, like the reference's analyzePattern
+// (qp_solver.hpp:424, LDLTWrapper :209-231); all problems of one solve_batch call must share that pattern.
 //
 // All numerics run on the GPU through libsfb.so; there is no CPU fallback: if no device is available the constructor of
 // the solver throws std::runtime_error with the library's message.
 #pragma once
 
+#include <algorithm>
 #include <chrono>
 #include <cstdint>
 #include <functional>
@@ -112,6 +118,31 @@ private:
   sfb_handle_t h_{nullptr};
 };
 
+/// Sparse problem types: compressed P (column-major) and A (row-major), as Eigen::SparseMatrix exposes them
+template<typename Pbm>
+concept SparsePbm = requires(const Pbm & p) {
+  p.A.outerIndexPtr(); p.A.innerIndexPtr(); p.A.valuePtr(); p.A.nonZeros();
+  p.P.outerIndexPtr(); p.P.innerIndexPtr(); p.P.valuePtr(); p.P.nonZeros();
+};
+
+/// Owner of an sfb_qp_sparse_pattern_t; a copy starts without a pattern (re-analysed on its first solve)
+class Pattern
+{
+public:
+  Pattern() = default;
+  Pattern(const Pattern &) {}
+  Pattern(Pattern && o) noexcept : p_(o.p_) { o.p_ = nullptr; }
+  Pattern & operator=(const Pattern &) { reset(); return *this; }
+  Pattern & operator=(Pattern && o) noexcept { std::swap(p_, o.p_); return *this; }
+  ~Pattern() { reset(); }
+  void reset() { if (p_) { sfb_qp_sparse_pattern_destroy(p_); p_ = nullptr; } }
+  sfb_qp_sparse_pattern_t get() const { return p_; }
+  sfb_qp_sparse_pattern_t * put() { reset(); return &p_; }
+
+private:
+  sfb_qp_sparse_pattern_t p_{nullptr};
+};
+
 }  // namespace detail
 
 template<typename Pbm>
@@ -136,6 +167,7 @@ public:
   {
     n_ = static_cast<int>(pbm.A.cols());
     m_ = static_cast<int>(pbm.A.rows());
+    if constexpr (detail::SparsePbm<Pbm>) { pattern_.reset(); }
     sol_.primal.resize(n_);
     sol_.dual.resize(m_);
     for (int i = 0; i < n_; ++i) { sol_.primal(i) = 0; }
@@ -163,6 +195,16 @@ public:
     if (pbms.empty()) { return; }
     const int64_t B = static_cast<int64_t>(pbms.size());
     const int n = static_cast<int>(pbms[0].A.cols()), m = static_cast<int>(pbms[0].A.rows());
+    if constexpr (detail::SparsePbm<Pbm>) {
+      solve_batch_sparse(pbms, sols, warm, B, n, m);
+    } else {
+      solve_batch_dense(pbms, sols, warm, B, n, m);
+    }
+  }
+
+private:
+  void solve_batch_dense(std::span<const Pbm> pbms, std::span<Solution> sols, std::span<const Solution> warm, int64_t B, int n, int m)
+  {
     P_.resize(B * n * n); q_.resize(B * n); A_.resize(B * m * n); l_.resize(B * m); u_.resize(B * m);
     x_.resize(B * n); y_.resize(B * m); obj_.resize(B); st_.resize(B); it_.resize(B);
     const bool has_warm = !warm.empty();
@@ -208,11 +250,72 @@ public:
     }
   }
 
-private:
+  /// sparse problems sharing one pattern (QuadraticProgramSparse, the MPC call site mpc.hpp:491)
+  void solve_batch_sparse(std::span<const Pbm> pbms, std::span<Solution> sols, std::span<const Solution> warm, int64_t B, int n, int m)
+  {
+    const Pbm & p0 = pbms[0];
+    const int64_t nnzP = static_cast<int64_t>(p0.P.nonZeros()), nnzA = static_cast<int64_t>(p0.A.nonZeros());
+    if (!pattern_.get() || n != n_ || m != m_) {  // analyzePattern, once per solver object (qp_solver.hpp:424)
+      n_ = n; m_ = m;
+      std::vector<int32_t> pc(p0.P.outerIndexPtr(), p0.P.outerIndexPtr() + n + 1), pr(p0.P.innerIndexPtr(), p0.P.innerIndexPtr() + nnzP);
+      std::vector<int32_t> ar(p0.A.outerIndexPtr(), p0.A.outerIndexPtr() + m + 1), ac(p0.A.innerIndexPtr(), p0.A.innerIndexPtr() + nnzA);
+      if (sfb_qp_sparse_analyze(handle_.get(), n, m, pc.data(), pr.data(), ar.data(), ac.data(), pattern_.put()) != SFB_OK) {
+        throw std::runtime_error(std::string("sfb_qp_sparse_analyze: ") + sfb_last_error_message(handle_.get()));
+      }
+      pat_P_ = std::move(pr); pat_A_ = std::move(ac);
+    }
+    P_.resize(B * nnzP); q_.resize(B * n); A_.resize(B * nnzA); l_.resize(B * m); u_.resize(B * m);
+    x_.resize(B * n); y_.resize(B * m); obj_.resize(B); st_.resize(B); it_.resize(B);
+    const bool has_warm = !warm.empty();
+    if (has_warm) { wx_.resize(B * n); wy_.resize(B * m); }
+    for (int64_t b = 0; b < B; ++b) {
+      const Pbm & p = pbms[b];
+      if (static_cast<int64_t>(p.P.nonZeros()) != nnzP || static_cast<int64_t>(p.A.nonZeros()) != nnzA ||
+          !std::equal(pat_P_.begin(), pat_P_.end(), p.P.innerIndexPtr()) || !std::equal(pat_A_.begin(), pat_A_.end(), p.A.innerIndexPtr())) {
+        throw std::invalid_argument("smooth::feedback (B200 engine): problems of one batch must share the analysed sparsity pattern");
+      }
+      std::copy(p.P.valuePtr(), p.P.valuePtr() + nnzP, P_.begin() + b * nnzP);
+      std::copy(p.A.valuePtr(), p.A.valuePtr() + nnzA, A_.begin() + b * nnzA);
+      for (int j = 0; j < n; ++j) {
+        q_[b * n + j] = p.q(j);
+        if (has_warm) { wx_[b * n + j] = warm[b].primal(j); }
+      }
+      for (int i = 0; i < m; ++i) {
+        l_[b * m + i] = p.l(i);
+        u_[b * m + i] = p.u(i);
+        if (has_warm) { wy_[b * m + i] = warm[b].dual(i); }
+      }
+    }
+    const sfb_qp_params c = detail::to_c(prm_);
+    int rc;
+    if constexpr (std::is_same_v<Scalar, double>) {
+      rc = sfb_qp_solve_sparse_batch_f64(handle_.get(), pattern_.get(), &c, B, P_.data(), q_.data(), A_.data(), l_.data(), u_.data(),
+        has_warm ? wx_.data() : nullptr, has_warm ? wy_.data() : nullptr, x_.data(), y_.data(), obj_.data(), st_.data(), it_.data(),
+        nullptr, nullptr);
+    } else {
+      rc = sfb_qp_solve_sparse_batch_f32(handle_.get(), pattern_.get(), &c, B, P_.data(), q_.data(), A_.data(), l_.data(), u_.data(),
+        has_warm ? wx_.data() : nullptr, has_warm ? wy_.data() : nullptr, x_.data(), y_.data(), obj_.data(), st_.data(), it_.data(),
+        nullptr, nullptr);
+    }
+    if (rc != SFB_OK) { throw std::runtime_error(std::string("sfb_qp_solve_sparse_batch: ") + sfb_last_error_message(handle_.get())); }
+    for (int64_t b = 0; b < B; ++b) {
+      Solution & s = sols[b];
+      s.code = static_cast<QPSolutionStatus>(st_[b]);
+      s.iter = it_[b];
+      s.objective = obj_[b];
+      s.primal.resize(n);
+      s.dual.resize(m);
+      for (int j = 0; j < n; ++j) { s.primal(j) = x_[b * n + j]; }
+      for (int i = 0; i < m; ++i) { s.dual(i) = y_[b * m + i]; }
+    }
+  }
+
   QPSolverParams prm_{};
   Solution sol_{};
   int n_{0}, m_{0};
   detail::Handle handle_{};
+  detail::Pattern pattern_{};
+  std::vector<int32_t> pat_P_, pat_A_;
   std::vector<Scalar> P_, q_, A_, l_, u_, wx_, wy_, x_, y_, obj_;
   std::vector<int32_t> st_;
   std::vector<uint32_t> it_;

@@ -26,6 +26,24 @@ template<typename S> struct Vector
   S & operator()(long i) { return d[i]; }
   const S & operator()(long i) const { return d[i]; }
 };
+// compressed sparse matrix with Eigen::SparseMatrix's raw-pointer interface (outer = columns for P, rows for A)
+template<typename S> struct SparseMatrix
+{
+  long r{0}, c{0};
+  std::vector<int> outer, inner;
+  std::vector<S> vals;
+  long rows() const { return r; }
+  long cols() const { return c; }
+  long nonZeros() const { return static_cast<long>(vals.size()); }
+  const int * outerIndexPtr() const { return outer.data(); }
+  const int * innerIndexPtr() const { return inner.data(); }
+  const S * valuePtr() const { return vals.data(); }
+  bool isCompressed() const { return true; }
+};
+template<typename S = double> struct QuadraticProgramSparse  // qp.hpp:60-79: P column-major, A row-major
+{
+  SparseMatrix<S> P; Vector<S> q; SparseMatrix<S> A; Vector<S> l, u;
+};
 template<typename S = double> struct QuadraticProgram  // qp.hpp:31-45
 {
   Matrix<S> P; Vector<S> q; Matrix<S> A; Vector<S> l, u;

@@ -48,6 +48,35 @@ int main()
   std::vector<QPSolver<Pbm>::Solution> sols(100);
   s1.solve_batch(batch, sols);
   for (int i = 0; i < 100; ++i) { CHECK(sols[i].code == QPSolutionStatus::Optimal && std::fabs(sols[i].primal(0) - 1) < 1e-4); }
+  // BasicSparse (tests/test_qp.cpp:100-122): the same QP as QuadraticProgramSparse -- the problem type MPC instantiates
+  {
+    using SPbm = mock::QuadraticProgramSparse<double>;
+    SPbm sp;
+    sp.P.r = sp.P.c = 2; sp.P.outer = {0, 1, 2}; sp.P.inner = {0, 1}; sp.P.vals = {1, 1};
+    sp.A.r = sp.A.c = 2; sp.A.outer = {0, 1, 2}; sp.A.inner = {0, 1}; sp.A.vals = {1, 1};
+    sp.q.resize(2); sp.q(0) = -4; sp.q(1) = 0.25;
+    sp.l.resize(2); sp.l(0) = -1; sp.l(1) = -1;
+    sp.u.resize(2); sp.u(0) = 1; sp.u(1) = 1;
+    QPSolver<SPbm> ss(sp, test_prm);
+    const auto ssol = ss.solve(sp);
+    CHECK(ssol.code == QPSolutionStatus::Optimal);
+    CHECK(std::fabs(ssol.primal(0) - 1) < 1e-4 && std::fabs(ssol.primal(1) + 0.25) < 1e-4);
+    CHECK(std::fabs(ssol.objective - (0.5 - 4 - 1. / 32)) < 1e-4);
+    const auto swarm = ss.solve(sp, ssol);
+    CHECK(swarm.code == QPSolutionStatus::Optimal && swarm.iter == 2);
+    QPSolver<SPbm> ss2 = ss;  // a copy drops the analysed pattern and re-analyses (LDLTWrapper semantics, SparseSolverAPI :374-415)
+    const auto x2s = ss2.solve(sp).primal;
+    CHECK(x2s(0) == ssol.primal(0) && x2s(1) == ssol.primal(1));
+    std::vector<SPbm> sbatch(50, sp);
+    for (int i = 0; i < 50; ++i) { sbatch[i].q(0) = -4 + 0.01 * i; }
+    std::vector<QPSolver<SPbm>::Solution> ssols(50);
+    ss.solve_batch(sbatch, ssols);
+    for (int i = 0; i < 50; ++i) { CHECK(ssols[i].code == QPSolutionStatus::Optimal && std::fabs(ssols[i].primal(0) - 1) < 1e-4); }
+    sbatch[7].A.inner = {1, 0};  // a different pattern inside one batch is an API error, not a status
+    bool threw = false;
+    try { ss.solve_batch(sbatch, ssols); } catch (const std::invalid_argument &) { threw = true; }
+    CHECK(threw);
+  }
   (void)inf;
   std::printf("overlay ok\n");
   return 0;
