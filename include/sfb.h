@@ -192,6 +192,11 @@ typedef struct sfb_qp_sparse_pattern* sfb_qp_sparse_pattern_t;
 int sfb_qp_sparse_analyze(sfb_handle_t h, int n, int m, const int32_t* P_colptr, const int32_t* P_rowidx,
                           const int32_t* A_rowptr, const int32_t* A_colidx, sfb_qp_sparse_pattern_t* out);
 int sfb_qp_sparse_pattern_destroy(sfb_qp_sparse_pattern_t p);
+/* The symbolic analysis alone (host only, no device needed): nnz(L), multiply-adds per factorisation, the ordering
+ * perm_out [n] (perm[new] = old) and the column pointers of L, L_colptr_out [n+1]; outputs may be NULL. */
+int sfb_qp_sparse_symbolic(int n, int m, const int32_t* P_colptr, const int32_t* P_rowidx, const int32_t* A_rowptr,
+                           const int32_t* A_colidx, int64_t* nnz_L, int64_t* factor_flops, int32_t* perm_out,
+                           int32_t* L_colptr_out);
 /* nnz of the strictly lower factor L, multiply-adds of one numeric factorisation, ordering (perm_out [n], may be NULL) */
 int sfb_qp_sparse_pattern_info(sfb_qp_sparse_pattern_t p, int64_t* nnz_L, int64_t* factor_flops, int32_t* perm_out);
 

@@ -8,7 +8,7 @@ from .qp import (  # noqa: F401
     QPBatchResult, QPSolution, QPSolutionStatus, QPSolver, QPSolverParams, QuadraticProgram, solve_dense_batch,
     solve_qp, to_colmajor,
 )
-from .qp_sparse import QuadraticProgramSparse, SparsePattern, solve_sparse_batch  # noqa: F401
+from .qp_sparse import QuadraticProgramSparse, SparsePattern, solve_sparse_batch, sparse_symbolic  # noqa: F401
 from .ekf import ekf_predict_batch, ekf_step_batch, ekf_update_batch  # noqa: F401
 
 __version__ = "0.1.0"

@@ -51,7 +51,7 @@ EXPORTED_SYMBOLS = [
     "sfb_synchronize", "sfb_kernel_launch_count", "sfb_qp_params_default", "sfb_qp_solve_dense_batch_f64",
     "sfb_qp_solve_dense_batch_f32", "sfb_qp_dense_max_m", "sfb_qp_scale_dense_batch_f64",
     "sfb_ekf_predict_batch_f64", "sfb_ekf_update_batch_f64", "sfb_ekf_step_batch_f64",
-    "sfb_qp_sparse_analyze", "sfb_qp_sparse_pattern_destroy", "sfb_qp_sparse_pattern_info",
+    "sfb_qp_sparse_analyze", "sfb_qp_sparse_symbolic", "sfb_qp_sparse_pattern_destroy", "sfb_qp_sparse_pattern_info",
     "sfb_qp_solve_sparse_batch_f64", "sfb_qp_solve_sparse_batch_f32",
 ]
 
@@ -115,6 +115,7 @@ def lib() -> C.CDLL:
     L.sfb_ekf_update_batch_f64.argtypes = [vp, i64, i32, i32] + [vp] * 6
     L.sfb_ekf_step_batch_f64.argtypes = [vp, i64, i32, i32, i32, vp, vp, vp, C.c_double, C.c_double] + [vp] * 5
     L.sfb_qp_sparse_analyze.argtypes = [vp, i32, i32, vp, vp, vp, vp, C.POINTER(vp)]
+    L.sfb_qp_sparse_symbolic.argtypes = [i32, i32, vp, vp, vp, vp, C.POINTER(i64), C.POINTER(i64), vp, vp]
     L.sfb_qp_sparse_pattern_destroy.argtypes = [vp]
     L.sfb_qp_sparse_pattern_info.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), vp]
     sp_sig = [vp, vp, C.POINTER(SfbQpParams), i64] + [vp] * 14

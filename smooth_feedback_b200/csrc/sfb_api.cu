@@ -894,6 +894,20 @@ int sfb_qp_sparse_analyze(sfb_handle_t h, int n, int m, const int32_t* P_colptr,
   return SFB_OK;
 }
 
+int sfb_qp_sparse_symbolic(int n, int m, const int32_t* P_colptr, const int32_t* P_rowidx, const int32_t* A_rowptr,
+                           const int32_t* A_colidx, int64_t* nnz_L, int64_t* factor_flops, int32_t* perm_out,
+                           int32_t* L_colptr_out)
+{
+  if (n <= 0 || m < 0 || !P_colptr || (m > 0 && !A_rowptr)) return SFB_ERR_INVALID_ARGUMENT;
+  sfb::SparseSymbolic S;
+  if (!sfb::sparse_analyze(n, m, P_colptr, P_rowidx, A_rowptr, A_colidx, S)) return fail(nullptr, SFB_ERR_INVALID_ARGUMENT, "sparse pattern rejected: %s", S.error.c_str());
+  if (nnz_L) *nnz_L = S.nnzL;
+  if (factor_flops) *factor_flops = S.flops;
+  if (perm_out) std::copy(S.perm.begin(), S.perm.end(), perm_out);
+  if (L_colptr_out) std::copy(S.L_colptr.begin(), S.L_colptr.end(), L_colptr_out);
+  return SFB_OK;
+}
+
 int sfb_qp_sparse_pattern_destroy(sfb_qp_sparse_pattern_t p)
 {
   if (!p) return SFB_OK;

@@ -85,6 +85,19 @@ class SparsePattern:
             pass
 
 
+def sparse_symbolic(n: int, m: int, P_colptr, P_rowidx, A_rowptr, A_colidx):
+    """Host-only symbolic analysis (sfb_qp_sparse_symbolic): -> dict(nnzL, factor_flops, perm [n], L_colptr [n+1])."""
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    pc, pr, ar, ac = i32(P_colptr), i32(P_rowidx), i32(A_rowptr), i32(A_colidx)
+    ip = lambda a: a.ctypes.data_as(C.c_void_p)
+    nnzL, flops = C.c_int64(), C.c_int64()
+    perm = np.empty(n, np.int32); lcp = np.empty(n + 1, np.int32)
+    rc = _lib.lib().sfb_qp_sparse_symbolic(int(n), int(m), ip(pc), ip(pr), ip(ar), ip(ac), C.byref(nnzL), C.byref(flops), ip(perm), ip(lcp))
+    if rc != 0:
+        raise _lib.SfbError(rc, _lib.lib().sfb_last_error_message(None).decode())
+    return dict(nnzL=int(nnzL.value), factor_flops=int(flops.value), perm=perm, L_colptr=lcp)
+
+
 def solve_sparse_batch(pattern: SparsePattern, P_vals, q, A_vals, l, u, prm: QPSolverParams | None = None, warm_x=None,
                        warm_y=None, out: QPBatchResult | None = None) -> QPBatchResult:
     """Solve B sparse QPs sharing ``pattern`` (sfb_qp_solve_sparse_batch_f64/_f32).

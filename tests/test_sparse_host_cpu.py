@@ -1,0 +1,91 @@
+"""CPU tests of the sparse path's host logic: workload generators, the densified-oracle equivalence they rely on, and the
+symbolic analysis (sfb_qp_sparse_symbolic: ordering + fill) checked against a numeric Cholesky."""
+import numpy as np
+import pytest
+
+import smooth_feedback_b200 as sfb
+from smooth_feedback_b200.generators import (_lgr_diff_matrix, mpc_structured_batch, mpc_structured_pattern,
+                                             random_sparse_qp_numpy, sparse_to_dense)
+
+
+def test_lgr_differentiation_matrix_is_exact_on_polynomials():
+    # collocation/mesh.hpp: K LGR nodes + end point; D differentiates polynomials of degree <= K exactly
+    for K in (2, 4, 7):
+        D, qw, tau = _lgr_diff_matrix(K)
+        assert abs(tau[0] + 1) < 1e-14 and abs(tau[-1] - 1) < 1e-14 and abs(qw.sum() - 2) < 1e-12
+        for p in range(K + 1):
+            assert np.abs(D @ tau ** p - p * tau[:K] ** max(p - 1, 0) * (p > 0)).max() < 1e-10
+
+
+def test_mpc_pattern_matches_ocp_to_qp_sizes():
+    # ocp_to_qp.hpp:58-96 for the SE(2) x R^3 bus, K = 50 -> 13 intervals x 4 nodes: n = m = 422
+    pat = mpc_structured_pattern()
+    Nx, Nu, N, Ki = 6, 2, 52, 4
+    assert pat["n"] == Nx * (N + 1) + Nu * N == 422 and pat["m"] == Nx * N + Nu * N + Nx == 422
+    rows = np.diff(pat["A_rowptr"])
+    assert (rows[: Nx * N] == Nx + Ki + Nu).all()                 # dynamics rows, :77-80
+    assert (rows[Nx * N: Nx * N + Nu * N] == Nx + Nu).all()       # running constraints, :81
+    assert (rows[-Nx:] == 2 * Nx).all()                           # end constraints, :82
+    cols = np.diff(pat["P_colptr"])                               # upper-triangular P, :86-96
+    assert list(cols[:Nx]) == [1, 2, 3, 4, 5, 6] and list(cols[Nx * N: Nx * (N + 1)]) == [7, 8, 9, 10, 11, 12]
+    assert list(cols[Nx * (N + 1): Nx * (N + 1) + Nu]) == [7, 8]
+    pc = np.repeat(np.arange(pat["n"]), cols)
+    assert (pat["P_rowidx"] <= pc).all()                          # nothing below the diagonal
+
+
+def test_mpc_surrogate_is_solved_by_the_oracle(oracle):
+    # the synthetic MPC workload must be a problem the reference algorithm solves (Optimal, ~50 iterations)
+    pat = mpc_structured_pattern(Nx=3, Nu=2, nivals=3, Ki=4)
+    Pv, q, Av, l, u = mpc_structured_batch(pat, 24, seed=1)
+    P, A = sparse_to_dense(pat, Pv, Av)
+    o = oracle.qp_solve_batch(P, q, A, l, u, params=oracle.default_params(max_iter=4000), nthreads=4)
+    assert (o.status == 0).all() and o.iter.max() <= 202
+    x = o.x
+    eq = np.isclose(l, u)
+    Ax = np.einsum("bij,bj->bi", A, x)
+    assert np.abs(Ax - u)[eq].max() < 1e-6                         # dynamics / initial state satisfied
+    assert (Ax <= u + 1e-6).all() and (Ax >= l - 1e-6).all()
+
+
+def test_upper_only_P_quirk_with_non_diagonal_weights(oracle):
+    # check_stopping multiplies with P as stored (upper triangle only for MPC), so a non-diagonal
+    # weight never passes the dual residual test -> MaxIterations.  Reproduced, not fixed.
+    pat = mpc_structured_pattern(Nx=3, Nu=2, nivals=2, Ki=3)
+    Pv, q, Av, l, u = mpc_structured_batch(pat, 4, seed=1)
+    kinds = [t[0] for t in pat["P_terms"]]
+    offdiag = np.array([k == "Q" and t[2] != t[3] for k, t in zip(kinds, pat["P_terms"])])
+    Pv2 = Pv.copy(); Pv2[:, offdiag] = 0.05
+    P, A = sparse_to_dense(pat, Pv2, Av)
+    o = oracle.qp_solve_batch(P, q, A, l, u, params=oracle.default_params(max_iter=600), nthreads=4)
+    assert (o.status == 4).all()
+
+
+@pytest.mark.parametrize("which", ["mpc", "random"])
+def test_symbolic_analysis_covers_the_numeric_factor(which):
+    if which == "mpc":
+        pat = mpc_structured_pattern()
+        Pv, q, Av, l, u = mpc_structured_batch(pat, 1, seed=3)
+    else:
+        pat, Pv, q, Av, l, u = random_sparse_qp_numpy(1, 60, 80, density=0.08, seed=2)
+    n, m = pat["n"], pat["m"]
+    sym = sfb.sparse_symbolic(n, m, pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], pat["A_colidx"])
+    perm = sym["perm"]
+    assert sorted(perm.tolist()) == list(range(n))
+    P, A = sparse_to_dense(pat, np.abs(Pv) + 1.0, np.abs(Av) + 1.0)   # no accidental cancellation in the pattern
+    Pu = np.triu(P[0]); M = Pu + Pu.T + A[0].T @ A[0] + n * 100.0 * np.eye(n)
+    Mp = M[np.ix_(perm, perm)]
+    L = np.linalg.cholesky(Mp)
+    numeric = [int((np.abs(L[j + 1:, j]) > 1e-14).sum()) for j in range(n)]
+    symbolic = np.diff(sym["L_colptr"])
+    assert (np.array(numeric) <= symbolic).all()                      # every numeric nonzero has a slot
+    assert sym["nnzL"] == symbolic.sum() and sym["nnzL"] <= 1.05 * sum(numeric) + 8
+    dense_lower = n * (n - 1) // 2
+    assert sym["nnzL"] < (0.12 if which == "mpc" else 0.9) * dense_lower
+    assert sym["factor_flops"] == int((symbolic * (symbolic + 1) // 2).sum())
+
+
+def test_symbolic_rejects_bad_patterns():
+    pat, *_ = random_sparse_qp_numpy(1, 8, 6, density=0.4, seed=1)
+    bad = pat["A_colidx"].copy(); bad[0] = 99
+    with pytest.raises(sfb.SfbError):
+        sfb.sparse_symbolic(8, 6, pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], bad)
