@@ -57,6 +57,7 @@ struct SpPattern
 
 constexpr int kSpStep = 32;  // == SparseSymbolic::kStepWidth
 constexpr int kSpDepth = 4;  // sweep steps in flight per lane
+constexpr int kSpPrefetch = 24;  // L2 prefetch distance of the sweeps, in steps
 constexpr int kSpPolishRefine = 1;  // refinement steps on Hp per application of the reduced polish solve
 
 // scalars per instance of the W block: factor (nnzL + n) followed by its two stream-ordered copies
@@ -102,11 +103,14 @@ template <typename T, int TW> struct SpSolver
   V q, qb, x, xold, v, sx, t1, t2, t3, t4;  // n-vectors (permuted order)
   V l, u, sy, rho, rinv, z, y, yold, w;    // m-vectors
   T c;
+  int nsteps_ = 0;  // length of the sweep in progress (prefetch bound)
+  int inst_ = 0;    // instance slot inside the tile
 
   // smem_v: [n][TW] scalars of shared memory for the solve vector (TW == 8 only, nullptr otherwise)
   __device__ SpSolver(const SpArgs<T>& a, long long tile, int lane, T* smem_v) : S(a.pat), n(a.pat.n), m(a.pat.m)
   {
     const int inst = lane & (TW - 1);
+    inst_ = inst;
     r = lane / TW;
     gmask = 0u;
 #pragma unroll
@@ -347,6 +351,15 @@ template <typename T, int TW> struct SpSolver
     return ok;
   }
 
+  // The solve vector through the shared-memory SYMBOL (TW < 32): via the member pointer the compiler only sees a generic
+  // address and emits generic loads, which cost more latency and are tracked like global loads; derived from the extern
+  // __shared__ array they are LDS / STS.
+  __device__ __forceinline__ T* v_shared() const
+  {
+    extern __shared__ __align__(16) unsigned char sp_smem_raw[];
+    return reinterpret_cast<T*>(sp_smem_raw) + inst_;
+  }
+
   // One sweep of the triangular solve in gather form over the stream-ordered factor copy LW:
   //   forward:  v[k] <- v[k] - sum_e LW[e] v[col[e]]          backward:  v[k] <- v[k] / D_k - sum_e LW[e] v[col[e]]
   // TW == 8: the sweep is a list of fixed-width STEPS (kSpStep padded entries, RL lanes x kSpU each); a row of L spans one
@@ -371,18 +384,25 @@ template <typename T, int TW> struct SpSolver
       B.j[t] = col[base + t * RL];
       B.a[t] = LW[base + t * RL];
     }
+    // the register pipeline covers an L2 hit, not a DRAM round trip under load: pull the factor entries of a later
+    // step into L2 now (no register or shared-memory cost)
+    if (st + kSpPrefetch < nsteps_) {
+#pragma unroll
+      for (int t = 0; t < SU; ++t)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(&LW[base + kSpPrefetch * kSpStep + t * RL]));
+    }
     const int k = B.meta >> 1;
-    B.vk = v[k];  // row k of the right-hand side is only written at its own (last) step
+    B.vk = v_shared()[(size_t)k * TW];  // row k of the right-hand side is only written at its own (last) step
     B.dk = FWD ? T(1) : W[S.nnzL + k];
   }
   template <bool FWD> __device__ __forceinline__ void step_apply(const StepBuf& B, T& acc)
   {
-    const V vv = v;
+    T* sv = v_shared();
 #pragma unroll
-    for (int t = 0; t < SU; ++t) acc += B.a[t] * vv[B.j[t]];  // padding carries a = 0, j = 0
+    for (int t = 0; t < SU; ++t) acc += B.a[t] * sv[(size_t)B.j[t] * TW];  // padding carries a = 0, j = 0
     if (B.meta & 1) {  // last step of the row (warp-uniform)
       const T s = gsum(acc);
-      if (r == 0) v[B.meta >> 1] = FWD ? B.vk - s : B.vk * B.dk - s;
+      if (r == 0) sv[(size_t)(B.meta >> 1) * TW] = FWD ? B.vk - s : B.vk * B.dk - s;
       acc = T(0);
       gsync();
     }
@@ -392,6 +412,7 @@ template <typename T, int TW> struct SpSolver
   template <bool FWD> __device__ void sweep_steps(int nsteps, const int* __restrict__ meta, const int* __restrict__ col, const V& LW)
   {
     if (nsteps == 0) return;
+    nsteps_ = nsteps;
     StepBuf b[kSpDepth];
 #pragma unroll
     for (int d = 0; d < kSpDepth; ++d) step_load<FWD>(b[d], d < nsteps ? d : nsteps - 1, meta, col, LW);

@@ -155,3 +155,147 @@ def test_device_path_equals_host_path_and_errors(sfb):
         sfb.SparsePattern(pat["n"], pat["m"], pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], bad)
     with pytest.raises(sfb.SfbError):  # host / device pointers mixed
         sfb.solve_sparse_batch(sp, t(Pv), t(q), t(Av), t(l), t(u), prm, out=rh)
+
+
+def test_full_size_properties_cfg3(sfb):
+    """BASELINE.json configs[2] at full size (MPC structure n = m = 422, batch 8192; fp64 and fp32): size-independent
+    properties.  The batch tiles 256 distinct agents, so replicas must agree bit for bit wherever they sit in the batch
+    (tile / lane independence), every instance must be Optimal with the KKT conditions of the ORIGINAL problem satisfied,
+    and a warm re-solve must exit at the first check (iter 2) with the same solution."""
+    import torch
+
+    from smooth_feedback_b200.generators import mpc_structured_batch, mpc_structured_pattern, sparse_to_dense
+
+    pat = mpc_structured_pattern()
+    base, B = 256, 8192
+    Pv, q, Av, l, u = mpc_structured_batch(pat, base, seed=9)
+    rep = B // base
+    t = lambda a, dt=torch.float64: torch.from_numpy(np.tile(a, (rep, 1))).to("cuda:0", dtype=dt).contiguous()
+    sp = sfb.SparsePattern(pat["n"], pat["m"], pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], pat["A_colidx"])
+    prm = sfb.QPSolverParams(max_iter=4000)
+    r = sfb.solve_sparse_batch(sp, t(Pv), t(q), t(Av), t(l), t(u), prm)
+    torch.cuda.synchronize()
+    st, it = r.status.cpu().numpy(), r.iter.cpu().numpy()
+    x, y = r.x.cpu().numpy(), r.y.cpu().numpy()
+    assert (st == 0).all() and ((r.flags.cpu().numpy() & 1) == 1).all()
+    # replicas identical
+    assert np.array_equal(x.reshape(rep, base, -1), np.broadcast_to(x[:base], (rep, base, x.shape[1])))
+    assert np.array_equal(it.reshape(rep, base), np.broadcast_to(it[:base], (rep, base)))
+    # KKT of the original problem on the distinct agents: stationarity with sym(triu P), primal feasibility (no sign property for the duals:
+    # polish solves an equality-constrained QP on the guessed active set and, like the reference, does not re-check signs)
+    P, A = sparse_to_dense(pat, Pv, Av)
+    Ps = np.triu(P) + np.transpose(np.triu(P, 1), (0, 2, 1))
+    xb, yb = x[:base], y[:base]
+    stat = np.einsum("bij,bj->bi", Ps, xb) + q + np.einsum("bji,bj->bi", A, yb)
+    assert np.abs(stat).max() <= 1e-8 * max(1.0, np.abs(q).max())
+    Ax = np.einsum("bij,bj->bi", A, xb)
+    # polish (like the reference's) enforces the rows it found ACTIVE exactly; a row the eps = 1e-3 ADMM iterate left
+    # inactive may end up violated at that level, so feasibility is an eps-level property, equality rows are exact
+    eq = np.isclose(l, u)
+    assert np.abs(Ax - u)[eq].max() <= 1e-7 * (1.0 + np.abs(u[eq]).max())
+    assert (Ax <= u + 2e-2).all() and (Ax >= l - 2e-2).all(), (np.max(Ax - u), np.max(l - Ax))
+    # (no sign property for the duals: polish solves an equality-constrained QP on the guessed active set and, like the
+    # reference's, does not re-check multiplier signs)
+    # warm re-solve: exits at the first check, like Mpc.Api's u(cold) == u(warm) (tests/test_mpc.cpp:73-118)
+    _, r2, o2, wp2 = _solve_both(sfb, oracle, pat, Pv, q, Av, l, u, warm=(o.x, o.y))
+    assert (r2.status == 0).all() and (r2.iter[wp2] == o2.iter[wp2]).all()
+    same = wp2 & (r2.active == o2.active).all(axis=1)
+    assert same.mean() > 0.9 and rel_err(r2.x[same], o2.x[same]).max() <= REL_F64
+
+
+def test_parity_mpc_cfg3_shape(sfb, oracle):
+    # BASELINE.json configs[2] shape: SE(2) x R^3 bus, K = 50 -> 13 intervals x 4 nodes, n = m = 422 (SURVEY D5)
+    from smooth_feedback_b200.generators import mpc_structured_batch, mpc_structured_pattern
+
+    pat = mpc_structured_pattern()
+    assert pat["n"] == 422 and pat["m"] == 422
+    Pv, q, Av, l, u = mpc_structured_batch(pat, 40, seed=5)
+    sp, r, o, wp = _solve_both(sfb, oracle, pat, Pv, q, Av, l, u)
+    assert sp.nnzL < 16000  # minimum-degree fill (dense would be 88831)
+    assert (o.status == 0).all()
+    _assert_parity(r, o, wp, REL_F64, min_well_posed=0.85)
+
+
+def test_fp32_against_fp64_oracle(sfb, oracle):
+    from smooth_feedback_b200.generators import mpc_structured_batch, mpc_structured_pattern
+
+    pat = mpc_structured_pattern(Nx=3, Nu=2, nivals=3, Ki=4)
+    Pv, q, Av, l, u = mpc_structured_batch(pat, 64, seed=4)
+    _, r, o, wp = _solve_both(sfb, oracle, pat, Pv, q, Av, l, u, prm_kw=dict(polish=False), dtype=np.float32)
+    assert (r.status == 0).mean() > 0.95
+    ok = (r.status == 0) & (o.status == 0)
+    assert np.median(rel_err(r.x[ok], o.x[ok])) <= REL_F32
+
+
+def test_device_path_equals_host_path_and_errors(sfb):
+    import torch
+
+    from smooth_feedback_b200.generators import random_sparse_qp_numpy
+
+    pat, Pv, q, Av, l, u = random_sparse_qp_numpy(70, 20, 30, density=0.2, seed=8)
+    sp = sfb.SparsePattern(pat["n"], pat["m"], pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], pat["A_colidx"])
+    prm = sfb.QPSolverParams(max_iter=4000)
+    rh = sfb.solve_sparse_batch(sp, Pv, q, Av, l, u, prm)
+    t = lambda a: torch.from_numpy(a).cuda()
+    rd = sfb.solve_sparse_batch(sp, t(Pv), t(q), t(Av), t(l), t(u), prm)
+    torch.cuda.synchronize()
+    assert np.array_equal(rh.status, rd.status.cpu().numpy()) and np.array_equal(rh.iter, rd.iter.cpu().numpy().astype(np.uint32))
+    assert np.array_equal(rh.x, rd.x.cpu().numpy()) and np.array_equal(rh.y, rd.y.cpu().numpy())
+    with pytest.raises(sfb.SfbError):  # column index out of range
+        bad = pat["A_colidx"].copy(); bad[0] = pat["n"]
+        sfb.SparsePattern(pat["n"], pat["m"], pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], bad)
+    with pytest.raises(sfb.SfbError):  # host / device pointers mixed
+        sfb.solve_sparse_batch(sp, t(Pv), t(q), t(Av), t(l), t(u), prm, out=rh)
+
+
+def test_full_size_properties_cfg3(sfb):
+    """BASELINE.json configs[2] at full size (MPC structure n = m = 422, batch 8192; fp64 and fp32): size-independent
+    properties.  The batch tiles 256 distinct agents, so replicas must agree bit for bit wherever they sit in the batch
+    (tile / lane independence), every instance must be Optimal with the KKT conditions of the ORIGINAL problem satisfied,
+    and a warm re-solve must exit at the first check (iter 2) with the same solution."""
+    import torch
+
+    from smooth_feedback_b200.generators import mpc_structured_batch, mpc_structured_pattern, sparse_to_dense
+
+    pat = mpc_structured_pattern()
+    base, B = 256, 8192
+    Pv, q, Av, l, u = mpc_structured_batch(pat, base, seed=9)
+    rep = B // base
+    t = lambda a, dt=torch.float64: torch.from_numpy(np.tile(a, (rep, 1))).to("cuda:0", dtype=dt).contiguous()
+    sp = sfb.SparsePattern(pat["n"], pat["m"], pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], pat["A_colidx"])
+    prm = sfb.QPSolverParams(max_iter=4000)
+    r = sfb.solve_sparse_batch(sp, t(Pv), t(q), t(Av), t(l), t(u), prm)
+    torch.cuda.synchronize()
+    st, it = r.status.cpu().numpy(), r.iter.cpu().numpy()
+    x, y = r.x.cpu().numpy(), r.y.cpu().numpy()
+    assert (st == 0).all() and ((r.flags.cpu().numpy() & 1) == 1).all()
+    # replicas identical
+    assert np.array_equal(x.reshape(rep, base, -1), np.broadcast_to(x[:base], (rep, base, x.shape[1])))
+    assert np.array_equal(it.reshape(rep, base), np.broadcast_to(it[:base], (rep, base)))
+    # KKT of the original problem on the distinct agents: stationarity with sym(triu P), primal feasibility (no sign property for the duals:
+    # polish solves an equality-constrained QP on the guessed active set and, like the reference, does not re-check signs)
+    P, A = sparse_to_dense(pat, Pv, Av)
+    Ps = np.triu(P) + np.transpose(np.triu(P, 1), (0, 2, 1))
+    xb, yb = x[:base], y[:base]
+    stat = np.einsum("bij,bj->bi", Ps, xb) + q + np.einsum("bji,bj->bi", A, yb)
+    assert np.abs(stat).max() <= 1e-8 * max(1.0, np.abs(q).max())
+    Ax = np.einsum("bij,bj->bi", A, xb)
+    # polish (like the reference's) enforces the rows it found ACTIVE exactly; a row the eps = 1e-3 ADMM iterate left
+    # inactive may end up violated at that level, so feasibility is an eps-level property, equality rows are exact
+    eq = np.isclose(l, u)
+    assert np.abs(Ax - u)[eq].max() <= 1e-7 * (1.0 + np.abs(u[eq]).max())
+    assert (Ax <= u + 2e-2).all() and (Ax >= l - 2e-2).all(), (np.max(Ax - u), np.max(l - Ax))
+    # warm re-solve
+    r2 = sfb.solve_sparse_batch(sp, t(Pv), t(q), t(Av), t(l), t(u), prm, warm_x=r.x, warm_y=r.y)
+    torch.cuda.synchronize()
+    assert (r2.status.cpu().numpy() == 0).all() and (r2.iter.cpu().numpy() == 2).mean() > 0.95
+    assert np.quantile(rel_err(r2.x.cpu().numpy(), x), 0.95) <= 1e-6  # a few re-solves pick a different active set in the polish
+    # fp32 (BASELINE configs[2] is quoted in fp32): same workload within the fp32 tolerance of the fp64 result
+    f32 = torch.float32
+    r32 = sfb.solve_sparse_batch(sp, t(Pv, f32), t(q, f32), t(Av, f32), t(l, f32), t(u, f32), sfb.QPSolverParams(max_iter=4000, polish=False))
+    r64 = sfb.solve_sparse_batch(sp, t(Pv), t(q), t(Av), t(l), t(u), sfb.QPSolverParams(max_iter=4000, polish=False))
+    torch.cuda.synchronize()
+    ok = (r32.status.cpu().numpy() == 0) & (r64.status.cpu().numpy() == 0)
+    assert ok.mean() > 0.95
+    e32 = rel_err(r32.x.cpu().numpy().astype(np.float64)[ok], r64.x.cpu().numpy()[ok])
+    assert np.median(e32) <= REL_F32 and np.quantile(e32, 0.95) <= 10 * REL_F32
