@@ -104,23 +104,54 @@ def solve_dense_batch_sharded(P_cm, q, A_cm, l, u, prm=None, group=None, solver:
     return unpack_qp_results(all_gather_rows(packed, B, group), n, m)
 
 
+def solve_sparse_batch_sharded(pattern, P_vals, q, A_vals, l, u, prm=None, group=None, solver: Optional[Callable] = None,
+                               warm_x=None, warm_y=None) -> GatheredQP:
+    """Sparse shared-pattern counterpart of `solve_dense_batch_sharded` (the MPC fleet: one pattern, agents sharded over
+    ranks).  `pattern` is this rank's `SparsePattern` (each rank analyses the pattern on its own device); `solver`
+    defaults to `solve_sparse_batch`, the CPU tests inject a stand-in with the same signature."""
+    import torch.distributed as dist
+
+    if solver is None:
+        from .qp_sparse import solve_sparse_batch as solver
+    B, n = q.shape
+    m = l.shape[1]
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lo, hi = shard_range(B, world, rank)
+    sl = slice(lo, hi)
+    kw = {}
+    if warm_x is not None:
+        kw = dict(warm_x=warm_x[sl].contiguous(), warm_y=warm_y[sl].contiguous())
+    res = solver(pattern, P_vals[sl].contiguous(), q[sl].contiguous(), A_vals[sl].contiguous(), l[sl].contiguous(),
+                 u[sl].contiguous(), prm, **kw)
+    packed = pack_qp_results(res, n, m)
+    return unpack_qp_results(all_gather_rows(packed, B, group), n, m)
+
+
 def ekf_step_sharded(P_cm, A_cm, Q_cm, H_cm, R_cm, innov, tau: float, group=None, predict: Optional[Callable] = None,
                      update: Optional[Callable] = None):
-    """One EKF predict + update for a replicated batch of filters: shard, run, all-gather {delta, P_new}."""
+    """One EKF predict + update for a replicated batch of filters: shard, run, all-gather {delta, P_new}.
+
+    Default: the fused single-pass kernel (`ekf_step_batch`); `predict` / `update` stand-ins (CPU tests) run the two
+    halves separately."""
     import torch
     import torch.distributed as dist
 
-    if predict is None:
-        from .ekf import ekf_predict_batch as predict
-    if update is None:
-        from .ekf import ekf_update_batch as update
     B, d, _ = P_cm.shape
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     lo, hi = shard_range(B, world, rank)
     sl = slice(lo, hi)
     c = lambda t: t[sl].contiguous()
-    Pp = predict(c(P_cm), c(A_cm), c(Q_cm), tau)
-    delta, Pu = update(Pp, c(H_cm), c(R_cm), c(innov))
+    if predict is None and update is None:
+        from .ekf import ekf_step_batch
+
+        delta, Pu = ekf_step_batch(c(P_cm), c(A_cm), c(Q_cm), tau, c(H_cm), c(R_cm), c(innov))
+    else:
+        if predict is None:
+            from .ekf import ekf_predict_batch as predict
+        if update is None:
+            from .ekf import ekf_update_batch as update
+        Pp = predict(c(P_cm), c(A_cm), c(Q_cm), tau)
+        delta, Pu = update(Pp, c(H_cm), c(R_cm), c(innov))
     packed = torch.cat([delta, Pu.reshape(hi - lo, d * d)], dim=1)
     out = all_gather_rows(packed, B, group)
     return out[:, :d], out[:, d:].reshape(B, d, d)

@@ -49,8 +49,20 @@ def _worker(rank, world, port, B, n, m, q_out):
             d_, Pn = orc.ekf_update_batch(cm(P_.numpy()), cm(H_.numpy()), cm(R_.numpy()), inn.numpy())
             return t(d_), t(cm(Pn))
         delta, Pu = sharding.ekf_step_sharded(t(cm(Pk)), t(cm(Ak)), t(cm(Qk)), t(cm(Hk)), t(cm(Rk)), t(innov), 0.1, predict=pred, update=upd)
+        # sparse shared-pattern fleet: stand-in = densified oracle
+        from smooth_feedback_b200.generators import mpc_structured_batch, mpc_structured_pattern, sparse_to_dense
+
+        pat = mpc_structured_pattern(Nx=2, Nu=1, nivals=2, Ki=3)
+        Pv, qs, Av, ls, us = mpc_structured_batch(pat, B, seed=7)
+
+        def sparse_solver(pattern, P_vals, q_, A_vals, l_, u_, prm=None, warm_x=None, warm_y=None):
+            Pd, Ad = sparse_to_dense(pattern, P_vals.numpy(), A_vals.numpy())
+            return _oracle_solver(t(to_colmajor(Pd)), q_, t(to_colmajor(Ad)), l_, u_, prm, warm_x, warm_y)
+
+        gs = sharding.solve_sparse_batch_sharded(pat, t(Pv), t(qs), t(Av), t(ls), t(us), None, solver=sparse_solver)
         if rank == 0:
-            q_out.put((g.x.numpy(), g.y.numpy(), g.obj.numpy(), g.status.numpy(), g.iter.numpy(), delta.numpy(), Pu.numpy()))
+            q_out.put((g.x.numpy(), g.y.numpy(), g.obj.numpy(), g.status.numpy(), g.iter.numpy(), delta.numpy(), Pu.numpy(),
+                       gs.x.numpy(), gs.status.numpy(), gs.iter.numpy()))
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -79,6 +91,14 @@ def test_sharded_solve_equals_single_process(oracle, B):
     oPp = oracle.ekf_predict_batch(Pk, Ak, Qk, 0.1)
     od, oPu = oracle.ekf_update_batch(oPp, Hk, Rk, innov)
     assert np.array_equal(got[5], od) and np.array_equal(np.swapaxes(got[6], 1, 2), oPu)
+    # sparse fleet: sharded == single process
+    from smooth_feedback_b200.generators import mpc_structured_batch, mpc_structured_pattern, sparse_to_dense
+
+    pat = mpc_structured_pattern(Nx=2, Nu=1, nivals=2, Ki=3)
+    Pv, qs, Av, ls, us = mpc_structured_batch(pat, B, seed=7)
+    Pd, Ad = sparse_to_dense(pat, Pv, Av)
+    os_ = oracle.qp_solve_batch(Pd, qs, Ad, ls, us, params=oracle.default_params(max_iter=4000))
+    assert np.array_equal(got[7], os_.x) and np.array_equal(got[8], os_.status) and np.array_equal(got[9], os_.iter.astype(np.int64))
 
 
 def test_shard_range_partitions_exactly():
