@@ -48,6 +48,7 @@ struct SparseSymbolic
   // padded sweep schedules (TW == 8 kernel): a sweep is a list of STEPS of exactly kStepWidth entries; a row of L takes
   // ceil(len / kStepWidth) consecutive steps.  meta = (row << 1) | last_step_of_row; col / slot are padded with 0 / -1.
   static constexpr int kStepWidth = 32;
+  static constexpr int kStepPad = 4;  // == kSpDepth on the device
   std::vector<int> FS_meta, FS_col, FS_slot;  // forward:  rows ascending, rows without entries skipped
   std::vector<int> BS_meta, BS_col, BS_slot;  // backward: rows descending, every row present (1 / D scaling)
   std::vector<int> PC_ptr;                    // P_colptr re-indexed by PERMUTED column (entries regrouped in PC_slot)
@@ -254,6 +255,16 @@ inline bool sparse_analyze(int n, int m, const int32_t* P_colptr, const int32_t*
       for (int e = S.L_colptr[k]; e < S.L_colptr[k + 1]; ++e) ent.push_back({S.L_row[e], e});
       emit(k, ent, true, S.BS_meta, S.BS_col, S.BS_slot);
     }
+    // pad both lists to a multiple of kStepPad with no-op steps (no entries, not a last step): the device loop is
+    // unrolled kStepPad times without bounds checks
+    auto pad = [&](std::vector<int>& meta, std::vector<int>& col, std::vector<int>& slt) {
+      while (meta.size() % SparseSymbolic::kStepPad != 0) {
+        meta.push_back(0);
+        for (int i = 0; i < SparseSymbolic::kStepWidth; ++i) { col.push_back(0); slt.push_back(-1); }
+      }
+    };
+    pad(S.FS_meta, S.FS_col, S.FS_slot);
+    pad(S.BS_meta, S.BS_col, S.BS_slot);
   }
 
   // ---- right-looking update schedule ----

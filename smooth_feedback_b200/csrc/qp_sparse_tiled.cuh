@@ -57,13 +57,12 @@ struct SpPattern
 
 constexpr int kSpStep = 32;  // == SparseSymbolic::kStepWidth
 constexpr int kSpDepth = 4;  // sweep steps in flight per lane
-constexpr int kSpPrefetch = 24;  // L2 prefetch distance of the sweeps, in steps
 constexpr int kSpPolishRefine = 1;  // refinement steps on Hp per application of the reduced polish solve
 
 // scalars per instance of the W block: factor (nnzL + n) followed by its two stream-ordered copies
 __host__ __device__ inline size_t sp_w_len(const SpPattern& p, int tw)
 {
-  const size_t copies = (tw < 32) ? (size_t)(p.nFS + p.nBS) * kSpStep : 2 * (size_t)p.nnzL;
+  const size_t copies = (tw < 32) ? (size_t)(p.nFS + p.nBS) * kSpStep + (size_t)p.nBS : 2 * (size_t)p.nnzL;
   return (size_t)p.nnzL + p.n + copies;
 }
 __host__ __device__ inline size_t sp_fwd_len(const SpPattern& p, int tw) { return (tw < 32) ? (size_t)p.nFS * kSpStep : (size_t)p.nnzL; }
@@ -100,10 +99,10 @@ template <typename T, int TW> struct SpSolver
   int n, m, r;
   unsigned gmask;
   V A, P, W, LRW, LBW;  // LRW / LBW: the factor's values again, in the forward / backward sweep's stream order
+  V LBD;                // 1 / D of the row of every backward step (TW < 32)
   V q, qb, x, xold, v, sx, t1, t2, t3, t4;  // n-vectors (permuted order)
   V l, u, sy, rho, rinv, z, y, yold, w;    // m-vectors
   T c;
-  int nsteps_ = 0;  // length of the sweep in progress (prefetch bound)
   int inst_ = 0;    // instance slot inside the tile
 
   // smem_v: [n][TW] scalars of shared memory for the solve vector (TW == 8 only, nullptr otherwise)
@@ -120,6 +119,7 @@ template <typename T, int TW> struct SpSolver
     W.p = a.wsW + (size_t)tile * sp_w_len(S, TW) * TW + inst;
     LRW.p = W.p + (size_t)(S.nnzL + n) * TW;
     LBW.p = LRW.p + sp_fwd_len(S, TW) * TW;
+    LBD.p = LBW.p + (size_t)S.nBS * kSpStep * TW;
     T* nv = a.wsN + (size_t)tile * kSpNV * n * TW + inst;
     T* mv = a.wsM + (size_t)tile * kSpMV * m * TW + inst;
     auto N = [&](int k) { return V{nv + (size_t)k * n * TW}; };
@@ -343,6 +343,7 @@ template <typename T, int TW> struct SpSolver
     if (RL > 1) {
       copy_stream(LRW, S.FS_slot, S.nFS * kSpStep);
       copy_stream(LBW, S.BS_slot, S.nBS * kSpStep);
+      for (int st = r; st < S.nBS; st += RL) LBD[st] = W[nL + (S.BS_meta[st] >> 1)];
     } else {
       copy_stream(LRW, S.LR_slot, nL);
       copy_stream(LBW, S.LB_slot, nL);
@@ -372,60 +373,62 @@ template <typename T, int TW> struct SpSolver
     int meta;
     int j[SU];
     T a[SU];
-    T vk, dk;
+    T dk;
   };
-  template <bool FWD> __device__ __forceinline__ void step_load(StepBuf& B, int st, const int* __restrict__ meta,
-                                                                const int* __restrict__ col, const V& LW) const
+  // The sweep is instruction-bound per warp (one warp's ~100 dependent instructions per step, not memory latency, set
+  // the pace: measured 1350 cycles per step), so the step is kept lean: every address is a running pointer plus an
+  // immediate, nothing depends on another load, the step lists are padded to a multiple of kSpDepth (no bounds checks).
+  template <bool FWD> __device__ __forceinline__ void step_load(StepBuf& B, const int* __restrict__ pm, const int* __restrict__ pc,
+                                                                const T* __restrict__ pa, const T* __restrict__ pd) const
   {
-    B.meta = meta[st];
-    const int base = st * kSpStep + r;
+    B.meta = *pm;
 #pragma unroll
     for (int t = 0; t < SU; ++t) {
-      B.j[t] = col[base + t * RL];
-      B.a[t] = LW[base + t * RL];
+      B.j[t] = pc[t * RL];
+      B.a[t] = pa[(size_t)t * RL * TW];
     }
-    // the register pipeline covers an L2 hit, not a DRAM round trip under load: pull the factor entries of a later
-    // step into L2 now (no register or shared-memory cost)
-    if (st + kSpPrefetch < nsteps_) {
-#pragma unroll
-      for (int t = 0; t < SU; ++t)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(&LW[base + kSpPrefetch * kSpStep + t * RL]));
-    }
-    const int k = B.meta >> 1;
-    B.vk = v_shared()[(size_t)k * TW];  // row k of the right-hand side is only written at its own (last) step
-    B.dk = FWD ? T(1) : W[S.nnzL + k];
+    B.dk = FWD ? T(1) : *pd;
   }
   template <bool FWD> __device__ __forceinline__ void step_apply(const StepBuf& B, T& acc)
   {
     T* sv = v_shared();
+    const int k = B.meta >> 1;
+    const T vk = sv[k * TW];  // row k of the right-hand side is only written at its own (last) step
 #pragma unroll
-    for (int t = 0; t < SU; ++t) acc += B.a[t] * sv[(size_t)B.j[t] * TW];  // padding carries a = 0, j = 0
+    for (int t = 0; t < SU; ++t) acc += B.a[t] * sv[B.j[t] * TW];  // padding carries a = 0, j = 0
     if (B.meta & 1) {  // last step of the row (warp-uniform)
       const T s = gsum(acc);
-      if (r == 0) sv[(size_t)(B.meta >> 1) * TW] = FWD ? B.vk - s : B.vk * B.dk - s;
+      if (r == 0) sv[k * TW] = FWD ? vk - s : vk * B.dk - s;
       acc = T(0);
       gsync();
     }
   }
-  // kSpDepth step buffers rotate through a loop unrolled kSpDepth times (static register indexing, no moves): a step's
-  // operands are requested kSpDepth steps (~ kSpDepth x 300 cycles) before they are used
+  // kSpDepth step buffers rotate through a loop unrolled kSpDepth times (static register indexing, no moves)
   template <bool FWD> __device__ void sweep_steps(int nsteps, const int* __restrict__ meta, const int* __restrict__ col, const V& LW)
   {
-    if (nsteps == 0) return;
-    nsteps_ = nsteps;
+    if (nsteps == 0) return;  // nsteps is a multiple of kSpDepth (host padding)
+    const int* pm = meta;
+    const int* pc = col + r;
+    const T* pa = LW.p + (size_t)r * TW;
+    const T* pd = LBD.p;
     StepBuf b[kSpDepth];
 #pragma unroll
-    for (int d = 0; d < kSpDepth; ++d) step_load<FWD>(b[d], d < nsteps ? d : nsteps - 1, meta, col, LW);
+    for (int d = 0; d < kSpDepth; ++d) {
+      step_load<FWD>(b[d], pm, pc, pa, pd);
+      pm += 1; pc += kSpStep; pa += (size_t)kSpStep * TW; pd += TW;
+    }
     T acc = T(0);
-    for (int st = 0; st < nsteps; st += kSpDepth) {
+    int st = 0;
+    for (; st + kSpDepth < nsteps; st += kSpDepth) {
 #pragma unroll
       for (int d = 0; d < kSpDepth; ++d) {
-        if (st + d < nsteps) {
-          step_apply<FWD>(b[d], acc);
-          if (st + d + kSpDepth < nsteps) step_load<FWD>(b[d], st + d + kSpDepth, meta, col, LW);
-        }
+        step_apply<FWD>(b[d], acc);
+        step_load<FWD>(b[d], pm, pc, pa, pd);
+        pm += 1; pc += kSpStep; pa += (size_t)kSpStep * TW; pd += TW;
       }
     }
+#pragma unroll
+    for (int d = 0; d < kSpDepth; ++d) step_apply<FWD>(b[d], acc);
   }
   // TW == 32: one lane per instance, rows walked with batched gathers over the contiguous copies
   template <bool FWD> __device__ void sweep_rows(const int* __restrict__ ptr, const int* __restrict__ col, const V& LW)
