@@ -389,16 +389,29 @@ template <typename T, int TW> struct SpSolver
     }
     B.dk = FWD ? T(1) : *pd;
   }
-  template <bool FWD> __device__ __forceinline__ void step_apply(const StepBuf& B, T& acc)
+  // shared-memory accesses with 32-bit addresses (one shift-add per gather instead of 64-bit pointer arithmetic)
+  static __device__ __forceinline__ T lds(unsigned addr)
   {
-    T* sv = v_shared();
-    const int k = B.meta >> 1;
-    const T vk = sv[k * TW];  // row k of the right-hand side is only written at its own (last) step
+    T val;
+    if constexpr (sizeof(T) == 8) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(val) : "r"(addr));
+    else asm volatile("ld.shared.f32 %0, [%1];" : "=f"(val) : "r"(addr));
+    return val;
+  }
+  static __device__ __forceinline__ void sts(unsigned addr, T val)
+  {
+    if constexpr (sizeof(T) == 8) asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(val) : "memory");
+    else asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(val) : "memory");
+  }
+  template <bool FWD> __device__ __forceinline__ void step_apply(const StepBuf& B, T& acc, unsigned sv)
+  {
+    constexpr unsigned kStride = TW * sizeof(T);
+    const unsigned ak = sv + (unsigned)(B.meta >> 1) * kStride;
+    const T vk = lds(ak);  // row k of the right-hand side is only written at its own (last) step
 #pragma unroll
-    for (int t = 0; t < SU; ++t) acc += B.a[t] * sv[B.j[t] * TW];  // padding carries a = 0, j = 0
+    for (int t = 0; t < SU; ++t) acc += B.a[t] * lds(sv + (unsigned)B.j[t] * kStride);  // padding carries a = 0, j = 0
     if (B.meta & 1) {  // last step of the row (warp-uniform)
       const T s = gsum(acc);
-      if (r == 0) sv[k * TW] = FWD ? vk - s : vk * B.dk - s;
+      if (r == 0) sts(ak, FWD ? vk - s : vk * B.dk - s);
       acc = T(0);
       gsync();
     }
@@ -418,17 +431,18 @@ template <typename T, int TW> struct SpSolver
       pm += 1; pc += kSpStep; pa += (size_t)kSpStep * TW; pd += TW;
     }
     T acc = T(0);
+    const unsigned sv = (unsigned)__cvta_generic_to_shared(v_shared());
     int st = 0;
     for (; st + kSpDepth < nsteps; st += kSpDepth) {
 #pragma unroll
       for (int d = 0; d < kSpDepth; ++d) {
-        step_apply<FWD>(b[d], acc);
+        step_apply<FWD>(b[d], acc, sv);
         step_load<FWD>(b[d], pm, pc, pa, pd);
         pm += 1; pc += kSpStep; pa += (size_t)kSpStep * TW; pd += TW;
       }
     }
 #pragma unroll
-    for (int d = 0; d < kSpDepth; ++d) step_apply<FWD>(b[d], acc);
+    for (int d = 0; d < kSpDepth; ++d) step_apply<FWD>(b[d], acc, sv);
   }
   // TW == 32: one lane per instance, rows walked with batched gathers over the contiguous copies
   template <bool FWD> __device__ void sweep_rows(const int* __restrict__ ptr, const int* __restrict__ col, const V& LW)
