@@ -51,6 +51,10 @@ struct SparseSymbolic
   static constexpr int kStepPad = 4;  // == kSpDepth on the device
   std::vector<int> FS_meta, FS_col, FS_slot;  // forward:  rows ascending, rows without entries skipped
   std::vector<int> BS_meta, BS_col, BS_slot;  // backward: rows descending, every row present (1 / D scaling)
+  // padded row / column streams of A for the pipelined SpMV passes (TW < 32): every row of A padded to WR entries, every
+  // column to WA entries (col / row index 0 and slot -1 on padding), rows and columns padded to a multiple of 32
+  int WR = 0, WA = 0, m_pad = 0, n_pad = 0;   // WR == 0: rows / columns too long, the kernel keeps the generic passes
+  std::vector<int> RP_col, RP_slot, ATP_row, ATP_slot;
   std::vector<int> PC_ptr;                    // P_colptr re-indexed by PERMUTED column (entries regrouped in PC_slot)
   std::vector<int> PC_slot;
   long long flops = 0;                // multiply-adds of the numeric factorisation
@@ -227,6 +231,34 @@ inline bool sparse_analyze(int n, int m, const int32_t* P_colptr, const int32_t*
     for (int e = 0; e < S.nnzP; ++e) trip.push_back({S.P_colp[e], S.P_rowp[e], e});
     std::vector<int> dummy;
     build_rows(n, trip, S.PC_ptr, dummy, S.PC_slot);
+  }
+
+  // ---- padded SpMV streams ----
+  {
+    int wr = 0, wa = 0;
+    for (int i = 0; i < m; ++i) wr = std::max(wr, S.A_rowptr[i + 1] - S.A_rowptr[i]);
+    for (int j = 0; j < n; ++j) wa = std::max(wa, S.AT_ptr[j + 1] - S.AT_ptr[j]);
+    wr = (wr + 7) & ~7;  // whole chunks of 8 entries (kSpU on the device)
+    wa = (wa + 7) & ~7;
+    if (m > 0 && wr > 0 && wr <= 32 && wa > 0 && wa <= 64) {
+      S.WR = wr; S.WA = wa;
+      S.m_pad = (m + 31) / 32 * 32;
+      S.n_pad = (n + 31) / 32 * 32;
+      S.RP_col.assign((size_t)S.m_pad * wr, 0);
+      S.RP_slot.assign((size_t)S.m_pad * wr, -1);
+      for (int i = 0; i < m; ++i)
+        for (int e = S.A_rowptr[i], t = 0; e < S.A_rowptr[i + 1]; ++e, ++t) {
+          S.RP_col[(size_t)i * wr + t] = S.A_col[e];
+          S.RP_slot[(size_t)i * wr + t] = e;
+        }
+      S.ATP_row.assign((size_t)S.n_pad * wa, 0);
+      S.ATP_slot.assign((size_t)S.n_pad * wa, -1);
+      for (int j = 0; j < n; ++j)
+        for (int e = S.AT_ptr[j], t = 0; e < S.AT_ptr[j + 1]; ++e, ++t) {
+          S.ATP_row[(size_t)j * wa + t] = S.AT_row[e];
+          S.ATP_slot[(size_t)j * wa + t] = S.AT_slot[e];
+        }
+    }
   }
 
   // ---- padded sweep schedules ----

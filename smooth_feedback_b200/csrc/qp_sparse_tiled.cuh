@@ -39,7 +39,7 @@
 namespace sfb {
 
 constexpr int kSpNV = 10;  // n-vectors of the working set
-constexpr int kSpMV = 9;   // m-vectors
+constexpr int kSpMV = 11;  // m-vectors
 constexpr int kSpU = 8;    // independent loads kept in flight per lane in the gather / update loops
 
 struct SpPattern
@@ -53,6 +53,9 @@ struct SpPattern
   // padded sweep schedules (TW == 8): nFS / nBS steps of kSpStep entries each
   const int *FS_meta, *FS_col, *FS_slot, *BS_meta, *BS_col, *BS_slot;
   int nFS, nBS;
+  // padded row / column streams of A (TW < 32; WR == 0: not available for this pattern)
+  const int *RP_col, *RP_slot, *ATP_row, *ATP_slot;
+  int WR, WA, m_pad, n_pad;
 };
 
 constexpr int kSpStep = 32;  // == SparseSymbolic::kStepWidth
@@ -64,6 +67,11 @@ __host__ __device__ inline size_t sp_w_len(const SpPattern& p, int tw)
 {
   const size_t copies = (tw < 32) ? (size_t)(p.nFS + p.nBS) * kSpStep + (size_t)p.nBS : 2 * (size_t)p.nnzL;
   return (size_t)p.nnzL + p.n + copies;
+}
+// scalars per instance of the A block: Abar (CSR order) followed by its padded row-stream and column-stream copies
+__host__ __device__ inline size_t sp_a_len(const SpPattern& p, int tw)
+{
+  return (size_t)p.nnzA + ((tw < 32 && p.WR > 0) ? (size_t)p.m_pad * p.WR + (size_t)p.n_pad * p.WA : 0);
 }
 __host__ __device__ inline size_t sp_fwd_len(const SpPattern& p, int tw) { return (tw < 32) ? (size_t)p.nFS * kSpStep : (size_t)p.nnzL; }
 
@@ -100,6 +108,8 @@ template <typename T, int TW> struct SpSolver
   unsigned gmask;
   V A, P, W, LRW, LBW;  // LRW / LBW: the factor's values again, in the forward / backward sweep's stream order
   V LBD;                // 1 / D of the row of every backward step (TW < 32)
+  V APW, ATW;           // Abar again: rows padded to WR entries, columns padded to WA entries (TW < 32)
+  V lo, hi;             // scaled bounds sy l, sy u
   V q, qb, x, xold, v, sx, t1, t2, t3, t4;  // n-vectors (permuted order)
   V l, u, sy, rho, rinv, z, y, yold, w;    // m-vectors
   T c;
@@ -114,7 +124,9 @@ template <typename T, int TW> struct SpSolver
     gmask = 0u;
 #pragma unroll
     for (int k = 0; k < RL; ++k) gmask |= 1u << (inst + k * TW);
-    A.p = a.wsA + (size_t)tile * S.nnzA * TW + inst;
+    A.p = a.wsA + (size_t)tile * sp_a_len(S, TW) * TW + inst;
+    APW.p = A.p + (size_t)S.nnzA * TW;
+    ATW.p = APW.p + (size_t)S.m_pad * S.WR * TW;
     P.p = a.wsP + (size_t)tile * S.nnzP * TW + inst;
     W.p = a.wsW + (size_t)tile * sp_w_len(S, TW) * TW + inst;
     LRW.p = W.p + (size_t)(S.nnzL + n) * TW;
@@ -125,7 +137,7 @@ template <typename T, int TW> struct SpSolver
     auto N = [&](int k) { return V{nv + (size_t)k * n * TW}; };
     auto M = [&](int k) { return V{mv + (size_t)k * m * TW}; };
     q = N(0); qb = N(1); x = N(2); xold = N(3); v = N(4); sx = N(5); t1 = N(6); t2 = N(7); t3 = N(8); t4 = N(9);
-    l = M(0); u = M(1); sy = M(2); rho = M(3); rinv = M(4); z = M(5); y = M(6); yold = M(7); w = M(8);
+    l = M(0); u = M(1); sy = M(2); rho = M(3); rinv = M(4); z = M(5); y = M(6); yold = M(7); w = M(8); lo = M(9); hi = M(10);
     if (smem_v != nullptr) v.p = smem_v + inst;  // the solve vector is gathered from ~40 times per row sweep: keep it on chip
     c = T(1);
   }
@@ -506,6 +518,114 @@ template <typename T, int TW> struct SpSolver
     return gather_sum(S.A_rowptr[i], S.A_rowptr[i + 1], 0, 1, S.A_col, [&](int e) { return Al[e]; }, [&](int j) { return vec[j]; });
   }
 
+  // ---------------------------------------------------------------- pipelined SpMV passes of the ADMM iteration (TW < 32)
+  // Rows (columns) of Abar are dealt round-robin to the RL lanes of an instance and padded to a fixed width, so every
+  // address is a running pointer plus an immediate; the operands of the NEXT row are requested before the current one is
+  // reduced (two register buffers, loop unrolled twice).
+  // fp64 at 128 registers spills in these loops and ends up slower than the generic passes (89.6 vs 81.7 ms at cfg3),
+  // fp32 gains 45 % (128k -> 186k solves/s): enabled for single precision only
+  __device__ __forceinline__ bool padded_passes() const { return RL > 1 && S.WR > 0 && sizeof(T) == 4; }
+
+  // A padded row (column) is a run of CHUNKS of kSpU entries; the flattened chunk stream of a lane is walked with two
+  // register buffers (loop unrolled twice): the operands of the next chunk are requested before the current one is used.
+  struct Chunk
+  {
+    int j[kSpU];
+    T a[kSpU];
+  };
+  static __device__ __forceinline__ void chunk_load(Chunk& B, const int*& pc, const T*& pa)
+  {
+#pragma unroll
+    for (int t = 0; t < kSpU; ++t) {
+      B.j[t] = pc[t];
+      B.a[t] = pa[(size_t)t * TW];
+    }
+    pc += kSpU;
+    pa += (size_t)kSpU * TW;
+  }
+  // walk `nslots` padded rows of `width` entries each (lane r owns rows r, r + RL, ...): dot(B, acc) accumulates one
+  // chunk, fin(slot, acc) closes a row
+  template <class DOT, class FIN>
+  __device__ __forceinline__ void walk_chunks(int nslots, int width, const int* idx, const T* val, DOT dot, FIN fin)
+  {
+    const int cpr = width / kSpU;          // chunks per row
+    const int total = nslots * cpr;        // chunks of this lane
+    const int* pc = idx + (size_t)r * width;
+    const T* pa = val + (size_t)r * width * TW;
+    const int skip = (RL - 1) * width;     // from the end of this lane's row to the start of its next one
+    Chunk b0, b1;
+    int c_in_row = 0, slot = 0;
+    auto advance_row = [&](int& cload) {   // called after loading a chunk: jump to the lane's next row at a row end
+      if (++cload == cpr) { cload = 0; pc += skip; pa += (size_t)skip * TW; }
+    };
+    int cload = 0;
+    chunk_load(b0, pc, pa); advance_row(cload);
+    T acc = T(0);
+    int q = 0;
+    auto consume = [&](const Chunk& B) {
+      dot(B, acc);
+      if (++c_in_row == cpr) { fin(slot, acc); acc = T(0); c_in_row = 0; ++slot; }
+    };
+    for (; q + 2 < total; q += 2) {
+      chunk_load(b1, pc, pa); advance_row(cload);
+      consume(b0);
+      chunk_load(b0, pc, pa); advance_row(cload);
+      consume(b1);
+    }
+    for (; q < total; ++q) {  // at most two chunks left
+      if (q + 1 < total) { chunk_load(b1, pc, pa); advance_row(cload); }
+      consume(b0);
+      b0 = b1;
+    }
+  }
+
+  // v[j] = sigma x[j] - qb[j] + sum_i Abar_ij w_i      (qp_solver.hpp:450-451, reduced system)
+  __device__ void rhs_pass(T sigma)
+  {
+    const V wl = w;
+    walk_chunks(S.n_pad / RL, S.WA, S.ATP_row, ATW.p,
+                [&](const Chunk& B, T& acc) {
+                  T g[kSpU];
+#pragma unroll
+                  for (int t = 0; t < kSpU; ++t) g[t] = wl[B.j[t]];  // padding: a = 0, row 0
+#pragma unroll
+                  for (int t = 0; t < kSpU; ++t) acc += B.a[t] * g[t];
+                },
+                [&](int slot, T acc) {
+                  const int j = r + slot * RL;
+                  if (j < n) v[j] = sigma * x[j] - qb[j] + acc;
+                });
+    gsync();
+  }
+
+  // zt = Abar_i . xt, then the z / y / w updates of row i      (qp_solver.hpp:470-477)
+  __device__ void row_pass(T alpha, T alpha_comp, bool chk)
+  {
+    const unsigned sv = (unsigned)__cvta_generic_to_shared(v_shared());
+    constexpr unsigned kStride = TW * sizeof(T);
+    walk_chunks(S.m_pad / RL, S.WR, S.RP_col, APW.p,
+                [&](const Chunk& B, T& acc) {
+#pragma unroll
+                  for (int t = 0; t < kSpU; ++t) acc += B.a[t] * lds(sv + (unsigned)B.j[t] * kStride);  // padding: a = 0, column 0
+                },
+                [&](int slot, T zt) {
+                  const int i = r + slot * RL;
+                  if (i < m) {
+                    const T zi = z[i], yi = y[i], ri = rho[i], rinvi = rinv[i];
+                    if (chk) yold[i] = yi;
+                    const T nu = ri * (zt - zi) + yi;
+                    T zn = alpha * (rinvi * nu) + alpha_comp * (rinvi * yi) + zi;  // :471-474
+                    zn = fmax(zn, lo[i]);
+                    zn = fmin(zn, hi[i]);
+                    const T yn = alpha_comp * yi + alpha * nu + ri * zi - ri * zn;  // :475-477
+                    y[i] = yn;
+                    z[i] = zn;
+                    w[i] = ri * zn - yn;
+                  }
+                });
+    gsync();
+  }
+
   // ---------------------------------------------------------------- check_stopping, qp_solver.hpp:574-644
   // Same evaluation as the dense kernel (qp_dense_group.cuh::check_stopping): A x_us = Sy^-1 (Abar x), A^T y_us = Sx^-1 Abar^T y / c.
   __device__ int check_stopping(const sfb_qp_params& prm)
@@ -749,7 +869,27 @@ template <typename T, int TW> struct SpSolver
         }
       }
     }
+    for (int i = r; i < m; i += RL) { lo[i] = sy[i] * l[i]; hi[i] = sy[i] * u[i]; }
     gsync();
+    if (padded_passes()) {  // padded row / column stream copies of Abar
+      const V Al = A;
+      auto copy_a = [&](const V& dst, const int* __restrict__ slot, int len) {
+        for (int e = r; e < len; e += kSpU * RL) {
+          int sl[kSpU];
+          T a0[kSpU];
+#pragma unroll
+          for (int k = 0; k < kSpU; ++k) sl[k] = (e + k * RL < len) ? slot[e + k * RL] : -1;
+#pragma unroll
+          for (int k = 0; k < kSpU; ++k) a0[k] = (sl[k] >= 0) ? Al[sl[k]] : T(0);
+#pragma unroll
+          for (int k = 0; k < kSpU; ++k)
+            if (e + k * RL < len) dst[e + k * RL] = a0[k];
+        }
+      };
+      copy_a(APW, S.RP_slot, S.m_pad * S.WR);
+      copy_a(ATW, S.ATP_slot, S.n_pad * S.WA);
+      gsync();
+    }
     assemble(sigma, rho);
     if (!factor()) code = SFB_QP_UNKNOWN;  // :433
     // ---- initial iterate  :436-445
@@ -774,7 +914,8 @@ template <typename T, int TW> struct SpSolver
     const unsigned sci = prm.stop_check_iter;
     unsigned iter = 0;
     for (; iter != a.max_iter_eff && code == kStatusUnset; ++iter) {
-      At_gather(w, v, [&](int j, T sum) { return sigma * x[j] - qb[j] + sum; });  // rhs = sigma x - qb + Abar^T w
+      if (padded_passes()) rhs_pass(sigma);
+      else At_gather(w, v, [&](int j, T sum) { return sigma * x[j] - qb[j] + sum; });  // rhs = sigma x - qb + Abar^T w
       solve();
       const bool chk = (iter % sci == 1u);
       for (int j = r; j < n; j += RL) {
@@ -782,21 +923,25 @@ template <typename T, int TW> struct SpSolver
         if (chk) xold[j] = xi;  // :465-468
         x[j] = alpha * v[j] + alpha_comp * xi;  // :470
       }
-      for (int i = r; i < m; i += RL) {
-        const T zi = z[i], yi = y[i], ri = rho[i], rinvi = rinv[i];  // issued before the dot: their latency overlaps it
-        const T lo = sy[i] * l[i], hi = sy[i] * u[i];
-        const T zt = A_row_dot(i, v);
-        if (chk) yold[i] = yi;
-        const T nu = ri * (zt - zi) + yi;
-        T zn = alpha * (rinvi * nu) + alpha_comp * (rinvi * yi) + zi;  // :471-474
-        zn = fmax(zn, lo);
-        zn = fmin(zn, hi);
-        const T yn = alpha_comp * yi + alpha * nu + ri * zi - ri * zn;  // :475-477
-        y[i] = yn;
-        z[i] = zn;
-        w[i] = ri * zn - yn;
+      if (padded_passes()) {
+        row_pass(alpha, alpha_comp, chk);
+      } else {
+        for (int i = r; i < m; i += RL) {
+          const T zi = z[i], yi = y[i], ri = rho[i], rinvi = rinv[i];  // issued before the dot: their latency overlaps it
+          const T lob = lo[i], hib = hi[i];
+          const T zt = A_row_dot(i, v);
+          if (chk) yold[i] = yi;
+          const T nu = ri * (zt - zi) + yi;
+          T zn = alpha * (rinvi * nu) + alpha_comp * (rinvi * yi) + zi;  // :471-474
+          zn = fmax(zn, lob);
+          zn = fmin(zn, hib);
+          const T yn = alpha_comp * yi + alpha * nu + ri * zi - ri * zn;  // :475-477
+          y[i] = yn;
+          z[i] = zn;
+          w[i] = ri * zn - yn;
+        }
+        gsync();
       }
-      gsync();
       if (chk) {
         code = check_stopping(prm);  // :488 (clobbers w, v, t1..t4, xold)
         if (code == kStatusUnset && prm.has_max_time) {
@@ -848,6 +993,8 @@ template <typename T, int TW> struct SpSolver
 };
 
 // One warp per tile of TW instances, one warp per CTA (small batches still spread over all SMs).
+// register budget: all instances of a batch should be resident at once with slack (TW = 4 at batch 8192 needs 14 warps
+// per SM; 144 registers fit exactly 14 and measured 1.6x slower because the last blocks wait for a second wave)
 template <typename T, int TW> __global__ void __launch_bounds__(32, TW == 8 ? 8 : 16) qp_sparse_tiled_kernel(const SpArgs<T> a)
 {
   extern __shared__ __align__(16) unsigned char sp_smem_raw[];

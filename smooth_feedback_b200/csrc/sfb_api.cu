@@ -517,7 +517,8 @@ int qp_sparse_solve_impl(sfb_context* h, const sfb_qp_sparse_pattern* pt, const 
   if (h->sparse_tw == 4 || h->sparse_tw == 8 || h->sparse_tw == 32) tw = h->sparse_tw;
   const long long tiles = (batch + tw - 1) / tw;
   const size_t wlen = sfb::sp_w_len(pt->pat, tw);  // factor + its stream-ordered copies
-  const size_t per_tile = ((size_t)S.nnzA + S.nnzP + wlen + (size_t)sfb::kSpNV * n + (size_t)sfb::kSpMV * m) * tw * sizeof(T);
+  const size_t alen = sfb::sp_a_len(pt->pat, tw);  // Abar + its padded row / column stream copies
+  const size_t per_tile = (alen + S.nnzP + wlen + (size_t)sfb::kSpNV * n + (size_t)sfb::kSpMV * m) * tw * sizeof(T);
   rc = ensure_scratch(h, h->sparse_ws, per_tile * (size_t)tiles, h->stream);
   if (rc != SFB_OK) return rc;
 
@@ -528,7 +529,7 @@ int qp_sparse_solve_impl(sfb_context* h, const sfb_qp_sparse_pattern* pt, const 
   a.max_iter_eff = prm->has_max_iter ? prm->max_iter : SFB_QP_DEVICE_ITER_CAP;
   {
     T* w = static_cast<T*>(h->sparse_ws.dev);
-    a.wsA = w; w += (size_t)tiles * S.nnzA * tw;
+    a.wsA = w; w += (size_t)tiles * alen * tw;
     a.wsP = w; w += (size_t)tiles * S.nnzP * tw;
     a.wsW = w; w += (size_t)tiles * wlen * tw;
     a.wsN = w; w += (size_t)tiles * sfb::kSpNV * n * tw;
@@ -861,7 +862,7 @@ int sfb_qp_sparse_analyze(sfb_handle_t h, int n, int m, const int32_t* P_colptr,
                                     &S.A_pair_tgt, &S.L_colptr, &S.L_row, &S.F_ptr, &S.F_tgt, &S.LR_ptr, &S.LR_col, &S.LR_slot,
                                     &S.AT_ptr, &S.AT_row, &S.AT_slot, &S.PR_ptr, &S.PR_col, &S.PR_slot, &S.PS_ptr, &S.PS_col,
                                     &S.PS_slot, &S.PC_ptr, &S.PC_slot, &S.LB_ptr, &S.LB_row, &S.LB_slot, &S.A_pair_ab, &S.F_ab, &S.FS_meta, &S.FS_col, &S.FS_slot,
-                                    &S.BS_meta, &S.BS_col, &S.BS_slot};
+                                    &S.BS_meta, &S.BS_col, &S.BS_slot, &S.RP_col, &S.RP_slot, &S.ATP_row, &S.ATP_slot};
   size_t total = 0;
   std::vector<size_t> off;
   for (auto* v : arrs) { off.push_back(total); total += (v->size() + 31) / 32 * 32; }
@@ -890,6 +891,8 @@ int sfb_qp_sparse_analyze(sfb_handle_t h, int n, int m, const int32_t* P_colptr,
   d.FS_meta = base + off[32]; d.FS_col = base + off[33]; d.FS_slot = base + off[34];
   d.BS_meta = base + off[35]; d.BS_col = base + off[36]; d.BS_slot = base + off[37];
   d.nFS = (int)S.FS_meta.size(); d.nBS = (int)S.BS_meta.size();
+  d.RP_col = base + off[38]; d.RP_slot = base + off[39]; d.ATP_row = base + off[40]; d.ATP_slot = base + off[41];
+  d.WR = S.WR; d.WA = S.WA; d.m_pad = S.m_pad; d.n_pad = S.n_pad;
   *out = p;
   return SFB_OK;
 }
