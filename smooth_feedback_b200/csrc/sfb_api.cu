@@ -511,8 +511,8 @@ int qp_sparse_solve_impl(sfb_context* h, const sfb_qp_sparse_pattern* pt, const 
   const sfb::SparseSymbolic& S = pt->sym;
   // tile width: the kernel is bound by memory latency, so resident warps are what buys throughput.  Large batches take
   // one lane per instance (32 instances per warp, no shuffles); below ~8 warps per SM of those, 4 instances per warp with
-  // 8 lanes cooperating on each (measured at n = m = 422: batch 8192 -> 71k solves/s with 4, 49k with 8, 14k with 32;
-  // batch 65536 -> 84k with 4, 95k with 32; profiles/README.md)
+  // 8 lanes cooperating on each (measured at n = m = 422, fp64: batch 8192 -> 99k solves/s with 4, ~60k with 8, 14k with
+  // 32; batch 65536 -> 100k with 32; profiles/README.md)
   int tw = (batch < 8ll * 32 * h->prop.multiProcessorCount) ? 4 : 32;
   if (h->sparse_tw == 4 || h->sparse_tw == 8 || h->sparse_tw == 32) tw = h->sparse_tw;
   const long long tiles = (batch + tw - 1) / tw;
