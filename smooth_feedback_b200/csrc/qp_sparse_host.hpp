@@ -244,7 +244,7 @@ inline bool sparse_analyze(int n, int m, const int32_t* P_colptr, const int32_t*
       S.WR = wr; S.WA = wa;
       S.m_pad = (m + 31) / 32 * 32;
       S.n_pad = (n + 31) / 32 * 32;
-      S.RP_col.assign((size_t)S.m_pad * wr, 0);
+      S.RP_col.assign((size_t)S.m_pad * wr, n);  // padding gathers the dummy slot v[n] == 0
       S.RP_slot.assign((size_t)S.m_pad * wr, -1);
       for (int i = 0; i < m; ++i)
         for (int e = S.A_rowptr[i], t = 0; e < S.A_rowptr[i + 1]; ++e, ++t) {
@@ -263,7 +263,7 @@ inline bool sparse_analyze(int n, int m, const int32_t* P_colptr, const int32_t*
 
   // ---- padded sweep schedules ----
   {
-    auto emit = [&](int k, const std::vector<std::pair<int, int>>& ent, bool keep_empty, std::vector<int>& meta,
+    auto emit = [&, n](int k, const std::vector<std::pair<int, int>>& ent, bool keep_empty, std::vector<int>& meta,
                     std::vector<int>& col, std::vector<int>& slt) {
       const int W = SparseSymbolic::kStepWidth;
       const int steps = ent.empty() ? (keep_empty ? 1 : 0) : (int)((ent.size() + W - 1) / W);
@@ -271,7 +271,7 @@ inline bool sparse_analyze(int n, int m, const int32_t* P_colptr, const int32_t*
         meta.push_back((k << 1) | (st == steps - 1 ? 1 : 0));
         for (int i = 0; i < W; ++i) {
           const size_t idx = (size_t)st * W + i;
-          col.push_back(idx < ent.size() ? ent[idx].first : 0);
+          col.push_back(idx < ent.size() ? ent[idx].first : n);  // padding gathers the dummy slot v[n] == 0
           slt.push_back(idx < ent.size() ? ent[idx].second : -1);
         }
       }
@@ -289,10 +289,10 @@ inline bool sparse_analyze(int n, int m, const int32_t* P_colptr, const int32_t*
     }
     // pad both lists to a multiple of kStepPad with no-op steps (no entries, not a last step): the device loop is
     // unrolled kStepPad times without bounds checks
-    auto pad = [&](std::vector<int>& meta, std::vector<int>& col, std::vector<int>& slt) {
+    auto pad = [&, n](std::vector<int>& meta, std::vector<int>& col, std::vector<int>& slt) {
       while (meta.size() % SparseSymbolic::kStepPad != 0) {
         meta.push_back(0);
-        for (int i = 0; i < SparseSymbolic::kStepWidth; ++i) { col.push_back(0); slt.push_back(-1); }
+        for (int i = 0; i < SparseSymbolic::kStepWidth; ++i) { col.push_back(n); slt.push_back(-1); }
       }
     };
     pad(S.FS_meta, S.FS_col, S.FS_slot);

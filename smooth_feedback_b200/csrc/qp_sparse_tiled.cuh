@@ -418,9 +418,9 @@ template <typename T, int TW> struct SpSolver
   {
     constexpr unsigned kStride = TW * sizeof(T);
     const unsigned ak = sv + (unsigned)(B.meta >> 1) * kStride;
-    const T vk = lds(ak);  // row k of the right-hand side is only written at its own (last) step
+    const T vk = (r == 0) ? lds(ak) : T(0);  // read and written by the row's first lane only; rhs row k is untouched until here
 #pragma unroll
-    for (int t = 0; t < SU; ++t) acc += B.a[t] * lds(sv + (unsigned)B.j[t] * kStride);  // padding carries a = 0, j = 0
+    for (int t = 0; t < SU; ++t) acc += B.a[t] * lds(sv + (unsigned)B.j[t] * kStride);  // padding: a = 0, j = n (dummy zero slot)
     if (B.meta & 1) {  // last step of the row (warp-uniform)
       const T s = gsum(acc);
       if (r == 0) sts(ak, FWD ? vk - s : vk * B.dk - s);
@@ -606,7 +606,7 @@ template <typename T, int TW> struct SpSolver
     walk_chunks(S.m_pad / RL, S.WR, S.RP_col, APW.p,
                 [&](const Chunk& B, T& acc) {
 #pragma unroll
-                  for (int t = 0; t < kSpU; ++t) acc += B.a[t] * lds(sv + (unsigned)B.j[t] * kStride);  // padding: a = 0, column 0
+                  for (int t = 0; t < kSpU; ++t) acc += B.a[t] * lds(sv + (unsigned)B.j[t] * kStride);  // padding: a = 0, column n (dummy zero slot)
                 },
                 [&](int slot, T zt) {
                   const int i = r + slot * RL;
@@ -1000,6 +1000,10 @@ template <typename T, int TW> __global__ void __launch_bounds__(32, TW == 8 ? 8 
   extern __shared__ __align__(16) unsigned char sp_smem_raw[];
   const int lane = threadIdx.x;
   T* smem_v = (TW < 32) ? reinterpret_cast<T*>(sp_smem_raw) : nullptr;
+  if (TW < 32) {  // dummy slot v[n] == 0: the target of every padding gather
+    if (lane < TW) smem_v[(size_t)a.pat.n * TW + lane] = T(0);
+    __syncwarp();
+  }
   const long long ntiles = (a.batch + TW - 1) / TW;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long b = tile * TW + (lane & (TW - 1));

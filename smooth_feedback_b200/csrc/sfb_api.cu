@@ -538,7 +538,7 @@ int qp_sparse_solve_impl(sfb_context* h, const sfb_qp_sparse_pattern* pt, const 
   auto launch = [&]() -> int {
     const unsigned grid = (unsigned)std::min<long long>(tiles, 1 << 30);
     if (tw < 32) {
-      const size_t smem = (size_t)n * tw * sizeof(T);  // the solve vector of the tile
+      const size_t smem = (size_t)(n + 1) * tw * sizeof(T);  // the solve vector of the tile + the dummy zero slot
       if (smem > h->prop.sharedMemPerBlockOptin) return fail(h, SFB_ERR_UNSUPPORTED_SIZE, "sparse QP n=%d: solve vector does not fit in shared memory", n);
       if (tw == 8) {
         SFB_CUDA(h, cudaFuncSetAttribute(sfb::qp_sparse_tiled_kernel<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -1,0 +1,30 @@
+"""Dev tool: tiny invocations of every kernel family for compute-sanitizer (memcheck / racecheck)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import smooth_feedback_b200 as sfb
+from smooth_feedback_b200.generators import (mpc_structured_batch, mpc_structured_pattern, random_ekf_numpy, random_qp_numpy,
+                                             random_sparse_qp_numpy)
+t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+cm = sfb.to_colmajor
+prm = sfb.QPSolverParams(max_iter=200)
+for (n, m, B) in [(50, 100, 24), (10, 20, 40), (3, 203, 16), (2, 2, 8)]:
+    P, q, A, l, u = random_qp_numpy(B, n, m, seed=1)
+    r = sfb.solve_dense_batch(t(cm(P)), t(q), t(cm(A)), t(l), t(u), prm)
+Pk, Ak, Qk, Hk, Rk, innov = random_ekf_numpy(200, 6, 3, seed=1)
+sfb.ekf_step_batch(t(cm(Pk)), t(cm(Ak)), t(cm(Qk)), 0.1, t(cm(Hk)), t(cm(Rk)), t(innov))
+sfb.ekf_predict_batch(t(cm(Pk)), t(cm(Ak)), t(cm(Qk)), 0.1, stepper="rk4", dt=0.05)
+pat = mpc_structured_pattern(Nx=3, Nu=2, nivals=3, Ki=4)
+Pv, q, Av, l, u = mpc_structured_batch(pat, 13, seed=2)
+for tw in (4, 8, 32):
+    os.environ["SFB_SPARSE_TW"] = str(tw)
+    h = sfb.Handle(0)
+    sp = sfb.SparsePattern(pat["n"], pat["m"], pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], pat["A_colidx"], handle=h)
+    sfb.solve_sparse_batch(sp, t(Pv), t(q), t(Av), t(l), t(u), prm)
+    f = lambda a: t(a).float()
+    sfb.solve_sparse_batch(sp, f(Pv), f(q), f(Av), f(l), f(u), prm)
+pat2, Pv, q, Av, l, u = random_sparse_qp_numpy(9, 20, 30, density=0.2, seed=3)
+sp = sfb.SparsePattern(pat2["n"], pat2["m"], pat2["P_colptr"], pat2["P_rowidx"], pat2["A_rowptr"], pat2["A_colidx"], handle=h)
+sfb.solve_sparse_batch(sp, t(Pv), t(q), t(Av), t(l), t(u), prm)
+torch.cuda.synchronize()
+print("sanitize workload done")
