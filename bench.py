@@ -116,7 +116,7 @@ def cpu_baseline(sample_target_s: float = 12.0):
         t0 = time.perf_counter()
         r = orc.qp_solve_batch(P, q, A, l, u, params=prm, nthreads=cores, fast=True)
         best = max(best, count / (time.perf_counter() - t0))
-    return {"value": best, "unit": UNIT, "cores": cores, "kind": "port",
+    return {"value": best, "unit": UNIT, "cores": cores, "kind": "port", "count": count,
             "sample": f"first {count} of the {BATCH} G+ instances (seed {SEED}), best of 2, oracle -O3 -march=x86-64-v3 (AVX2+FMA), "
                       f"OpenMP dynamic over {cores} threads, one reusable workspace per thread",
             "mean_iter": float(r.iter.mean()), "optimal_frac": float((r.status == 0).mean())}
@@ -178,7 +178,7 @@ def run_reference(args):
     v = sum(vals) / len(vals)
     base["value"] = v
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": 1e3 * base["count"] / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"dense QP n={N_VARS} m={M_CONS} G+ (bench_types.hpp recipe, delta~U(0,1)), fp64, "
                                    f"defaults + max_iter={MAX_ITER}; CPU arm runs a bounded sample per step"},
