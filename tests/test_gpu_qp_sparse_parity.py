@@ -299,3 +299,54 @@ def test_full_size_properties_cfg3(sfb):
     assert ok.mean() > 0.95
     e32 = rel_err(r32.x.cpu().numpy().astype(np.float64)[ok], r64.x.cpu().numpy()[ok])
     assert np.median(e32) <= REL_F32 and np.quantile(e32, 0.95) <= 10 * REL_F32
+
+
+def _case_as_sparse(case):
+    """A known-answer case as QuadraticProgramSparse: the stored patterns are what Eigen's sparseView keeps (non-zeros)."""
+    from qp_cases import as_batch
+
+    P, q, A, l, u = as_batch(case)
+    n, m = P.shape[1], A.shape[1]
+    pc, pr = np.nonzero(P[0].T)   # column-major order
+    ar, ac = np.nonzero(A[0])
+    pat = dict(n=n, m=m, P_colptr=np.concatenate([[0], np.cumsum(np.bincount(pc, minlength=n))]).astype(np.int32),
+               P_rowidx=pr.astype(np.int32), A_rowptr=np.concatenate([[0], np.cumsum(np.bincount(ar, minlength=m))]).astype(np.int32),
+               A_colidx=ac.astype(np.int32))
+    return pat, np.ascontiguousarray(P[:, pr, pc]), q, np.ascontiguousarray(A[:, ar, ac]), l, u
+
+
+from qp_cases import CASES, OPTIMAL, is_approx  # noqa: E402
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_known_answers_through_sparse_c_abi(sfb, case):
+    # the reference's own unit tests (tests/test_qp.cpp: BasicSparse :100-122, PortfolioOptimizationSparse :274-312 and the
+    # dense cases as sparse problems, cf. TwoDimensional :314-336 dense == sparse) against the sparse CUDA path, including
+    # empty rows (Unconstrained: A = 0 has no stored entry) and the warm re-solve of every Optimal case
+    pat, Pv, q, Av, l, u = _case_as_sparse(case)
+    sp = sfb.SparsePattern(pat["n"], pat["m"], pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], pat["A_colidx"])
+    r = sfb.solve_sparse_batch(sp, Pv, q, Av, l, u)
+    assert r.status[0] == case["status"]
+    if case["x"] is not None:
+        assert is_approx(r.x[0], case["x"], case["x_rtol"])
+    if case["obj"] is not None:
+        assert abs(r.obj[0] - case["obj"]) <= case["obj_atol"]
+    if case["status"] == OPTIMAL:
+        r2 = sfb.solve_sparse_batch(sp, Pv, q, Av, l, u, warm_x=r.x, warm_y=r.y)
+        assert r2.status[0] == OPTIMAL and r2.iter[0] == 2
+        assert is_approx(r2.x[0], case["x"], case["x_rtol"])
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_known_answers_sparse_match_oracle(sfb, oracle, case):
+    from qp_cases import as_batch
+
+    pat, Pv, q, Av, l, u = _case_as_sparse(case)
+    sp = sfb.SparsePattern(pat["n"], pat["m"], pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], pat["A_colidx"])
+    r = sfb.solve_sparse_batch(sp, Pv, q, Av, l, u)
+    P, q_, A, l_, u_ = as_batch(case)
+    o = oracle.qp_solve_batch(P, q_, A, l_, u_)
+    assert r.status[0] == o.status[0] and r.iter[0] == o.iter[0]
+    assert np.array_equal(r.active, o.active)
+    if case["status"] == OPTIMAL:
+        assert rel_err(r.x, o.x).max() <= REL_F64 and rel_err(r.y, o.y).max() <= REL_F64
