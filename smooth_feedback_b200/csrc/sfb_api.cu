@@ -19,6 +19,7 @@
 #include "ekf_fused_tma.cuh"
 #include "ekf_kernels.cuh"
 #include "qp_dense_group.cuh"
+#include "qp_dense_skinny.cuh"
 #include "qp_sparse_host.hpp"
 #include "qp_sparse_tiled.cuh"
 
@@ -59,6 +60,7 @@ struct sfb_context
   Scratch scratch[kNumSlots + 1];  // [kNumSlots] belongs to the handle's own stream
   cudaEvent_t ev_start = nullptr;
   bool ekf_force_generic = false;
+  bool dense_force_generic = false;  // SFB_DENSE_FORCE_GENERIC=1: bypass the tall-skinny register kernel (A/B measurements)
   int sparse_tw = 0;     // SFB_SPARSE_TW=4|8|32 overrides the tile-width heuristic of the sparse QP path (A/B measurements)
   Scratch sparse_ws;     // tiled working set of the sparse QP path
   Scratch sparse_stage;  // device copies of host buffers (sparse path)
@@ -225,10 +227,48 @@ int qp_launch_g(sfb_context* h, cudaStream_t st, sfb::QpArgs<T>& args, const QpG
   return SFB_OK;
 }
 
+// tall-skinny problems without polish (the ASIF shape): warp per instance, working set in registers
+template <typename T, int N, int R> int qp_launch_skinny_nr(sfb_context* h, cudaStream_t st, sfb::QpArgs<T>& args)
+{
+  auto kern = sfb::qp_dense_skinny_kernel<T, N, R>;
+  int nb = 0;
+  SFB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 32 * sfb::kSkinnyWarps, 0));
+  if (nb < 1) return fail(h, SFB_ERR_CUDA, "skinny QP kernel cannot be resident");
+  const long long ctas = (args.batch + sfb::kSkinnyWarps - 1) / sfb::kSkinnyWarps;
+  const int grid = (int)std::max<long long>(1, std::min<long long>(ctas, (long long)h->prop.multiProcessorCount * nb));
+  kern<<<grid, 32 * sfb::kSkinnyWarps, 0, st>>>(args);
+  SFB_CUDA(h, cudaGetLastError());
+  return SFB_OK;
+}
+template <typename T, int N> int qp_launch_skinny_n(sfb_context* h, cudaStream_t st, sfb::QpArgs<T>& args)
+{
+  return args.m <= 128 ? qp_launch_skinny_nr<T, N, 4>(h, st, args) : qp_launch_skinny_nr<T, N, 8>(h, st, args);
+}
+bool qp_is_skinny(const sfb_context* h, int n, int m, int mode, const sfb_qp_params& prm)
+{
+  return !h->dense_force_generic && mode == 0 && !prm.polish && n <= sfb::kSkinnyMaxN && m >= 1 && m <= sfb::kSkinnyMaxM;
+}
+
 template <typename T>
 int qp_launch(sfb_context* h, cudaStream_t st, int scratch_slot, const sfb::QpArgs<T>& args_in)
 {
   sfb::QpArgs<T> args = args_in;
+  if (qp_is_skinny(h, args.n, args.m, args.mode, args.prm)) {
+    args.scratch = nullptr;
+    args.scratch_per_cta = 0;
+    args.work_counter = next_counter(h);
+    SFB_CUDA(h, cudaMemsetAsync(args.work_counter, 0, sizeof(unsigned long long), st));
+    int rc;
+    switch (args.n) {
+      case 1: rc = qp_launch_skinny_n<T, 1>(h, st, args); break;
+      case 2: rc = qp_launch_skinny_n<T, 2>(h, st, args); break;
+      case 3: rc = qp_launch_skinny_n<T, 3>(h, st, args); break;
+      default: rc = qp_launch_skinny_n<T, 4>(h, st, args); break;
+    }
+    if (rc != SFB_OK) return rc;
+    h->launches += 1;
+    return SFB_OK;
+  }
   QpGeom g;
   if (qp_geometry<T>(h, args.n, args.m, &g) != SFB_OK)
     return fail(h, SFB_ERR_UNSUPPORTED_SIZE, "dense QP n=%d m=%d (%zu-byte scalars) does not fit in shared memory",
@@ -643,6 +683,7 @@ int sfb_create(int device, void* stream, sfb_handle_t* out)
   h->device = device;
   { const char* e = getenv("SFB_EKF_FORCE_GENERIC"); h->ekf_force_generic = e && e[0] == '1'; }
   { const char* e = getenv("SFB_SPARSE_TW"); h->sparse_tw = e ? atoi(e) : 0; }
+  { const char* e = getenv("SFB_DENSE_FORCE_GENERIC"); h->dense_force_generic = e && e[0] == '1'; }
   h->stream = static_cast<cudaStream_t>(stream);
   if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&h->prop, device) != cudaSuccess) {
     const char* msg = cudaGetErrorString(cudaGetLastError());

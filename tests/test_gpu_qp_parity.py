@@ -299,3 +299,58 @@ def test_full_size_properties(sfb, oracle):
     r2 = sfb.solve_dense_batch(P_cm, q, A_cm, l, u, prm, warm_x=r.x, warm_y=r.y)
     torch.cuda.synchronize()
     assert (r2.status == 0).all() and (r2.iter <= 27).float().mean().item() > 0.99
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# tall-skinny register kernel (qp_dense_skinny.cuh): n <= 4, m <= 256, polish off -- the ASIF shape and setting
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,m", [(3, 203), (1, 5), (2, 40), (4, 256), (4, 129), (3, 64), (1, 1), (4, 33)])
+def test_skinny_parity(sfb, oracle, n, m):
+    # BASELINE.json configs[4] shape (n = 3, m = 203: examples/mpc_asif_vehicle.cpp:96-129, polish = false) and its edges
+    r, o, wp = _parity(sfb, oracle, 96, n, m, seed=7000 + 10 * n + m, prm_kw=dict(polish=False))
+    # n = m = 1: the unpolished dual of an inactive row is ~1e-10 and its relative error carries no information
+    _assert_parity(r, o, wp, REL_F64 if (n, m) != (1, 1) else 1e-4, min_well_posed=0.9)
+
+
+def test_skinny_infeasible_mix_warm_and_no_scaling(sfb, oracle):
+    r, o, wp = _parity(sfb, oracle, 128, 3, 7, seed=31, feasible=False, prm_kw=dict(polish=False), max_iter=5000)
+    assert (o.status == 2).any() and (o.status == 0).any()
+    _assert_parity(r, o, wp, REL_F64, min_well_posed=0.9)
+    r, o, wp = _parity(sfb, oracle, 128, 3, 60, seed=32, prm_kw=dict(polish=False, scaling=False))
+    _assert_parity(r, o, wp, REL_F64, min_well_posed=0.9)
+    # warm start from the oracle's solution: same iterates as the oracle's warm re-solve
+    from smooth_feedback_b200.generators import random_qp_numpy
+
+    P, q, A, l, u = random_qp_numpy(64, 3, 203, seed=33)
+    prm = sfb.QPSolverParams(max_iter=4000, polish=False)
+    op = oracle.default_params(max_iter=4000, polish=0)
+    o1 = oracle.qp_solve_batch(P, q, A, l, u, params=op, nthreads=8)
+    o2 = oracle.qp_solve_batch(P, q, A, l, u, params=op, warm_x=o1.x, warm_y=o1.y, nthreads=8)
+    r2 = gpu_solve(sfb, P, q, A, l, u, prm, warm=(o1.x, o1.y))
+    assert np.array_equal(r2.status, o2.status) and (r2.iter == o2.iter).mean() > 0.95
+    assert rel_err(r2.x, o2.x).max() <= REL_F64
+
+
+def test_skinny_fp32_and_matches_generic_kernel(sfb, oracle):
+    import os
+
+    from smooth_feedback_b200.generators import random_qp_numpy
+
+    P, q, A, l, u = random_qp_numpy(256, 3, 203, seed=41)
+    prm = sfb.QPSolverParams(max_iter=4000, polish=False)
+    o = oracle.qp_solve_batch(P, q, A, l, u, params=oracle.default_params(max_iter=4000, polish=0), nthreads=8)
+    r32 = gpu_solve(sfb, P, q, A, l, u, prm, dtype=np.float32)
+    ok = (r32.status == 0) & (o.status == 0)
+    assert ok.mean() > 0.9 and np.median(rel_err(r32.x[ok], o.x[ok])) <= REL_F32
+    # A/B against the generic shared-memory kernel (SFB_DENSE_FORCE_GENERIC=1): same discrete outcomes, 1e-6 solutions
+    r_sk = gpu_solve(sfb, P, q, A, l, u, prm)
+    os.environ["SFB_DENSE_FORCE_GENERIC"] = "1"
+    try:
+        hg = sfb.Handle(0)
+    finally:
+        os.environ.pop("SFB_DENSE_FORCE_GENERIC")
+    cm = sfb.to_colmajor
+    r_g = sfb.solve_dense_batch(cm(P), q, cm(A), l, u, prm, handle=hg)
+    same = (r_sk.status == r_g.status) & (r_sk.iter == r_g.iter)
+    assert same.mean() >= 0.97
+    assert rel_err(r_sk.x[same], r_g.x[same]).max() <= REL_F64
