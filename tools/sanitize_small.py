@@ -11,6 +11,12 @@ prm = sfb.QPSolverParams(max_iter=200)
 for (n, m, B) in [(50, 100, 24), (10, 20, 40), (3, 203, 16), (2, 2, 8)]:
     P, q, A, l, u = random_qp_numpy(B, n, m, seed=1)
     r = sfb.solve_dense_batch(t(cm(P)), t(q), t(cm(A)), t(l), t(u), prm)
+for (n, m, B) in [(3, 203, 40), (4, 256, 9), (1, 1, 5), (2, 33, 17)]:  # tall-skinny register kernel (polish off), fp64 + fp32
+    P, q, A, l, u = random_qp_numpy(B, n, m, seed=2)
+    prm_np = sfb.QPSolverParams(max_iter=200, polish=False)
+    sfb.solve_dense_batch(t(cm(P)), t(q), t(cm(A)), t(l), t(u), prm_np)
+    f = lambda a: t(a).float()
+    sfb.solve_dense_batch(f(cm(P)), f(q), f(cm(A)), f(l), f(u), prm_np)
 Pk, Ak, Qk, Hk, Rk, innov = random_ekf_numpy(200, 6, 3, seed=1)
 sfb.ekf_step_batch(t(cm(Pk)), t(cm(Ak)), t(cm(Qk)), 0.1, t(cm(Hk)), t(cm(Rk)), t(innov))
 sfb.ekf_predict_batch(t(cm(Pk)), t(cm(Ak)), t(cm(Qk)), 0.1, stepper="rk4", dt=0.05)
