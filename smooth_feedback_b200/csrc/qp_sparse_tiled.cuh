@@ -60,6 +60,7 @@ struct SpPattern
 
 constexpr int kSpStep = 32;  // == SparseSymbolic::kStepWidth
 constexpr int kSpDepth = 4;  // sweep steps in flight per lane
+constexpr bool kSpPaddedF64 = false;  // fp64 at 128 registers: measured slower than the generic passes even with 4-wide chunks (91.8 vs 82.4 ms at cfg3)
 constexpr int kSpPolishRefine = 1;  // refinement steps on Hp per application of the reduced polish solve
 
 // scalars per instance of the W block: factor (nnzL + n) followed by its two stream-ordered copies
@@ -524,31 +525,32 @@ template <typename T, int TW> struct SpSolver
   // reduced (two register buffers, loop unrolled twice).
   // fp64 at 128 registers spills in these loops and ends up slower than the generic passes (89.6 vs 81.7 ms at cfg3),
   // fp32 gains 45 % (128k -> 186k solves/s): enabled for single precision only
-  __device__ __forceinline__ bool padded_passes() const { return RL > 1 && S.WR > 0 && sizeof(T) == 4; }
+  __device__ __forceinline__ bool padded_passes() const { return RL > 1 && S.WR > 0 && (sizeof(T) == 4 || kSpPaddedF64); }
 
   // A padded row (column) is a run of CHUNKS of kSpU entries; the flattened chunk stream of a lane is walked with two
   // register buffers (loop unrolled twice): the operands of the next chunk are requested before the current one is used.
+  static constexpr int CW = (sizeof(T) == 8) ? 4 : 8;  // chunk width: fp64 at 128 registers cannot afford two 8-wide buffers
   struct Chunk
   {
-    int j[kSpU];
-    T a[kSpU];
+    int j[CW];
+    T a[CW];
   };
   static __device__ __forceinline__ void chunk_load(Chunk& B, const int*& pc, const T*& pa)
   {
 #pragma unroll
-    for (int t = 0; t < kSpU; ++t) {
+    for (int t = 0; t < CW; ++t) {
       B.j[t] = pc[t];
       B.a[t] = pa[(size_t)t * TW];
     }
-    pc += kSpU;
-    pa += (size_t)kSpU * TW;
+    pc += CW;
+    pa += (size_t)CW * TW;
   }
   // walk `nslots` padded rows of `width` entries each (lane r owns rows r, r + RL, ...): dot(B, acc) accumulates one
   // chunk, fin(slot, acc) closes a row
   template <class DOT, class FIN>
   __device__ __forceinline__ void walk_chunks(int nslots, int width, const int* idx, const T* val, DOT dot, FIN fin)
   {
-    const int cpr = width / kSpU;          // chunks per row
+    const int cpr = width / CW;            // chunks per row (the host pads widths to a multiple of 8)
     const int total = nslots * cpr;        // chunks of this lane
     const int* pc = idx + (size_t)r * width;
     const T* pa = val + (size_t)r * width * TW;
@@ -585,11 +587,11 @@ template <typename T, int TW> struct SpSolver
     const V wl = w;
     walk_chunks(S.n_pad / RL, S.WA, S.ATP_row, ATW.p,
                 [&](const Chunk& B, T& acc) {
-                  T g[kSpU];
+                  T g[CW];
 #pragma unroll
-                  for (int t = 0; t < kSpU; ++t) g[t] = wl[B.j[t]];  // padding: a = 0, row 0
+                  for (int t = 0; t < CW; ++t) g[t] = wl[B.j[t]];  // padding: a = 0, row 0
 #pragma unroll
-                  for (int t = 0; t < kSpU; ++t) acc += B.a[t] * g[t];
+                  for (int t = 0; t < CW; ++t) acc += B.a[t] * g[t];
                 },
                 [&](int slot, T acc) {
                   const int j = r + slot * RL;
@@ -606,7 +608,7 @@ template <typename T, int TW> struct SpSolver
     walk_chunks(S.m_pad / RL, S.WR, S.RP_col, APW.p,
                 [&](const Chunk& B, T& acc) {
 #pragma unroll
-                  for (int t = 0; t < kSpU; ++t) acc += B.a[t] * lds(sv + (unsigned)B.j[t] * kStride);  // padding: a = 0, column n (dummy zero slot)
+                  for (int t = 0; t < CW; ++t) acc += B.a[t] * lds(sv + (unsigned)B.j[t] * kStride);  // padding: a = 0, column n (dummy zero slot)
                 },
                 [&](int slot, T zt) {
                   const int i = r + slot * RL;

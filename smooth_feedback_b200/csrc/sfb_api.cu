@@ -549,11 +549,18 @@ int qp_sparse_solve_impl(sfb_context* h, const sfb_qp_sparse_pattern* pt, const 
   if (space < 0) return fail(h, SFB_ERR_MIXED_MEMORY, "host and device pointers mixed in one call");
 
   const sfb::SparseSymbolic& S = pt->sym;
-  // tile width: the kernel is bound by memory latency, so resident warps are what buys throughput.  Large batches take
-  // one lane per instance (32 instances per warp, no shuffles); below ~8 warps per SM of those, 4 instances per warp with
-  // 8 lanes cooperating on each (measured at n = m = 422, fp64: batch 8192 -> 99k solves/s with 4, ~60k with 8, 14k with
-  // 32; batch 65536 -> 100k with 32; profiles/README.md)
-  int tw = (batch < 8ll * 32 * h->prop.multiProcessorCount) ? 4 : 32;
+  // tile width.  4 instances per warp with 8 lanes cooperating on each wins at every batch size measured (n = m = 422:
+  // batch 8192 -> 99k solves/s fp64 / 186k fp32 against 14k / - with one lane per instance; batch 65536 -> 105k / 235k
+  // against 100k / 150k; profiles/README.md); one lane per instance (32 per warp) needs ~40 % less workspace and is kept
+  // for batches whose 4-wide working set would not fit in half of the free device memory.
+  int tw = 4;
+  {
+    const size_t per_inst4 = (sfb::sp_a_len(pt->pat, 4) + pt->sym.nnzP + sfb::sp_w_len(pt->pat, 4) + (size_t)sfb::kSpNV * n +
+                              (size_t)sfb::kSpMV * m) * sizeof(T);
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = 0; }
+    if (h->sparse_ws.bytes < per_inst4 * (size_t)batch && per_inst4 * (size_t)batch > free_b / 2) tw = 32;
+  }
   if (h->sparse_tw == 4 || h->sparse_tw == 8 || h->sparse_tw == 32) tw = h->sparse_tw;
   const long long tiles = (batch + tw - 1) / tw;
   const size_t wlen = sfb::sp_w_len(pt->pat, tw);  // factor + its stream-ordered copies
