@@ -152,6 +152,8 @@ typedef enum { SFB_STEPPER_EULER = 0, SFB_STEPPER_RK4 = 1 } sfb_stepper;
  * over [0, tau] with the reference's step schedule (dt <= 0 -> one step of length tau, ekf.hpp:92-102).
  * A = -ad(f) + d^r f/dx is evaluated by the caller at the pre-step estimate (user lambdas + autodiff stay
  * on the host) and held constant over the call.  P, A, Q, out_P: [batch][d*d] column-major.  1 <= d <= 16.
+ * All-device pointers (asynchronous on the handle's stream) or all-host pointers (staged, returns with the result in place),
+ * like every entry point of this header.
  */
 int sfb_ekf_predict_batch_f64(sfb_handle_t h, int64_t batch, int d, int stepper, const double* P,
                               const double* A, const double* Q, double tau, double dt, double* out_P);

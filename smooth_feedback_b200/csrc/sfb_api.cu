@@ -649,6 +649,38 @@ int qp_sparse_solve_impl(sfb_context* h, const sfb_qp_sparse_pattern* pt, const 
   return SFB_OK;
 }
 
+// device staging of host buffers for the EKF entry points (doubles; every block 256-byte aligned)
+struct EkfStage
+{
+  sfb_context* h;
+  char* base = nullptr;
+  size_t off = 0;
+  explicit EkfStage(sfb_context* h_) : h(h_) {}
+  static size_t al(size_t elems) { return (elems * sizeof(double) + 255) / 256 * 256; }
+  int reserve(size_t bytes)
+  {
+    const int rc = ensure_scratch(h, h->sparse_stage, bytes, h->stream);
+    if (rc == SFB_OK) base = static_cast<char*>(h->sparse_stage.dev);
+    return rc;
+  }
+  double* out(size_t elems)
+  {
+    double* p = reinterpret_cast<double*>(base + off);
+    off += al(elems);
+    return p;
+  }
+  cudaError_t up(const double** dev, const double* host, size_t elems)
+  {
+    double* p = out(elems);
+    *dev = p;
+    return cudaMemcpyAsync(p, host, elems * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+  }
+  cudaError_t down(double* host, const double* dev, size_t elems)
+  {
+    return cudaMemcpyAsync(host, dev, elems * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  }
+};
+
 }  // namespace
 
 // =======================================================================================================
@@ -838,9 +870,25 @@ int sfb_ekf_predict_batch_f64(sfb_handle_t h, int64_t batch, int d, int stepper,
   if (!h) return SFB_ERR_INVALID_ARGUMENT;
   if (batch < 0 || d <= 0 || (stepper != SFB_STEPPER_EULER && stepper != SFB_STEPPER_RK4) || !P || !A || !Q || !out_P)
     return fail(h, SFB_ERR_INVALID_ARGUMENT, "bad argument to sfb_ekf_predict_batch_f64");
-  if (classify({P, A, Q, out_P}) != 1) return fail(h, SFB_ERR_MIXED_MEMORY, "EKF entry points take device pointers only");
+  const int space = classify({P, A, Q, out_P});
+  if (space < 0) return fail(h, SFB_ERR_MIXED_MEMORY, "host and device pointers mixed in one call");
   if (batch == 0) return SFB_OK;
   SFB_CUDA(h, cudaSetDevice(h->device));
+  if (space == 0) {  // host buffers: one staged round trip on the handle's stream
+    const size_t dd = (size_t)d * d * batch;
+    EkfStage stg(h);
+    const double *dP, *dA, *dQ;
+    double* dO;
+    int rc = stg.reserve(3 * stg.al(dd) + stg.al(dd));
+    if (rc != SFB_OK) return rc;
+    SFB_CUDA(h, stg.up(&dP, P, dd)); SFB_CUDA(h, stg.up(&dA, A, dd)); SFB_CUDA(h, stg.up(&dQ, Q, dd));
+    dO = stg.out(dd);
+    rc = sfb_ekf_predict_batch_f64(h, batch, d, stepper, dP, dA, dQ, tau, dt, dO);
+    if (rc != SFB_OK) return rc;
+    SFB_CUDA(h, stg.down(out_P, dO, dd));
+    SFB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return SFB_OK;
+  }
   if (stepper == SFB_STEPPER_EULER && aligned16({P, A, Q, out_P})) {
     sfb::EkfStepArgs a{P, A, Q, nullptr, nullptr, nullptr, nullptr, out_P, batch, tau, dt};
     const int rc = ekf_fused_dispatch<true, false>(h, d, 1, a);
@@ -855,9 +903,25 @@ int sfb_ekf_update_batch_f64(sfb_handle_t h, int64_t batch, int d, int ny, const
   if (!h) return SFB_ERR_INVALID_ARGUMENT;
   if (batch < 0 || d <= 0 || ny <= 0 || ny > sfb::kEkfMaxNy || !P || !H || !R || !innov || !out_delta || !out_P)
     return fail(h, SFB_ERR_INVALID_ARGUMENT, "bad argument to sfb_ekf_update_batch_f64");
-  if (classify({P, H, R, innov, out_delta, out_P}) != 1) return fail(h, SFB_ERR_MIXED_MEMORY, "EKF entry points take device pointers only");
+  const int space = classify({P, H, R, innov, out_delta, out_P});
+  if (space < 0) return fail(h, SFB_ERR_MIXED_MEMORY, "host and device pointers mixed in one call");
   if (batch == 0) return SFB_OK;
   SFB_CUDA(h, cudaSetDevice(h->device));
+  if (space == 0) {
+    const size_t B = (size_t)batch, dd = (size_t)d * d * B, nd = (size_t)ny * d * B, nn = (size_t)ny * ny * B;
+    EkfStage stg(h);
+    const double *dP, *dH, *dR, *dI;
+    int rc = stg.reserve(stg.al(dd) + stg.al(nd) + stg.al(nn) + stg.al(ny * B) + stg.al(d * B) + stg.al(dd));
+    if (rc != SFB_OK) return rc;
+    SFB_CUDA(h, stg.up(&dP, P, dd)); SFB_CUDA(h, stg.up(&dH, H, nd)); SFB_CUDA(h, stg.up(&dR, R, nn)); SFB_CUDA(h, stg.up(&dI, innov, ny * B));
+    double* dD = stg.out(d * B);
+    double* dO = stg.out(dd);
+    rc = sfb_ekf_update_batch_f64(h, batch, d, ny, dP, dH, dR, dI, dD, dO);
+    if (rc != SFB_OK) return rc;
+    SFB_CUDA(h, stg.down(out_delta, dD, d * B)); SFB_CUDA(h, stg.down(out_P, dO, dd));
+    SFB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return SFB_OK;
+  }
   if (aligned16({P, H, R, innov, out_delta, out_P})) {
     sfb::EkfStepArgs a{P, nullptr, nullptr, H, R, innov, out_delta, out_P, batch, 0.0, 0.0};
     const int rc = ekf_fused_dispatch<false, true>(h, d, ny, a);
@@ -874,10 +938,26 @@ int sfb_ekf_step_batch_f64(sfb_handle_t h, int64_t batch, int d, int ny, int ste
   if (batch < 0 || d <= 0 || ny <= 0 || ny > sfb::kEkfMaxNy || (stepper != SFB_STEPPER_EULER && stepper != SFB_STEPPER_RK4) ||
       !P || !A || !Q || !H || !R || !innov || !out_delta || !out_P)
     return fail(h, SFB_ERR_INVALID_ARGUMENT, "bad argument to sfb_ekf_step_batch_f64");
-  if (classify({P, A, Q, H, R, innov, out_delta, out_P}) != 1)
-    return fail(h, SFB_ERR_MIXED_MEMORY, "EKF entry points take device pointers only");
+  const int space = classify({P, A, Q, H, R, innov, out_delta, out_P});
+  if (space < 0) return fail(h, SFB_ERR_MIXED_MEMORY, "host and device pointers mixed in one call");
   if (batch == 0) return SFB_OK;
   SFB_CUDA(h, cudaSetDevice(h->device));
+  if (space == 0) {
+    const size_t B = (size_t)batch, dd = (size_t)d * d * B, nd = (size_t)ny * d * B, nn = (size_t)ny * ny * B;
+    EkfStage stg(h);
+    const double *dP, *dA, *dQ, *dH, *dR, *dI;
+    int rc = stg.reserve(3 * stg.al(dd) + stg.al(nd) + stg.al(nn) + stg.al(ny * B) + stg.al(d * B) + stg.al(dd));
+    if (rc != SFB_OK) return rc;
+    SFB_CUDA(h, stg.up(&dP, P, dd)); SFB_CUDA(h, stg.up(&dA, A, dd)); SFB_CUDA(h, stg.up(&dQ, Q, dd));
+    SFB_CUDA(h, stg.up(&dH, H, nd)); SFB_CUDA(h, stg.up(&dR, R, nn)); SFB_CUDA(h, stg.up(&dI, innov, ny * B));
+    double* dD = stg.out(d * B);
+    double* dO = stg.out(dd);
+    rc = sfb_ekf_step_batch_f64(h, batch, d, ny, stepper, dP, dA, dQ, tau, dt, dH, dR, dI, dD, dO);
+    if (rc != SFB_OK) return rc;
+    SFB_CUDA(h, stg.down(out_delta, dD, d * B)); SFB_CUDA(h, stg.down(out_P, dO, dd));
+    SFB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return SFB_OK;
+  }
   if (stepper == SFB_STEPPER_EULER && aligned16({P, A, Q, H, R, innov, out_delta, out_P})) {
     sfb::EkfStepArgs a{P, A, Q, H, R, innov, out_delta, out_P, batch, tau, dt};
     const int rc = ekf_fused_dispatch<true, true>(h, d, ny, a);

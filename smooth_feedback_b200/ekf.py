@@ -88,3 +88,21 @@ def ekf_step_batch(P_cm, A_cm, Q_cm, tau: float, H_cm, R_cm, innov, dt: float | 
                                               float(tau), -1.0 if dt is None else float(dt), _ptr(H_cm), _ptr(R_cm),
                                               _ptr(innov), _ptr(out_delta), _ptr(out_P)))
     return out_delta, out_P
+
+
+def ekf_step_batch_host(P_cm, A_cm, Q_cm, tau: float, H_cm, R_cm, innov, dt: float | None = None, stepper: str = "euler",
+                        handle: Handle | None = None):
+    """`ekf_step_batch` on contiguous float64 NUMPY arrays (host path of the C ABI: staged through the engine, returns with
+    the results in place).  Same layouts as `ekf_step_batch`."""
+    import numpy as np
+
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (P_cm, A_cm, Q_cm, H_cm, R_cm, innov)]
+    P_cm, A_cm, Q_cm, H_cm, R_cm, innov = arrs
+    B, d, _ = P_cm.shape
+    ny = innov.shape[1]
+    h = handle or default_handle(0)
+    out_delta = np.empty((B, d)); out_P = np.empty((B, d, d))
+    h.check(_lib.lib().sfb_ekf_step_batch_f64(h.raw, B, d, ny, STEPPERS[stepper], _ptr(P_cm), _ptr(A_cm), _ptr(Q_cm),
+                                              float(tau), -1.0 if dt is None else float(dt), _ptr(H_cm), _ptr(R_cm),
+                                              _ptr(innov), _ptr(out_delta), _ptr(out_P)))
+    return out_delta, out_P

@@ -146,3 +146,17 @@ def test_fused_step_in_place_and_equals_two_calls(sfb):
     d1, P1 = sfb.ekf_step_batch(Pin, tA, tQ, 0.1, tH, tR, ti, out_P=Pin)
     assert P1.data_ptr() == Pin.data_ptr()
     assert relmax(P1.cpu().numpy(), P2.cpu().numpy()) <= 1e-12 and relmax(d1.cpu().numpy(), d2.cpu().numpy()) <= 1e-12
+
+
+def test_host_pointer_path(sfb, oracle):
+    """All-host pointers through the C ABI (staged round trip) == the device path == the oracle."""
+    from smooth_feedback_b200.generators import random_ekf_numpy
+
+    B, d, ny = 777, 6, 3
+    P, A, Q, H, R, innov = random_ekf_numpy(B, d, ny, seed=21)
+    dh, Ph = sfb.ekf_step_batch_host(cm(P), cm(A), cm(Q), 0.1, cm(H), cm(R), innov)
+    dd, Pd = sfb.ekf_step_batch(dev(cm(P)), dev(cm(A)), dev(cm(Q)), 0.1, dev(cm(H)), dev(cm(R)), dev(innov))
+    assert np.array_equal(dh, dd.cpu().numpy()) and np.array_equal(Ph, Pd.cpu().numpy())
+    oPp = oracle.ekf_predict_batch(P, A, Q, 0.1)
+    od, oPu = oracle.ekf_update_batch(oPp, H, R, innov)
+    assert relmax(np.swapaxes(Ph, 1, 2), oPu) <= 1e-9 and relmax(dh, od) <= 1e-9
