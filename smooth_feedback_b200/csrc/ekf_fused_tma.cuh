@@ -152,8 +152,7 @@ __device__ __forceinline__ void ldlt_small_static(const SmMat<T>& W, int (&tr)[S
 {
   if constexpr (SZ <= 1) {
     tr[0] = 0;
-    return;
-  }
+  } else {
 #pragma unroll
   for (int kk = 0; kk < SZ; ++kk) {
     int big = kk;
@@ -191,6 +190,7 @@ __device__ __forceinline__ void ldlt_small_static(const SmMat<T>& W, int (&tr)[S
 #pragma unroll
       for (int i = kk + 1; i < SZ; ++i) W(i, kk) /= akk;
     }
+  }
   }
 }
 

@@ -479,13 +479,21 @@ template <bool PRED, bool UPD> int ekf_fused_dispatch(sfb_context* h, int d, int
 {
   if (h->ekf_force_generic) return -1;  // SFB_EKF_FORCE_GENERIC=1: A/B measurements against the generic kernels
   if (!UPD) {
+    if (d == 2) return ekf_fused_launch<2, 1, PRED, false>(h, a);
     if (d == 3) return ekf_fused_launch<3, 1, PRED, false>(h, a);
+    if (d == 4) return ekf_fused_launch<4, 1, PRED, false>(h, a);
     if (d == 6) return ekf_fused_launch<6, 1, PRED, false>(h, a);
     return -1;
   }
+  // (state dof, measurement dim) pairs with a register-resident specialisation; everything else takes the generic kernels
   if (d == 6 && ny == 3) return ekf_fused_launch<6, 3, PRED, true>(h, a);
   if (d == 6 && ny == 6) return ekf_fused_launch<6, 6, PRED, true>(h, a);
+  if (d == 6 && ny == 2) return ekf_fused_launch<6, 2, PRED, true>(h, a);
+  if (d == 6 && ny == 1) return ekf_fused_launch<6, 1, PRED, true>(h, a);
+  if (d == 4 && ny == 2) return ekf_fused_launch<4, 2, PRED, true>(h, a);
   if (d == 3 && ny == 3) return ekf_fused_launch<3, 3, PRED, true>(h, a);
+  if (d == 3 && ny == 1) return ekf_fused_launch<3, 1, PRED, true>(h, a);
+  if (d == 2 && ny == 2) return ekf_fused_launch<2, 2, PRED, true>(h, a);
   return -1;
 }
 

@@ -104,10 +104,10 @@ def test_full_size_properties(sfb, oracle):
     assert relmax(c(Pu), oPu) <= REL_F64 and relmax(c(delta), od) <= REL_F64
 
 
-@pytest.mark.parametrize("d,ny", [(6, 3), (6, 6), (3, 3), (4, 2)])
+@pytest.mark.parametrize("d,ny", [(6, 3), (6, 6), (3, 3), (4, 2), (6, 1), (6, 2), (3, 1), (2, 2), (5, 2)])
 @pytest.mark.parametrize("B", [1, 63, 64, 65, 1000, 12345])
 def test_fused_step_parity(sfb, oracle, d, ny, B):
-    """sfb_ekf_step_batch_f64 (TMA-staged fused predict+update; (4,2) takes the generic kernels) == oracle predict->update,
+    """sfb_ekf_step_batch_f64 (TMA-staged fused predict+update; (5,2) takes the generic kernels) == oracle predict->update,
     including ragged last tiles (B not a multiple of the 64-instance tile)."""
     from smooth_feedback_b200.generators import random_ekf_numpy
 
