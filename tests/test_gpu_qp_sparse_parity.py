@@ -350,3 +350,31 @@ def test_known_answers_sparse_match_oracle(sfb, oracle, case):
     assert np.array_equal(r.active, o.active)
     if case["status"] == OPTIMAL:
         assert rel_err(r.x, o.x).max() <= REL_F64 and rel_err(r.y, o.y).max() <= REL_F64
+
+
+def test_edge_patterns(sfb, oracle):
+    """m = 0 (no constraint rows at all), n = 1, an empty row in A, and P stored with BOTH triangles vs upper only."""
+    rng = np.random.default_rng(4)
+    # unconstrained, diagonal + one off-diagonal pair stored in both triangles
+    n, B = 5, 33
+    P = np.zeros((B, n, n)); d = 1.0 + rng.random((B, n)); P[:, np.arange(n), np.arange(n)] = d
+    P[:, 0, 3] = P[:, 3, 0] = 0.3
+    q = rng.uniform(-1, 1, (B, n))
+    pc, pr = np.nonzero(P[0].T)
+    pat = dict(n=n, m=0, P_colptr=np.concatenate([[0], np.cumsum(np.bincount(pc, minlength=n))]).astype(np.int32),
+               P_rowidx=pr.astype(np.int32), A_rowptr=np.zeros(1, np.int32), A_colidx=np.zeros(0, np.int32))
+    sp = sfb.SparsePattern(n, 0, pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], pat["A_colidx"])
+    z = np.zeros((B, 0))
+    r = sfb.solve_sparse_batch(sp, np.ascontiguousarray(P[:, pr, pc]), q, z, z, z, sfb.QPSolverParams(max_iter=4000))
+    o = oracle.qp_solve_batch(P, q, np.zeros((B, 0, n)), z, z, params=oracle.default_params(max_iter=4000))
+    assert np.array_equal(r.status, o.status) and np.array_equal(r.iter, o.iter)
+    assert rel_err(r.x, o.x).max() <= REL_F64 and rel_err(r.x, -np.linalg.solve(P, q[..., None])[..., 0]).max() <= 1e-3
+    # n = 1 with three rows, the middle one structurally empty
+    P1 = 1.0 + rng.random((B, 1, 1)); q1 = rng.uniform(-1, 1, (B, 1))
+    A1 = np.zeros((B, 3, 1)); A1[:, 0, 0] = 1.0; A1[:, 2, 0] = -2.0
+    l1 = np.tile([-0.1, -np.inf, -0.3], (B, 1)); u1 = np.tile([0.1, np.inf, 0.3], (B, 1))
+    sp1 = sfb.SparsePattern(1, 3, np.array([0, 1], np.int32), np.array([0], np.int32), np.array([0, 1, 1, 2], np.int32), np.array([0, 0], np.int32))
+    r1 = sfb.solve_sparse_batch(sp1, P1[:, :, 0], q1, np.ascontiguousarray(A1[:, [0, 2], 0]), l1, u1, sfb.QPSolverParams(max_iter=4000))
+    o1 = oracle.qp_solve_batch(P1, q1, A1, l1, u1, params=oracle.default_params(max_iter=4000))
+    assert np.array_equal(r1.status, o1.status) and np.array_equal(r1.iter, o1.iter) and np.array_equal(r1.active, o1.active)
+    assert np.abs(r1.x - o1.x).max() <= 1e-9
