@@ -354,3 +354,45 @@ def test_skinny_fp32_and_matches_generic_kernel(sfb, oracle):
     same = (r_sk.status == r_g.status) & (r_sk.iter == r_g.iter)
     assert same.mean() >= 0.97
     assert rel_err(r_sk.x[same], r_g.x[same]).max() <= REL_F64
+
+
+def test_full_size_properties_cfg5_shape(sfb):
+    """BASELINE.json configs[4] shape at full size (n = 3, m = 203, batch 32768, fp32, polish off): the register kernel
+    against the generic shared-memory kernel in fp64 on a strided sample, and replica independence."""
+    import os
+
+    import torch
+
+    from smooth_feedback_b200.generators import random_qp_torch
+
+    B, n, m = 32768, 3, 203
+    P, q, A, l, u = random_qp_torch(B, n, m, seed=5, device="cuda", dtype=torch.float32)
+    prm = sfb.QPSolverParams(max_iter=4000, polish=False)
+    r = sfb.solve_dense_batch(P, q, A, l, u, prm)
+    torch.cuda.synchronize()
+    st = r.status.cpu().numpy()
+    assert (st == 0).mean() > 0.99 and np.isin(st, [0, 4]).all()
+    # the same problems again, shuffled: results must not depend on where an instance sits in the batch
+    perm = torch.randperm(B, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    r2 = sfb.solve_dense_batch(P[perm].contiguous(), q[perm].contiguous(), A[perm].contiguous(), l[perm].contiguous(),
+                               u[perm].contiguous(), prm)
+    torch.cuda.synchronize()
+    assert torch.equal(r2.x, r.x[perm]) and torch.equal(r2.iter, r.iter[perm]) and torch.equal(r2.status, r.status[perm])
+    # fp64 generic kernel on every 16th instance
+    os.environ["SFB_DENSE_FORCE_GENERIC"] = "1"
+    try:
+        hg = sfb.Handle(0)
+    finally:
+        os.environ.pop("SFB_DENSE_FORCE_GENERIC")
+    sl = slice(0, B, 16)
+    d = lambda t_: t_[sl].double().contiguous()
+    rg = sfb.solve_dense_batch(d(P), d(q), d(A), d(l), d(u), prm, handle=hg)
+    torch.cuda.synchronize()
+    ok = ((rg.status == 0) & (r.status[sl] == 0)).cpu().numpy()
+    assert ok.mean() > 0.98
+    e = rel_err(r.x[sl].double().cpu().numpy()[ok], rg.x.cpu().numpy()[ok])
+    assert np.median(e) <= REL_F32 and np.quantile(e, 0.95) <= 10 * REL_F32
+    # feasibility of the fp32 solutions at the solver's own tolerance (eps = 1e-3 relative to the row scale)
+    Ax = torch.einsum("bjm,bj->bm", A.double(), r.x.double())  # A is column-major: A[b, j, i] = A_ij
+    viol = (Ax - u.double()).clamp(min=0).amax(dim=1).cpu().numpy()
+    assert np.quantile(viol[st == 0], 0.99) <= 5e-2
