@@ -124,6 +124,10 @@ void sfb_qp_params_default(sfb_qp_params* p);
  *   out_active [batch][m] int8, may be NULL: -1 lower-active, +1 upper-active, 0 inactive -- the sets
  *       polish_qp builds (qp_solver.hpp:113-123) evaluated on the scaled dual when the ADMM loop ends
  *   out_flags [batch] uint32, may be NULL: SFB_QP_FLAG_* diagnostics
+ *
+ * Kernel selection is internal and does not change results beyond rounding: problems that fit in shared memory run the
+ * group kernel (1, 2 or 4 warps per instance); tall-skinny problems without polish (n <= 4, m <= 256 -- the shape and the
+ * setting of ASIFilter's call, asif.hpp:97) run a warp-per-instance kernel that keeps the working set in registers.
  */
 int sfb_qp_solve_dense_batch_f64(sfb_handle_t h, const sfb_qp_params* prm, int64_t batch, int n, int m,
                                  const double* P, const double* q, const double* A, const double* l,
