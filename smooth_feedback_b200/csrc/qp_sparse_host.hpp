@@ -321,4 +321,94 @@ inline bool sparse_analyze(int n, int m, const int32_t* P_colptr, const int32_t*
   return true;
 }
 
+// Self-check of every schedule the device kernel relies on (used by sfb_qp_sparse_symbolic, i.e. by the CPU tests):
+// each factor slot is streamed exactly once by the forward and once by the backward step list, each entry of A exactly
+// once by the padded row and column streams, every target lies inside the factor, pairs address their own row / column.
+inline bool sparse_validate(const SparseSymbolic& S, std::string& why)
+{
+  const int n = S.n, m = S.m, nL = S.nnzL, nW = S.nnzL + S.n;
+  auto fail = [&](const char* msg) { why = msg; return false; };
+  std::vector<char> seen(n, 0);
+  for (int k = 0; k < n; ++k) {
+    if (S.perm[k] < 0 || S.perm[k] >= n || seen[S.perm[k]]) return fail("perm is not a permutation");
+    seen[S.perm[k]] = 1;
+    if (S.iperm[S.perm[k]] != k) return fail("iperm is not the inverse of perm");
+  }
+  for (int k = 0; k < n; ++k)
+    for (int e = S.L_colptr[k]; e < S.L_colptr[k + 1]; ++e)
+      if (S.L_row[e] <= k || S.L_row[e] >= n || (e > S.L_colptr[k] && S.L_row[e] <= S.L_row[e - 1])) return fail("L column not strictly below the diagonal / not ascending");
+  for (int t : S.P_tgt) if (t < -1 || t >= nW) return fail("P target out of range");
+  for (int t : S.A_pair_tgt) if (t < 0 || t >= nW) return fail("A pair target out of range");
+  for (int t : S.F_tgt) if (t < 0 || t >= nW) return fail("factor update target out of range");
+  if (S.A_pair_ab.size() != S.A_pair_tgt.size() || S.F_ab.size() != S.F_tgt.size()) return fail("pair lists of different length");
+  for (int i = 0; i < m; ++i) {
+    const int len = S.A_rowptr[i + 1] - S.A_rowptr[i];
+    for (int p = S.A_pair_ptr[i]; p < S.A_pair_ptr[i + 1]; ++p) {
+      const int a = S.A_pair_ab[p] >> 16, b = S.A_pair_ab[p] & 0xffff;
+      if (a > b || b >= len) return fail("A pair outside its row");
+    }
+  }
+  for (int k = 0; k < n; ++k) {
+    const int len = S.L_colptr[k + 1] - S.L_colptr[k];
+    std::set<int> tg;
+    for (int p = S.F_ptr[k]; p < S.F_ptr[k + 1]; ++p) {
+      const int a = S.F_ab[p] >> 16, b = S.F_ab[p] & 0xffff;
+      if (a > b || b >= len) return fail("factor pair outside its column");
+      if (!tg.insert(S.F_tgt[p]).second) return fail("two updates of one column share a target (the kernel batches them)");
+    }
+  }
+  auto once = [&](const std::vector<int>& slots, int count, const char* msg) {
+    std::vector<int> hits(count, 0);
+    for (int sl : slots) {
+      if (sl < -1 || sl >= count) return fail(msg);
+      if (sl >= 0) hits[sl]++;
+    }
+    for (int c : hits) if (c != 1) return fail(msg);
+    return true;
+  };
+  if (!once(S.LR_slot, nL, "LR mirror does not cover L exactly once")) return false;
+  if (!once(S.LB_slot, nL, "LB mirror does not cover L exactly once")) return false;
+  if (!once(S.FS_slot, nL, "forward step list does not cover L exactly once")) return false;
+  if (!once(S.BS_slot, nL, "backward step list does not cover L exactly once")) return false;
+  if (!once(S.AT_slot, S.nnzA, "AT mirror does not cover A exactly once")) return false;
+  if (S.WR > 0) {
+    if (!once(S.RP_slot, S.nnzA, "padded row stream does not cover A exactly once")) return false;
+    if (!once(S.ATP_slot, S.nnzA, "padded column stream does not cover A exactly once")) return false;
+    if (S.WR % 8 || S.WA % 8 || S.m_pad % 32 || S.n_pad % 32 || S.m_pad < m || S.n_pad < n) return fail("padded stream geometry");
+  }
+  if (S.FS_meta.size() % SparseSymbolic::kStepPad || S.BS_meta.size() % SparseSymbolic::kStepPad) return fail("step lists not padded");
+  if (S.FS_col.size() != S.FS_meta.size() * SparseSymbolic::kStepWidth || S.BS_col.size() != S.BS_meta.size() * SparseSymbolic::kStepWidth) return fail("step list geometry");
+  // step lists: entries of a step belong to the row in its meta; forward rows ascend, backward rows descend; every backward
+  // row closes exactly once
+  {
+    std::vector<int> closed(n, 0);
+    int prev = n;
+    for (size_t st = 0; st < S.BS_meta.size(); ++st) {
+      const int k = S.BS_meta[st] >> 1;
+      bool empty = true;
+      for (int i = 0; i < SparseSymbolic::kStepWidth; ++i) {
+        const int sl = S.BS_slot[st * SparseSymbolic::kStepWidth + i];
+        if (sl < 0) { if (S.BS_col[st * SparseSymbolic::kStepWidth + i] != n) return fail("padding does not point at the dummy slot"); continue; }
+        empty = false;
+        if (sl < S.L_colptr[k] || sl >= S.L_colptr[k + 1]) return fail("backward step entry outside its column");
+        if (S.BS_col[st * SparseSymbolic::kStepWidth + i] != S.L_row[sl]) return fail("backward step column index mismatch");
+      }
+      if (S.BS_meta[st] & 1) { if (k > prev) return fail("backward rows not descending"); prev = k; closed[k]++; }
+      else if (empty && S.BS_meta[st] != 0) return fail("open step without entries");
+    }
+    for (int c : closed) if (c != 1) return fail("a backward row is not closed exactly once");
+  }
+  for (size_t st = 0; st < S.FS_meta.size(); ++st) {
+    const int k = S.FS_meta[st] >> 1;
+    for (int i = 0; i < SparseSymbolic::kStepWidth; ++i) {
+      const int sl = S.FS_slot[st * SparseSymbolic::kStepWidth + i];
+      if (sl < 0) continue;
+      if (S.L_row[sl] != k) return fail("forward step entry outside its row");
+      const int col = S.FS_col[st * SparseSymbolic::kStepWidth + i];
+      if (sl < S.L_colptr[col] || sl >= S.L_colptr[col + 1]) return fail("forward step column index mismatch");
+    }
+  }
+  return true;
+}
+
 }  // namespace sfb

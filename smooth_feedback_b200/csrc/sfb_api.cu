@@ -1040,6 +1040,10 @@ int sfb_qp_sparse_symbolic(int n, int m, const int32_t* P_colptr, const int32_t*
   if (n <= 0 || m < 0 || !P_colptr || (m > 0 && !A_rowptr)) return SFB_ERR_INVALID_ARGUMENT;
   sfb::SparseSymbolic S;
   if (!sfb::sparse_analyze(n, m, P_colptr, P_rowidx, A_rowptr, A_colidx, S)) return fail(nullptr, SFB_ERR_INVALID_ARGUMENT, "sparse pattern rejected: %s", S.error.c_str());
+  {
+    std::string why;  // every schedule the device kernel relies on is self-checked on this (test-facing) entry point
+    if (!sfb::sparse_validate(S, why)) return fail(nullptr, SFB_ERR_INVALID_ARGUMENT, "internal: inconsistent sparse schedules: %s", why.c_str());
+  }
   if (nnz_L) *nnz_L = S.nnzL;
   if (factor_flops) *factor_flops = S.flops;
   if (perm_out) std::copy(S.perm.begin(), S.perm.end(), perm_out);

@@ -89,3 +89,15 @@ def test_symbolic_rejects_bad_patterns():
     bad = pat["A_colidx"].copy(); bad[0] = 99
     with pytest.raises(sfb.SfbError):
         sfb.sparse_symbolic(8, 6, pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], bad)
+
+
+@pytest.mark.parametrize("n,m,density,seed", [(1, 1, 1.0, 0), (7, 3, 0.5, 1), (30, 80, 0.1, 2), (64, 64, 0.05, 3), (40, 5, 1.0, 4),
+                                               (90, 200, 0.03, 5), (50, 100, 1.0, 6)])
+def test_schedules_are_self_consistent(n, m, density, seed):
+    # sfb_qp_sparse_symbolic validates every schedule the device kernel relies on (qp_sparse_host.hpp::sparse_validate):
+    # each factor slot streamed once per sweep, each A entry once per padded stream, targets in range, pairs inside their
+    # row / column, distinct targets per column update.  Dense rows (> 32 entries) switch the padded SpMV streams off.
+    pat, *_ = random_sparse_qp_numpy(1, n, m, density=density, seed=seed)
+    sym = sfb.sparse_symbolic(n, m, pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], pat["A_colidx"])
+    assert sorted(sym["perm"].tolist()) == list(range(n))
+    assert 0 <= sym["nnzL"] <= n * (n - 1) // 2
