@@ -82,3 +82,36 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dp, fn)).read()
                 assert "oracle" not in src.replace("the oracle", "").replace("oracle's", "").replace("oracle/", "") or \
                     not re.search(r"^\s*(from|import)\s+oracle|#include\s+\"[^\"]*oracle", src, re.M), fn
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/sfb.h must be consumable from C (cgo / JNI / ctypes-style bindings): compile and link a C99 translation unit
+    that takes the address of every declared entry point."""
+    import re
+    import subprocess
+
+    from smooth_feedback_b200 import _lib
+
+    hdr = os.path.join(ROOT, "include", "sfb.h")
+    names = sorted(set(re.findall(r"\b(sfb_[a-z0-9_]+)\s*\(", open(hdr).read())))
+    assert set(names) == set(_lib.EXPORTED_SYMBOLS)
+    src = tmp_path / "use_sfb.c"
+    src.write_text('#include "sfb.h"\n#include <stdio.h>\ntypedef void (*fn_t)(void);\nint main(void) {\n  fn_t p[] = {' +
+                   ", ".join(f"(fn_t){n}" for n in names) +
+                   '};\n  sfb_qp_params prm; sfb_qp_params_default(&prm);\n'
+                   '  printf("%d %d %g\\n", (int)(sizeof(p) / sizeof(p[0])), sfb_version(), (double)prm.rho);\n  return prm.stop_check_iter == 25 ? 0 : 1;\n}\n')
+    exe = tmp_path / "use_sfb"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    import glob
+    import sysconfig
+
+    cudart = None
+    for base in {sysconfig.get_paths()["purelib"], sysconfig.get_paths()["platlib"]}:
+        hits = glob.glob(os.path.join(base, "nvidia", "cuda_runtime", "lib"))
+        if hits:
+            cudart = hits[0]
+    cudart = cudart or "/usr/local/cuda/lib64"
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", f"-I{os.path.join(ROOT, 'include')}",
+                           "-o", str(exe), str(src), f"-L{libdir}", "-lsfb", f"-Wl,-rpath,{libdir}", f"-L{cudart}", f"-Wl,-rpath,{cudart}"])
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.split()[0] == str(len(names)), r.stdout + r.stderr
