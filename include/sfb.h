@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define SFB_VERSION 100 /* 0.1.0 */
+#define SFB_VERSION 200 /* 0.2.0 */
 
 typedef struct sfb_context* sfb_handle_t;
 
@@ -224,6 +224,67 @@ int sfb_qp_solve_sparse_batch_f32(sfb_handle_t h, sfb_qp_sparse_pattern_t patter
                                   const float* l, const float* u, const float* warm_x, const float* warm_y, float* out_x,
                                   float* out_y, float* out_obj, int32_t* out_status, uint32_t* out_iter,
                                   int8_t* out_active, uint32_t* out_flags);
+
+/*
+ * ---- ASIFilter on the device for the built-in SE(2) x R^3 vehicle family (SURVEY 8(f) rows f1 + f3) -----------------
+ *
+ * Replaces ASIFilter<G, U, Dyn>::operator()(g, u_des, h, bu) (asif.hpp:82-102) -- asif_to_qp_update (asif_func.hpp:104-199)
+ * followed by solve_qp (asif.hpp:97) and the warm-start retention rule (asif.hpp:99: kept only if Optimal) -- for a FLEET of
+ * agents that share one parameter set, for the model family of examples/mpc_asif_vehicle.cpp:
+ *     G = Bundle<SE2, R^3>, coefficients (x, y, sin, cos, v1, v2, v3);  U = R^2
+ *     d^r g = (v1, v2, v3, -drag1 v1 + u1, 0, -drag3 v3 + u2)                  (:42-52)
+ *     h(g)  = |p - centre| - radius                (nh = 1)                     (:96-100)
+ *     bu(g) = (bu_gain v1, bu_const)                                            (:103)
+ * The reference differentiates user lambdas with autodiff on the host (they cannot cross a C ABI); for this family the
+ * derivatives are closed forms evaluated on the device.  One kernel launch maps (g, u_des) -> u; the QP (n = 3, m = K + 3)
+ * never exists in host memory and the warm starts stay resident on the device between control steps.
+ * K + 3 <= 256 (the register-resident tall-skinny solver); qp.polish must be 0 (as in mpc_asif_vehicle.cpp:127).
+ */
+typedef struct {
+  double T;             /* 2.5    ASIFilterParams::T        asif.hpp:20   look-ahead horizon */
+  int32_t K;            /* 200    ASIFtoQPParams::K         asif_func.hpp:61 */
+  double alpha;         /* 5      ASIFtoQPParams::alpha     :63 */
+  double dt;            /* 0.01   ASIFtoQPParams::dt        :65 */
+  double relax_cost;    /* 100    ASIFtoQPParams::relax_cost :67 */
+  double u_weight[2];   /* 20, 1  ASIFilterParams::u_weight asif.hpp:24 */
+  double ulim_l[2];     /* -0.2, -0.5   ManifoldBounds with A = I, c = 0 (mpc_asif_vehicle.cpp:105-110) */
+  double ulim_u[2];     /* 0.5, 0.5 */
+  double drag1, drag3;  /* 0.2, 0.4 */
+  double centre[2];     /* 0, -2.3 */
+  double radius;        /* 0.7 */
+  double bu_gain;       /* 0.2 */
+  double bu_const;      /* -0.5 */
+  sfb_qp_params qp;     /* ASIFilterParams::qp; defaults + polish = 0 */
+} sfb_asif_vehicle_params;
+
+/* the parameter set of examples/mpc_asif_vehicle.cpp:96-129 */
+void sfb_asif_vehicle_params_default(sfb_asif_vehicle_params* p);
+
+typedef struct sfb_asif_fleet* sfb_asif_fleet_t;
+
+/* scalar_bytes: 8 (the reference's arithmetic) or 4.  The trajectory / sensitivity integration always runs in fp64. */
+int sfb_asif_fleet_create(sfb_handle_t h, const sfb_asif_vehicle_params* p, int64_t batch, int scalar_bytes,
+                          sfb_asif_fleet_t* out);
+int sfb_asif_fleet_destroy(sfb_asif_fleet_t f);
+/* forget every agent's warm start (a freshly constructed ASIFilter, asif.hpp:109) */
+int sfb_asif_fleet_reset_warmstart(sfb_asif_fleet_t f);
+/* warm = 0: ignore and do not update the resident warm starts (every call is a cold solve_qp) */
+int sfb_asif_fleet_set_warmstart(sfb_asif_fleet_t f, int warm);
+/*
+ * One control step of every agent: x [batch][7], u_des [batch][2] -> out_u [batch][2] = u_des + primal.head<2>(),
+ * out_status [batch] (sfb_qp_status), out_iter [batch].  All-host or all-device pointers (host: 72 B in, 24 B out per
+ * agent cross PCIe per step).
+ */
+int sfb_asif_fleet_filter_f64(sfb_asif_fleet_t f, const double* x, const double* u_des, double* out_u,
+                              int32_t* out_status, uint32_t* out_iter);
+int sfb_asif_fleet_filter_f32(sfb_asif_fleet_t f, const float* x, const float* u_des, float* out_u, int32_t* out_status,
+                              uint32_t* out_iter);
+/*
+ * asif_to_qp (asif_func.hpp:246-261) alone: the dense QP of every agent in the reference's storage,
+ * P [batch][9], q [batch][3], A [batch][(K+3)*3] column-major, l, u [batch][K+3].  fp64 fleets only.
+ */
+int sfb_asif_fleet_to_qp_f64(sfb_asif_fleet_t f, const double* x, const double* u_des, double* P, double* q, double* A,
+                             double* l, double* u);
 
 #ifdef __cplusplus
 }

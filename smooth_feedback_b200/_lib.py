@@ -53,6 +53,8 @@ EXPORTED_SYMBOLS = [
     "sfb_ekf_predict_batch_f64", "sfb_ekf_update_batch_f64", "sfb_ekf_step_batch_f64",
     "sfb_qp_sparse_analyze", "sfb_qp_sparse_symbolic", "sfb_qp_sparse_pattern_destroy", "sfb_qp_sparse_pattern_info",
     "sfb_qp_solve_sparse_batch_f64", "sfb_qp_solve_sparse_batch_f32",
+    "sfb_asif_vehicle_params_default", "sfb_asif_fleet_create", "sfb_asif_fleet_destroy", "sfb_asif_fleet_reset_warmstart",
+    "sfb_asif_fleet_set_warmstart", "sfb_asif_fleet_filter_f64", "sfb_asif_fleet_filter_f32", "sfb_asif_fleet_to_qp_f64",
 ]
 
 
@@ -121,10 +123,17 @@ def lib() -> C.CDLL:
     sp_sig = [vp, vp, C.POINTER(SfbQpParams), i64] + [vp] * 14
     L.sfb_qp_solve_sparse_batch_f64.argtypes = sp_sig
     L.sfb_qp_solve_sparse_batch_f32.argtypes = sp_sig
+    L.sfb_asif_vehicle_params_default.argtypes = [vp]
+    L.sfb_asif_vehicle_params_default.restype = None
+    L.sfb_asif_fleet_create.argtypes = [vp, vp, i64, i32, C.POINTER(vp)]
+    L.sfb_asif_fleet_destroy.argtypes = [vp]
+    L.sfb_asif_fleet_reset_warmstart.argtypes = [vp]
+    L.sfb_asif_fleet_set_warmstart.argtypes = [vp, i32]
+    L.sfb_asif_fleet_filter_f64.argtypes = [vp] * 6
+    L.sfb_asif_fleet_filter_f32.argtypes = [vp] * 6
+    L.sfb_asif_fleet_to_qp_f64.argtypes = [vp] * 8
     for name in EXPORTED_SYMBOLS:
-        fn = getattr(L, name)
-        if fn.restype is C.c_int and name not in ("sfb_version", "sfb_qp_dense_max_m"):
-            pass
+        getattr(L, name)
     _lib = L
     return L
 

@@ -239,10 +239,21 @@ template <typename T, int N, int R> struct QpSkinny
 
   __device__ void solve(const QpArgs<T>& a, long long b)
   {
-    const T inf = Num<T>::inf();
-    const sfb_qp_params& prm = a.prm;
-    const unsigned long long t0 = prm.has_max_time ? global_timer_ns() : 0ull;
+    const unsigned long long t0 = a.prm.has_max_time ? global_timer_ns() : 0ull;
     load(a, b);
+    int code;
+    unsigned iter;
+    run(a.prm, a.max_iter_eff, t0, a.warm_x ? a.warm_x + b * N : nullptr, a.warm_y ? a.warm_y + b * (long long)m : nullptr, code, iter);
+    store(a, b, code, iter);
+  }
+
+  // Everything between the staged problem data (A, l, u, P, q, valid, m, lane set by the caller) and the final iterate:
+  // scale, rho classes, reduced KKT inverse, warm start, ADMM loop with stop checks.  On return x / y hold the SCALED
+  // iterate (unscaled: sx x, sy y / c), code the status (kStatusUnset = iteration budget exhausted), iter the counter.
+  __device__ void run(const sfb_qp_params& prm, unsigned max_iter_eff, unsigned long long t0, const T* warm_x, const T* warm_y,
+                      int& code_out, unsigned& iter_out)
+  {
+    const T inf = Num<T>::inf();
     if (prm.scaling) scale();
     else {
       c = T(1);
@@ -295,13 +306,13 @@ template <typename T, int N, int R> struct QpSkinny
 #pragma unroll
       for (int j = 0; j < N; ++j) Minv[i][j] = M[i][j];
     // initial iterate  :436-445
-    if (a.warm_x != nullptr) {
+    if (warm_x != nullptr) {
 #pragma unroll
-      for (int j = 0; j < N; ++j) x[j] = (T(1) / sx[j]) * __ldg(a.warm_x + b * N + j);
+      for (int j = 0; j < N; ++j) x[j] = (T(1) / sx[j]) * warm_x[j];
 #pragma unroll
       for (int k = 0; k < R; ++k) {
         const int i = lane + 32 * k;
-        y[k] = valid[k] ? c * ((T(1) / sy[k]) * __ldg(a.warm_y + b * (long long)m + i)) : T(0);
+        y[k] = valid[k] ? c * ((T(1) / sy[k]) * warm_y[i]) : T(0);
         T zt = T(0);
 #pragma unroll
         for (int j = 0; j < N; ++j) zt += A[k][j] * x[j];
@@ -321,7 +332,7 @@ template <typename T, int N, int R> struct QpSkinny
     const unsigned sci = prm.stop_check_iter;
     unsigned iter = 0;
 #pragma unroll 1
-    for (; iter != a.max_iter_eff && code == kStatusUnset; ++iter) {
+    for (; iter != max_iter_eff && code == kStatusUnset; ++iter) {
       // rhs = sigma x - qb + Abar^T (R z - y)
       T t[N];
 #pragma unroll
@@ -368,7 +379,14 @@ template <typename T, int N, int R> struct QpSkinny
       }
     }
 
-    // active sets (qp_solver.hpp:113-123) on the scaled dual, outputs, objective  :544-548
+    code_out = code;
+    iter_out = iter;
+  }
+
+  // active sets (qp_solver.hpp:113-123) on the scaled dual, outputs, objective  :544-548
+  __device__ void store(const QpArgs<T>& a, long long b, int code, unsigned iter)
+  {
+    const T inf = Num<T>::inf();
     const T thr = T(100) * Num<T>::eps();
 #pragma unroll
     for (int k = 0; k < R; ++k) {

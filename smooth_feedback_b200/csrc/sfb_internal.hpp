@@ -1,0 +1,82 @@
+// sfb_internal.hpp -- host-side internals shared by the translation units of libsfb.so (not part of the C ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <initializer_list>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "../../include/sfb.h"
+
+namespace sfbi {
+
+constexpr int kNumSlots = 3;  // staging slots of the host-buffer pipeline (H2D / compute / D2H overlap)
+
+struct Slot
+{
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+  void* dev = nullptr;
+  size_t bytes = 0;
+};
+
+// device workspace owned by a handle (polish scratch, sparse working set, staging of host buffers)
+struct Scratch
+{
+  void* dev = nullptr;
+  size_t bytes = 0;
+};
+
+std::string& create_error();
+
+}  // namespace sfbi
+
+struct sfb_context
+{
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaDeviceProp prop{};
+  unsigned long long* counters = nullptr;  // work-queue heads, one per launch in flight
+  int num_counters = 64;
+  int next_counter = 0;
+  uint64_t launches = 0;
+  std::string last_error;
+  sfbi::Slot slots[sfbi::kNumSlots];
+  sfbi::Scratch scratch[sfbi::kNumSlots + 1];  // [kNumSlots] belongs to the handle's own stream
+  cudaEvent_t ev_start = nullptr;
+  bool ekf_force_generic = false;
+  bool dense_force_generic = false;  // SFB_DENSE_FORCE_GENERIC=1: bypass the tall-skinny register kernel (A/B measurements)
+  int sparse_tw = 0;     // SFB_SPARSE_TW=4|8|32 overrides the tile-width heuristic of the sparse QP path (A/B measurements)
+  sfbi::Scratch sparse_ws;     // tiled working set of the sparse QP path
+  sfbi::Scratch sparse_stage;  // device copies of host buffers (sparse path)
+};
+
+namespace sfbi {
+
+int fail(sfb_context* h, int code, const char* fmt, ...);
+#define SFB_CUDA(h, call)                                                                              \
+  do {                                                                                                 \
+    cudaError_t e__ = (call);                                                                          \
+    if (e__ != cudaSuccess)                                                                            \
+      return fail(h, SFB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__,  \
+                  __LINE__);                                                                           \
+  } while (0)
+
+// 0 = host, 1 = device
+int mem_space(const void* p);
+// classify a set of pointers (nullptr entries ignored): 0 all host, 1 all device, -1 mixed
+int classify(std::initializer_list<const void*> ps);
+unsigned long long* next_counter(sfb_context* h);
+int ensure_slot(sfb_context* h, Slot& s, size_t bytes);
+int ensure_scratch(sfb_context* h, Scratch& s, size_t bytes, cudaStream_t st);
+int check_params(sfb_context* h, const sfb_qp_params* prm, int64_t batch, int n, int m);
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace sfbi

@@ -1,0 +1,260 @@
+// sfb_sparse.cu -- host side of the sparse (shared-pattern) QP entry points of include/sfb.h.
+#include "sfb_internal.hpp"
+
+#include "qp_dense_group.cuh"
+#include "qp_sparse_host.hpp"
+#include "qp_sparse_tiled.cuh"
+
+using namespace sfbi;
+
+// device-resident result of sfb_qp_sparse_analyze (index arrays shared by every instance of a batch)
+struct sfb_qp_sparse_pattern
+{
+  int device = 0;
+  sfb::SparseSymbolic sym;
+  int* dev = nullptr;  // one allocation holding all index arrays
+  sfb::SpPattern pat{};
+};
+
+namespace {
+
+// ---- sparse QP (shared pattern) --------------------------------------------------------------------------
+template <typename T>
+int qp_sparse_solve_impl(sfb_context* h, const sfb_qp_sparse_pattern* pt, const sfb_qp_params* prm, int64_t batch,
+                         const T* P, const T* q, const T* A, const T* l, const T* u, const T* warm_x, const T* warm_y,
+                         T* out_x, T* out_y, T* out_obj, int32_t* out_status, uint32_t* out_iter, int8_t* out_active,
+                         uint32_t* out_flags)
+{
+  if (!h) return SFB_ERR_INVALID_ARGUMENT;
+  if (!pt) return fail(h, SFB_ERR_INVALID_ARGUMENT, "pattern is NULL");
+  const int n = pt->sym.n, m = pt->sym.m;
+  int rc = check_params(h, prm, batch, n, m);
+  if (rc != SFB_OK) return rc;
+  if (pt->device != h->device) return fail(h, SFB_ERR_INVALID_ARGUMENT, "pattern was analysed for device %d, handle is on %d", pt->device, h->device);
+  if (!q || !out_x || !out_y || !out_obj || !out_status || !out_iter || (pt->sym.nnzP > 0 && !P) ||
+      (m > 0 && (!l || !u)) || (pt->sym.nnzA > 0 && !A))
+    return fail(h, SFB_ERR_INVALID_ARGUMENT, "required pointer is NULL");
+  if ((warm_x == nullptr) != (warm_y == nullptr))
+    return fail(h, SFB_ERR_INVALID_ARGUMENT, "warm_x and warm_y must both be given or both be NULL");
+  if (batch == 0) return SFB_OK;
+  SFB_CUDA(h, cudaSetDevice(h->device));
+  const int space = classify({P, q, A, l, u, warm_x, warm_y, out_x, out_y, out_obj, out_status, out_iter, out_active, out_flags});
+  if (space < 0) return fail(h, SFB_ERR_MIXED_MEMORY, "host and device pointers mixed in one call");
+
+  const sfb::SparseSymbolic& S = pt->sym;
+  // tile width.  4 instances per warp with 8 lanes cooperating on each wins at every batch size measured (n = m = 422:
+  // batch 8192 -> 99k solves/s fp64 / 186k fp32 against 14k / - with one lane per instance; batch 65536 -> 105k / 235k
+  // against 100k / 150k; profiles/README.md); one lane per instance (32 per warp) needs ~40 % less workspace and is kept
+  // for batches whose 4-wide working set would not fit in half of the free device memory.
+  int tw = 4;
+  {
+    const size_t per_inst4 = (sfb::sp_a_len(pt->pat, 4) + pt->sym.nnzP + sfb::sp_w_len(pt->pat, 4) + (size_t)sfb::kSpNV * n +
+                              (size_t)sfb::kSpMV * m) * sizeof(T);
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = 0; }
+    if (h->sparse_ws.bytes < per_inst4 * (size_t)batch && per_inst4 * (size_t)batch > free_b / 2) tw = 32;
+  }
+  if (h->sparse_tw == 4 || h->sparse_tw == 8 || h->sparse_tw == 32) tw = h->sparse_tw;
+  const long long tiles = (batch + tw - 1) / tw;
+  const size_t wlen = sfb::sp_w_len(pt->pat, tw);  // factor + its stream-ordered copies
+  const size_t alen = sfb::sp_a_len(pt->pat, tw);  // Abar + its padded row / column stream copies
+  const size_t per_tile = (alen + S.nnzP + wlen + (size_t)sfb::kSpNV * n + (size_t)sfb::kSpMV * m) * tw * sizeof(T);
+  rc = ensure_scratch(h, h->sparse_ws, per_tile * (size_t)tiles, h->stream);
+  if (rc != SFB_OK) return rc;
+
+  sfb::SpArgs<T> a{};
+  a.pat = pt->pat;
+  a.batch = batch;
+  a.prm = *prm;
+  a.max_iter_eff = prm->has_max_iter ? prm->max_iter : SFB_QP_DEVICE_ITER_CAP;
+  {
+    T* w = static_cast<T*>(h->sparse_ws.dev);
+    a.wsA = w; w += (size_t)tiles * alen * tw;
+    a.wsP = w; w += (size_t)tiles * S.nnzP * tw;
+    a.wsW = w; w += (size_t)tiles * wlen * tw;
+    a.wsN = w; w += (size_t)tiles * sfb::kSpNV * n * tw;
+    a.wsM = w;
+  }
+  auto launch = [&]() -> int {
+    const unsigned grid = (unsigned)std::min<long long>(tiles, 1 << 30);
+    if (tw < 32) {
+      const size_t smem = (size_t)(n + 1) * tw * sizeof(T);  // the solve vector of the tile + the dummy zero slot
+      if (smem > h->prop.sharedMemPerBlockOptin) return fail(h, SFB_ERR_UNSUPPORTED_SIZE, "sparse QP n=%d: solve vector does not fit in shared memory", n);
+      if (tw == 8) {
+        SFB_CUDA(h, cudaFuncSetAttribute(sfb::qp_sparse_tiled_kernel<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sfb::qp_sparse_tiled_kernel<T, 8><<<grid, 32, smem, h->stream>>>(a);
+      } else {
+        SFB_CUDA(h, cudaFuncSetAttribute(sfb::qp_sparse_tiled_kernel<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sfb::qp_sparse_tiled_kernel<T, 4><<<grid, 32, smem, h->stream>>>(a);
+      }
+    } else {
+      sfb::qp_sparse_tiled_kernel<T, 32><<<grid, 32, 0, h->stream>>>(a);
+    }
+    SFB_CUDA(h, cudaGetLastError());
+    h->launches += 1;
+    return SFB_OK;
+  };
+  if (space == 1) {
+    a.P = P; a.q = q; a.A = A; a.l = l; a.u = u; a.warm_x = warm_x; a.warm_y = warm_y;
+    a.out_x = out_x; a.out_y = out_y; a.out_obj = out_obj; a.out_status = out_status; a.out_iter = out_iter;
+    a.out_active = out_active; a.out_flags = out_flags;
+    return launch();
+  }
+  // host buffers: one staged round trip on the handle's stream (inputs are ~1 % of the per-solve traffic of this path)
+  auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+  const size_t B = (size_t)batch;
+  const size_t sP = al(sizeof(T) * S.nnzP * B), sq = al(sizeof(T) * n * B), sA = al(sizeof(T) * S.nnzA * B),
+               sm_ = al(sizeof(T) * m * B), s4 = al(4 * B), sact = al((size_t)m * B), s1 = al(sizeof(T) * B);
+  const size_t total = sP + sq + sA + 2 * sm_ + (warm_x ? sq + sm_ : 0) + sq + sm_ + s1 + 3 * s4 + sact;
+  rc = ensure_scratch(h, h->sparse_stage, total, h->stream);
+  if (rc != SFB_OK) return rc;
+  char* d = static_cast<char*>(h->sparse_stage.dev);
+  auto take = [&](size_t bytes) { char* r = d; d += bytes; return r; };
+  T* dP = (T*)take(sP); T* dq = (T*)take(sq); T* dA = (T*)take(sA); T* dl = (T*)take(sm_); T* du = (T*)take(sm_);
+  T* dwx = warm_x ? (T*)take(sq) : nullptr; T* dwy = warm_x ? (T*)take(sm_) : nullptr;
+  T* dox = (T*)take(sq); T* doy = (T*)take(sm_); T* dobj = (T*)take(s1);
+  int32_t* dst = (int32_t*)take(s4); uint32_t* dit = (uint32_t*)take(s4); uint32_t* dfl = (uint32_t*)take(s4);
+  int8_t* dact = (int8_t*)take(sact);
+  auto up = [&](void* dst_, const void* src, size_t bytes) { return bytes ? cudaMemcpyAsync(dst_, src, bytes, cudaMemcpyHostToDevice, h->stream) : cudaSuccess; };
+  SFB_CUDA(h, up(dP, P, sizeof(T) * S.nnzP * B));
+  SFB_CUDA(h, up(dq, q, sizeof(T) * n * B));
+  SFB_CUDA(h, up(dA, A, sizeof(T) * S.nnzA * B));
+  SFB_CUDA(h, up(dl, l, sizeof(T) * m * B));
+  SFB_CUDA(h, up(du, u, sizeof(T) * m * B));
+  if (warm_x) {
+    SFB_CUDA(h, up(dwx, warm_x, sizeof(T) * n * B));
+    SFB_CUDA(h, up(dwy, warm_y, sizeof(T) * m * B));
+  }
+  a.P = dP; a.q = dq; a.A = dA; a.l = dl; a.u = du; a.warm_x = dwx; a.warm_y = dwy;
+  a.out_x = dox; a.out_y = doy; a.out_obj = dobj; a.out_status = dst; a.out_iter = dit;
+  a.out_active = out_active ? dact : nullptr; a.out_flags = out_flags ? dfl : nullptr;
+  rc = launch();
+  if (rc != SFB_OK) return rc;
+  auto down = [&](void* dst_, const void* src, size_t bytes) { return bytes ? cudaMemcpyAsync(dst_, src, bytes, cudaMemcpyDeviceToHost, h->stream) : cudaSuccess; };
+  SFB_CUDA(h, down(out_x, dox, sizeof(T) * n * B));
+  SFB_CUDA(h, down(out_y, doy, sizeof(T) * m * B));
+  SFB_CUDA(h, down(out_obj, dobj, sizeof(T) * B));
+  SFB_CUDA(h, down(out_status, dst, 4 * B));
+  SFB_CUDA(h, down(out_iter, dit, 4 * B));
+  if (out_active) SFB_CUDA(h, down(out_active, dact, (size_t)m * B));
+  if (out_flags) SFB_CUDA(h, down(out_flags, dfl, 4 * B));
+  SFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return SFB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sfb_qp_sparse_analyze(sfb_handle_t h, int n, int m, const int32_t* P_colptr, const int32_t* P_rowidx,
+                          const int32_t* A_rowptr, const int32_t* A_colidx, sfb_qp_sparse_pattern_t* out)
+{
+  if (!h) return SFB_ERR_INVALID_ARGUMENT;
+  if (!out) return fail(h, SFB_ERR_INVALID_ARGUMENT, "out is NULL");
+  *out = nullptr;
+  if (n <= 0 || m < 0 || !P_colptr || (m > 0 && !A_rowptr)) return fail(h, SFB_ERR_INVALID_ARGUMENT, "bad pattern arguments");
+  if ((P_colptr[n] > 0 && !P_rowidx) || (m > 0 && A_rowptr[m] > 0 && !A_colidx)) return fail(h, SFB_ERR_INVALID_ARGUMENT, "index array is NULL");
+  auto* p = new sfb_qp_sparse_pattern();
+  p->device = h->device;
+  if (!sfb::sparse_analyze(n, m, P_colptr, P_rowidx, A_rowptr, A_colidx, p->sym)) {
+    const std::string msg = p->sym.error;
+    delete p;
+    return fail(h, SFB_ERR_INVALID_ARGUMENT, "sparse pattern rejected: %s", msg.c_str());
+  }
+  const sfb::SparseSymbolic& S = p->sym;
+  const std::vector<int>* arrs[] = {&S.perm, &S.iperm, &S.P_rowp, &S.P_colp, &S.P_tgt, &S.A_rowptr, &S.A_col, &S.A_pair_ptr,
+                                    &S.A_pair_tgt, &S.L_colptr, &S.L_row, &S.F_ptr, &S.F_tgt, &S.LR_ptr, &S.LR_col, &S.LR_slot,
+                                    &S.AT_ptr, &S.AT_row, &S.AT_slot, &S.PR_ptr, &S.PR_col, &S.PR_slot, &S.PS_ptr, &S.PS_col,
+                                    &S.PS_slot, &S.PC_ptr, &S.PC_slot, &S.LB_ptr, &S.LB_row, &S.LB_slot, &S.A_pair_ab, &S.F_ab, &S.FS_meta, &S.FS_col, &S.FS_slot,
+                                    &S.BS_meta, &S.BS_col, &S.BS_slot, &S.RP_col, &S.RP_slot, &S.ATP_row, &S.ATP_slot};
+  size_t total = 0;
+  std::vector<size_t> off;
+  for (auto* v : arrs) { off.push_back(total); total += (v->size() + 31) / 32 * 32; }
+  std::vector<int> flat(total, 0);
+  for (size_t k = 0; k < off.size(); ++k) std::copy(arrs[k]->begin(), arrs[k]->end(), flat.begin() + off[k]);
+  if (cudaSetDevice(h->device) != cudaSuccess || cudaMalloc(&p->dev, total * sizeof(int)) != cudaSuccess ||
+      cudaMemcpy(p->dev, flat.data(), total * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
+    const char* msg = cudaGetErrorString(cudaGetLastError());
+    if (p->dev) cudaFree(p->dev);
+    delete p;
+    return fail(h, SFB_ERR_CUDA, "uploading the sparse pattern failed: %s", msg);
+  }
+  sfb::SpPattern& d = p->pat;
+  d.n = n; d.m = m; d.nnzP = S.nnzP; d.nnzA = S.nnzA; d.nnzL = S.nnzL;
+  const int* base = p->dev;
+  d.perm = base + off[0]; d.iperm = base + off[1]; d.P_rowp = base + off[2]; d.P_colp = base + off[3]; d.P_tgt = base + off[4];
+  d.A_rowptr = base + off[5]; d.A_col = base + off[6]; d.A_pair_ptr = base + off[7]; d.A_pair_tgt = base + off[8];
+  d.L_colptr = base + off[9]; d.L_row = base + off[10]; d.F_ptr = base + off[11]; d.F_tgt = base + off[12];
+  d.LR_ptr = base + off[13]; d.LR_col = base + off[14]; d.LR_slot = base + off[15];
+  d.AT_ptr = base + off[16]; d.AT_row = base + off[17]; d.AT_slot = base + off[18];
+  d.PR_ptr = base + off[19]; d.PR_col = base + off[20]; d.PR_slot = base + off[21];
+  d.PS_ptr = base + off[22]; d.PS_col = base + off[23]; d.PS_slot = base + off[24];
+  d.PC_ptr = base + off[25]; d.PC_slot = base + off[26];
+  d.LB_ptr = base + off[27]; d.LB_row = base + off[28]; d.LB_slot = base + off[29];
+  d.A_pair_ab = base + off[30]; d.F_ab = base + off[31];
+  d.FS_meta = base + off[32]; d.FS_col = base + off[33]; d.FS_slot = base + off[34];
+  d.BS_meta = base + off[35]; d.BS_col = base + off[36]; d.BS_slot = base + off[37];
+  d.nFS = (int)S.FS_meta.size(); d.nBS = (int)S.BS_meta.size();
+  d.RP_col = base + off[38]; d.RP_slot = base + off[39]; d.ATP_row = base + off[40]; d.ATP_slot = base + off[41];
+  d.WR = S.WR; d.WA = S.WA; d.m_pad = S.m_pad; d.n_pad = S.n_pad;
+  *out = p;
+  return SFB_OK;
+}
+
+int sfb_qp_sparse_symbolic(int n, int m, const int32_t* P_colptr, const int32_t* P_rowidx, const int32_t* A_rowptr,
+                           const int32_t* A_colidx, int64_t* nnz_L, int64_t* factor_flops, int32_t* perm_out,
+                           int32_t* L_colptr_out)
+{
+  if (n <= 0 || m < 0 || !P_colptr || (m > 0 && !A_rowptr)) return SFB_ERR_INVALID_ARGUMENT;
+  sfb::SparseSymbolic S;
+  if (!sfb::sparse_analyze(n, m, P_colptr, P_rowidx, A_rowptr, A_colidx, S)) return fail(nullptr, SFB_ERR_INVALID_ARGUMENT, "sparse pattern rejected: %s", S.error.c_str());
+  {
+    std::string why;  // every schedule the device kernel relies on is self-checked on this (test-facing) entry point
+    if (!sfb::sparse_validate(S, why)) return fail(nullptr, SFB_ERR_INVALID_ARGUMENT, "internal: inconsistent sparse schedules: %s", why.c_str());
+  }
+  if (nnz_L) *nnz_L = S.nnzL;
+  if (factor_flops) *factor_flops = S.flops;
+  if (perm_out) std::copy(S.perm.begin(), S.perm.end(), perm_out);
+  if (L_colptr_out) std::copy(S.L_colptr.begin(), S.L_colptr.end(), L_colptr_out);
+  return SFB_OK;
+}
+
+int sfb_qp_sparse_pattern_destroy(sfb_qp_sparse_pattern_t p)
+{
+  if (!p) return SFB_OK;
+  cudaSetDevice(p->device);
+  if (p->dev) cudaFree(p->dev);
+  delete p;
+  return SFB_OK;
+}
+
+int sfb_qp_sparse_pattern_info(sfb_qp_sparse_pattern_t p, int64_t* nnz_L, int64_t* factor_flops, int32_t* perm_out)
+{
+  if (!p) return SFB_ERR_INVALID_ARGUMENT;
+  if (nnz_L) *nnz_L = p->sym.nnzL;
+  if (factor_flops) *factor_flops = p->sym.flops;
+  if (perm_out) std::copy(p->sym.perm.begin(), p->sym.perm.end(), perm_out);
+  return SFB_OK;
+}
+
+int sfb_qp_solve_sparse_batch_f64(sfb_handle_t h, sfb_qp_sparse_pattern_t pattern, const sfb_qp_params* prm,
+                                  int64_t batch, const double* P_vals, const double* q, const double* A_vals,
+                                  const double* l, const double* u, const double* warm_x, const double* warm_y,
+                                  double* out_x, double* out_y, double* out_obj, int32_t* out_status,
+                                  uint32_t* out_iter, int8_t* out_active, uint32_t* out_flags)
+{
+  return qp_sparse_solve_impl<double>(h, pattern, prm, batch, P_vals, q, A_vals, l, u, warm_x, warm_y, out_x, out_y,
+                                      out_obj, out_status, out_iter, out_active, out_flags);
+}
+
+int sfb_qp_solve_sparse_batch_f32(sfb_handle_t h, sfb_qp_sparse_pattern_t pattern, const sfb_qp_params* prm,
+                                  int64_t batch, const float* P_vals, const float* q, const float* A_vals,
+                                  const float* l, const float* u, const float* warm_x, const float* warm_y, float* out_x,
+                                  float* out_y, float* out_obj, int32_t* out_status, uint32_t* out_iter,
+                                  int8_t* out_active, uint32_t* out_flags)
+{
+  return qp_sparse_solve_impl<float>(h, pattern, prm, batch, P_vals, q, A_vals, l, u, warm_x, warm_y, out_x, out_y,
+                                     out_obj, out_status, out_iter, out_active, out_flags);
+}
+
+}  // extern "C"

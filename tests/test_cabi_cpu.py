@@ -115,3 +115,27 @@ def test_header_is_plain_c(tmp_path):
                            "-o", str(exe), str(src), f"-L{libdir}", "-lsfb", f"-Wl,-rpath,{libdir}", f"-L{cudart}", f"-Wl,-rpath,{cudart}"])
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.split()[0] == str(len(names)), r.stdout + r.stderr
+
+
+def test_struct_layouts_match_ctypes(tmp_path):
+    """The ctypes mirrors of the POD parameter structs must have the C compiler's layout (size and every offset)."""
+    from smooth_feedback_b200 import _lib
+    from smooth_feedback_b200.asif import SfbAsifVehicleParams
+
+    structs = {"sfb_qp_params": _lib.SfbQpParams, "sfb_asif_vehicle_params": SfbAsifVehicleParams}
+    body = []
+    for cname, ct in structs.items():
+        body.append(f'printf("{cname} %zu", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            body.append(f'printf(" %zu", offsetof({cname}, {fname}));')
+        body.append('printf("\\n");')
+    src = tmp_path / "layout.c"
+    src.write_text('#include "sfb.h"\n#include <stdio.h>\n#include <stddef.h>\nint main(void) {\n' + "\n".join(body) + "\nreturn 0;\n}\n")
+    exe = tmp_path / "layout"
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", f"-I{os.path.join(ROOT, 'include')}", "-o", str(exe), str(src)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    for line in out:
+        tok = line.split()
+        ct = structs[tok[0]]
+        assert int(tok[1]) == C.sizeof(ct), tok[0]
+        assert [int(t) for t in tok[2:]] == [getattr(ct, f).offset for f, _ in ct._fields_], tok[0]
