@@ -84,18 +84,20 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
   return t;
 }
 
-template <typename T> struct QpArgs
+// T: the scalar the kernel computes in; TIO: the scalar of the caller's arrays.  TIO != T only in the mixed-precision
+// polish pass (mode 2: T = double over float data, see solve()).
+template <typename T, typename TIO = T> struct QpArgs
 {
-  const T* P;
-  const T* q;
-  const T* A;
-  const T* l;
-  const T* u;
-  const T* warm_x;
-  const T* warm_y;
-  T* out_x;
-  T* out_y;
-  T* out_obj;
+  const TIO* P;
+  const TIO* q;
+  const TIO* A;
+  const TIO* l;
+  const TIO* u;
+  const TIO* warm_x;
+  const TIO* warm_y;
+  TIO* out_x;
+  TIO* out_y;
+  TIO* out_obj;
   int32_t* out_status;
   uint32_t* out_iter;
   int8_t* out_active;
@@ -108,7 +110,7 @@ template <typename T> struct QpArgs
   long long scratch_per_cta;
   long long batch;
   int n, m;
-  int mode;  // 0 = solve, 1 = scale only
+  int mode;  // 0 = solve, 1 = scale only, 2 = polish only (instances already solved: out_* hold the unpolished result)
   sfb_qp_params prm;
   unsigned max_iter_eff;
   unsigned long long* work_counter;
@@ -152,12 +154,13 @@ struct QpLayout
 // fetch (profiles/).
 template <typename T, int G, int NS, int MS> __device__ __noinline__ bool qp_stage_gj(int n, int m, int where, int sz);
 template <typename T, int G, int NS, int MS> __device__ __noinline__ bool qp_stage_gj_generic(int n, int m, T* Mx, int ld, int sz);
-template <typename T, int G, int NS, int MS> __device__ __noinline__ T qp_stage_load_scale(const QpArgs<T>* a, long long b);
-template <typename T, int G, int NS, int MS> __device__ __noinline__ int qp_stage_setup(const QpArgs<T>* a, T c);
-template <typename T, int G, int NS, int MS> __device__ __noinline__ int qp_stage_check(const QpArgs<T>* a, long long b, T c);
-template <typename T, int G, int NS, int MS> __device__ __noinline__ unsigned qp_stage_polish(const QpArgs<T>* a, long long b, T c, int na, T* gscratch);
-template <typename T, int G, int NS, int MS>
-__device__ __noinline__ int qp_stage_loop(const QpArgs<T>* a, long long b, T c, unsigned long long t0, int code, unsigned* iter_out);
+template <typename T, int G, int NS, int MS, typename TIO> __device__ __noinline__ T qp_stage_load_scale(const QpArgs<T, TIO>* a, long long b);
+template <typename T, int G, int NS, int MS, typename TIO> __device__ __noinline__ int qp_stage_setup(const QpArgs<T, TIO>* a, T c);
+template <typename T, int G, int NS, int MS, typename TIO> __device__ __noinline__ int qp_stage_check(const QpArgs<T, TIO>* a, long long b, T c);
+template <typename T, int G, int NS, int MS, typename TIO>
+__device__ __noinline__ unsigned qp_stage_polish(const QpArgs<T, TIO>* a, long long b, T c, int na, T* gscratch);
+template <typename T, int G, int NS, int MS, typename TIO>
+__device__ __noinline__ int qp_stage_loop(const QpArgs<T, TIO>* a, long long b, T c, unsigned long long t0, int code, unsigned* iter_out);
 
 // NS, MS: compile-time problem shape (0 = runtime).  A shape-specialised instantiation lets the compiler fold every
 // leading dimension / trip count into immediates, which removes most of the integer overhead of the GEMV passes.
@@ -284,20 +287,20 @@ template <typename T, int G, int NS, int MS> struct QpGroup
   }
 
   // ---------------------------------------------------------------- stage one instance HBM -> shared memory
-  __device__ void load(const QpArgs<T>& a, long long b)
+  template <typename TIO> __device__ void load(const QpArgs<T, TIO>& a, long long b)
   {
-    const T* gA = a.A + b * (long long)m * n;
-    const T* gP = a.P + b * (long long)n * n;
+    const TIO* gA = a.A + b * (long long)m * n;
+    const TIO* gP = a.P + b * (long long)n * n;
     // Coalesced streaming loads, 8 independent requests in flight per thread (the copy is pure DRAM latency:
     // with one request in flight it cost ~40k cycles per instance, profiles/r01_ncu_v5_summary.txt).
-    auto copy = [&](const T* g, T* sm, int rows, int ld, int total) {
+    auto copy = [&](const TIO* g, T* sm, int rows, int ld, int total) {
       constexpr int U = 8;
       int e = tid;
 #pragma unroll 1
       for (; e + (U - 1) * NT < total; e += U * NT) {
         T v[U];
 #pragma unroll
-        for (int k = 0; k < U; ++k) v[k] = __ldg(g + e + k * NT);
+        for (int k = 0; k < U; ++k) v[k] = (T)__ldg(g + e + k * NT);
 #pragma unroll
         for (int k = 0; k < U; ++k) {
           const int ee = e + k * NT;
@@ -308,17 +311,17 @@ template <typename T, int G, int NS, int MS> struct QpGroup
 #pragma unroll 1
       for (; e < total; e += NT) {
         const int j = e / rows, i = e - j * rows;
-        sm[i + ld * j] = __ldg(g + e);
+        sm[i + ld * j] = (T)__ldg(g + e);
       }
     };
     if (m > 0) copy(gA, As, m, ldA, m * n);
     copy(gP, Ms, n, ldN, n * n);
 #pragma unroll 1
-    for (int j = tid; j < n; j += NT) q[j] = __ldg(a.q + b * (long long)n + j);
+    for (int j = tid; j < n; j += NT) q[j] = (T)__ldg(a.q + b * (long long)n + j);
 #pragma unroll 1
     for (int i = tid; i < m; i += NT) {
-      l[i] = __ldg(a.l + b * (long long)m + i);
-      u[i] = __ldg(a.u + b * (long long)m + i);
+      l[i] = (T)__ldg(a.l + b * (long long)m + i);
+      u[i] = (T)__ldg(a.u + b * (long long)m + i);
     }
     gsync();
   }
@@ -660,7 +663,7 @@ template <typename T, int G, int NS, int MS> struct QpGroup
   // ---------------------------------------------------------------- check_stopping, qp_solver.hpp:574-644
   // Called right after the iterate update of a check iteration; xold / yold hold the pre-update iterates.
   // A x_us is evaluated as Sy^-1 (Abar x) and A^T y_us as Sx^-1 Abar^T y / c (the same quantities).
-  __device__ int check_stopping(const QpArgs<T>& a, const T* gP)
+  template <typename TIO> __device__ int check_stopping(const QpArgs<T, TIO>& a, const TIO* gP)
   {
     const T eps_abs = T(a.prm.eps_abs), eps_rel = T(a.prm.eps_rel);
     const T eps_pinf = T(a.prm.eps_primal_inf), eps_dinf = T(a.prm.eps_dual_inf);
@@ -747,7 +750,7 @@ template <typename T, int G, int NS, int MS> struct QpGroup
       T px = T(0), pdx = T(0);
 #pragma unroll 10
       for (int k = 0; k < n; ++k) {  // unrolled: the L2 loads are independent, keep ~10 in flight
-        const T pjk = __ldg(gP + j + (long long)n * k);  // row j of the unscaled P (coalesced across threads)
+        const T pjk = (T)__ldg(gP + j + (long long)n * k);  // row j of the unscaled P (coalesced across threads)
         px += pjk * nv1[k];
         pdx += pjk * xold[k];
       }
@@ -780,15 +783,15 @@ template <typename T, int G, int NS, int MS> struct QpGroup
   }
 
   // Pbar(i, j): upper triangle of c Sx P Sx mirrored (selfadjointView<Upper>), from the unscaled global P
-  __device__ __forceinline__ T pbar(const T* gP, int i, int j) const
+  template <typename TIO> __device__ __forceinline__ T pbar(const TIO* gP, int i, int j) const
   {
     const int r = i <= j ? i : j, cc = i <= j ? j : i;
-    return ((c * sx[r]) * __ldg(gP + r + (long long)n * cc)) * sx[cc];
+    return ((c * sx[r]) * (T)__ldg(gP + r + (long long)n * cc)) * sx[cc];
   }
 
   // ---------------------------------------------------------------- detail::polish_qp, qp_solver.hpp:92-204
   // `na` active rows (ascending) are listed in idx[], their scaled bounds in bnd[].  Returns SFB_QP_FLAG_* bits.
-  __device__ unsigned polish(const QpArgs<T>& a, const T* gP, int na, const int* idx, const T* bnd, T* gscratch)
+  template <typename TIO> __device__ unsigned polish(const QpArgs<T, TIO>& a, const TIO* gP, int na, const int* idx, const T* bnd, T* gscratch)
   {
     // fp32: the delta = 1e-6 regularised polish systems are not resolvable in single precision (8 ulp); until the
     // mixed-precision refinement lands the f32 entry point reports the polish as skipped, which is also what the
@@ -822,7 +825,7 @@ template <typename T, int G, int NS, int MS> struct QpGroup
 #pragma unroll 1
       for (int e = tid; e < n * n; e += NT) {
         if (i <= j) {
-          T h = ((c * sx[i]) * __ldg(gP + e)) * sx[j];
+          T h = ((c * sx[i]) * (T)__ldg(gP + e)) * sx[j];
           if (i == j) h += delta;
           Ms[i + ldN * j] = h;
           Ms[j + ldN * i] = h;
@@ -1079,7 +1082,7 @@ template <typename T, int G, int NS, int MS> struct QpGroup
   }
 
   // rho classes, trivially empty feasible set, in-place data scaling, reduced KKT matrix and its inverse
-  __device__ int setup(const QpArgs<T>& a)
+  template <typename TIO> __device__ int setup(const QpArgs<T, TIO>& a)
   {
     const T inf = Num<T>::inf();
     const T rho_bar = T(a.prm.rho), sigma = T(a.prm.sigma);
@@ -1118,6 +1121,7 @@ template <typename T, int G, int NS, int MS> struct QpGroup
     }
     gsync();
 
+    if (a.mode == 2) return code;  // polish-only pass: the ADMM matrix is not needed
     form_reduced_kkt(sigma);
     if (!gj_invert_at(0, n)) code = SFB_QP_UNKNOWN;  // :433
     return code;
@@ -1125,7 +1129,7 @@ template <typename T, int G, int NS, int MS> struct QpGroup
 
   // ---------------------------------------------------------------- main ADMM loop  qp_solver.hpp:449-510
   // Outlined as its own stage (qp_stage_loop).  Returns the status code (kStatusUnset when the iteration budget ran out).
-  __device__ int admm_loop(const QpArgs<T>& a, long long b, unsigned long long t0, int code, unsigned* iter_out)
+  template <typename TIO> __device__ int admm_loop(const QpArgs<T, TIO>& a, long long b, unsigned long long t0, int code, unsigned* iter_out)
   {
     const T alpha = T(a.prm.alpha), alpha_comp = T(1) - alpha, sigma = T(a.prm.sigma);
     const unsigned sci = a.prm.stop_check_iter;
@@ -1190,10 +1194,10 @@ template <typename T, int G, int NS, int MS> struct QpGroup
   }
 
   // ---------------------------------------------------------------- QPSolver::solve, qp_solver.hpp:343-568
-  __device__ void solve(const QpArgs<T>& a, long long b, T* gscratch)
+  template <typename TIO> __device__ void solve(const QpArgs<T, TIO>& a, long long b, T* gscratch)
   {
     const T inf = Num<T>::inf();
-    const T* gP = a.P + b * (long long)n * n;
+    const TIO* gP = a.P + b * (long long)n * n;
     const unsigned long long t0 = a.prm.has_max_time ? global_timer_ns() : 0ull;
 
     c = qp_stage_load_scale<T, G, NS, MS>(&a, b);  // :347
@@ -1207,14 +1211,28 @@ template <typename T, int G, int NS, int MS> struct QpGroup
       return;
     }
 
+    // Mixed-precision polish (mode 2, T = double over TIO = float data): the instance was solved by the single-precision
+    // kernel, whose delta = 1e-6 regularised polish systems are not resolvable in fp32; this pass re-stages the problem in
+    // double, takes the unpolished iterate and the active set from the outputs and runs only polish_qp on them.
+    const bool polish_only = a.mode == 2;
+    if (polish_only && a.out_status[b] != (int32_t)SFB_QP_OPTIMAL) return;  // uniform: every thread reads the same word
+
     int code = qp_stage_setup<T, G, NS, MS>(&a, c);  // rho classes, trivial infeasibility, in-place scaling, M, Minv
 
     // initial iterate  :436-445
-    if (a.warm_x != nullptr) {
+    if (polish_only) {
 #pragma unroll 1
-      for (int j = tid; j < n; j += NT) x[j] = (T(1) / sx[j]) * __ldg(a.warm_x + b * (long long)n + j);
+      for (int j = tid; j < n; j += NT) x[j] = (T(1) / sx[j]) * (T)a.out_x[b * (long long)n + j];
 #pragma unroll 1
-      for (int i = tid; i < m; i += NT) y[i] = c * ((T(1) / sy[i]) * __ldg(a.warm_y + b * (long long)m + i));
+      for (int i = tid; i < m; i += NT) {
+        y[i] = c * ((T(1) / sy[i]) * (T)a.out_y[b * (long long)m + i]);
+        z[i] = T(0);
+      }
+    } else if (a.warm_x != nullptr) {
+#pragma unroll 1
+      for (int j = tid; j < n; j += NT) x[j] = (T(1) / sx[j]) * (T)__ldg(a.warm_x + b * (long long)n + j);
+#pragma unroll 1
+      for (int i = tid; i < m; i += NT) y[i] = c * ((T(1) / sy[i]) * (T)__ldg(a.warm_y + b * (long long)m + i));
       gsync();
 #pragma unroll 1
       for (int i = tid; i < m; i += NT) z[i] = rowdot(As, ldA, i, n, x);
@@ -1233,7 +1251,8 @@ template <typename T, int G, int NS, int MS> struct QpGroup
     gsync();
 
     unsigned iter = 0;
-    code = qp_stage_loop<T, G, NS, MS>(&a, b, c, t0, code, &iter);
+    if (polish_only) { code = SFB_QP_OPTIMAL; iter = a.out_iter[b]; }
+    else code = qp_stage_loop<T, G, NS, MS>(&a, b, c, t0, code, &iter);
 
     // active sets as polish_qp builds them (:113-123), ascending order, on the scaled dual
     int na = 0;
@@ -1248,9 +1267,15 @@ template <typename T, int G, int NS, int MS> struct QpGroup
         int act = 0;
         T bv = T(0);
         if (i < m) {
-          if (y[i] < -thr && l[i] != -inf) { act = -1; bv = sy[i] * l[i]; }
-          if (y[i] > thr && u[i] != inf) { act = 1; bv = sy[i] * u[i]; }
-          if (a.out_active) a.out_active[b * (long long)m + i] = (int8_t)act;
+          if (polish_only) {  // the active set the lower-precision solve determined
+            act = a.out_active[b * (long long)m + i];
+            if (act < 0) bv = sy[i] * l[i];
+            if (act > 0) bv = sy[i] * u[i];
+          } else {
+            if (y[i] < -thr && l[i] != -inf) { act = -1; bv = sy[i] * l[i]; }
+            if (y[i] > thr && u[i] != inf) { act = 1; bv = sy[i] * u[i]; }
+            if (a.out_active) a.out_active[b * (long long)m + i] = (int8_t)act;
+          }
         }
         const unsigned bal = __ballot_sync(kFullMask, act != 0);
         int before = 0, total = __popc(bal);
@@ -1282,22 +1307,22 @@ template <typename T, int G, int NS, int MS> struct QpGroup
     for (int j = tid; j < n; j += NT) {
       const T v = sx[j] * x[j];
       nv1[j] = v;
-      a.out_x[b * (long long)n + j] = v;
+      a.out_x[b * (long long)n + j] = (TIO)v;
     }
 #pragma unroll 1
-    for (int i = tid; i < m; i += NT) a.out_y[b * (long long)m + i] = sy[i] * y[i] / c;
+    for (int i = tid; i < m; i += NT) a.out_y[b * (long long)m + i] = (TIO)(sy[i] * y[i] / c);
     gsync();
     T obj = T(0);
 #pragma unroll 1
     for (int i = tid; i < n; i += NT) {
       T acc = T(0);
 #pragma unroll 10
-      for (int j = 0; j < n; ++j) acc += T(0.5) * __ldg(gP + i + (long long)n * j) * nv1[j];
+      for (int j = 0; j < n; ++j) acc += T(0.5) * (T)__ldg(gP + i + (long long)n * j) * nv1[j];
       obj += nv1[i] * (acc + q[i]);
     }
     obj = gsum(obj);
     if (tid == 0) {
-      a.out_obj[b] = obj;
+      a.out_obj[b] = (TIO)obj;
       a.out_status[b] = (code == kStatusUnset) ? (int32_t)SFB_QP_MAX_ITERATIONS : (int32_t)code;
       a.out_iter[b] = iter;
       if (a.out_flags) a.out_flags[b] = flags;
@@ -1318,7 +1343,7 @@ template <typename T, int G, int NS, int MS> __device__ __forceinline__ QpGroup<
   return s;
 }
 
-template <typename T, int G, int NS, int MS> __device__ __noinline__ T qp_stage_load_scale(const QpArgs<T>* a, long long b)
+template <typename T, int G, int NS, int MS, typename TIO> __device__ __noinline__ T qp_stage_load_scale(const QpArgs<T, TIO>* a, long long b)
 {
   QpGroup<T, G, NS, MS> s = qp_view<T, G, NS, MS>(a->n, a->m, T(1));
   s.load(*a, b);
@@ -1335,7 +1360,7 @@ template <typename T, int G, int NS, int MS> __device__ __noinline__ T qp_stage_
   return s.c;
 }
 
-template <typename T, int G, int NS, int MS> __device__ __noinline__ int qp_stage_setup(const QpArgs<T>* a, T c)
+template <typename T, int G, int NS, int MS, typename TIO> __device__ __noinline__ int qp_stage_setup(const QpArgs<T, TIO>* a, T c)
 {
   QpGroup<T, G, NS, MS> s = qp_view<T, G, NS, MS>(a->n, a->m, c);
   const int code = s.setup(*a);
@@ -1361,7 +1386,7 @@ template <typename T, int G, int NS, int MS> __device__ __noinline__ bool qp_sta
   return ok;
 }
 
-template <typename T, int G, int NS, int MS> __device__ __noinline__ int qp_stage_check(const QpArgs<T>* a, long long b, T c)
+template <typename T, int G, int NS, int MS, typename TIO> __device__ __noinline__ int qp_stage_check(const QpArgs<T, TIO>* a, long long b, T c)
 {
   QpGroup<T, G, NS, MS> s = qp_view<T, G, NS, MS>(a->n, a->m, c);
   const int code = s.check_stopping(*a, a->P + b * (long long)a->n * a->n);
@@ -1369,8 +1394,8 @@ template <typename T, int G, int NS, int MS> __device__ __noinline__ int qp_stag
   return code;
 }
 
-template <typename T, int G, int NS, int MS>
-__device__ __noinline__ unsigned qp_stage_polish(const QpArgs<T>* a, long long b, T c, int na, T* gscratch)
+template <typename T, int G, int NS, int MS, typename TIO>
+__device__ __noinline__ unsigned qp_stage_polish(const QpArgs<T, TIO>* a, long long b, T c, int na, T* gscratch)
 {
   QpGroup<T, G, NS, MS> s = qp_view<T, G, NS, MS>(a->n, a->m, c);
   const unsigned fl = s.polish(*a, a->P + b * (long long)a->n * a->n, na, reinterpret_cast<const int*>(s.mv1), s.w, gscratch);
@@ -1378,8 +1403,8 @@ __device__ __noinline__ unsigned qp_stage_polish(const QpArgs<T>* a, long long b
   return fl;
 }
 
-template <typename T, int G, int NS, int MS>
-__device__ __noinline__ int qp_stage_loop(const QpArgs<T>* a, long long b, T c, unsigned long long t0, int code, unsigned* iter_out)
+template <typename T, int G, int NS, int MS, typename TIO>
+__device__ __noinline__ int qp_stage_loop(const QpArgs<T, TIO>* a, long long b, T c, unsigned long long t0, int code, unsigned* iter_out)
 {
   QpGroup<T, G, NS, MS> s = qp_view<T, G, NS, MS>(a->n, a->m, c);
   const int r = s.admm_loop(*a, b, t0, code, iter_out);
@@ -1389,8 +1414,8 @@ __device__ __noinline__ int qp_stage_loop(const QpArgs<T>* a, long long b, T c, 
 
 // One CTA of G warps per instance; CTAs pull instances from a global work counter (iteration counts are
 // heavy-tailed), so a slow instance never idles the rest of the grid.
-template <typename T, int G, int MINB, int NS, int MS>
-__global__ void __launch_bounds__(32 * G, MINB) qp_dense_group_kernel(const __grid_constant__ QpArgs<T> a)
+template <typename T, int G, int MINB, int NS, int MS, typename TIO = T>
+__global__ void __launch_bounds__(32 * G, MINB) qp_dense_group_kernel(const __grid_constant__ QpArgs<T, TIO> a)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* base = reinterpret_cast<T*>(smem_raw);

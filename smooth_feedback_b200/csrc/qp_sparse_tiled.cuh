@@ -77,12 +77,14 @@ __host__ __device__ inline size_t sp_a_len(const SpPattern& p, int tw)
 }
 __host__ __device__ inline size_t sp_fwd_len(const SpPattern& p, int tw) { return (tw < 32) ? (size_t)p.nFS * kSpStep : (size_t)p.nnzL; }
 
-template <typename T> struct SpArgs
+// T: the scalar the kernel computes in; TIO: the scalar of the caller's arrays (TIO != T only in the mixed-precision
+// polish pass, mode 2: T = double over float data).
+template <typename T, typename TIO = T> struct SpArgs
 {
   SpPattern pat;
   // inputs, array-of-instances:  P_vals [batch][nnzP], q [batch][n], A_vals [batch][nnzA], l,u [batch][m]
-  const T *P, *q, *A, *l, *u, *warm_x, *warm_y;
-  T *out_x, *out_y, *out_obj;
+  const TIO *P, *q, *A, *l, *u, *warm_x, *warm_y;
+  TIO *out_x, *out_y, *out_obj;
   int32_t* out_status;
   uint32_t* out_iter;
   int8_t* out_active;
@@ -92,6 +94,7 @@ template <typename T> struct SpArgs
   long long batch;
   sfb_qp_params prm;
   unsigned max_iter_eff;
+  int mode;  // 0 = solve, 2 = polish only (instances already solved in lower precision: out_* hold the unpolished result)
 };
 
 // element e of this lane's instance inside a [len][TW] tile block
@@ -118,7 +121,7 @@ template <typename T, int TW> struct SpSolver
   int inst_ = 0;    // instance slot inside the tile
 
   // smem_v: [n][TW] scalars of shared memory for the solve vector (TW == 8 only, nullptr otherwise)
-  __device__ SpSolver(const SpArgs<T>& a, long long tile, int lane, T* smem_v) : S(a.pat), n(a.pat.n), m(a.pat.m)
+  template <typename TIO> __device__ SpSolver(const SpArgs<T, TIO>& a, long long tile, int lane, T* smem_v) : S(a.pat), n(a.pat.n), m(a.pat.m)
   {
     const int inst = lane & (TW - 1);
     inst_ = inst;
@@ -813,21 +816,21 @@ template <typename T, int TW> struct SpSolver
   }
 
   // ---------------------------------------------------------------- QPSolver::solve, qp_solver.hpp:343-568
-  __device__ void run(const SpArgs<T>& a, long long b)
+  template <typename TIO> __device__ void run(const SpArgs<T, TIO>& a, long long b)
   {
     const T inf = Num<T>::inf();
     const sfb_qp_params& prm = a.prm;
     const unsigned long long t0 = prm.has_max_time ? global_timer_ns() : 0ull;
     // ---- ingest (array-of-instances -> tile; each lane streams its own rows, lines are reused through L1)
     {
-      const T* gA = a.A + b * (long long)S.nnzA;
-      const T* gP = a.P + b * (long long)S.nnzP;
-      for (int e = r; e < S.nnzA; e += RL) A[e] = __ldg(gA + e);
-      for (int e = r; e < S.nnzP; e += RL) P[e] = __ldg(gP + e);
-      for (int j = r; j < n; j += RL) q[S.iperm[j]] = __ldg(a.q + b * (long long)n + j);
+      const TIO* gA = a.A + b * (long long)S.nnzA;
+      const TIO* gP = a.P + b * (long long)S.nnzP;
+      for (int e = r; e < S.nnzA; e += RL) A[e] = (T)__ldg(gA + e);
+      for (int e = r; e < S.nnzP; e += RL) P[e] = (T)__ldg(gP + e);
+      for (int j = r; j < n; j += RL) q[S.iperm[j]] = (T)__ldg(a.q + b * (long long)n + j);
       for (int i = r; i < m; i += RL) {
-        l[i] = __ldg(a.l + b * (long long)m + i);
-        u[i] = __ldg(a.u + b * (long long)m + i);
+        l[i] = (T)__ldg(a.l + b * (long long)m + i);
+        u[i] = (T)__ldg(a.u + b * (long long)m + i);
       }
       gsync();
     }
@@ -893,17 +896,33 @@ template <typename T, int TW> struct SpSolver
       copy_a(ATW, S.ATP_slot, S.n_pad * S.WA);
       gsync();
     }
-    assemble(sigma, rho);
-    if (!factor()) code = SFB_QP_UNKNOWN;  // :433
+    // Mixed-precision polish (mode 2, T = double over TIO = float data): the instance was solved by the single-precision
+    // kernel; this pass re-stages it in double, takes the unpolished iterate and the active set from the outputs and runs
+    // only polish_qp (which assembles and factorises its own system).  Every lane of an instance reads the same status.
+    const bool polish_only = a.mode == 2;
+    const bool skip = polish_only && a.out_status[b] != (int32_t)SFB_QP_OPTIMAL;
+    if (!polish_only) {
+      assemble(sigma, rho);
+      if (!factor()) code = SFB_QP_UNKNOWN;  // :433
+    }
     // ---- initial iterate  :436-445
-    if (a.warm_x != nullptr) {
+    if (polish_only) {
       for (int j = r; j < n; j += RL) {
         const int pj = S.iperm[j];
-        x[pj] = (T(1) / sx[pj]) * __ldg(a.warm_x + b * (long long)n + j);
+        x[pj] = (T(1) / sx[pj]) * (T)a.out_x[b * (long long)n + j];
+      }
+      for (int i = r; i < m; i += RL) {
+        y[i] = c * ((T(1) / sy[i]) * (T)a.out_y[b * (long long)m + i]);
+        z[i] = T(0);
+      }
+    } else if (a.warm_x != nullptr) {
+      for (int j = r; j < n; j += RL) {
+        const int pj = S.iperm[j];
+        x[pj] = (T(1) / sx[pj]) * (T)__ldg(a.warm_x + b * (long long)n + j);
       }
       gsync();
       for (int i = r; i < m; i += RL) {
-        y[i] = c * ((T(1) / sy[i]) * __ldg(a.warm_y + b * (long long)m + i));
+        y[i] = c * ((T(1) / sy[i]) * (T)__ldg(a.warm_y + b * (long long)m + i));
         z[i] = A_row_dot(i, x);
       }
     } else {
@@ -916,6 +935,7 @@ template <typename T, int TW> struct SpSolver
     // ---- main loop  :449-510
     const unsigned sci = prm.stop_check_iter;
     unsigned iter = 0;
+    if (polish_only) { code = skip ? kStatusUnset - 1 : (int)SFB_QP_OPTIMAL; iter = a.out_iter[b]; }
     for (; iter != a.max_iter_eff && code == kStatusUnset; ++iter) {
       if (padded_passes()) rhs_pass(sigma);
       else At_gather(w, v, [&](int j, T sum) { return sigma * x[j] - qb[j] + sum; });  // rhs = sigma x - qb + Abar^T w
@@ -961,9 +981,15 @@ template <typename T, int TW> struct SpSolver
     for (int i = r; i < m; i += RL) {
       int act = 0;
       T bv = T(0);
-      if (y[i] < -thr && l[i] != -inf) { act = -1; bv = sy[i] * l[i]; }
-      if (y[i] > thr && u[i] != inf) { act = 1; bv = sy[i] * u[i]; }
-      if (a.out_active) a.out_active[b * (long long)m + i] = (int8_t)act;
+      if (polish_only) {  // the active set the lower-precision solve determined
+        act = a.out_active[b * (long long)m + i];
+        if (act < 0) bv = sy[i] * l[i];
+        if (act > 0) bv = sy[i] * u[i];
+      } else {
+        if (y[i] < -thr && l[i] != -inf) { act = -1; bv = sy[i] * l[i]; }
+        if (y[i] > thr && u[i] != inf) { act = 1; bv = sy[i] * u[i]; }
+        if (a.out_active) a.out_active[b * (long long)m + i] = (int8_t)act;
+      }
       w[i] = (act != 0) ? T(1) : T(0);
       yold[i] = bv;
     }
@@ -973,6 +999,7 @@ template <typename T, int TW> struct SpSolver
       if (sizeof(T) == 4) flags = SFB_QP_FLAG_POLISH_SKIPPED;  // delta = 1e-6 is not resolvable in fp32 (as in the dense kernel)
       else flags = polish(prm);
     }
+    if (skip) return;  // polish-only pass over an instance that is not Optimal: outputs stay as they are (instance-uniform)
     // ---- unscale + objective  :544-548
     for (int j = r; j < n; j += RL) t1[j] = sx[j] * x[j];
     gsync();
@@ -981,13 +1008,13 @@ template <typename T, int TW> struct SpSolver
     for (int jo = r; jo < n; jo += RL) {
       const int j = S.iperm[jo];
       const T xv = t1[j];
-      a.out_x[b * (long long)n + jo] = xv;
+      a.out_x[b * (long long)n + jo] = (TIO)xv;
       obj += xv * (t3[j] + q[j]);
     }
     obj = gsum(obj);
-    for (int i = r; i < m; i += RL) a.out_y[b * (long long)m + i] = sy[i] * y[i] / c;
+    for (int i = r; i < m; i += RL) a.out_y[b * (long long)m + i] = (TIO)(sy[i] * y[i] / c);
     if (r == 0) {
-      a.out_obj[b] = obj;
+      a.out_obj[b] = (TIO)obj;
       a.out_status[b] = (code == kStatusUnset) ? (int32_t)SFB_QP_MAX_ITERATIONS : (int32_t)code;
       a.out_iter[b] = iter;
       if (a.out_flags) a.out_flags[b] = flags;
@@ -998,7 +1025,7 @@ template <typename T, int TW> struct SpSolver
 // One warp per tile of TW instances, one warp per CTA (small batches still spread over all SMs).
 // register budget: all instances of a batch should be resident at once with slack (TW = 4 at batch 8192 needs 14 warps
 // per SM; 144 registers fit exactly 14 and measured 1.6x slower because the last blocks wait for a second wave)
-template <typename T, int TW> __global__ void __launch_bounds__(32, TW == 8 ? 8 : 16) qp_sparse_tiled_kernel(const SpArgs<T> a)
+template <typename T, int TW, typename TIO = T> __global__ void __launch_bounds__(32, TW == 8 ? 8 : 16) qp_sparse_tiled_kernel(const SpArgs<T, TIO> a)
 {
   extern __shared__ __align__(16) unsigned char sp_smem_raw[];
   const int lane = threadIdx.x;

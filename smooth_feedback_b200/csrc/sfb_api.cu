@@ -163,10 +163,10 @@ template <typename T> int qp_geometry(sfb_context* h, int n, int m, QpGeom* g)
 }
 
 
-template <typename T, int G, int NS, int MS>
-int qp_launch_g(sfb_context* h, cudaStream_t st, sfb::QpArgs<T>& args, const QpGeom& g, int grid)
+template <typename T, int G, int NS, int MS, typename TIO = T>
+int qp_launch_g(sfb_context* h, cudaStream_t st, sfb::QpArgs<T, TIO>& args, const QpGeom& g, int grid)
 {
-  auto kern = sfb::qp_dense_group_kernel<T, G, qp_minb<T, G>(), NS, MS>;
+  auto kern = sfb::qp_dense_group_kernel<T, G, qp_minb<T, G>(), NS, MS, TIO>;
   SFB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_per_cta));
   kern<<<grid, 32 * G, g.smem_per_cta, st>>>(args);
   SFB_CUDA(h, cudaGetLastError());
@@ -195,6 +195,9 @@ bool qp_is_skinny(const sfb_context* h, int n, int m, int mode, const sfb_qp_par
   return !h->dense_force_generic && mode == 0 && !prm.polish && n <= sfb::kSkinnyMaxN && m >= 1 && m <= sfb::kSkinnyMaxM;
 }
 
+template <typename T, typename TIO>
+int qp_launch_group(sfb_context* h, cudaStream_t st, int scratch_slot, sfb::QpArgs<T, TIO>& args);
+
 template <typename T>
 int qp_launch(sfb_context* h, cudaStream_t st, int scratch_slot, const sfb::QpArgs<T>& args_in)
 {
@@ -215,6 +218,30 @@ int qp_launch(sfb_context* h, cudaStream_t st, int scratch_slot, const sfb::QpAr
     h->launches += 1;
     return SFB_OK;
   }
+  int rc = qp_launch_group<T, T>(h, st, scratch_slot, args);
+  if (rc != SFB_OK) return rc;
+  // fp32 + polish: the delta = 1e-6 regularised polish systems are not resolvable in single precision.  Mixed precision:
+  // the ADMM iterations ran in fp32 above (the instance is flagged POLISH_SKIPPED); a second pass re-stages the Optimal
+  // instances in fp64 and runs polish_qp (qp_solver.hpp:92-204) on the fp32 iterate and its active set.  Shapes whose
+  // fp64 working set does not fit in shared memory keep the unpolished solution and the POLISH_SKIPPED flag.
+  if (std::is_same<T, float>::value && args.mode == 0 && args.prm.polish && (args.out_active != nullptr || args.m == 0)) {
+    QpGeom gd;
+    if (qp_geometry<double>(h, args.n, args.m, &gd) == SFB_OK) {
+      sfb::QpArgs<double, T> pa{};
+      pa.P = args.P; pa.q = args.q; pa.A = args.A; pa.l = args.l; pa.u = args.u;
+      pa.out_x = args.out_x; pa.out_y = args.out_y; pa.out_obj = args.out_obj; pa.out_status = args.out_status;
+      pa.out_iter = args.out_iter; pa.out_active = args.out_active; pa.out_flags = args.out_flags;
+      pa.batch = args.batch; pa.n = args.n; pa.m = args.m; pa.mode = 2; pa.prm = args.prm; pa.max_iter_eff = args.max_iter_eff;
+      rc = qp_launch_group<double, T>(h, st, scratch_slot, pa);
+      if (rc != SFB_OK) return rc;
+    }
+  }
+  return SFB_OK;
+}
+
+template <typename T, typename TIO>
+int qp_launch_group(sfb_context* h, cudaStream_t st, int scratch_slot, sfb::QpArgs<T, TIO>& args)
+{
   QpGeom g;
   if (qp_geometry<T>(h, args.n, args.m, &g) != SFB_OK)
     return fail(h, SFB_ERR_UNSUPPORTED_SIZE, "dense QP n=%d m=%d (%zu-byte scalars) does not fit in shared memory",
@@ -224,7 +251,7 @@ int qp_launch(sfb_context* h, cudaStream_t st, int scratch_slot, const sfb::QpAr
   // polish workspace: the Schur block S (na x na, na <= min(n, m)) lives in shared memory when 2 na <= ldA
   args.scratch = nullptr;
   args.scratch_per_cta = 0;
-  if (args.mode == 0 && args.prm.polish) {
+  if (args.mode != 1 && args.prm.polish) {
     const long long k = std::min(args.n, args.m);
     const sfb::QpLayout L(args.n, args.m, 32 * g.G);
     if (2 * k > L.ldA) {
@@ -239,14 +266,15 @@ int qp_launch(sfb_context* h, cudaStream_t st, int scratch_slot, const sfb::QpAr
   SFB_CUDA(h, cudaMemsetAsync(args.work_counter, 0, sizeof(unsigned long long), st));
   int rc;
   // shape-specialised instantiations (compile-time n, m) for the headline shapes, generic kernels otherwise
+  constexpr bool kPlain = std::is_same<T, TIO>::value;  // shape-specialised kernels exist for the plain fp64 path only
   if (g.G == 4) {
-    if (std::is_same<T, double>::value && args.n == 50 && args.m == 100) rc = qp_launch_g<T, 4, 50, 100>(h, st, args, g, grid);
-    else rc = qp_launch_g<T, 4, 0, 0>(h, st, args, g, grid);
+    if (kPlain && std::is_same<T, double>::value && args.n == 50 && args.m == 100) rc = qp_launch_g<T, 4, kPlain ? 50 : 0, kPlain ? 100 : 0, TIO>(h, st, args, g, grid);
+    else rc = qp_launch_g<T, 4, 0, 0, TIO>(h, st, args, g, grid);
   } else if (g.G == 2) {
-    rc = qp_launch_g<T, 2, 0, 0>(h, st, args, g, grid);
+    rc = qp_launch_g<T, 2, 0, 0, TIO>(h, st, args, g, grid);
   } else {
-    if (std::is_same<T, double>::value && args.n == 10 && args.m == 20) rc = qp_launch_g<T, 1, 10, 20>(h, st, args, g, grid);
-    else rc = qp_launch_g<T, 1, 0, 0>(h, st, args, g, grid);
+    if (kPlain && std::is_same<T, double>::value && args.n == 10 && args.m == 20) rc = qp_launch_g<T, 1, kPlain ? 10 : 0, kPlain ? 20 : 0, TIO>(h, st, args, g, grid);
+    else rc = qp_launch_g<T, 1, 0, 0, TIO>(h, st, args, g, grid);
   }
   if (rc != SFB_OK) return rc;
   h->launches += 1;
@@ -288,6 +316,12 @@ int qp_solve_impl(sfb_context* h, const sfb_qp_params* prm, int64_t batch, int n
     a.P = P; a.q = q; a.A = A; a.l = l; a.u = u; a.warm_x = warm_x; a.warm_y = warm_y;
     a.out_x = out_x; a.out_y = out_y; a.out_obj = out_obj; a.out_status = out_status; a.out_iter = out_iter;
     a.out_active = out_active; a.out_flags = out_flags;
+    if (std::is_same<T, float>::value && prm->polish && !out_active && m > 0) {
+      // the mixed-precision polish pass reads the active set the fp32 solve determined
+      rc = ensure_scratch(h, h->act_tmp, (size_t)batch * m, h->stream);
+      if (rc != SFB_OK) return rc;
+      a.out_active = static_cast<int8_t*>(h->act_tmp.dev);
+    }
     return qp_launch<T>(h, h->stream, kNumSlots, a);
   }
 
@@ -345,7 +379,7 @@ int qp_solve_impl(sfb_context* h, const sfb_qp_params* prm, int64_t batch, int n
     c.out_x = reinterpret_cast<T*>(d + oox); c.out_y = reinterpret_cast<T*>(d + ooy);
     c.out_obj = reinterpret_cast<T*>(d + oobj); c.out_status = reinterpret_cast<int32_t*>(d + ost);
     c.out_iter = reinterpret_cast<uint32_t*>(d + oit);
-    c.out_active = out_active ? reinterpret_cast<int8_t*>(d + oact) : nullptr;
+    c.out_active = (out_active || (std::is_same<T, float>::value && prm->polish)) ? reinterpret_cast<int8_t*>(d + oact) : nullptr;
     c.out_flags = out_flags ? reinterpret_cast<uint32_t*>(d + ofl) : nullptr;
     rc = qp_launch<T>(h, s.stream, k % kNumSlots, c);
     if (rc != SFB_OK) return rc;
@@ -452,6 +486,7 @@ int sfb_destroy(sfb_handle_t h)
     if (sc.dev) cudaFree(sc.dev);
   if (h->sparse_ws.dev) cudaFree(h->sparse_ws.dev);
   if (h->sparse_stage.dev) cudaFree(h->sparse_stage.dev);
+  if (h->act_tmp.dev) cudaFree(h->act_tmp.dev);
   if (h->counters) cudaFree(h->counters);
   delete h;
   return SFB_OK;

@@ -56,6 +56,7 @@ struct sfb_context
   int sparse_tw = 0;     // SFB_SPARSE_TW=4|8|32 overrides the tile-width heuristic of the sparse QP path (A/B measurements)
   sfbi::Scratch sparse_ws;     // tiled working set of the sparse QP path
   sfbi::Scratch sparse_stage;  // device copies of host buffers (sparse path)
+  sfbi::Scratch act_tmp;       // active sets of an fp32 solve when the caller did not ask for them (mixed-precision polish)
 };
 
 namespace sfbi {

@@ -19,6 +19,49 @@ struct sfb_qp_sparse_pattern
 namespace {
 
 // ---- sparse QP (shared pattern) --------------------------------------------------------------------------
+// workspace bytes of one tile of tw instances computed in scalar T
+template <typename T> size_t sp_tile_bytes(const sfb_qp_sparse_pattern* pt, int tw)
+{
+  const sfb::SparseSymbolic& S = pt->sym;
+  return (sfb::sp_a_len(pt->pat, tw) + S.nnzP + sfb::sp_w_len(pt->pat, tw) + (size_t)sfb::kSpNV * S.n + (size_t)sfb::kSpMV * S.m) * tw * sizeof(T);
+}
+
+// carve the handle's tiled workspace for scalar T and launch the kernel (a's I/O pointers, mode, prm are set by the caller)
+template <typename T, typename TIO>
+int sp_launch(sfb_context* h, const sfb_qp_sparse_pattern* pt, sfb::SpArgs<T, TIO>& a, int tw)
+{
+  const sfb::SparseSymbolic& S = pt->sym;
+  const int n = S.n, m = S.m;
+  const long long tiles = (a.batch + tw - 1) / tw;
+  const size_t wlen = sfb::sp_w_len(pt->pat, tw);  // factor + its stream-ordered copies
+  const size_t alen = sfb::sp_a_len(pt->pat, tw);  // Abar + its padded row / column stream copies
+  {
+    T* w = static_cast<T*>(h->sparse_ws.dev);
+    a.wsA = w; w += (size_t)tiles * alen * tw;
+    a.wsP = w; w += (size_t)tiles * S.nnzP * tw;
+    a.wsW = w; w += (size_t)tiles * wlen * tw;
+    a.wsN = w; w += (size_t)tiles * sfb::kSpNV * n * tw;
+    a.wsM = w;
+  }
+  const unsigned grid = (unsigned)std::min<long long>(tiles, 1 << 30);
+  if (tw < 32) {
+    const size_t smem = (size_t)(n + 1) * tw * sizeof(T);  // the solve vector of the tile + the dummy zero slot
+    if (smem > h->prop.sharedMemPerBlockOptin) return fail(h, SFB_ERR_UNSUPPORTED_SIZE, "sparse QP n=%d: solve vector does not fit in shared memory", n);
+    if (tw == 8) {
+      SFB_CUDA(h, cudaFuncSetAttribute(sfb::qp_sparse_tiled_kernel<T, 8, TIO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      sfb::qp_sparse_tiled_kernel<T, 8, TIO><<<grid, 32, smem, h->stream>>>(a);
+    } else {
+      SFB_CUDA(h, cudaFuncSetAttribute(sfb::qp_sparse_tiled_kernel<T, 4, TIO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      sfb::qp_sparse_tiled_kernel<T, 4, TIO><<<grid, 32, smem, h->stream>>>(a);
+    }
+  } else {
+    sfb::qp_sparse_tiled_kernel<T, 32, TIO><<<grid, 32, 0, h->stream>>>(a);
+  }
+  SFB_CUDA(h, cudaGetLastError());
+  h->launches += 1;
+  return SFB_OK;
+}
+
 template <typename T>
 int qp_sparse_solve_impl(sfb_context* h, const sfb_qp_sparse_pattern* pt, const sfb_qp_params* prm, int64_t batch,
                          const T* P, const T* q, const T* A, const T* l, const T* u, const T* warm_x, const T* warm_y,
@@ -55,11 +98,11 @@ int qp_sparse_solve_impl(sfb_context* h, const sfb_qp_sparse_pattern* pt, const 
     if (h->sparse_ws.bytes < per_inst4 * (size_t)batch && per_inst4 * (size_t)batch > free_b / 2) tw = 32;
   }
   if (h->sparse_tw == 4 || h->sparse_tw == 8 || h->sparse_tw == 32) tw = h->sparse_tw;
+  // fp32 + polish runs a second, fp64 pass over the same instances (mixed precision, see sp_polish_pass): size the workspace once
+  const bool mixed = std::is_same<T, float>::value && prm->polish;
   const long long tiles = (batch + tw - 1) / tw;
-  const size_t wlen = sfb::sp_w_len(pt->pat, tw);  // factor + its stream-ordered copies
-  const size_t alen = sfb::sp_a_len(pt->pat, tw);  // Abar + its padded row / column stream copies
-  const size_t per_tile = (alen + S.nnzP + wlen + (size_t)sfb::kSpNV * n + (size_t)sfb::kSpMV * m) * tw * sizeof(T);
-  rc = ensure_scratch(h, h->sparse_ws, per_tile * (size_t)tiles, h->stream);
+  const size_t ws_bytes = std::max(sp_tile_bytes<T>(pt, tw), mixed ? sp_tile_bytes<double>(pt, tw) : (size_t)0) * (size_t)tiles;
+  rc = ensure_scratch(h, h->sparse_ws, ws_bytes, h->stream);
   if (rc != SFB_OK) return rc;
 
   sfb::SpArgs<T> a{};
@@ -67,37 +110,28 @@ int qp_sparse_solve_impl(sfb_context* h, const sfb_qp_sparse_pattern* pt, const 
   a.batch = batch;
   a.prm = *prm;
   a.max_iter_eff = prm->has_max_iter ? prm->max_iter : SFB_QP_DEVICE_ITER_CAP;
-  {
-    T* w = static_cast<T*>(h->sparse_ws.dev);
-    a.wsA = w; w += (size_t)tiles * alen * tw;
-    a.wsP = w; w += (size_t)tiles * S.nnzP * tw;
-    a.wsW = w; w += (size_t)tiles * wlen * tw;
-    a.wsN = w; w += (size_t)tiles * sfb::kSpNV * n * tw;
-    a.wsM = w;
-  }
+  a.mode = 0;
+  // Mixed-precision polish: the ADMM iterations ran in fp32 (instances flagged POLISH_SKIPPED); the Optimal ones are
+  // re-staged in fp64 and polish_qp (qp_solver.hpp:92-204) runs on the fp32 iterate and its active set.
   auto launch = [&]() -> int {
-    const unsigned grid = (unsigned)std::min<long long>(tiles, 1 << 30);
-    if (tw < 32) {
-      const size_t smem = (size_t)(n + 1) * tw * sizeof(T);  // the solve vector of the tile + the dummy zero slot
-      if (smem > h->prop.sharedMemPerBlockOptin) return fail(h, SFB_ERR_UNSUPPORTED_SIZE, "sparse QP n=%d: solve vector does not fit in shared memory", n);
-      if (tw == 8) {
-        SFB_CUDA(h, cudaFuncSetAttribute(sfb::qp_sparse_tiled_kernel<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        sfb::qp_sparse_tiled_kernel<T, 8><<<grid, 32, smem, h->stream>>>(a);
-      } else {
-        SFB_CUDA(h, cudaFuncSetAttribute(sfb::qp_sparse_tiled_kernel<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        sfb::qp_sparse_tiled_kernel<T, 4><<<grid, 32, smem, h->stream>>>(a);
-      }
-    } else {
-      sfb::qp_sparse_tiled_kernel<T, 32><<<grid, 32, 0, h->stream>>>(a);
-    }
-    SFB_CUDA(h, cudaGetLastError());
-    h->launches += 1;
-    return SFB_OK;
+    int rc2 = sp_launch<T, T>(h, pt, a, tw);
+    if (rc2 != SFB_OK || !mixed) return rc2;
+    sfb::SpArgs<double, T> pa{};
+    pa.pat = a.pat; pa.batch = a.batch; pa.prm = a.prm; pa.max_iter_eff = a.max_iter_eff; pa.mode = 2;
+    pa.P = a.P; pa.q = a.q; pa.A = a.A; pa.l = a.l; pa.u = a.u;
+    pa.out_x = a.out_x; pa.out_y = a.out_y; pa.out_obj = a.out_obj; pa.out_status = a.out_status; pa.out_iter = a.out_iter;
+    pa.out_active = a.out_active; pa.out_flags = a.out_flags;
+    return sp_launch<double, T>(h, pt, pa, tw);
   };
   if (space == 1) {
     a.P = P; a.q = q; a.A = A; a.l = l; a.u = u; a.warm_x = warm_x; a.warm_y = warm_y;
     a.out_x = out_x; a.out_y = out_y; a.out_obj = out_obj; a.out_status = out_status; a.out_iter = out_iter;
     a.out_active = out_active; a.out_flags = out_flags;
+    if (mixed && !out_active && m > 0) {  // the polish pass reads the active set the fp32 solve determined
+      rc = ensure_scratch(h, h->act_tmp, (size_t)batch * m, h->stream);
+      if (rc != SFB_OK) return rc;
+      a.out_active = static_cast<int8_t*>(h->act_tmp.dev);
+    }
     return launch();
   }
   // host buffers: one staged round trip on the handle's stream (inputs are ~1 % of the per-solve traffic of this path)
@@ -127,7 +161,7 @@ int qp_sparse_solve_impl(sfb_context* h, const sfb_qp_sparse_pattern* pt, const 
   }
   a.P = dP; a.q = dq; a.A = dA; a.l = dl; a.u = du; a.warm_x = dwx; a.warm_y = dwy;
   a.out_x = dox; a.out_y = doy; a.out_obj = dobj; a.out_status = dst; a.out_iter = dit;
-  a.out_active = out_active ? dact : nullptr; a.out_flags = out_flags ? dfl : nullptr;
+  a.out_active = (out_active || mixed) ? dact : nullptr; a.out_flags = out_flags ? dfl : nullptr;
   rc = launch();
   if (rc != SFB_OK) return rc;
   auto down = [&](void* dst_, const void* src, size_t bytes) { return bytes ? cudaMemcpyAsync(dst_, src, bytes, cudaMemcpyDeviceToHost, h->stream) : cudaSuccess; };

@@ -69,7 +69,9 @@ def _parity(sfb, oracle, B, n, m, seed, feasible=True, prm_kw=None, rel=REL_F64,
     iterations, |y_i| > 100 eps active-set tests) on floating-point data, so a handful of instances are decided by
     rounding noise: for those even the oracle disagrees with ITSELF when it is compiled with FMA contraction
     (liboracle_fast.so).  `well_posed` marks the instances where both oracle builds agree on status, iteration
-    count and active set; exact integer parity is demanded there.
+    count and active set; exact integer parity is demanded there.  The other instances are NOT left unchecked:
+    _assert_parity demands that the engine agrees with one of the two oracle builds, or else returns a finite point
+    that satisfies the KKT conditions of the problem at the solver's own tolerance.
     """
     from smooth_feedback_b200.generators import random_qp_numpy
 
@@ -82,10 +84,45 @@ def _parity(sfb, oracle, B, n, m, seed, feasible=True, prm_kw=None, rel=REL_F64,
     o2 = oracle.qp_solve_batch(P, q, A, l, u, params=oracle.default_params(max_iter=max_iter, **okw), nthreads=8, fast=True)
     well_posed = (o.status == o2.status) & (o.iter == o2.iter) & (o.active == o2.active).all(axis=1)
     _parity.last_fast = o2
+    _parity.last_problem = (P, q, A, l, u)
     return r, o, well_posed
 
 
-def _assert_parity(r, o, wp, rel, min_well_posed=0.97):
+def kkt_residuals(P, q, A, l, u, x, y):
+    """Relative primal / dual residuals of (x, y) for  min 1/2 x'Px + q'x, l <= Ax <= u  (P symmetric, math layout)."""
+    Ax = np.einsum("bij,bj->bi", A, x)
+    viol = np.maximum(np.maximum(l - Ax, Ax - u), 0.0)
+    viol[~np.isfinite(viol)] = np.inf
+    prim = viol.max(axis=1, initial=0.0) / np.maximum(1.0, np.abs(Ax).max(axis=1, initial=0.0))
+    Px = np.einsum("bij,bj->bi", P, x)
+    Aty = np.einsum("bij,bi->bj", A, y)
+    sc = np.maximum.reduce([np.abs(Px).max(axis=1), np.abs(q).max(axis=1), np.abs(Aty).max(axis=1, initial=0.0), np.ones(len(x))])
+    dual = np.abs(Px + q + Aty).max(axis=1) / sc
+    return prim, dual
+
+
+def _assert_unmasked(r, o, o2, wp, problem, kkt_tol=5e-2):
+    """Instances that are NOT well posed (the two oracle builds disagree with each other): the engine must reproduce one of
+    the two builds' discrete outcomes, or at least return a finite KKT point of the problem at the solver tolerance."""
+    nwp = ~wp
+    if not nwp.any():
+        return
+    m1 = (r.status == o.status) & (r.iter == o.iter) & (r.active == o.active).all(axis=1)
+    m2 = (r.status == o2.status) & (r.iter == o2.iter) & (r.active == o2.active).all(axis=1)
+    rest = nwp & ~(m1 | m2)
+    assert np.isfinite(r.x[nwp]).all() and np.isfinite(r.y[nwp]).all()
+    if rest.any() and problem is not None:
+        opt = rest & (r.status == 0)
+        if opt.any():
+            P, q, A, l, u = (t[opt] for t in problem)
+            Ps = np.triu(P) + np.transpose(np.triu(P, 1), (0, 2, 1))  # the matrix the solver works with (upper triangle)
+            prim, dual = kkt_residuals(Ps, q, A, l, u, r.x[opt], r.y[opt])
+            assert prim.max() <= kkt_tol and dual.max() <= kkt_tol, (prim.max(), dual.max())
+        # a non-Optimal verdict on a knife-edge instance must still be one the algorithm can produce
+        assert np.isin(r.status[rest], [0, 2, 3, 4]).all()
+
+
+def _assert_parity(r, o, wp, rel, min_well_posed=0.97, o2=None, problem=None):
     assert wp.mean() >= min_well_posed, f"only {wp.mean():.3f} of the instances are well posed"
     assert np.array_equal(r.status[wp], o.status[wp]), f"status mismatches: {(r.status != o.status)[wp].sum()}"
     assert np.array_equal(r.iter[wp], o.iter[wp]), f"iteration-count mismatches: {(r.iter != o.iter)[wp].sum()} of {wp.sum()}"
@@ -95,6 +132,26 @@ def _assert_parity(r, o, wp, rel, min_well_posed=0.97):
         assert rel_err(r.x[ok], o.x[ok]).max() <= rel
         assert rel_err(r.y[ok], o.y[ok]).max() <= rel
         assert np.abs(r.obj[ok] - o.obj[ok]).max() <= rel * np.maximum(1.0, np.abs(o.obj[ok])).max()
+    o2 = o2 if o2 is not None else getattr(_parity, "last_fast", None)
+    problem = problem if problem is not None else getattr(_parity, "last_problem", None)
+    if o2 is not None and len(o2.status) == len(o.status):
+        _assert_unmasked(r, o, o2, wp, problem if (problem is not None and len(problem[0]) == len(o.status)) else None)
+
+
+def _assert_fp32(r, o, o2, min_same=0.95, rel=REL_F32):
+    """fp32 entry points against the fp64 oracle on the same (float-rounded) data.  Status exact on the well-posed instances;
+    on EVERY instance whose iteration count and active set agree -- the large majority: an fp32 stop check that fires one
+    period earlier or later, or a dual within 100 eps32 of zero, selects a different (equally valid) polish system -- the
+    MAX relative error of primal and dual is within the north-star 1e-3."""
+    wp = (o.status == o2.status) & (o.iter == o2.iter) & (o.active == o2.active).all(axis=1)
+    assert np.array_equal(r.status[wp], o.status[wp])
+    opt = wp & (o.status == 0)
+    same = opt & (r.iter == o.iter) & (r.active == o.active).all(axis=1)
+    assert same.sum() >= min_same * opt.sum(), (same.sum(), opt.sum())
+    ex, ey = rel_err(r.x[same], o.x[same]), rel_err(r.y[same], o.y[same])
+    assert ex.max() <= rel and ey.max() <= rel, (ex.max(), ey.max())
+    assert np.isfinite(np.asarray(r.x, dtype=np.float64)).all()
+    return same
 
 
 def test_parity_cfg1_n10_m20(sfb, oracle):
@@ -211,19 +268,26 @@ def test_max_iter_and_statuses(sfb, oracle):
 
 def test_fp32_against_fp64_oracle(sfb, oracle):
     # fp32 is new functionality (the reference has no float instantiation): its oracle is the fp64 path on
-    # the same (float-rounded) data at 1e-3 relative.  The f32 entry point does not polish yet (flag POLISH_SKIPPED).
+    # the same (float-rounded) data at 1e-3 relative.  ADMM iterations run in fp32; polish_qp runs as a mixed-precision
+    # second pass in fp64 on the fp32 iterate and active set (flag POLISHED).
     from smooth_feedback_b200.generators import random_qp_numpy
 
+    for (B, n, m, seed) in [(256, 10, 20, 41), (256, 50, 100, 42)]:
+        P, q, A, l, u = (np.asarray(t, dtype=np.float32).astype(np.float64) for t in random_qp_numpy(B, n, m, seed=seed))
+        prm = sfb.QPSolverParams(max_iter=4000)
+        r = gpu_solve(sfb, P, q, A, l, u, prm, dtype=np.float32)
+        o = oracle.qp_solve_batch(P, q, A, l, u, params=oracle.default_params(max_iter=4000), nthreads=8)
+        o2 = oracle.qp_solve_batch(P, q, A, l, u, params=oracle.default_params(max_iter=4000), nthreads=8, fast=True)
+        assert (r.flags[r.status == 0] == 1).all()  # every Optimal instance was polished
+        _assert_fp32(r, o, o2)
+    # polish off: parity rests on the fp32 ADMM iterates alone
     P, q, A, l, u = (np.asarray(t, dtype=np.float32).astype(np.float64) for t in random_qp_numpy(256, 10, 20, seed=41))
-    prm = sfb.QPSolverParams(max_iter=4000)
+    prm = sfb.QPSolverParams(max_iter=4000, polish=False)
     r = gpu_solve(sfb, P, q, A, l, u, prm, dtype=np.float32)
     o = oracle.qp_solve_batch(P, q, A, l, u, params=oracle.default_params(max_iter=4000, polish=0), nthreads=8)
-    assert np.array_equal(r.status, o.status)
-    assert (r.iter == o.iter).mean() >= 0.98
-    assert (r.flags == 2).all()
+    assert np.array_equal(r.status, o.status) and (r.flags == 0).all()
     same = r.iter == o.iter
-    assert rel_err(r.x[same], o.x[same]).max() <= REL_F32
-    assert ((r.active == o.active).all(axis=1)).mean() >= 0.98
+    assert same.mean() >= 0.98 and rel_err(r.x[same], o.x[same]).max() <= REL_F32
 
 
 def test_solver_object_api(sfb):
@@ -341,7 +405,9 @@ def test_skinny_fp32_and_matches_generic_kernel(sfb, oracle):
     o = oracle.qp_solve_batch(P, q, A, l, u, params=oracle.default_params(max_iter=4000, polish=0), nthreads=8)
     r32 = gpu_solve(sfb, P, q, A, l, u, prm, dtype=np.float32)
     ok = (r32.status == 0) & (o.status == 0)
-    assert ok.mean() > 0.9 and np.median(rel_err(r32.x[ok], o.x[ok])) <= REL_F32
+    same = ok & (r32.iter == o.iter)  # polish off: an iterate is comparable only at the same iteration count
+    assert ok.mean() > 0.9 and same.sum() >= 0.9 * ok.sum()
+    assert rel_err(r32.x[same], o.x[same]).max() <= REL_F32 and rel_err(r32.y[same], o.y[same]).max() <= REL_F32
     # A/B against the generic shared-memory kernel (SFB_DENSE_FORCE_GENERIC=1): same discrete outcomes, 1e-6 solutions
     r_sk = gpu_solve(sfb, P, q, A, l, u, prm)
     os.environ["SFB_DENSE_FORCE_GENERIC"] = "1"
@@ -390,8 +456,9 @@ def test_full_size_properties_cfg5_shape(sfb):
     torch.cuda.synchronize()
     ok = ((rg.status == 0) & (r.status[sl] == 0)).cpu().numpy()
     assert ok.mean() > 0.98
-    e = rel_err(r.x[sl].double().cpu().numpy()[ok], rg.x.cpu().numpy()[ok])
-    assert np.median(e) <= REL_F32 and np.quantile(e, 0.95) <= 10 * REL_F32
+    e = rel_err(r.x[sl].double().cpu().numpy(), rg.x.cpu().numpy())
+    same = ok & (r.iter[sl] == rg.iter).cpu().numpy()  # polish off: iterates are comparable at equal iteration counts
+    assert same.sum() >= 0.9 * ok.sum() and e[same].max() <= REL_F32 and e[ok].max() <= 30 * REL_F32
     # feasibility of the fp32 solutions at the solver's own tolerance (eps = 1e-3 relative to the row scale)
     Ax = torch.einsum("bjm,bj->bm", A.double(), r.x.double())  # A is column-major: A[b, j, i] = A_ij
     viol = (Ax - u.double()).clamp(min=0).amax(dim=1).cpu().numpy()
