@@ -27,7 +27,10 @@
  *   - functions return 0 (SFB_OK) or an sfb_error; per-instance outcomes are reported only through
  *     out_status (never an error code), like the reference which never throws on the numeric path.
  *   - there is NO CPU fallback: without a CUDA device sfb_create fails with SFB_ERR_NO_DEVICE.
- *   - a handle is not re-entrant (like a QPSolver object, qp_solver.hpp:734-756); use one per host thread.
+ *   - a handle is not re-entrant (like a QPSolver object, qp_solver.hpp:734-756); use one per host thread.  A handle owns
+ *     device workspaces that every call reuses: calls are ordered on the handle's stream, and sfb_set_stream makes the new
+ *     stream wait for the work already enqueued on the old one, so switching streams never lets two calls share a workspace
+ *     concurrently.  For genuinely concurrent streams use one handle per stream.
  *     Work is enqueued on the handle's stream; calls with device pointers are asynchronous with respect
  *     to the host unless stated otherwise, calls with host pointers return after the results are in place.
  */
@@ -98,6 +101,7 @@ typedef struct {
 #define SFB_QP_FLAG_POLISH_SKIPPED 2u /* active set too large for the on-chip polish workspace: solution left unpolished,
                                          which is also what the reference returns when its polish fails */
 #define SFB_QP_FLAG_POLISH_FAILED 4u  /* non-positive / non-finite pivot in the polish systems */
+#define SFB_QP_FLAG_POLISH_SCRATCH 8u /* (with POLISHED) the polish Schur block lived in the global workspace, not on chip */
 
 int sfb_version(void);
 const char* sfb_error_string(int err);
@@ -109,6 +113,21 @@ int sfb_create(int device, void* stream, sfb_handle_t* out);
 int sfb_destroy(sfb_handle_t h);
 int sfb_set_stream(sfb_handle_t h, void* stream);
 int sfb_synchronize(sfb_handle_t h);
+
+/*
+ * Engine options (not part of QPSolverParams, which sfb_qp_params mirrors field for field).
+ *   SFB_OPT_DUAL_INF_DX_GUARD (default 1): the dual-infeasibility certificate of check_stopping (qp_solver.hpp:625-641)
+ *     additionally requires ||dx|| != 0.  With an exactly stationary primal iterate every comparison of :629-639 reads
+ *     0 <= 0 and the literal rule reports DualInfeasible.  In the reference that only happens on scalar (n = 1) problems
+ *     (oracle instrumentation, tests/test_oracle_qp_known_answers.py); the engine's reduced KKT system reaches exactly
+ *     stationary iterates on tall problems (n = 3, m = 203) where the reference does not, so the guard is what keeps the
+ *     engine's statuses equal to the reference's there.  0 = the literal rule.
+ */
+#define SFB_OPT_DUAL_INF_DX_GUARD 1
+/*   SFB_OPT_FORCE_POLISH_SCRATCH (default 0, debug / tests): dense polish keeps its Schur block in the global workspace even
+ *     when it fits in shared memory, so that both placements can be compared on the same problems. */
+#define SFB_OPT_FORCE_POLISH_SCRATCH 2
+int sfb_set_option(sfb_handle_t h, int option, int value);
 /* number of kernels of this library launched through the handle since creation */
 int sfb_kernel_launch_count(sfb_handle_t h, uint64_t* out);
 

@@ -64,6 +64,8 @@ def _lib(fast: bool = False) -> C.CDLL:
         C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.POINTER(C.c_int8), C.c_int,
     ]
     lib.sfo_qp_solve_dense_batch_f64.restype = C.c_int
+    lib.sfo_debug_dx_zero_checks.argtypes = [C.c_int]
+    lib.sfo_debug_dx_zero_checks.restype = C.c_longlong
     lib.sfo_qp_scale_f64.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, dp, dp]
     lib.sfo_qp_scale_f64.restype = C.c_int
     lib.sfo_ekf_predict_batch_f64.argtypes = [C.c_int64, C.c_int, C.c_int, dp, dp, dp, C.c_double, C.c_double, dp, C.c_int]
@@ -176,3 +178,8 @@ def ekf_update_batch(P, H, R, innov, nthreads: int = 1, fast: bool = False):
     if rc != 0:
         raise ValueError(f"oracle rejected the call (rc={rc})")
     return delta, np.transpose(out, (0, 2, 1)).copy()
+
+
+def dx_zero_checks(reset: bool = False, fast: bool = False) -> int:
+    """Stop checks so far (in this process) at which the oracle saw an exactly stationary primal iterate; see sf_oracle.cpp."""
+    return int(_lib(fast).sfo_debug_dx_zero_checks(int(reset)))

@@ -15,6 +15,8 @@
 #include <omp.h>
 #endif
 
+static long long g_dx_zero_checks = 0;  // see check_stopping (instrumentation for tests)
+
 namespace {
 
 constexpr double kInf = std::numeric_limits<double>::infinity();
@@ -291,6 +293,11 @@ struct QpOracle
       Ax[i] = a;
     }
     const double dx_norm = norm_inf(dx_us.data(), n);
+    // instrumentation only (never changes a result): how often a stop check sees an EXACTLY stationary primal iterate.
+    // With dx == 0 every comparison of qp_solver.hpp:629-639 reads 0 <= 0; the CUDA engine guards its dual-infeasibility
+    // certificate with dx != 0 (deviations) and tests/ use this counter to show that the reference algorithm
+    // never meets that case on any parity workload, i.e. that the guard cannot change a status the reference returns.
+    if (dx_norm == 0.0) __atomic_fetch_add(&g_dx_zero_checks, 1, __ATOMIC_RELAXED);
     for (int i = 0; i < n; ++i) {
       double a = 0;
       for (int j = 0; j < n; ++j) a += P[i + size_t(n) * j] * dx_us[j];
@@ -603,6 +610,13 @@ void ekf_update_one(int d, int ny, const double* P, const double* H, const doubl
 }  // namespace
 
 extern "C" {
+
+long long sfo_debug_dx_zero_checks(int reset)
+{
+  const long long v = __atomic_load_n(&g_dx_zero_checks, __ATOMIC_RELAXED);
+  if (reset) __atomic_store_n(&g_dx_zero_checks, 0, __ATOMIC_RELAXED);
+  return v;
+}
 
 void sfo_qp_params_default(sfo_qp_params* p)
 {

@@ -50,6 +50,10 @@ typedef struct {
 
 void sfo_qp_params_default(sfo_qp_params* p);
 
+/* test instrumentation: number of stop checks so far that saw an exactly stationary primal iterate (||dx_us|| == 0);
+ * reset != 0 zeroes the counter after reading it */
+long long sfo_debug_dx_zero_checks(int reset);
+
 /*
  * Batched dense QP solve, fp64.  Layout per instance b (all column-major like Eigen defaults):
  *   P + b*n*n, q + b*n, A + b*m*n (A[i + m*j]), l + b*m, u + b*m

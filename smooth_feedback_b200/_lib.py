@@ -48,7 +48,7 @@ class SfbQpParams(C.Structure):
 # every symbol include/sfb.h declares (tests check the library exports exactly these)
 EXPORTED_SYMBOLS = [
     "sfb_version", "sfb_error_string", "sfb_last_error_message", "sfb_create", "sfb_destroy", "sfb_set_stream",
-    "sfb_synchronize", "sfb_kernel_launch_count", "sfb_qp_params_default", "sfb_qp_solve_dense_batch_f64",
+    "sfb_synchronize", "sfb_set_option", "sfb_kernel_launch_count", "sfb_qp_params_default", "sfb_qp_solve_dense_batch_f64",
     "sfb_qp_solve_dense_batch_f32", "sfb_qp_dense_max_m", "sfb_qp_scale_dense_batch_f64",
     "sfb_ekf_predict_batch_f64", "sfb_ekf_update_batch_f64", "sfb_ekf_step_batch_f64",
     "sfb_qp_sparse_analyze", "sfb_qp_sparse_symbolic", "sfb_qp_sparse_pattern_destroy", "sfb_qp_sparse_pattern_info",
@@ -83,6 +83,9 @@ def _preload_cudart() -> None:
         return
 
 
+OPT_DUAL_INF_DX_GUARD = 1
+OPT_FORCE_POLISH_SCRATCH = 2
+
 _lib = None
 
 
@@ -105,6 +108,7 @@ def lib() -> C.CDLL:
     L.sfb_destroy.argtypes = [vp]
     L.sfb_set_stream.argtypes = [vp, vp]
     L.sfb_synchronize.argtypes = [vp]
+    L.sfb_set_option.argtypes = [vp, i32, i32]
     L.sfb_kernel_launch_count.argtypes = [vp, C.POINTER(u64)]
     L.sfb_qp_params_default.argtypes = [C.POINTER(SfbQpParams)]
     L.sfb_qp_params_default.restype = None
@@ -159,6 +163,9 @@ class Handle:
 
     def set_stream(self, stream: int | None) -> None:
         self.check(lib().sfb_set_stream(self._h, C.c_void_p(stream or 0)))
+
+    def set_option(self, option: int, value: int) -> None:
+        self.check(lib().sfb_set_option(self._h, int(option), int(value)))
 
     def synchronize(self) -> None:
         self.check(lib().sfb_synchronize(self._h))

@@ -41,6 +41,7 @@ template <typename T> struct AsifArgs
   AsifVehicleDev mdl;
   sfb_qp_params prm;
   unsigned max_iter_eff;
+  int dinf_guard;  // see QpArgs::dinf_guard
   long long batch;
   const T* x;      // [batch][7]  (x, y, sin, cos, v1, v2, v3): smooth::Bundle<SE2, R^3> coefficient order
   const T* u_des;  // [batch][2]
@@ -153,6 +154,7 @@ __global__ void __launch_bounds__(32 * kSkinnyWarps, sizeof(T) == 4 ? 3 : 2) asi
       QpSkinny<T, 3, R> s;
       s.lane = lane;
       s.m = m;
+      s.dinf_guard = a.dinf_guard != 0;
       const T inf = Num<T>::inf();
       const T* rw = a.rows + b * 3 * (long long)K;
       const double ud0 = (double)a.u_des[b * 2], ud1 = (double)a.u_des[b * 2 + 1];

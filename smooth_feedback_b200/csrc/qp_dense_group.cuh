@@ -113,6 +113,8 @@ template <typename T, typename TIO = T> struct QpArgs
   int mode;  // 0 = solve, 1 = scale only, 2 = polish only (instances already solved: out_* hold the unpolished result)
   sfb_qp_params prm;
   unsigned max_iter_eff;
+  int force_polish_scratch;  // debug (SFB_OPT_FORCE_POLISH_SCRATCH): keep the polish Schur block in the global workspace even when it fits on chip
+  int dinf_guard;  // 1: the dual-infeasibility certificate needs dx != 0 (SFB_OPT_DUAL_INF_DX_GUARD, default); 0: literal reference rule
   unsigned long long* work_counter;
 };
 
@@ -128,10 +130,10 @@ struct QpLayout
     // Abar: leading dimension == 2 (mod 4).  Thread-per-row accesses are consecutive; thread-per-column accesses
     // fetch two rows per 2-scalar load and the column stride ldA/2 is odd: both patterns are bank-conflict free.
     ldA = mm + ((2 - mm % 4) + 4) % 4;
-    // m == 2: keep room for the 2 x 2 polish Schur block below the compacted rows (2 na <= ldA).  The global-scratch
-    // fallback is wrong for a 2 x 2 block (n = m = 2 and n = 3, m = 2 with both rows active disagreed with the oracle,
-    // tools/diag22.py); every other shape that reaches it (na >= 4) is covered by the parity tests.
-    if (mm == 2) ldA = 6;
+    // (The polish Schur block lives below the compacted active rows when 2 na <= ldA, else in a global workspace.  Both
+    // placements give bit-identical results on every shape incl. 2 x 2 blocks -- SFB_OPT_FORCE_POLISH_SCRATCH A/B,
+    // profiles/r02_polish_scratch_vs_onchip.txt; the round-1 "2 x 2 disagreement" was the conditioning of the duals when
+    // both rows of an n = 2 problem are active: the oracle's two builds disagree with each other by more than the engine.)
     ldN = odd(n);  // Minv / P: only row-wise and scalar column accesses -> odd stride
     npad = (n + 1) & ~1;
     mpad = (mm + 1) & ~1;
@@ -775,10 +777,11 @@ template <typename T, int G, int NS, int MS> struct QpGroup
     // PRIMAL INFEASIBILITY :619
     if (fmax(n_Atdy, s_pinf) < eps_pinf * Edy) return SFB_QP_PRIMAL_INFEASIBLE;
     // DUAL INFEASIBILITY :629-641
-    // Deliberate guard ("reference quirks"): with dx == 0 exactly every test of :629-639 reads 0 <= 0 and the
-    // reference would report DualInfeasible for an iterate that merely stopped moving.  Its own x carries rounding
-    // noise from the (n+m)-long LDL^T sweeps so it never sees an exact zero; the reduced system here can.
-    if ((dxn > T(0)) && (n_Pdx <= eps_dinf * dxn) && (qdx <= eps_dinf * dxn) && dinf_rows_ok) return SFB_QP_DUAL_INFEASIBLE;
+    // Guard (deviations; sfb_set_option(SFB_OPT_DUAL_INF_DX_GUARD)): with dx == 0 exactly every test of :629-639
+    // reads 0 <= 0 and the literal rule reports DualInfeasible for an iterate that merely stopped moving.  The reference's
+    // x carries rounding noise from its (n+m)-long LDL^T sweeps and is exactly stationary only on scalar (n = 1) problems
+    // (tests/test_oracle_qp_known_answers.py); the reduced system here can be during active-set plateaus of tall problems.
+    if ((dxn > T(0) || !a.dinf_guard) && (n_Pdx <= eps_dinf * dxn) && (qdx <= eps_dinf * dxn) && dinf_rows_ok) return SFB_QP_DUAL_INFEASIBLE;
     return kStatusUnset;
   }
 
@@ -802,7 +805,7 @@ template <typename T, int G, int NS, int MS> struct QpGroup
     T* S = nullptr;
     int ldS = 0;
     if (!woodbury && na > 0) {
-      if (2 * na <= ldA) { S = As + na; ldS = ldA; }                       // below the compacted rows
+      if (2 * na <= ldA && !a.force_polish_scratch) { S = As + na; ldS = ldA; }  // below the compacted rows
       else if (gscratch != nullptr && (long long)na * na <= a.scratch_per_cta) { S = gscratch; ldS = na; }
       else return SFB_QP_FLAG_POLISH_SKIPPED;
     }
@@ -1022,7 +1025,7 @@ template <typename T, int G, int NS, int MS> struct QpGroup
 #pragma unroll 1
     for (int r = tid; r < na; r += NT) y[idx[r]] = ty[r];
     gsync();
-    return SFB_QP_FLAG_POLISHED;
+    return SFB_QP_FLAG_POLISHED | ((S != nullptr && !s_shared) ? SFB_QP_FLAG_POLISH_SCRATCH : 0u);
   }
 
   // ---------------------------------------------------------------- M = Pbar + sigma I + Abar^T R Abar

@@ -34,6 +34,7 @@ template <typename T, int N, int R> struct QpSkinny
   T l[R], u[R], sy[R], rho[R], rinv[R], z[R], y[R], yold[R], lo[R], hi[R];
   T P[N][N], q[N], qb[N], x[N], xold[N], sx[N], Minv[N][N];
   T c;
+  bool dinf_guard = true;  // see QpArgs::dinf_guard
 
   __device__ __forceinline__ T wmax(T v) const { return warp_max(v); }
   __device__ __forceinline__ T wsum(T v) const { return warp_sum(v); }
@@ -233,7 +234,7 @@ template <typename T, int N, int R> struct QpSkinny
     }
     if (fmax(n_Atdy, s_pinf) < eps_pinf * Edy) return SFB_QP_PRIMAL_INFEASIBLE;
     // dx == 0 guard: DESIGN.md, "deliberate deviations"
-    if ((dxn > T(0)) && (n_Pdx <= eps_dinf * dxn) && (qdx <= eps_dinf * dxn) && dinf_rows_ok) return SFB_QP_DUAL_INFEASIBLE;
+    if ((dxn > T(0) || !dinf_guard) && (n_Pdx <= eps_dinf * dxn) && (qdx <= eps_dinf * dxn) && dinf_rows_ok) return SFB_QP_DUAL_INFEASIBLE;
     return kStatusUnset;
   }
 
@@ -241,6 +242,7 @@ template <typename T, int N, int R> struct QpSkinny
   {
     const unsigned long long t0 = a.prm.has_max_time ? global_timer_ns() : 0ull;
     load(a, b);
+    dinf_guard = a.dinf_guard != 0;
     int code;
     unsigned iter;
     run(a.prm, a.max_iter_eff, t0, a.warm_x ? a.warm_x + b * N : nullptr, a.warm_y ? a.warm_y + b * (long long)m : nullptr, code, iter);

@@ -68,22 +68,24 @@ inline bool sparse_analyze(int n, int m, const int32_t* P_colptr, const int32_t*
   S.n = n;
   S.m = m;
   if (n <= 0 || m < 0 || !P_colptr || (m > 0 && !A_rowptr)) { S.error = "bad sizes or null pattern"; return false; }
+  // validate BEFORE anything is copied or dereferenced through the caller's arrays
+  if (P_colptr[0] != 0 || (m > 0 && A_rowptr[0] != 0)) { S.error = "pattern pointers must start at 0"; return false; }
+  for (int j = 0; j < n; ++j)
+    if (P_colptr[j + 1] < P_colptr[j]) { S.error = "P_colptr not monotone"; return false; }
+  for (int i = 0; i < m; ++i)
+    if (A_rowptr[i + 1] < A_rowptr[i]) { S.error = "A_rowptr not monotone"; return false; }
   S.nnzP = P_colptr[n];
   S.nnzA = m > 0 ? A_rowptr[m] : 0;
-  if (P_colptr[0] != 0 || (m > 0 && A_rowptr[0] != 0)) { S.error = "pattern pointers must start at 0"; return false; }
+  if ((S.nnzP > 0 && !P_rowidx) || (S.nnzA > 0 && !A_colidx)) { S.error = "index array is NULL"; return false; }
+  for (int e = 0; e < S.nnzP; ++e)
+    if (P_rowidx[e] < 0 || P_rowidx[e] >= n) { S.error = "P row index out of range"; return false; }
+  for (int e = 0; e < S.nnzA; ++e)
+    if (A_colidx[e] < 0 || A_colidx[e] >= n) { S.error = "A column index out of range"; return false; }
   S.P_colptr.assign(P_colptr, P_colptr + n + 1);
   S.P_row.assign(P_rowidx, P_rowidx + S.nnzP);
   S.A_rowptr.assign(m + 1, 0);
   if (m > 0) S.A_rowptr.assign(A_rowptr, A_rowptr + m + 1);
   std::vector<int> A_col_orig(A_colidx, A_colidx + S.nnzA);
-  for (int j = 0; j < n; ++j)
-    if (P_colptr[j + 1] < P_colptr[j]) { S.error = "P_colptr not monotone"; return false; }
-  for (int e = 0; e < S.nnzP; ++e)
-    if (P_rowidx[e] < 0 || P_rowidx[e] >= n) { S.error = "P row index out of range"; return false; }
-  for (int i = 0; i < m; ++i)
-    if (A_rowptr[i + 1] < A_rowptr[i]) { S.error = "A_rowptr not monotone"; return false; }
-  for (int e = 0; e < S.nnzA; ++e)
-    if (A_colidx[e] < 0 || A_colidx[e] >= n) { S.error = "A column index out of range"; return false; }
 
   // ---- pattern of M (original indices) ----
   std::vector<std::set<int>> adj(n);

@@ -94,6 +94,7 @@ template <typename T, typename TIO = T> struct SpArgs
   long long batch;
   sfb_qp_params prm;
   unsigned max_iter_eff;
+  int dinf_guard;  // see QpArgs::dinf_guard
   int mode;  // 0 = solve, 2 = polish only (instances already solved in lower precision: out_* hold the unpolished result)
 };
 
@@ -634,7 +635,7 @@ template <typename T, int TW> struct SpSolver
 
   // ---------------------------------------------------------------- check_stopping, qp_solver.hpp:574-644
   // Same evaluation as the dense kernel (qp_dense_group.cuh::check_stopping): A x_us = Sy^-1 (Abar x), A^T y_us = Sx^-1 Abar^T y / c.
-  __device__ int check_stopping(const sfb_qp_params& prm)
+  __device__ int check_stopping(const sfb_qp_params& prm, bool dinf_guard)
   {
     const T eps_abs = T(prm.eps_abs), eps_rel = T(prm.eps_rel);
     const T eps_pinf = T(prm.eps_primal_inf), eps_dinf = T(prm.eps_dual_inf);
@@ -713,7 +714,7 @@ template <typename T, int TW> struct SpSolver
     }
     if (fmax(n_Atdy, s_pinf) < eps_pinf * Edy) return SFB_QP_PRIMAL_INFEASIBLE;  // :619
     // dx == 0 guard: see qp_dense_group.cuh / DESIGN.md ("deliberate deviations")
-    if ((dxn > T(0)) && (n_Pdx <= eps_dinf * dxn) && (qdx <= eps_dinf * dxn) && dinf_rows_ok) return SFB_QP_DUAL_INFEASIBLE;
+    if ((dxn > T(0) || !dinf_guard) && (n_Pdx <= eps_dinf * dxn) && (qdx <= eps_dinf * dxn) && dinf_rows_ok) return SFB_QP_DUAL_INFEASIBLE;
     return kStatusUnset;
   }
 
@@ -966,7 +967,7 @@ template <typename T, int TW> struct SpSolver
         gsync();
       }
       if (chk) {
-        code = check_stopping(prm);  // :488 (clobbers w, v, t1..t4, xold)
+        code = check_stopping(prm, a.dinf_guard != 0);  // :488 (clobbers w, v, t1..t4, xold)
         if (code == kStatusUnset && prm.has_max_time) {
           const bool late = (long long)(global_timer_ns() - t0) > prm.max_time_ns;  // :504-508
           if (gany(late)) code = SFB_QP_MAX_TIME;

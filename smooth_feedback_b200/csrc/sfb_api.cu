@@ -57,10 +57,14 @@ int classify(std::initializer_list<const void*> ps)
   return seen == -2 ? 1 : seen;
 }
 
-unsigned long long* next_counter(sfb_context* h)
+// Work-queue heads.  One ring per stream the handle launches on (slot < kNumSlots: the staging streams, kNumSlots: the
+// handle's own stream): a counter is reused only after kCountersPerStream later launches on the SAME stream, i.e. in
+// stream order, so a long-running launch on another stream can never share a counter with a later one.
+unsigned long long* next_counter(sfb_context* h, int slot)
 {
-  unsigned long long* c = h->counters + h->next_counter;
-  h->next_counter = (h->next_counter + 1) % h->num_counters;
+  int& nx = h->next_counter[slot];
+  unsigned long long* c = h->counters + slot * kCountersPerStream + nx;
+  nx = (nx + 1) % kCountersPerStream;
   return c;
 }
 
@@ -205,7 +209,7 @@ int qp_launch(sfb_context* h, cudaStream_t st, int scratch_slot, const sfb::QpAr
   if (qp_is_skinny(h, args.n, args.m, args.mode, args.prm)) {
     args.scratch = nullptr;
     args.scratch_per_cta = 0;
-    args.work_counter = next_counter(h);
+    args.work_counter = next_counter(h, scratch_slot);
     SFB_CUDA(h, cudaMemsetAsync(args.work_counter, 0, sizeof(unsigned long long), st));
     int rc;
     switch (args.n) {
@@ -231,7 +235,7 @@ int qp_launch(sfb_context* h, cudaStream_t st, int scratch_slot, const sfb::QpAr
       pa.P = args.P; pa.q = args.q; pa.A = args.A; pa.l = args.l; pa.u = args.u;
       pa.out_x = args.out_x; pa.out_y = args.out_y; pa.out_obj = args.out_obj; pa.out_status = args.out_status;
       pa.out_iter = args.out_iter; pa.out_active = args.out_active; pa.out_flags = args.out_flags;
-      pa.batch = args.batch; pa.n = args.n; pa.m = args.m; pa.mode = 2; pa.prm = args.prm; pa.max_iter_eff = args.max_iter_eff;
+      pa.batch = args.batch; pa.n = args.n; pa.m = args.m; pa.mode = 2; pa.prm = args.prm; pa.max_iter_eff = args.max_iter_eff; pa.dinf_guard = args.dinf_guard; pa.force_polish_scratch = args.force_polish_scratch;
       rc = qp_launch_group<double, T>(h, st, scratch_slot, pa);
       if (rc != SFB_OK) return rc;
     }
@@ -254,7 +258,7 @@ int qp_launch_group(sfb_context* h, cudaStream_t st, int scratch_slot, sfb::QpAr
   if (args.mode != 1 && args.prm.polish) {
     const long long k = std::min(args.n, args.m);
     const sfb::QpLayout L(args.n, args.m, 32 * g.G);
-    if (2 * k > L.ldA) {
+    if (2 * k > L.ldA || args.force_polish_scratch) {
       const size_t bytes = sizeof(T) * (size_t)(k * k) * (size_t)grid;
       int rc = ensure_scratch(h, h->scratch[scratch_slot], bytes, st);
       if (rc != SFB_OK) return rc;
@@ -262,7 +266,7 @@ int qp_launch_group(sfb_context* h, cudaStream_t st, int scratch_slot, sfb::QpAr
       args.scratch_per_cta = k * k;
     }
   }
-  args.work_counter = next_counter(h);
+  args.work_counter = next_counter(h, scratch_slot);
   SFB_CUDA(h, cudaMemsetAsync(args.work_counter, 0, sizeof(unsigned long long), st));
   int rc;
   // shape-specialised instantiations (compile-time n, m) for the headline shapes, generic kernels otherwise
@@ -311,6 +315,8 @@ int qp_solve_impl(sfb_context* h, const sfb_qp_params* prm, int64_t batch, int n
   a.mode = 0;
   a.prm = *prm;
   a.max_iter_eff = prm->has_max_iter ? prm->max_iter : SFB_QP_DEVICE_ITER_CAP;
+  a.dinf_guard = h->dinf_guard;
+  a.force_polish_scratch = h->force_polish_scratch;
 
   if (space == 1) {
     a.P = P; a.q = q; a.A = A; a.l = l; a.u = u; a.warm_x = warm_x; a.warm_y = warm_y;
@@ -457,8 +463,9 @@ int sfb_create(int device, void* stream, sfb_handle_t* out)
     delete h;
     return fail(nullptr, SFB_ERR_NO_DEVICE, "device %d is sm_%d%d; libsfb is built for sm_100a only", device, mj, mn);
   }
-  bool ok = cudaMalloc(&h->counters, sizeof(unsigned long long) * h->num_counters) == cudaSuccess;
+  bool ok = cudaMalloc(&h->counters, sizeof(unsigned long long) * kCountersPerStream * (kNumSlots + 1)) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&h->ev_order, cudaEventDisableTiming) == cudaSuccess;
   for (int s = 0; ok && s < kNumSlots; ++s) {
     ok = ok && cudaStreamCreateWithFlags(&h->slots[s].stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->slots[s].done, cudaEventDisableTiming) == cudaSuccess;
@@ -482,6 +489,7 @@ int sfb_destroy(sfb_handle_t h)
     if (h->slots[s].dev) cudaFree(h->slots[s].dev);
   }
   if (h->ev_start) cudaEventDestroy(h->ev_start);
+  if (h->ev_order) cudaEventDestroy(h->ev_order);
   for (auto& sc : h->scratch)
     if (sc.dev) cudaFree(sc.dev);
   if (h->sparse_ws.dev) cudaFree(h->sparse_ws.dev);
@@ -495,8 +503,26 @@ int sfb_destroy(sfb_handle_t h)
 int sfb_set_stream(sfb_handle_t h, void* stream)
 {
   if (!h) return SFB_ERR_INVALID_ARGUMENT;
-  h->stream = static_cast<cudaStream_t>(stream);
+  cudaStream_t ns = static_cast<cudaStream_t>(stream);
+  if (ns != h->stream) {
+    // The handle owns device workspaces (sparse working set, polish scratch, staging buffers, work counters) that every call
+    // reuses.  Work already enqueued on the old stream must finish with them before work on the new stream touches them.
+    SFB_CUDA(h, cudaSetDevice(h->device));
+    SFB_CUDA(h, cudaEventRecord(h->ev_order, h->stream));
+    SFB_CUDA(h, cudaStreamWaitEvent(ns, h->ev_order, 0));
+    h->stream = ns;
+  }
   return SFB_OK;
+}
+
+int sfb_set_option(sfb_handle_t h, int option, int value)
+{
+  if (!h) return SFB_ERR_INVALID_ARGUMENT;
+  switch (option) {
+    case SFB_OPT_DUAL_INF_DX_GUARD: h->dinf_guard = value ? 1 : 0; return SFB_OK;
+    case SFB_OPT_FORCE_POLISH_SCRATCH: h->force_polish_scratch = value ? 1 : 0; return SFB_OK;
+    default: return fail(h, SFB_ERR_INVALID_ARGUMENT, "unknown option %d", option);
+  }
 }
 
 int sfb_synchronize(sfb_handle_t h)

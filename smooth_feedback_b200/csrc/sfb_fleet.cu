@@ -72,6 +72,7 @@ int asif_launch(sfb_asif_fleet* f, const T* x, const T* ud, T* out_u, int32_t* o
   a.mdl.dt_act = f->d_dt;
   a.prm = p.qp;
   a.max_iter_eff = p.qp.has_max_iter ? p.qp.max_iter : SFB_QP_DEVICE_ITER_CAP;
+  a.dinf_guard = h->dinf_guard;
   a.batch = f->batch;
   a.x = x; a.u_des = ud;
   a.rows = static_cast<T*>(f->d_rows);
@@ -81,7 +82,7 @@ int asif_launch(sfb_asif_fleet* f, const T* x, const T* ud, T* out_u, int32_t* o
   a.warm_valid = f->d_warm_valid;
   a.out_u = out_u; a.out_status = out_status; a.out_iter = out_iter;
   a.qp_P = qP; a.qp_q = qq; a.qp_A = qA; a.qp_l = ql; a.qp_u = qu;
-  a.work_counter = next_counter(h);
+  a.work_counter = next_counter(h, kNumSlots);
   SFB_CUDA(h, cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), h->stream));
   const long long tiles = (f->batch + 31) / 32;
   const long long ctas = (tiles + sfb::kSkinnyWarps - 1) / sfb::kSkinnyWarps;

@@ -18,6 +18,7 @@
 namespace sfbi {
 
 constexpr int kNumSlots = 3;  // staging slots of the host-buffer pipeline (H2D / compute / D2H overlap)
+constexpr int kCountersPerStream = 16;  // work-queue heads per stream, recycled in stream order
 
 struct Slot
 {
@@ -44,13 +45,15 @@ struct sfb_context
   cudaStream_t stream = nullptr;
   cudaDeviceProp prop{};
   unsigned long long* counters = nullptr;  // work-queue heads, one per launch in flight
-  int num_counters = 64;
-  int next_counter = 0;
+  int next_counter[sfbi::kNumSlots + 1] = {};
   uint64_t launches = 0;
   std::string last_error;
   sfbi::Slot slots[sfbi::kNumSlots];
   sfbi::Scratch scratch[sfbi::kNumSlots + 1];  // [kNumSlots] belongs to the handle's own stream
   cudaEvent_t ev_start = nullptr;
+  cudaEvent_t ev_order = nullptr;  // orders the handle's workspaces across a change of stream (sfb_set_stream)
+  int dinf_guard = 1;  // SFB_OPT_DUAL_INF_DX_GUARD
+  int force_polish_scratch = 0;  // SFB_OPT_FORCE_POLISH_SCRATCH
   bool ekf_force_generic = false;
   bool dense_force_generic = false;  // SFB_DENSE_FORCE_GENERIC=1: bypass the tall-skinny register kernel (A/B measurements)
   int sparse_tw = 0;     // SFB_SPARSE_TW=4|8|32 overrides the tile-width heuristic of the sparse QP path (A/B measurements)
@@ -74,7 +77,7 @@ int fail(sfb_context* h, int code, const char* fmt, ...);
 int mem_space(const void* p);
 // classify a set of pointers (nullptr entries ignored): 0 all host, 1 all device, -1 mixed
 int classify(std::initializer_list<const void*> ps);
-unsigned long long* next_counter(sfb_context* h);
+unsigned long long* next_counter(sfb_context* h, int slot);
 int ensure_slot(sfb_context* h, Slot& s, size_t bytes);
 int ensure_scratch(sfb_context* h, Scratch& s, size_t bytes, cudaStream_t st);
 int check_params(sfb_context* h, const sfb_qp_params* prm, int64_t batch, int n, int m);

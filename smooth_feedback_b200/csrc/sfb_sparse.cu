@@ -111,13 +111,14 @@ int qp_sparse_solve_impl(sfb_context* h, const sfb_qp_sparse_pattern* pt, const 
   a.prm = *prm;
   a.max_iter_eff = prm->has_max_iter ? prm->max_iter : SFB_QP_DEVICE_ITER_CAP;
   a.mode = 0;
+  a.dinf_guard = h->dinf_guard;
   // Mixed-precision polish: the ADMM iterations ran in fp32 (instances flagged POLISH_SKIPPED); the Optimal ones are
   // re-staged in fp64 and polish_qp (qp_solver.hpp:92-204) runs on the fp32 iterate and its active set.
   auto launch = [&]() -> int {
     int rc2 = sp_launch<T, T>(h, pt, a, tw);
     if (rc2 != SFB_OK || !mixed) return rc2;
     sfb::SpArgs<double, T> pa{};
-    pa.pat = a.pat; pa.batch = a.batch; pa.prm = a.prm; pa.max_iter_eff = a.max_iter_eff; pa.mode = 2;
+    pa.pat = a.pat; pa.batch = a.batch; pa.prm = a.prm; pa.max_iter_eff = a.max_iter_eff; pa.mode = 2; pa.dinf_guard = a.dinf_guard;
     pa.P = a.P; pa.q = a.q; pa.A = a.A; pa.l = a.l; pa.u = a.u;
     pa.out_x = a.out_x; pa.out_y = a.out_y; pa.out_obj = a.out_obj; pa.out_status = a.out_status; pa.out_iter = a.out_iter;
     pa.out_active = a.out_active; pa.out_flags = a.out_flags;
@@ -187,7 +188,6 @@ int sfb_qp_sparse_analyze(sfb_handle_t h, int n, int m, const int32_t* P_colptr,
   if (!out) return fail(h, SFB_ERR_INVALID_ARGUMENT, "out is NULL");
   *out = nullptr;
   if (n <= 0 || m < 0 || !P_colptr || (m > 0 && !A_rowptr)) return fail(h, SFB_ERR_INVALID_ARGUMENT, "bad pattern arguments");
-  if ((P_colptr[n] > 0 && !P_rowidx) || (m > 0 && A_rowptr[m] > 0 && !A_colidx)) return fail(h, SFB_ERR_INVALID_ARGUMENT, "index array is NULL");
   auto* p = new sfb_qp_sparse_pattern();
   p->device = h->device;
   if (!sfb::sparse_analyze(n, m, P_colptr, P_rowidx, A_rowptr, A_colidx, p->sym)) {

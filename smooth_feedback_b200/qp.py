@@ -41,6 +41,7 @@ class QPSolutionStatus(enum.IntEnum):
 FLAG_POLISHED = 1
 FLAG_POLISH_SKIPPED = 2
 FLAG_POLISH_FAILED = 4
+FLAG_POLISH_SCRATCH = 8
 
 
 @dataclass

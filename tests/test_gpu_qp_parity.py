@@ -290,6 +290,57 @@ def test_fp32_against_fp64_oracle(sfb, oracle):
     assert same.mean() >= 0.98 and rel_err(r.x[same], o.x[same]).max() <= REL_F32
 
 
+@pytest.mark.parametrize("n,m", [(2, 2), (3, 2), (10, 20), (50, 100), (64, 64), (70, 40)])
+def test_polish_schur_block_in_global_workspace(sfb, n, m):
+    """polish_qp keeps its Schur block S below the compacted active rows when 2 na <= ldA and in a global workspace
+    otherwise (n = m = 64 with na > 33, (70, 40) with na > 21 ...).  SFB_OPT_FORCE_POLISH_SCRATCH sends EVERY instance down
+    the workspace path: the flag bit proves the path ran, and its results must equal the on-chip placement bit for bit."""
+    from smooth_feedback_b200 import _lib
+    from smooth_feedback_b200.generators import random_qp_numpy
+    from smooth_feedback_b200.qp import FLAG_POLISH_SCRATCH, FLAG_POLISHED
+
+    P, q, A, l, u = random_qp_numpy(128, n, m, seed=n * 1000 + m)
+    prm = sfb.QPSolverParams(max_iter=4000)
+    h = sfb.Handle(0)
+    cm = sfb.to_colmajor
+    r0 = sfb.solve_dense_batch(cm(P), q, cm(A), l, u, prm, handle=h)
+    h.set_option(_lib.OPT_FORCE_POLISH_SCRATCH, 1)
+    r1 = sfb.solve_dense_batch(cm(P), q, cm(A), l, u, prm, handle=h)
+    na = (r0.active != 0).sum(axis=1)
+    took = (r1.flags & FLAG_POLISH_SCRATCH) != 0
+    assert took[(r1.status == 0) & (na > 0) & (na <= n)].all() and took.sum() > 0
+    assert ((r1.flags & FLAG_POLISHED) != 0)[r1.status == 0].all()
+    assert np.array_equal(r0.x, r1.x) and np.array_equal(r0.y, r1.y) and np.array_equal(r0.status, r1.status)
+
+
+def test_dual_infeasibility_guard_option(sfb, oracle):
+    """SFB_OPT_DUAL_INF_DX_GUARD: A/B of the dx != 0 guard on the dual-infeasibility certificate (qp_solver.hpp:625-641)
+    against the literal rule, counted as status mismatches against the oracle (see the CPU test
+    test_where_the_reference_algorithm_sees_an_exactly_stationary_iterate and profiles/r02_dual_inf_guard_ab.txt).
+    The default (guard on) must be exact on the BASELINE shape n = 3 / m = 203 and at least as good as the literal rule on
+    every shape with n >= 2; on scalar problems the literal rule is the closer one."""
+    from smooth_feedback_b200 import _lib
+    from smooth_feedback_b200.generators import random_qp_numpy
+
+    cm = sfb.to_colmajor
+    prm = sfb.QPSolverParams(max_iter=5000, polish=False)
+    h = sfb.Handle(0)
+    mism = {}
+    for (n, m) in [(1, 5), (2, 40), (3, 64), (3, 203)]:
+        P, q, A, l, u = random_qp_numpy(512, n, m, seed=7000 + 10 * n + m + 1)
+        o = oracle.qp_solve_batch(P, q, A, l, u, params=oracle.default_params(max_iter=5000, polish=0), nthreads=8)
+        for guard in (1, 0):
+            h.set_option(_lib.OPT_DUAL_INF_DX_GUARD, guard)
+            r = sfb.solve_dense_batch(cm(P), q, cm(A), l, u, prm, handle=h)
+            mism[(n, m, guard)] = int((r.status != o.status).sum())
+            if guard:
+                assert (r.status != 3).all()  # a dual-infeasibility certificate needs a direction
+    assert mism[(3, 203, 1)] == 0
+    for (n, m) in [(2, 40), (3, 64), (3, 203)]:
+        assert mism[(n, m, 1)] <= mism[(n, m, 0)], mism
+    assert mism[(1, 5, 0)] <= mism[(1, 5, 1)], mism
+
+
 def test_solver_object_api(sfb):
     # tests/test_qp.cpp:338-372 SolverAPI: copies / fresh solvers give the same primal
     import copy
@@ -337,7 +388,7 @@ def test_full_size_properties(sfb, oracle):
     assert (r.status == 0).all()
     it = r.iter.to(torch.int64)
     assert ((it % 25) == 2).all()                                   # exits only at stop checks
-    assert (r.flags == 1).all()                                     # every instance was polished on chip
+    assert (r.flags == 1).all()                                     # every instance was polished, Schur block on chip
     A = A_cm.transpose(1, 2)
     Ax = torch.einsum("bij,bj->bi", A, r.x)
     stat = torch.einsum("bij,bj->bi", P_cm, r.x) + q + torch.einsum("bij,bi->bj", A, r.y)

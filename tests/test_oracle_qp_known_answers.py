@@ -72,3 +72,38 @@ def test_scipy_crosscheck_random(oracle):
     assert np.abs(stat).max() < 1e-6
     assert (r.y >= -1e-9).all()                       # l = -inf -> multipliers of upper bounds are >= 0
     assert np.abs(r.y * (Ax - u)).max() < 1e-6        # complementarity
+
+
+def test_where_the_reference_algorithm_sees_an_exactly_stationary_iterate(oracle):
+    """The CUDA engine guards the dual-infeasibility certificate (qp_solver.hpp:625-641) with ||dx|| != 0 by default
+    (SFB_OPT_DUAL_INF_DX_GUARD): with dx == 0 every comparison there reads 0 <= 0 and the literal rule reports
+    DualInfeasible for an iterate that merely stopped moving.  Where does the reference algorithm itself meet that case?
+    Measured on the oracle (the literal algorithm, no guard) with its instrumentation counter:
+      * the reference's own known-answer cases, the BASELINE shapes (n = 10 / m = 20, n = 50 / m = 100, n = 3 / m = 203),
+        the infeasible mixes and the real ASIF workload: never -- the guard cannot change a status the reference returns;
+      * tall problems with 1-3 variables (n = 1 / m = 5, n = 2 / m = 40, ...): in ~0.5 % of the instances the reference
+        itself stops with a spurious DualInfeasible.  The engine's arithmetic reaches exactly stationary iterates on
+        DIFFERENT instances, so neither rule reproduces those verdicts instance by instance; the A/B on the GPU
+        (profiles/r02_dual_inf_guard_ab.txt, tests/test_gpu_qp_parity.py::test_dual_infeasibility_guard_option) shows the
+        guard gives fewer status mismatches on every shape with n >= 2 and the literal rule only for n = 1."""
+    from qp_cases import CASES, as_batch
+    from smooth_feedback_b200.generators import random_qp_numpy
+
+    oracle.dx_zero_checks(reset=True)
+    for case in CASES:
+        oracle.qp_solve_batch(*as_batch(case))
+    for (B, n, m, seed, feas, pol) in [(256, 10, 20, 5, True, 1), (64, 50, 100, 5, True, 1), (512, 3, 203, 7234, True, 0),
+                                       (128, 3, 7, 31, False, 0), (256, 10, 20, 11, False, 1)]:
+        P, q, A, l, u = random_qp_numpy(B, n, m, seed=seed, feasible=feas)
+        oracle.qp_solve_batch(P, q, A, l, u, params=oracle.default_params(max_iter=5000, polish=pol), nthreads=4)
+    from oracle import transcribe as tr
+
+    _, x0 = tr.sample_vehicle_states(32, seed=5)
+    ud = np.random.default_rng(5).uniform(-0.5, 0.5, (32, 2))
+    P, q, A, l, u = tr.vehicle_asif_qp_batch(x0, ud)
+    oracle.qp_solve_batch(P, q, A, l, u, params=oracle.default_params(max_iter=4000, polish=0), nthreads=4)
+    assert oracle.dx_zero_checks(reset=True) == 0
+    # tall problems with very few variables: the literal rule does fire in the reference algorithm
+    P, q, A, l, u = random_qp_numpy(96, 1, 5, seed=7015)
+    o = oracle.qp_solve_batch(P, q, A, l, u, params=oracle.default_params(max_iter=5000, polish=0), nthreads=1)
+    assert oracle.dx_zero_checks(reset=True) > 0 and (o.status == 3).any()

@@ -101,3 +101,29 @@ def test_schedules_are_self_consistent(n, m, density, seed):
     sym = sfb.sparse_symbolic(n, m, pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], pat["A_colidx"])
     assert sorted(sym["perm"].tolist()) == list(range(n))
     assert 0 <= sym["nnzL"] <= n * (n - 1) // 2
+
+
+def test_malformed_patterns_are_rejected_not_dereferenced():
+    """sfb_qp_sparse_symbolic validates pointer arrays (monotone, starting at 0, nnz >= 0, non-NULL index arrays) before it
+    copies or dereferences anything: a malformed pattern is SFB_ERR_INVALID_ARGUMENT, not undefined behaviour."""
+    import ctypes as C
+
+    from smooth_feedback_b200 import _lib
+
+    L = _lib.lib()
+    i32 = lambda a: np.asarray(a, np.int32)
+    ptr = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+
+    def rc(n, m, pc, pr, ar, ac):
+        keep = [i32(t) if t is not None else None for t in (pc, pr, ar, ac)]
+        return L.sfb_qp_sparse_symbolic(n, m, ptr(keep[0]), ptr(keep[1]), ptr(keep[2]), ptr(keep[3]), None, None, None, None)
+
+    assert rc(2, 1, [0, 1, 2], [0, 1], [0, 2], [0, 1]) == 0                    # well formed
+    assert rc(2, 1, [0, 2, 1], [0, 1], [0, 2], [0, 1]) == 1                    # P_colptr not monotone
+    assert rc(2, 1, [0, 1, -5], [0, 1], [0, 2], [0, 1]) == 1                   # negative nnz
+    assert rc(2, 1, [1, 1, 2], [0, 1], [0, 2], [0, 1]) == 1                    # does not start at 0
+    assert rc(2, 1, [0, 1, 2], None, [0, 2], [0, 1]) == 1                      # NULL row indices with nnz > 0
+    assert rc(2, 1, [0, 1, 2], [0, 1], [0, 2], None) == 1                      # NULL column indices with nnz > 0
+    assert rc(2, 1, [0, 1, 2], [0, 1], [0, 2], [0, 2]) == 1                    # column index out of range
+    assert rc(2, 1, [0, 1, 2], [0, 1], [0, 2], [1, 1]) == 1                    # duplicate column in a row
+    assert rc(2, 0, [0, 0, 0], None, None, None) == 0                          # empty P, no rows
