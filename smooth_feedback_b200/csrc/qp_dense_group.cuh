@@ -130,10 +130,8 @@ struct QpLayout
     // Abar: leading dimension == 2 (mod 4).  Thread-per-row accesses are consecutive; thread-per-column accesses
     // fetch two rows per 2-scalar load and the column stride ldA/2 is odd: both patterns are bank-conflict free.
     ldA = mm + ((2 - mm % 4) + 4) % 4;
-    // (The polish Schur block lives below the compacted active rows when 2 na <= ldA, else in a global workspace.  Both
-    // placements give bit-identical results on every shape incl. 2 x 2 blocks -- SFB_OPT_FORCE_POLISH_SCRATCH A/B,
-    // profiles/r02_polish_scratch_vs_onchip.txt; the round-1 "2 x 2 disagreement" was the conditioning of the duals when
-    // both rows of an n = 2 problem are active: the oracle's two builds disagree with each other by more than the engine.)
+    // (The polish Schur block lives below the compacted active rows when 2 na <= ldA, else in a global workspace; both
+    // placements give bit-identical results, SFB_OPT_FORCE_POLISH_SCRATCH A/B in profiles/r02_polish_scratch_vs_onchip.txt.)
     ldN = odd(n);  // Minv / P: only row-wise and scalar column accesses -> odd stride
     npad = (n + 1) & ~1;
     mpad = (mm + 1) & ~1;
@@ -804,13 +802,14 @@ template <typename T, int G, int NS, int MS> struct QpGroup
     const bool woodbury = na > n;  // more active rows than variables: S would be na x na and singular-ish
     T* S = nullptr;
     int ldS = 0;
+    bool s_shared = false;  // NOT derivable from ldS == ldA: with every row of an m == ldA problem active, na == ldA too (the
+                            // root cause of the round-1 "2 x 2" polish failures: S in the workspace was addressed as if on chip)
     if (!woodbury && na > 0) {
-      if (2 * na <= ldA && !a.force_polish_scratch) { S = As + na; ldS = ldA; }  // below the compacted rows
+      if (2 * na <= ldA && !a.force_polish_scratch) { S = As + na; ldS = ldA; s_shared = true; }  // below the compacted rows
       else if (gscratch != nullptr && (long long)na * na <= a.scratch_per_cta) { S = gscratch; ldS = na; }
       else return SFB_QP_FLAG_POLISH_SKIPPED;
     }
 
-    const bool s_shared = (S != nullptr) && (ldS == ldA);
     // compact the active rows of Abar to the top of every column (idx ascending => in-place safe)
 #pragma unroll 1
     for (int j = tid; j < n; j += NT) {

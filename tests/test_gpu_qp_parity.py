@@ -290,7 +290,7 @@ def test_fp32_against_fp64_oracle(sfb, oracle):
     assert same.mean() >= 0.98 and rel_err(r.x[same], o.x[same]).max() <= REL_F32
 
 
-@pytest.mark.parametrize("n,m", [(2, 2), (3, 2), (10, 20), (50, 100), (64, 64), (70, 40)])
+@pytest.mark.parametrize("n,m", [(2, 2), (3, 2), (8, 6), (10, 20), (50, 100), (64, 64), (70, 40)])
 def test_polish_schur_block_in_global_workspace(sfb, n, m):
     """polish_qp keeps its Schur block S below the compacted active rows when 2 na <= ldA and in a global workspace
     otherwise (n = m = 64 with na > 33, (70, 40) with na > 21 ...).  SFB_OPT_FORCE_POLISH_SCRATCH sends EVERY instance down
@@ -311,6 +311,30 @@ def test_polish_schur_block_in_global_workspace(sfb, n, m):
     assert took[(r1.status == 0) & (na > 0) & (na <= n)].all() and took.sum() > 0
     assert ((r1.flags & FLAG_POLISHED) != 0)[r1.status == 0].all()
     assert np.array_equal(r0.x, r1.x) and np.array_equal(r0.y, r1.y) and np.array_equal(r0.status, r1.status)
+
+
+def test_polish_all_rows_active_unpadded_leading_dimension(sfb, oracle):
+    """Regression for the round-1 "2 x 2 polish" defect: when m == ldA (m = 2, 6, 10, ...: no padding) and EVERY row is
+    active, na == ldA, and the kernel used to infer "S is on chip" from ldS == ldA -- so the workspace copy of S was
+    addressed as if it sat in shared memory.  Problems built so that all m rows are active at the solution."""
+    rng = np.random.default_rng(12)
+    for (n, m) in [(2, 2), (3, 2), (8, 6), (12, 10)]:
+        B = 64
+        L = np.tril(rng.uniform(-1, 1, (B, n, n))); L[:, np.arange(n), np.arange(n)] = 1.0 + rng.random((B, n))
+        P = L @ np.transpose(L, (0, 2, 1))
+        A = rng.uniform(-1, 1, (B, m, n))
+        xs = rng.uniform(-1, 1, (B, n))
+        ys = 0.5 + rng.random((B, m))                       # strictly positive duals: every row active at its upper bound
+        q = -(np.einsum("bij,bj->bi", P, xs) + np.einsum("bij,bi->bj", A, ys))
+        u = np.einsum("bij,bj->bi", A, xs)
+        l = np.full((B, m), -np.inf)
+        r = gpu_solve(sfb, P, q, A, l, u, sfb.QPSolverParams(max_iter=20000))
+        o = oracle.qp_solve_batch(P, q, A, l, u, params=oracle.default_params(max_iter=20000), nthreads=8)
+        ok = (o.status == 0) & (o.active == 1).all(axis=1) & (r.iter == o.iter)
+        assert ok.mean() > 0.8
+        assert np.array_equal(r.active[ok], o.active[ok]) and np.array_equal(r.status[ok], o.status[ok])
+        assert rel_err(r.x[ok], xs[ok]).max() <= 1e-6 and rel_err(r.x[ok], o.x[ok]).max() <= 1e-6
+        assert rel_err(r.y[ok], ys[ok]).max() <= 1e-5
 
 
 def test_dual_infeasibility_guard_option(sfb, oracle):
