@@ -305,6 +305,66 @@ int sfb_asif_fleet_filter_f32(sfb_asif_fleet_t f, const float* x, const float* u
 int sfb_asif_fleet_to_qp_f64(sfb_asif_fleet_t f, const double* x, const double* u_des, double* P, double* q, double* A,
                              double* l, double* u);
 
+/*
+ * ---- MPC on the device for the built-in SE(2) x R^3 vehicle family (SURVEY 8(f) rows f2 + f3) -----------------------
+ *
+ * Replaces MPC<T, X, U, F, CR, Kmesh>::operator()(t, x) (mpc.hpp:458-519) -- ocp_to_qp_update_dyn / _ce (ocp_to_qp.hpp:
+ * 198-276, 326-373), makeCompressed, qp_solver_.solve(qp_, warmstart_) (:491), the warm-start retention rule (:510-516:
+ * kept if Optimal, MaxTime or MaxIterations) and u = udes(0) (+) primal.segment<Nu>(uvar_B) (:518) -- for a FLEET of agents
+ * that share one parameter set, for the model family of examples/mpc_asif_vehicle.cpp:42-89:
+ *     X = Bundle<SE2, R^3>, coefficients (x, y, sin, cos, v1, v2, v3);  U = R^2
+ *     d^r x = (v1, v2, v3, -drag1 v1 + u1, 0, -drag3 v3 + u2),  running constraint crl <= u <= cru
+ *     xdes(t) = X{SE2(g0) * exp(t vdes), vdes}  (mpc_asif_vehicle.cpp:72-78),  udes(t) = udes
+ * The sparse QP (K = 50: n = m = 422) is transcribed on the device straight into the value layout of
+ * sfb_qp_solve_sparse_batch_* (pattern = QuadraticProgramSparse after makeCompressed); symbolic analysis is done once at
+ * creation (MPC's constructor, mpc.hpp:424); warm starts stay resident on the device.  Per control step only (t, x) of
+ * every agent go in and (u, code, iter) come out.
+ * The cost is transcribed at creation from Q, R, Qtf exactly as the reference's constructor does (mpc.hpp:423); the
+ * reference never re-transcribes it, so MPC::set_weights after construction has no effect there either.
+ */
+typedef struct {
+  int32_t K;         /* 50   MPCParams::K       mpc.hpp:317   -> ceil(K / Kmesh) mesh intervals */
+  double tf;         /* 5    MPCParams::tf      :322 */
+  int32_t Kmesh;     /* 4    template parameter Kmesh of MPC (collocation points per interval) */
+  int32_t warmstart; /* 1    MPCParams::warmstart :327 */
+  double Q[6];       /* 1..  MPCWeights (diagonal), in effect at construction */
+  double R[2];
+  double Qtf[6];
+  double crl[2];     /* -0.5, -0.5 */
+  double cru[2];     /*  0.5,  0.5 */
+  double drag1, drag3; /* 0.2, 0.4 */
+  double g0[3];      /* 2.5, 0, pi/2   SE(2) element (x, y, angle) the desired trajectory starts from */
+  double vdes[3];    /* 1, 0, 0.4      its constant body velocity = the desired R^3 part */
+  double udes[2];    /* 0, 0 */
+  sfb_qp_params qp;  /* MPCParams::qp (defaults: polish on) */
+} sfb_mpc_vehicle_params;
+
+/* the parameter set of examples/mpc_asif_vehicle.cpp:42-89 with K = 50 (BASELINE configs[2]); weights as the reference
+ * actually uses them (identity: its set_weights call comes after the cost was transcribed) */
+void sfb_mpc_vehicle_params_default(sfb_mpc_vehicle_params* p);
+
+typedef struct sfb_mpc_fleet* sfb_mpc_fleet_t;
+
+int sfb_mpc_fleet_create(sfb_handle_t h, const sfb_mpc_vehicle_params* p, int64_t batch, int scalar_bytes,
+                         sfb_mpc_fleet_t* out);
+int sfb_mpc_fleet_destroy(sfb_mpc_fleet_t f);
+int sfb_mpc_fleet_reset_warmstart(sfb_mpc_fleet_t f); /* MPC::reset_warmstart, mpc.hpp:611 */
+/* QP sizes: n, m, nnz(P), nnz(A), nnz of the factor; any output may be NULL */
+int sfb_mpc_fleet_dims(sfb_mpc_fleet_t f, int* n, int* m, int* nnzP, int* nnzA, int64_t* nnzL);
+/* the shared sparsity pattern (host arrays): P_colptr [n+1], P_rowidx [nnzP], A_rowptr [m+1], A_colidx [nnzA] */
+int sfb_mpc_fleet_pattern(sfb_mpc_fleet_t f, int32_t* P_colptr, int32_t* P_rowidx, int32_t* A_rowptr, int32_t* A_colidx);
+/* the transcription alone: t [batch], x [batch][7] -> P_vals [batch][nnzP], q [batch][n], A_vals [batch][nnzA], l, u [batch][m] */
+int sfb_mpc_fleet_to_qp_f64(sfb_mpc_fleet_t f, const double* t, const double* x, double* P_vals, double* q,
+                            double* A_vals, double* l, double* u);
+/*
+ * One control step of every agent: t [batch] (absolute time), x [batch][7] -> out_u [batch][2], out_status [batch],
+ * out_iter [batch]; out_primal [batch][n] / out_dual [batch][m] may be NULL.  All-host or all-device pointers.
+ */
+int sfb_mpc_fleet_step_f64(sfb_mpc_fleet_t f, const double* t, const double* x, double* out_u, int32_t* out_status,
+                           uint32_t* out_iter, double* out_primal, double* out_dual);
+int sfb_mpc_fleet_step_f32(sfb_mpc_fleet_t f, const float* t, const float* x, float* out_u, int32_t* out_status,
+                           uint32_t* out_iter, float* out_primal, float* out_dual);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,8 @@ EXPORTED_SYMBOLS = [
     "sfb_qp_solve_sparse_batch_f64", "sfb_qp_solve_sparse_batch_f32",
     "sfb_asif_vehicle_params_default", "sfb_asif_fleet_create", "sfb_asif_fleet_destroy", "sfb_asif_fleet_reset_warmstart",
     "sfb_asif_fleet_set_warmstart", "sfb_asif_fleet_filter_f64", "sfb_asif_fleet_filter_f32", "sfb_asif_fleet_to_qp_f64",
+    "sfb_mpc_vehicle_params_default", "sfb_mpc_fleet_create", "sfb_mpc_fleet_destroy", "sfb_mpc_fleet_reset_warmstart",
+    "sfb_mpc_fleet_dims", "sfb_mpc_fleet_pattern", "sfb_mpc_fleet_to_qp_f64", "sfb_mpc_fleet_step_f64", "sfb_mpc_fleet_step_f32",
 ]
 
 
@@ -136,6 +138,16 @@ def lib() -> C.CDLL:
     L.sfb_asif_fleet_filter_f64.argtypes = [vp] * 6
     L.sfb_asif_fleet_filter_f32.argtypes = [vp] * 6
     L.sfb_asif_fleet_to_qp_f64.argtypes = [vp] * 8
+    L.sfb_mpc_vehicle_params_default.argtypes = [vp]
+    L.sfb_mpc_vehicle_params_default.restype = None
+    L.sfb_mpc_fleet_create.argtypes = [vp, vp, i64, i32, C.POINTER(vp)]
+    L.sfb_mpc_fleet_destroy.argtypes = [vp]
+    L.sfb_mpc_fleet_reset_warmstart.argtypes = [vp]
+    L.sfb_mpc_fleet_dims.argtypes = [vp] + [C.POINTER(C.c_int)] * 4 + [C.POINTER(i64)]
+    L.sfb_mpc_fleet_pattern.argtypes = [vp] * 5
+    L.sfb_mpc_fleet_to_qp_f64.argtypes = [vp] * 8
+    L.sfb_mpc_fleet_step_f64.argtypes = [vp] * 8
+    L.sfb_mpc_fleet_step_f32.argtypes = [vp] * 8
     for name in EXPORTED_SYMBOLS:
         getattr(L, name)
     _lib = L

@@ -1,0 +1,223 @@
+// mpc_vehicle_host.hpp -- host side (once per fleet) of the MPC transcription for the built-in SE(2) x R^3 vehicle family.
+//
+// Replaces, for that family (reference paths relative to pettni/smooth_feedback @ 9a08971):
+//   MPC<T, X, U, F, CR, Kmesh>::MPC           include/smooth/feedback/mpc.hpp:405-425   (mesh, allocate, cost, analyze)
+//   ocp_to_qp_allocate / update_cost / _dyn / _cr   include/smooth/feedback/ocp_to_qp.hpp:40-323
+//   Mesh<Kmesh, Kmesh>                        include/smooth/feedback/collocation/mesh.hpp:69-366 (LGR nodes, weights, D)
+// What the reference recomputes per control step with autodiff -- the collocation rows of ocp_to_qp_update_dyn -- is constant
+// for this family: f(x, u) depends on x only through the R^3 part and the desired trajectory xdes(t) = g0 exp(t vdes) has
+// a constant body velocity, so df/dx, df/du, ad(f + d^r xdes/dt) and the right-hand sides do not depend on t or on the agent.
+// Per agent and step only the Nce = 6 end-constraint rows change (ocp_to_qp_update_ce, :326-373); those are written on the
+// device (mpc_vehicle.cuh).  The pattern is emitted in the reference's storage (CSC P, CSR A, sorted indices) so that it is
+// also exactly what QuadraticProgramSparse holds after makeCompressed (mpc.hpp:487-488).
+//
+// Reference quirks reproduced (verified in the cited lines; see oracle/transcribe.py for the restatement these are tested
+// against): the cost is transcribed ONCE at construction (mpc.hpp:423; set_weights afterwards never reaches the QP); MPCObj::
+// hessian stores Qtf in the x0 block (mpc.hpp:103-107) which ocp_to_qp.hpp:190 scales by 0.5; x_N carries no cost; the uu
+// Hessian entries are gated by Q(i,j) != 0 (mpc.hpp:219-223); only the upper triangle of P is stored.
+#pragma once
+
+#include <cmath>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/sfb.h"
+
+namespace sfb {
+
+struct MpcVehicleHost
+{
+  static constexpr int Nx = 6, Nu = 2, Ncr = 2, Nce = 6;
+  int nivals = 0, Ki = 0, N = 0, n = 0, m = 0, xvar_L = 0;
+  std::vector<int> P_colptr, P_rowidx, A_rowptr, A_colidx;
+  std::vector<double> P_vals, A_base, l_base, u_base;
+  int ce_slot[Nce][Nce];  // position in A_vals of end-constraint entry (r, c), -1 outside d_exp_sparse_pattern<X>
+  int ce_row0 = 0;
+  std::string error;
+};
+
+// K Legendre-Gauss-Radau nodes on [-1, 1) (roots of P_{K-1} + P_K, -1 included) and weights (1 - x) / (K^2 P_{K-1}(x)^2)
+inline void lgr_nodes(int K, std::vector<double>& x, std::vector<double>& w)
+{
+  auto leg = [](int k, double t, double& p, double& dp) {  // P_k(t) and its derivative by the three-term recurrence
+    double p0 = 1.0, p1 = t;
+    if (k == 0) { p = 1.0; dp = 0.0; return; }
+    for (int j = 2; j <= k; ++j) {
+      const double pj = ((2 * j - 1) * t * p1 - (j - 1) * p0) / j;
+      p0 = p1; p1 = pj;
+    }
+    p = p1;
+    dp = k * (t * p1 - p0) / (t * t - 1.0);  // only evaluated strictly inside (-1, 1)
+  };
+  x.assign(K, 0.0);
+  w.assign(K, 0.0);
+  const double pi = 3.14159265358979323846;
+  for (int i = 0; i < K; ++i) {
+    double t = -std::cos(2.0 * pi * i / (2 * K - 1));
+    if (i == 0) { x[0] = -1.0; continue; }
+    for (int it = 0; it < 100; ++it) {
+      double pk, dpk, pk1, dpk1;
+      leg(K, t, pk, dpk);
+      leg(K - 1, t, pk1, dpk1);
+      // deflate the known root at -1 so that Newton cannot fall into it: g(t) = (P_{K-1} + P_K) / (1 + t)
+      const double f = pk + pk1, df = dpk + dpk1;
+      const double g = f / (1.0 + t), dg = (df * (1.0 + t) - f) / ((1.0 + t) * (1.0 + t));
+      const double step = g / dg;
+      t -= step;
+      if (std::fabs(step) < 1e-16) break;
+    }
+    x[i] = t;
+  }
+  for (int i = 0; i < K; ++i) {
+    double pk1, dpk1;
+    leg(K - 1, x[i], pk1, dpk1);
+    w[i] = (1.0 - x[i]) / (K * K * pk1 * pk1);
+  }
+}
+
+// D[j][i] = l_j'(nodes[i]): derivative of the j-th Lagrange basis polynomial at node i (barycentric form)
+inline std::vector<std::vector<double>> lagrange_diffmat(const std::vector<double>& nodes)
+{
+  const int nn = (int)nodes.size();
+  std::vector<double> wb(nn, 1.0);
+  for (int j = 0; j < nn; ++j) {
+    double prod = 1.0;
+    for (int k = 0; k < nn; ++k)
+      if (k != j) prod *= (nodes[j] - nodes[k]);
+    wb[j] = 1.0 / prod;
+  }
+  std::vector<std::vector<double>> D(nn, std::vector<double>(nn, 0.0));
+  for (int i = 0; i < nn; ++i) {
+    double s = 0.0;
+    for (int j = 0; j < nn; ++j)
+      if (i != j) {
+        D[j][i] = (wb[j] / wb[i]) / (nodes[i] - nodes[j]);
+        s += D[j][i];
+      }
+    D[i][i] = -s;
+  }
+  return D;
+}
+
+inline bool mpc_vehicle_build(const sfb_mpc_vehicle_params& p, MpcVehicleHost& H)
+{
+  constexpr int Nx = MpcVehicleHost::Nx, Nu = MpcVehicleHost::Nu, Ncr = MpcVehicleHost::Ncr, Nce = MpcVehicleHost::Nce;
+  if (p.K < 1 || p.Kmesh < 1 || p.Kmesh > 16 || !(p.tf > 0)) { H.error = "bad K / Kmesh / tf"; return false; }
+  H.Ki = p.Kmesh;
+  H.nivals = (p.K + p.Kmesh - 1) / p.Kmesh;  // mpc.hpp:408
+  const int Ki = H.Ki, nivals = H.nivals;
+  const int N = H.N = nivals * Ki;
+  H.xvar_L = Nx * (N + 1);
+  const int uvar_B = H.xvar_L;
+  H.n = Nx * (N + 1) + Nu * N;
+  H.m = Nx * N + Ncr * N + Nce;
+  const int crcon_B = Nx * N, cecon_B = crcon_B + Ncr * N;
+  H.ce_row0 = cecon_B;
+  const double tf = p.tf;
+
+  std::vector<double> lx, lw;
+  lgr_nodes(Ki, lx, lw);
+  std::vector<double> ext(lx);
+  ext.push_back(1.0);
+  const auto Dus = lagrange_diffmat(ext);  // Dus[j][i], i < Ki used
+
+  std::vector<std::map<int, double>> rows(H.m), pcols(H.n);
+  H.l_base.assign(H.m, 0.0);
+  H.u_base.assign(H.m, 0.0);
+
+  // ---- cost, ocp_to_qp_update_cost specialised to the MPC functors (ctor only, mpc.hpp:423)
+  {
+    int i = 0;
+    for (int iv = 0; iv < nivals; ++iv) {
+      const double tau0 = (nivals < 2) ? 0.0 : (double)iv * (1.0 / (double)nivals);  // mesh.hpp:91-99
+      const double tauf = (iv + 1 < nivals) ? (double)(iv + 1) * (1.0 / (double)nivals) : 1.0;
+      const double al = (tauf - tau0) / 2;
+      for (int k = 0; k < Ki; ++k, ++i) {
+        const double w = al * lw[k];  // mesh.hpp:230-254
+        for (int a = 0; a < Nx; ++a)
+          if (p.Q[a] != 0) pcols[i * Nx + a][i * Nx + a] += (w * tf) * p.Q[a];  // mesh_function.hpp:388 (t0 = 0, lambda = 1)
+        for (int a = 0; a < Nu; ++a)
+          if (p.Q[a] != 0) pcols[uvar_B + i * Nu + a][uvar_B + i * Nu + a] += (w * tf) * p.R[a];  // gated by Q (mpc.hpp:219-223)
+      }
+    }
+    for (int a = 0; a < Nx; ++a)
+      if (p.Qtf[a] != 0) pcols[a][a] += 0.5 * p.Qtf[a];  // ocp_to_qp.hpp:190 with MPCObj::hessian's x0 placement (mpc.hpp:103-107)
+  }
+
+  // ---- dynamics rows, ocp_to_qp_update_dyn (:198-276), evaluated on xdes(t): v = vdes, u = udes
+  {
+    const double v1 = p.vdes[0], v2 = p.vdes[1], v3 = p.vdes[2];
+    const double f[Nx] = {v1, v2, v3, -p.drag1 * v1 + p.udes[0], 0.0, -p.drag3 * v3 + p.udes[1]};
+    const double dxl[Nx] = {v1, v2, v3, 0.0, 0.0, 0.0};  // d^r xdes / dt: the body velocity of g0 exp(t vdes); the R^3 part is constant
+    double dfx[Nx][Nx] = {}, dfu[Nx][Nu] = {}, ad[Nx][Nx] = {};
+    dfx[0][3] = dfx[1][4] = dfx[2][5] = 1.0;
+    dfx[3][3] = -p.drag1;
+    dfx[5][5] = -p.drag3;
+    dfu[3][0] = 1.0;
+    dfu[5][1] = 1.0;
+    const double a0 = f[0] + dxl[0], a1 = f[1] + dxl[1], a2 = f[2] + dxl[2];  // ad<X>(f_i + dxl_i): SE(2) block only
+    ad[0][1] = -a2; ad[0][2] = a1; ad[1][0] = a2; ad[1][2] = -a0;
+    int M = 0;
+    for (int iv = 0; iv < nivals; ++iv) {
+      const double tau0 = (nivals < 2) ? 0.0 : (double)iv * (1.0 / (double)nivals);
+      const double tauf = (iv + 1 < nivals) ? (double)(iv + 1) * (1.0 / (double)nivals) : 1.0;
+      const double alpha = 2.0 / (tauf - tau0);  // mesh.hpp:341-366
+      for (int i = 0; i < Ki; ++i) {
+        const int r0 = (M + i) * Nx;
+        for (int r = 0; r < Nx; ++r) {
+          auto& row = rows[r0 + r];
+          for (int c = 0; c < Nx; ++c) row[(M + i) * Nx + c] += tf * dfx[r][c];               // :251 (dense block: zeros stored)
+          for (int c = 0; c < Nu; ++c) row[uvar_B + (M + i) * Nu + c] += tf * dfu[r][c];       // :252
+          for (int c = 0; c < Nx; ++c) row[(M + i) * Nx + c] += (-tf / 2) * ad[r][c];          // :255-257
+          for (int j = 0; j < Ki + 1; ++j) row[(M + j) * Nx + r] -= alpha * Dus[j][i];         // :259-263
+          H.l_base[r0 + r] = -tf * (f[r] - dxl[r]);                                            // :265
+          H.u_base[r0 + r] = H.l_base[r0 + r];
+        }
+      }
+      M += Ki;
+    }
+  }
+  // ---- running constraints cr(x, u) = u, ocp_to_qp_update_cr (:279-323): dense Ncr x (Nx + Nu) Jacobian blocks
+  for (int i = 0; i < N; ++i)
+    for (int r = 0; r < Ncr; ++r) {
+      auto& row = rows[crcon_B + i * Ncr + r];
+      for (int c = 0; c < Nx; ++c) row[i * Nx + c] = 0.0;
+      for (int c = 0; c < Nu; ++c) row[uvar_B + i * Nu + c] = (c == r) ? 1.0 : 0.0;
+      H.l_base[crcon_B + i * Ncr + r] = p.crl[r] - p.udes[r];
+      H.u_base[crcon_B + i * Ncr + r] = p.cru[r] - p.udes[r];
+    }
+  // ---- end constraints: pattern only (d_exp_sparse_pattern<Bundle<SE2, R^3>>), values per agent on the device
+  for (int r = 0; r < Nce; ++r)
+    for (int c = 0; c < Nce; ++c) {
+      const bool in = (r < 2 && c < 3) || (r == 2 && c == 2) || (r >= 3 && c == r);
+      H.ce_slot[r][c] = in ? 0 : -1;
+      if (in) rows[cecon_B + r][c] = 0.0;
+    }
+
+  // ---- compressed storage
+  H.A_rowptr.assign(H.m + 1, 0);
+  H.A_colidx.clear();
+  H.A_base.clear();
+  for (int r = 0; r < H.m; ++r) {
+    for (const auto& kv : rows[r]) {
+      if (r >= cecon_B && kv.first < Nce) H.ce_slot[r - cecon_B][kv.first] = (int)H.A_colidx.size();
+      H.A_colidx.push_back(kv.first);
+      H.A_base.push_back(kv.second);
+    }
+    H.A_rowptr[r + 1] = (int)H.A_colidx.size();
+  }
+  H.P_colptr.assign(H.n + 1, 0);
+  H.P_rowidx.clear();
+  H.P_vals.clear();
+  for (int c = 0; c < H.n; ++c) {
+    for (const auto& kv : pcols[c]) {
+      H.P_rowidx.push_back(kv.first);
+      H.P_vals.push_back(kv.second);
+    }
+    H.P_colptr[c + 1] = (int)H.P_rowidx.size();
+  }
+  return true;
+}
+
+}  // namespace sfb

@@ -121,8 +121,10 @@ def test_struct_layouts_match_ctypes(tmp_path):
     """The ctypes mirrors of the POD parameter structs must have the C compiler's layout (size and every offset)."""
     from smooth_feedback_b200 import _lib
     from smooth_feedback_b200.asif import SfbAsifVehicleParams
+    from smooth_feedback_b200.mpc import SfbMpcVehicleParams
 
-    structs = {"sfb_qp_params": _lib.SfbQpParams, "sfb_asif_vehicle_params": SfbAsifVehicleParams}
+    structs = {"sfb_qp_params": _lib.SfbQpParams, "sfb_asif_vehicle_params": SfbAsifVehicleParams,
+               "sfb_mpc_vehicle_params": SfbMpcVehicleParams}
     body = []
     for cname, ct in structs.items():
         body.append(f'printf("{cname} %zu", sizeof({cname}));')
@@ -139,3 +141,27 @@ def test_struct_layouts_match_ctypes(tmp_path):
         ct = structs[tok[0]]
         assert int(tok[1]) == C.sizeof(ct), tok[0]
         assert [int(t) for t in tok[2:]] == [getattr(ct, f).offset for f, _ in ct._fields_], tok[0]
+
+
+def test_fleet_param_defaults_match_python_mirrors():
+    """sfb_*_vehicle_params_default (the constants of examples/mpc_asif_vehicle.cpp) == the defaults of the python dataclasses."""
+    from smooth_feedback_b200 import ASIFVehicleParams, MPCVehicleParams, _lib
+    from smooth_feedback_b200.asif import SfbAsifVehicleParams
+    from smooth_feedback_b200.mpc import SfbMpcVehicleParams
+
+    def flat(s):
+        out = []
+        for name, _ in s._fields_:
+            v = getattr(s, name)
+            if isinstance(v, C.Structure):
+                out += flat(v)
+            elif hasattr(v, "__len__"):
+                out += [float(t) for t in v]
+            else:
+                out.append(v)
+        return out
+
+    a = SfbAsifVehicleParams(); _lib.lib().sfb_asif_vehicle_params_default(C.byref(a))
+    assert flat(a) == flat(ASIFVehicleParams().to_c())
+    m = SfbMpcVehicleParams(); _lib.lib().sfb_mpc_vehicle_params_default(C.byref(m))
+    assert flat(m) == flat(MPCVehicleParams().to_c())
