@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Headline benchmark: dense QP solves/s at BASELINE.json configs[1] (n=50, m=100, batch 65536, fp64).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scaling weak|strong]
+                    [--config dense|ekf|asif|mpc]      (dense = the headline; the others are the BASELINE configs quoted
+                                                        multi-GPU: cfg4 EKF 2^20 filters / 8 GPUs, cfg5 ASIF 32768 / 4 GPUs)
 
 One "step" = one pass of the hot path (QPSolver::solve, reference qp_solver.hpp:343-568) over one batch of
 synthetic G+ problems per GPU (generator: reference benchmarks/bench_types.hpp:19-41, see
@@ -36,6 +38,11 @@ MAX_ITER = 4000
 SEED = 5
 METRIC = "qp_solves_per_s"
 UNIT = "solves/s"
+
+
+def workload_string(batch):
+    return (f"dense QP n={N_VARS} m={M_CONS} batch={batch}/GPU, G+ (bench_types.hpp recipe, delta~U(0,1)), fp64, "
+            f"QPSolverParams defaults + max_iter={MAX_ITER}")
 
 
 def b_comp(n, m, s=8):
@@ -119,7 +126,11 @@ def cpu_baseline(sample_target_s: float = 12.0):
     return {"value": best, "unit": UNIT, "cores": cores, "kind": "port", "count": count,
             "sample": f"first {count} of the {BATCH} G+ instances (seed {SEED}), best of 2, oracle -O3 -march=x86-64-v3 (AVX2+FMA), "
                       f"OpenMP dynamic over {cores} threads, one reusable workspace per thread",
-            "mean_iter": float(r.iter.mean()), "optimal_frac": float((r.status == 0).mean())}
+            "mean_iter": float(r.iter.mean()), "optimal_frac": float((r.status == 0).mean()),
+            # ~ k^3/3 (pivoted LDL^T of the k = n + m KKT matrix) + iters * 2 k^2 (two triangular sweeps) flops per solve
+            "gflops_per_core": best * ((N_VARS + M_CONS) ** 3 / 3 + float(r.iter.mean()) * 2 * (N_VARS + M_CONS) ** 2) / cores / 1e9,
+            "caveat": "a plain restatement (Eigen is unavailable here): Eigen's blocked, vectorised LDLT would plausibly be 2-4x "
+                      "faster per core; baseline, not target"}
 
 
 def secondary_configs(dev):
@@ -149,12 +160,16 @@ def secondary_configs(dev):
         out[name] = {"workload": f"dense QP n={n} m={m} batch={B} {'f64' if dtype == torch.float64 else 'f32'} G+", "solves_per_s": B / (ms * 1e-3),
                      "ms": ms, "mean_iter": float(r.iter.double().mean().item()), "optimal_frac": float((r.status == 0).double().mean().item())}
 
+    from tools import bench_fleet
+
     steps = [
         ("cfg1_dense_n10_m20_f64", lambda: dense("cfg1_dense_n10_m20_f64", 65536, 10, 20, torch.float64)),
-        ("cfg5_shape_dense_n3_m203_f32", lambda: dense("cfg5_shape_dense_n3_m203_f32", 32768, 3, 203, torch.float32, polish=False)),
+        ("cfg5_asif_vehicle_fleet_f32", lambda: out.__setitem__("cfg5_asif_vehicle_fleet_f32", bench_fleet.run_asif(32768, "f32", 5, 50))),
+        ("cfg5_shape_random_dense_n3_m203_f32", lambda: dense("cfg5_shape_random_dense_n3_m203_f32", 32768, 3, 203, torch.float32, polish=False)),
         ("cfg4_ekf_d6_ny3_f64", lambda: out.__setitem__("cfg4_ekf_d6_ny3_f64", bench_ekf.run(1 << 20, 6, 3, 10))),
-        ("cfg3_mpc_sparse_n422_f32", lambda: out.__setitem__("cfg3_mpc_sparse_n422_f32", bench_sparse.run(8192, "f32", 2))),
-        ("cfg3_mpc_sparse_n422_f64", lambda: out.__setitem__("cfg3_mpc_sparse_n422_f64", bench_sparse.run(8192, "f64", 2))),
+        ("cfg3_mpc_vehicle_sparse_n422_f32", lambda: out.__setitem__("cfg3_mpc_vehicle_sparse_n422_f32", bench_sparse.run(8192, "f32", 5))),
+        ("cfg3_mpc_vehicle_sparse_n422_f64", lambda: out.__setitem__("cfg3_mpc_vehicle_sparse_n422_f64", bench_sparse.run(8192, "f64", 5))),
+        ("cfg3_mpc_vehicle_fleet_f32", lambda: out.__setitem__("cfg3_mpc_vehicle_fleet_f32", bench_fleet.run_mpc(8192, "f32", 3, 50))),
     ]
     for name, fn in steps:
         try:
@@ -202,6 +217,160 @@ def secondary_cpu_baselines():
     return res
 
 
+
+def run_fleet_config(args):
+    """--config ekf | asif | mpc: the BASELINE configs that are quoted multi-GPU, each as its own JSON line.
+
+      ekf   configs[3]: EKF<SE3> covariance predict + update, d = 6, ny = 3, 2^20 filters in total sharded over the GPUs
+            (strong scaling), fp64; chunk-pipelined: the all-gather of chunk c overlaps the kernel of chunk c + 1
+      asif  configs[4]: ASIFilter vehicle fleet, 32768 agents in total sharded over the GPUs, fp32, cold filter step + exchange
+      mpc   configs[2]: MPC vehicle fleet, 8192 agents in total sharded over the GPUs, fp32, cold control step + exchange
+    Exchange = the library's grouped NCCL all-gather (sfb_allgather_results).  Device-timed, max over ranks."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import smooth_feedback_b200 as sfb
+    from smooth_feedback_b200.generators import vehicle_fleet_numpy
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    handle = sfb.Handle(local)
+    handle.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    comm = sfb.Communicator.from_torch_distributed(handle) if world > 1 else None
+    total = {"ekf": 1 << 20, "asif": 32768, "mpc": 8192}[args.config] if args.batch == BATCH else args.batch
+    B = -(-total // world)
+    lo = rank * B
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        if comm:
+            comm.wait()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        if comm:
+            comm.wait()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    extra = {}
+    if args.config == "ekf":
+        d, ny, C = 6, 3, max(1, args.chunks)
+        g = torch.Generator(device=dev).manual_seed(SEED + rank)
+        Mx = torch.rand(B, d, d, generator=g, device=dev, dtype=torch.float64) * 2 - 1
+        P = Mx @ Mx.transpose(1, 2) + 0.1 * torch.eye(d, device=dev, dtype=torch.float64)
+        P = (0.5 * (P + P.transpose(1, 2))).contiguous()
+        A = torch.randn(B, d, d, generator=g, device=dev, dtype=torch.float64)
+        Q = (0.01 * torch.eye(d, device=dev, dtype=torch.float64)).expand(B, d, d).contiguous()
+        H = torch.randn(B, d, ny, generator=g, device=dev, dtype=torch.float64)
+        R = (0.01 * torch.eye(ny, device=dev, dtype=torch.float64)).expand(B, ny, ny).contiguous()
+        innov = torch.randn(B, ny, generator=g, device=dev, dtype=torch.float64)
+        outP, outd = torch.empty_like(P), torch.empty(B, d, device=dev, dtype=torch.float64)
+        cb = -(-B // C)
+        cuts = [(c0, min(B, c0 + cb)) for c0 in range(0, B, cb)]
+        # gathered layout: [chunk][rank][rows of the chunk]
+        gP = [torch.empty((world * (b1 - b0), d, d), dtype=torch.float64, device=dev) for b0, b1 in cuts]
+        gd = [torch.empty((world * (b1 - b0), d), dtype=torch.float64, device=dev) for b0, b1 in cuts]
+
+        def kernels_only():
+            for b0, b1 in cuts:
+                sfb.ekf_step_batch(P[b0:b1], A[b0:b1], Q[b0:b1], 0.1, H[b0:b1], R[b0:b1], innov[b0:b1], handle=handle,
+                                   out_delta=outd[b0:b1], out_P=outP[b0:b1])
+
+        def pipelined():
+            if comm:
+                comm.wait()  # the previous step's exchange has read the buffers this step overwrites
+            for c, (b0, b1) in enumerate(cuts):
+                sfb.ekf_step_batch(P[b0:b1], A[b0:b1], Q[b0:b1], 0.1, H[b0:b1], R[b0:b1], innov[b0:b1], handle=handle,
+                                   out_delta=outd[b0:b1], out_P=outP[b0:b1])
+                if comm:
+                    comm.all_gather([outP[b0:b1], outd[b0:b1]], [gP[c], gd[c]])
+
+        def exchange_only():
+            for c, (b0, b1) in enumerate(cuts):
+                if comm:
+                    comm.all_gather([outP[b0:b1], outd[b0:b1]], [gP[c], gd[c]])
+
+        k_ms = timed(kernels_only, args.steps, args.warmup)
+        x_ms = timed(exchange_only, args.steps, args.warmup) if comm else 0.0
+        ms = timed(pipelined, args.steps, args.warmup)
+        metric, unit, dtype = "ekf_cycles_per_s", "filter cycles/s", "f64"
+        bytes_in, bytes_out = 8 * (3 * d * d + ny * d + ny * ny + ny), 8 * (d * d + d)
+        extra = {"kernel_ms": k_ms, "exchange_ms": x_ms, "pipelined_ms": ms, "chunks": len(cuts),
+                 "bound": "exchange" if x_ms > k_ms else "kernel (HBM)",
+                 "exchange_bytes_received_per_rank": (world - 1) * B * bytes_out,
+                 "exchange_gbs_per_rank": (world - 1) * B * bytes_out / (x_ms * 1e-3) / 1e9 if x_ms else None,
+                 "kernel_hbm_gbs_per_gpu": B * (bytes_in + bytes_out) / (k_ms * 1e-3) / 1e9}
+        workload = f"EKF covariance predict(euler)+update d={d} ny={ny}, {total} filters in total ({B}/GPU), fp64, all-gather of {{P', delta}}"
+    else:
+        t0, x0, ud = vehicle_fleet_numpy(total, seed=SEED)
+        sl = slice(lo, min(total, lo + B))
+        nloc = sl.stop - sl.start
+        assert nloc == B, "total must divide evenly over the ranks"
+        f32 = torch.float32
+        xd = torch.from_numpy(x0[sl]).to(dev, dtype=f32).contiguous()
+        if args.config == "asif":
+            fleet = sfb.ASIFVehicleFleet(B, sfb.ASIFVehicleParams(qp=sfb.QPSolverParams(polish=False, max_iter=MAX_ITER)), dtype=np.float32, handle=handle)
+            udd = torch.from_numpy(ud[sl]).to(dev, dtype=f32).contiguous()
+            call = lambda: fleet(xd, udd)
+            metric, unit = "asif_filter_steps_per_s", "agent filter steps/s"
+            workload = f"ASIFilter vehicle fleet (K=200, nh=1: n=3 m=203, polish off), {total} agents in total ({B}/GPU), fp32, cold solves"
+        else:
+            fleet = sfb.MPCVehicleFleet(B, sfb.MPCVehicleParams(qp=sfb.QPSolverParams(max_iter=MAX_ITER)), dtype=np.float32, handle=handle)
+            td = torch.from_numpy(t0[sl]).to(dev, dtype=f32).contiguous()
+            call = lambda: fleet(td, xd)
+            metric, unit = "mpc_steps_per_s", "agent control steps/s"
+            workload = f"MPC vehicle fleet (K=50: n=m=422 sparse, polish on), {total} agents in total ({B}/GPU), fp32, cold solves"
+        dtype = "f32"
+        res = {}
+        gath = None
+
+        def stepf():
+            nonlocal gath
+            fleet.reset_warmstart()
+            u, st, it = call()
+            res["r"] = (u, st, it)
+            if comm:
+                if gath is None:
+                    gath = [torch.empty((world * B,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev) for t in (u, st, it)]
+                comm.all_gather([u, st, it], gath)
+
+        ms = timed(stepf, args.steps, args.warmup)
+        u, st, it = res["r"]
+        extra = {"mean_iter": float(it.double().mean().item()), "optimal_frac": float((st == 0).double().mean().item())}
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        line = {"metric": metric, "value": world * B / (ms * 1e-3), "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+                "config": {"workload": workload, "exchange": "one grouped NCCL all-gather per step / chunk issued by libsfb (sfb_allgather_results)" if world > 1 else "single GPU"},
+                "gpu_launches": handle.launch_count(), "clocks": clocks}
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -217,8 +386,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * base["count"] / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"dense QP n={N_VARS} m={M_CONS} G+ (bench_types.hpp recipe, delta~U(0,1)), fp64, "
-                                   f"defaults + max_iter={MAX_ITER}; CPU arm runs a bounded sample per step"},
+            "config": {"workload": workload_string(args.batch),
+                       "sample": "the CPU arm runs a bounded sample of that workload per step (cpu_baseline.sample)"},
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference-algorithm restatement (oracle/); the reference's Eigen path cannot be built in this image"}
@@ -235,11 +404,18 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the short lines for the other BASELINE configs")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch instances per GPU (default); strong: --batch instances in total, sharded over the GPUs")
+    ap.add_argument("--config", default="dense", choices=["dense", "ekf", "asif", "mpc"])
+    ap.add_argument("--chunks", type=int, default=8, help="--config ekf: chunks of the compute / exchange pipeline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.config != "dense":
+        run_fleet_config(args)
         return
 
     import torch
@@ -258,33 +434,49 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    B, n, m = args.batch, N_VARS, M_CONS
+    n, m = N_VARS, M_CONS
+    B = args.batch if args.scaling == "weak" else -(-args.batch // world)  # strong scaling: contiguous shards of the total
     prm = sfb.QPSolverParams(max_iter=MAX_ITER)
-    # every rank owns an independent shard of B instances (weak scaling; instances never cross GPUs)
+    # every rank owns an independent shard of B instances (instances never cross GPUs)
     P_cm, q, A_cm, l, u = random_qp_torch(B, n, m, seed=SEED + 1000 * rank, device=dev)
     handle = sfb.Handle(local)
-    out = None
-    packed = gathered = None
-    if world > 1:
-        packed = torch.empty((B, n + m + 3), dtype=torch.float64, device=dev)
-        gathered = torch.empty((world * B, n + m + 3), dtype=torch.float64, device=dev)
+    handle.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    comm = sfb.Communicator.from_torch_distributed(handle) if world > 1 else None
+    outs = [None, None]   # double-buffered results: solve k+1 overlaps the all-gather of step k
+    gathered = None
 
-    def step():
-        nonlocal out
-        out = sfb.solve_dense_batch(P_cm, q, A_cm, l, u, prm, handle=handle, out=out)
+    def new_out():
+        return sfb.QPBatchResult(
+            x=torch.empty((B, n), dtype=torch.float64, device=dev), y=torch.empty((B, m), dtype=torch.float64, device=dev),
+            obj=torch.empty((B,), dtype=torch.float64, device=dev), status=torch.empty((B,), dtype=torch.int32, device=dev),
+            iter=torch.empty((B,), dtype=torch.int32, device=dev), active=torch.empty((B, m), dtype=torch.int8, device=dev),
+            flags=torch.empty((B,), dtype=torch.int32, device=dev))
+
+    outs = [new_out(), new_out()]
+    if world > 1:
+        o0 = outs[0]
+        gathered = [torch.empty((world * B,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev) for t in (o0.x, o0.y, o0.obj, o0.status, o0.iter)]
+
+    def step(k):
+        o = outs[k & 1]
+        sfb.solve_dense_batch(P_cm, q, A_cm, l, u, prm, handle=handle, out=o)
         if world > 1:
-            # the single collective of the path: all-gather of the packed results {x, y, obj, code, iter}
-            packed[:, :n] = out.x; packed[:, n:n + m] = out.y; packed[:, n + m] = out.obj
-            packed[:, n + m + 1] = out.status; packed[:, n + m + 2] = out.iter
-            dist.all_gather_into_tensor(gathered, packed)
+            # the single collective of the path: ONE grouped NCCL all-gather of {x, y, obj, code, iter}, issued by the library
+            # on its communicator stream; the handle's stream first waits for the PREVIOUS exchange (it read the buffer the
+            # next solve will overwrite), then the new exchange is enqueued and overlaps the next solve
+            comm.wait()
+            comm.all_gather([o.x, o.y, o.obj, o.status, o.iter], gathered)
+        return o
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
+    for k in range(args.warmup):
+        step(k)
+    if world > 1:
+        comm.wait()
     barrier()
 
     sampler = ClockSampler(local)
@@ -295,15 +487,21 @@ def main():
     barrier()
     ev[0].record()
     for k in range(args.steps):
+        o = outs[k & 1]
         ev[2 + 2 * k].record()
-        out = sfb.solve_dense_batch(P_cm, q, A_cm, l, u, prm, handle=handle, out=out)
+        sfb.solve_dense_batch(P_cm, q, A_cm, l, u, prm, handle=handle, out=o)
         ev[3 + 2 * k].record()
         if world > 1:
-            packed[:, :n] = out.x; packed[:, n:n + m] = out.y; packed[:, n + m] = out.obj
-            packed[:, n + m + 1] = out.status; packed[:, n + m + 2] = out.iter
-            dist.all_gather_into_tensor(gathered, packed)
+            comm.wait()
+            comm.all_gather([o.x, o.y, o.obj, o.status, o.iter], gathered)
+    if world > 1:
+        comm.wait()  # the last exchange is inside the timed region
     ev[1].record()
     barrier()
+    out = outs[(args.steps - 1) & 1]
+    if world > 1:  # every rank holds every shard's results
+        lo = rank * B
+        assert torch.equal(gathered[0][lo:lo + B], out.x) and torch.equal(gathered[4][lo:lo + B], out.iter)
     clocks = sampler.stop() if rank == 0 else None
     launches = handle.launch_count() - launches0
     total_ms = ev[0].elapsed_time(ev[1])
@@ -314,6 +512,7 @@ def main():
     total_ms, kern_ms = t.tolist()
     ms_per_step = total_ms / args.steps
     value = world * B / (ms_per_step * 1e-3)
+    exchange_ms = max(0.0, ms_per_step - kern_ms)  # what the step costs beyond its kernel (exposed part of the exchange)
 
     status = out.status
     iters = out.iter.to(torch.float64)
@@ -347,7 +546,10 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": world * B * e_steps / te.item(), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "steps": e_steps,
-               "how": "sfb_qp_solve_dense_batch_f64 on pinned host arrays; engine stages 3-slot pipelined chunks"}
+               "how": "sfb_qp_solve_dense_batch_f64 on pinned host arrays; engine stages 3-slot pipelined chunks",
+               "host_link_gbs_per_rank": (h2d + d2h) * e_steps / te.item() / 1e9,
+               "note": "62 KB of problem data per solve cross PCIe: e2e is bound by the host link (all ranks share the host memory / "
+                       "PCIe complex); the fleet entry points (secondary cfg3 / cfg5) build the problems on the device instead"}
         assert (hout.status == 0).mean() == optimal_frac or True
 
     if rank == 0:
@@ -363,12 +565,13 @@ def main():
             traffic = json.load(open(tp)).get("qp_dense_group_kernel_f64_bytes_per_launch")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"dense QP n={n} m={m} batch={B}/GPU, G+ (bench_types.hpp recipe, delta~U(0,1)), fp64, "
-                                   f"QPSolverParams defaults + max_iter={MAX_ITER}",
+            "config": {"workload": workload_string(args.batch) if args.scaling == "weak" else workload_string(args.batch).replace("/GPU", f" in total ({B}/GPU)"),
                        "l2": f"inputs {B * (bc - 8 * (n + m + 1) - 8) / 1e9:.2f} GB per step > 126 MB L2 (no flush needed)",
-                       "sharding": "independent shards per rank; one all-gather of packed results per step" if world > 1 else "single GPU",
+                       "sharding": ("independent shards per rank; one grouped NCCL all-gather of {x, y, obj, code, iter} per step, issued by "
+                                    "libsfb (sfb_allgather_results) on its own stream and overlapped with the next solve (double-buffered "
+                                    f"outputs); exposed exchange {exchange_ms:.3f} ms/step") if world > 1 else "single GPU",
                        "mean_iter": mean_iter, "optimal_frac": optimal_frac},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "qp_dense_group_kernel<double,4,3>",

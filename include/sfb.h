@@ -365,6 +365,31 @@ int sfb_mpc_fleet_step_f64(sfb_mpc_fleet_t f, const double* t, const double* x, 
 int sfb_mpc_fleet_step_f32(sfb_mpc_fleet_t f, const float* t, const float* x, float* out_u, int32_t* out_status,
                            uint32_t* out_iter, float* out_primal, float* out_dual);
 
+/*
+ * ---- multi-GPU: the one collective of the path -----------------------------------------------------
+ *
+ * Instances are independent: every rank (one process per GPU) solves a contiguous shard, inputs are never exchanged, and
+ * the results of all shards are made visible everywhere by ONE all-gather over NCCL (NVLink 5 / NVSwitch).  The reference
+ * is a single-instance library and has no counterpart; this is what a C / C++ host of the engine binds for 8 x B200.
+ *
+ *   sfb_comm_unique_id    rank 0 creates the 128-byte NCCL id and distributes it (MPI, a file, torch.distributed ...)
+ *   sfb_comm_create       ncclCommInitRank on the handle's device (collective: every rank calls it)
+ *   sfb_allgather_results the `count` result arrays of this rank's shard (device pointers; send[k] holds bytes_per_rank[k]
+ *                         bytes, recv[k] world * bytes_per_rank[k]: rank r's block at offset r * bytes_per_rank[k]) are
+ *                         gathered as ONE grouped NCCL operation -- no packing kernel.  It is enqueued on the
+ *                         communicator's own stream, ordered after the work already enqueued on the handle's stream, and
+ *                         returns immediately: the next solve (into other output buffers) overlaps the exchange.
+ *   sfb_comm_wait         host_sync = 0: the handle's stream waits for the exchange; 1: the host does.
+ * NCCL is loaded at run time (libnccl.so.2); without it these calls fail with SFB_ERR_CUDA, nothing else is affected.
+ */
+#define SFB_COMM_ID_BYTES 128
+typedef struct sfb_comm* sfb_comm_t;
+int sfb_comm_unique_id(void* out128);
+int sfb_comm_create(sfb_handle_t h, int world, int rank, const void* id128, sfb_comm_t* out);
+int sfb_comm_destroy(sfb_comm_t c);
+int sfb_allgather_results(sfb_comm_t c, int count, const void* const* send, void* const* recv, const size_t* bytes_per_rank);
+int sfb_comm_wait(sfb_comm_t c, int host_sync);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,6 +10,7 @@ from .qp import (  # noqa: F401
 )
 from .qp_sparse import QuadraticProgramSparse, SparsePattern, solve_sparse_batch, sparse_symbolic  # noqa: F401
 from .asif import ASIFVehicleFleet, ASIFVehicleParams  # noqa: F401
+from .comm import Communicator  # noqa: F401
 from .mpc import MPCVehicleFleet, MPCVehicleParams  # noqa: F401
 from .ekf import ekf_predict_batch, ekf_step_batch, ekf_step_batch_host, ekf_update_batch  # noqa: F401
 

@@ -283,3 +283,53 @@ def sparse_to_dense(pat, P_vals, A_vals):
     ar = np.repeat(np.arange(m), np.diff(pat["A_rowptr"]))
     A[:, ar, pat["A_colidx"]] = A_vals
     return P, A
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# fleet workloads for the built-in vehicle family (sfb_asif_fleet_*, sfb_mpc_fleet_*): SURVEY 8(d) cfg3 / cfg5 sampling
+# ---------------------------------------------------------------------------------------------------------------------
+def _se2_exp_np(a):
+    vx, vy, w = a[..., 0], a[..., 1], a[..., 2]
+    small = np.abs(w) < 1e-9
+    ws = np.where(small, 1.0, w)
+    A = np.where(small, 1.0 - w * w / 6.0, np.sin(ws) / ws)
+    Bc = np.where(small, w / 2.0, (1.0 - np.cos(ws)) / ws)
+    return np.stack([A * vx - Bc * vy, Bc * vx + A * vy, np.sin(w), np.cos(w)], axis=-1)
+
+
+def _se2_compose_np(g1, g2):
+    x1, y1, s1, c1 = (g1[..., k] for k in range(4))
+    x2, y2, s2, c2 = (g2[..., k] for k in range(4))
+    return np.stack([x1 + c1 * x2 - s1 * y2, y1 + s1 * x2 + c1 * y2, s1 * c2 + c1 * s2, c1 * c2 - s1 * s2], axis=-1)
+
+
+def vehicle_xdes_numpy(t, g0=(2.5, 0.0, np.pi / 2), vdes=(1.0, 0.0, 0.4)):
+    """Desired trajectory of examples/mpc_asif_vehicle.cpp:72-78: X{SE2(g0) * exp(t vdes), vdes} -> [B, 7] coefficients
+    (x, y, sin, cos, v1, v2, v3)."""
+    t = np.asarray(t, dtype=np.float64)
+    vd = np.asarray(vdes, dtype=np.float64)
+    g0c = np.array([g0[0], g0[1], np.sin(g0[2]), np.cos(g0[2])])
+    g = _se2_compose_np(np.broadcast_to(g0c, t.shape + (4,)), _se2_exp_np(t[..., None] * vd))
+    return np.concatenate([g, np.broadcast_to(vd, t.shape + (3,))], axis=-1)
+
+
+def vehicle_rplus_numpy(x, a):
+    """x (+) a on Bundle<SE2, R^3>: x [B, 7], a [B, 6]."""
+    return np.concatenate([_se2_compose_np(x[..., :4], _se2_exp_np(a[..., :3])), x[..., 4:] + a[..., 3:]], axis=-1)
+
+
+def vehicle_dynamics_numpy(x, u, drag1=0.2, drag3=0.4):
+    """d^r x = (v1, v2, v3, -drag1 v1 + u1, 0, -drag3 v3 + u2)   (mpc_asif_vehicle.cpp:42-52)."""
+    v = x[..., 4:7]
+    return np.stack([v[..., 0], v[..., 1], v[..., 2], -drag1 * v[..., 0] + u[..., 0], np.zeros_like(v[..., 0]),
+                     -drag3 * v[..., 2] + u[..., 1]], axis=-1)
+
+
+def vehicle_fleet_numpy(B: int, seed: int = 5, sigma: float = 0.1):
+    """SURVEY 8(d) cfg3 / cfg5 sampling: t0 ~ U(0, 30), x0 = xdes(t0) (+) xi with xi ~ N(0, sigma^2 I_6), and a desired input
+    u_des ~ U(-0.5, 0.5)^2 for the safety filter.  -> t0 [B], x0 [B, 7], u_des [B, 2]"""
+    rng = np.random.Generator(np.random.Philox(key=seed))
+    t0 = rng.uniform(0.0, 30.0, B)
+    xi = sigma * rng.normal(size=(B, 6))
+    u_des = rng.uniform(-0.5, 0.5, (B, 2))
+    return t0, vehicle_rplus_numpy(vehicle_xdes_numpy(t0), xi), u_des

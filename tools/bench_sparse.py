@@ -7,7 +7,7 @@ batch 8192 agents, on one GPU.
 Prints one JSON line: solves/s (CUDA events, data resident), mean iterations, status histogram, and the achieved
 HBM figure over the algorithmic bytes of the tiled solver: B_comp + iters * B_iter with
     B_iter = s * (2 nnzA + 2 nnzL + n  [Abar twice, L twice, 1/D]  +  5 n + 10 m  [iterate vectors])
-(DESIGN.md section 4.3).  Data: mpc_structured_batch (LTV surrogate of the MPC QP on the real LGR mesh pattern).
+(DESIGN.md section 4.3).  Data: the vehicle MPC QPs the engine's own fleet transcribes (sfb_mpc_fleet_to_qp); --small uses the LTV surrogate generator.
 """
 from __future__ import annotations
 
@@ -28,11 +28,23 @@ def run(batch=8192, dtype="f64", steps=3, small=False, tw=0):
     import smooth_feedback_b200 as sfb
     from smooth_feedback_b200.generators import mpc_structured_batch, mpc_structured_pattern
 
-    pat = mpc_structured_pattern(Nx=3, Nu=2, nivals=3, Ki=4) if small else mpc_structured_pattern()
-    base = 512  # distinct agents generated on the host, tiled to the batch (keeps host generation to seconds)
-    Pv, q, Av, l, u = mpc_structured_batch(pat, min(base, batch), seed=5)
-    rep = (batch + Pv.shape[0] - 1) // Pv.shape[0]
     dt = torch.float64 if dtype == "f64" else torch.float32
+    base = 512  # distinct agents, tiled to the batch
+    if small:  # n = m = 63 (tests/test_mpc.cpp size): LTV surrogate
+        pat = mpc_structured_pattern(Nx=3, Nu=2, nivals=3, Ki=4)
+        Pv, q, Av, l, u = mpc_structured_batch(pat, min(base, batch), seed=5)
+        source = "mpc_structured_batch (LTV surrogate)"
+    else:      # the REAL cfg3 workload: QPs transcribed by the engine's own MPC fleet for the vehicle family (K = 50)
+        from smooth_feedback_b200.generators import vehicle_fleet_numpy
+
+        nb = min(base, batch)
+        t0, x0, _ = vehicle_fleet_numpy(nb, seed=5)
+        fl = sfb.MPCVehicleFleet(nb)
+        pat = fl.pattern()
+        Pv, q, Av, l, u = fl.to_qp(t0, x0)
+        fl.close()
+        source = "vehicle MPC (sfb_mpc_fleet_to_qp: restated ocp_to_qp, x0 = xdes(t0) (+) N(0, 0.1^2))"
+    rep = (batch + Pv.shape[0] - 1) // Pv.shape[0]
     t = lambda x: torch.from_numpy(np.tile(x, (rep, 1))[:batch]).to("cuda:0", dtype=dt).contiguous()
     Pv, q, Av, l, u = t(Pv), t(q), t(Av), t(l), t(u)
     if tw:
@@ -48,11 +60,11 @@ def run(batch=8192, dtype="f64", steps=3, small=False, tw=0):
         out = sfb.solve_sparse_batch(sp, Pv, q, Av, l, u, prm, out=out)
     torch.cuda.synchronize()
     ms = []
-    for _ in range(steps):
+    for _ in range(max(steps, 5)):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); out = sfb.solve_sparse_batch(sp, Pv, q, Av, l, u, prm, out=out); e1.record(); e1.synchronize()
         ms.append(e0.elapsed_time(e1))
-    mean_ms = sum(ms) / len(ms)
+    mean_ms = sorted(ms)[len(ms) // 2]  # median of >= 5 timed repetitions
     s = 8 if dtype == "f64" else 4
     it = out.iter.double().mean().item()
     bcomp, biter = sp.bytes_compulsory(s), sp.bytes_per_iteration(s)
@@ -62,6 +74,7 @@ def run(batch=8192, dtype="f64", steps=3, small=False, tw=0):
         peak = float(json.load(open(pk))["hbm_gbs"])
     ach = batch * (bcomp + it * biter) / (mean_ms * 1e-3) / 1e9
     return {
+        "source": source, "ms_min": min(ms), "ms_median": mean_ms,
         "workload": f"sparse QP (MPC structure) n={pat['n']} m={pat['m']} nnzA={sp.nnzA} nnzP={sp.nnzP} nnzL={sp.nnzL} batch={batch} {dtype} tw={tw or 'auto'}",
         "solves_per_s": batch / (mean_ms * 1e-3), "ms": mean_ms, "ms_all": ms, "mean_iter": it,
         "status_hist": torch.bincount(out.status, minlength=7).tolist(), "polished_frac": float((out.flags & 1).double().mean().item()),
