@@ -1,21 +1,25 @@
-// qp_solver_b200.hpp -- C++20 host-side overlay: smooth_feedback's QP solver surface on top of the sfb C ABI.
+// qp_solver.hpp -- drop-in replacement for the reference's include/smooth/feedback/qp_solver.hpp on top of the sfb C ABI.
 //
-// Same names, argument meaning and error behaviour as the reference headers
-//   include/smooth/feedback/qp.hpp:82-108          QPSolutionStatus, QPSolution
-//   include/smooth/feedback/qp_solver.hpp:29-68    QPSolverParams
-//   include/smooth/feedback/qp_solver.hpp:242-757  QPSolver<Pbm>::{QPSolver, analyze, solve, sol}
-//   include/smooth/feedback/qp_solver.hpp:779-787  solve_qp
-// so that `qp_solver_.solve(qp_, warmstart_)` (mpc.hpp:491) and `solve_qp(qp_, prm_.qp, warmstart_)` (asif.hpp:97)
-// compile unchanged; plus the one extension the GPU engine exists for: QPSolver::solve_batch.
+// It replaces that ONE header and nothing else: problem and solution types stay the reference's own
+//   #include <smooth/feedback/qp.hpp>   QuadraticProgram<M,N,S>, QuadraticProgramSparse<S>, QPSolutionStatus, QPSolution<M,N,S>
+// (asif_func.hpp and ocp_to_qp.hpp keep including qp.hpp for the problem types, so nothing may be redefined here), and this
+// file provides exactly what qp_solver.hpp provides to its includers (mpc.hpp:10, asif.hpp:9):
+//   QPSolverParams                       qp_solver.hpp:29-68
+//   detail::qp_solution_t<Pbm>           qp_solver.hpp:72-76
+//   QPSolver<Pbm>::{QPSolver, analyze, solve, sol}   qp_solver.hpp:242-757, with the reference's signatures:
+//        const QPSolution<M,N,Scalar> & solve(const Pbm &, std::optional<std::reference_wrapper<const QPSolution<M,N,Scalar>>> = {})
+//   solve_qp(pbm, prm, warmstart) -> detail::qp_solution_t<Pbm>          qp_solver.hpp:779-787
+// so that the call sites compile unchanged:  `const auto & sol = qp_solver_.solve(qp_, warmstart_); warmstart_ = sol;`
+// (mpc.hpp:491,513 with std::optional<QPSolution<-1,-1,double>> warmstart_, :635) and
+// `auto sol = feedback::solve_qp(qp_, prm_.qp, warmstart_); warmstart_ = sol;` (asif.hpp:97-99,109).
+// tests/cpp/replay_mpc_asif.cpp replays those declarations and calls verbatim against this header.
+// Plus the one extension the GPU engine exists for: QPSolver::solve_batch.
 //
 // `Pbm` is any type with public members P, q, A, l, u, exactly as in the reference (qp_solver.hpp:245-251 only looks at
-// decltype(Pbm::A)):
-//   dense  (QuadraticProgram<M,N,Scalar>, qp.hpp:31-45): P, A offer rows(), cols(), operator()(i,j)  -> sfb_qp_solve_dense_batch_*
-//   sparse (QuadraticProgramSparse<Scalar>, qp.hpp:60-79): P column-major, A row-major compressed matrices offering
-//          outerIndexPtr(), innerIndexPtr(), valuePtr(), nonZeros()                                  -> sfb_qp_solve_sparse_batch_*
-// (Eigen matrices do; tests/cpp/mock_eigen.hpp is the stand-in used where Eigen is not installed).  For sparse problems
-// the pattern is analysed on the first solve after construction or copy, like the reference's analyzePattern
-// (qp_solver.hpp:424, LDLTWrapper :209-231); all problems of one solve_batch call must share that pattern.
+// decltype(Pbm::A)): dense problems go to sfb_qp_solve_dense_batch_*, sparse ones (A derives from Eigen::SparseMatrixBase,
+// the reference's own test, qp_solver.hpp:247) to sfb_qp_solve_sparse_batch_*.  For sparse problems the pattern is analysed
+// on the first solve after construction or copy, like the reference's analyzePattern (qp_solver.hpp:424, LDLTWrapper
+// :209-231); all problems of one solve_batch call must share that pattern (compressed storage required).
 //
 // All numerics run on the GPU through libsfb.so; there is no CPU fallback: if no device is available the constructor of
 // the solver throws std::runtime_error with the library's message.
@@ -32,20 +36,11 @@
 #include <type_traits>
 #include <vector>
 
+#include <smooth/feedback/qp.hpp>
+
 #include "../sfb.h"
 
 namespace smooth::feedback {
-
-/// Solver exit codes (qp.hpp:82-92; the numeric values are the C ABI's sfb_qp_status)
-enum class QPSolutionStatus {
-  Optimal,
-  PolishFailed,
-  PrimalInfeasible,
-  DualInfeasible,
-  MaxIterations,
-  MaxTime,
-  Unknown
-};
 
 /// Options (qp_solver.hpp:29-68) -- float members stay float on purpose
 struct QPSolverParams
@@ -67,18 +62,14 @@ struct QPSolverParams
   float delta = 1e-6f;
 };
 
-/// Solution (qp.hpp:95-108); PrimalT / DualT are the problem's own vector types
-template<typename PrimalT, typename DualT, typename Scalar = double>
-struct QPSolutionT
-{
-  QPSolutionStatus code = QPSolutionStatus::Unknown;
-  uint32_t iter{0};
-  PrimalT primal{};
-  DualT dual{};
-  Scalar objective{0};
-};
-
 namespace detail {
+
+/// qp_solver.hpp:72-76
+template<typename Pbm>
+using qp_solution_t = QPSolution<
+  decltype(Pbm::A)::RowsAtCompileTime,
+  decltype(Pbm::A)::ColsAtCompileTime,
+  typename decltype(Pbm::A)::Scalar>;
 
 inline sfb_qp_params to_c(const QPSolverParams & p)
 {
@@ -118,13 +109,6 @@ private:
   sfb_handle_t h_{nullptr};
 };
 
-/// Sparse problem types: compressed P (column-major) and A (row-major), as Eigen::SparseMatrix exposes them
-template<typename Pbm>
-concept SparsePbm = requires(const Pbm & p) {
-  p.A.outerIndexPtr(); p.A.innerIndexPtr(); p.A.valuePtr(); p.A.nonZeros();
-  p.P.outerIndexPtr(); p.P.innerIndexPtr(); p.P.valuePtr(); p.P.nonZeros();
-};
-
 /// Owner of an sfb_qp_sparse_pattern_t; a copy starts without a pattern (re-analysed on its first solve)
 class Pattern
 {
@@ -148,13 +132,15 @@ private:
 template<typename Pbm>
 class QPSolver
 {
-  using Scalar  = std::remove_cvref_t<decltype(std::declval<Pbm>().q(0))>;
-  using PrimalT = std::remove_cvref_t<decltype(Pbm::q)>;
-  using DualT   = std::remove_cvref_t<decltype(Pbm::l)>;
+  using AmatT                  = decltype(Pbm::A);
+  using Scalar                 = typename AmatT::Scalar;
+  static constexpr bool sparse = std::is_base_of_v<Eigen::SparseMatrixBase<AmatT>, AmatT>;  // qp_solver.hpp:247
+  static constexpr Eigen::Index M = AmatT::RowsAtCompileTime;
+  static constexpr Eigen::Index N = AmatT::ColsAtCompileTime;
   static_assert(std::is_same_v<Scalar, double> || std::is_same_v<Scalar, float>, "double or float problems only");
 
 public:
-  using Solution = QPSolutionT<PrimalT, DualT, Scalar>;
+  using Solution = QPSolution<M, N, Scalar>;  // == detail::qp_solution_t<Pbm>
 
   QPSolver(const QPSolverParams & prm = {}) : prm_(prm) {}
   QPSolver(const Pbm & pbm, const QPSolverParams & prm = {}) : prm_(prm) { analyze(pbm); }
@@ -167,7 +153,7 @@ public:
   {
     n_ = static_cast<int>(pbm.A.cols());
     m_ = static_cast<int>(pbm.A.rows());
-    if constexpr (detail::SparsePbm<Pbm>) { pattern_.reset(); }
+    if constexpr (sparse) { pattern_.reset(); }
     sol_.primal.resize(n_);
     sol_.dual.resize(m_);
     for (int i = 0; i < n_; ++i) { sol_.primal(i) = 0; }
@@ -195,7 +181,7 @@ public:
     if (pbms.empty()) { return; }
     const int64_t B = static_cast<int64_t>(pbms.size());
     const int n = static_cast<int>(pbms[0].A.cols()), m = static_cast<int>(pbms[0].A.rows());
-    if constexpr (detail::SparsePbm<Pbm>) {
+    if constexpr (sparse) {
       solve_batch_sparse(pbms, sols, warm, B, n, m);
     } else {
       solve_batch_dense(pbms, sols, warm, B, n, m);
@@ -254,6 +240,9 @@ private:
   void solve_batch_sparse(std::span<const Pbm> pbms, std::span<Solution> sols, std::span<const Solution> warm, int64_t B, int n, int m)
   {
     const Pbm & p0 = pbms[0];
+    if (!p0.P.isCompressed() || !p0.A.isCompressed()) {
+      throw std::invalid_argument("smooth::feedback (B200 engine): sparse problems must be in compressed storage (makeCompressed)");
+    }
     const int64_t nnzP = static_cast<int64_t>(p0.P.nonZeros()), nnzA = static_cast<int64_t>(p0.A.nonZeros());
     if (!pattern_.get() || n != n_ || m != m_) {  // analyzePattern, once per solver object (qp_solver.hpp:424)
       n_ = n; m_ = m;
@@ -262,7 +251,7 @@ private:
       if (sfb_qp_sparse_analyze(handle_.get(), n, m, pc.data(), pr.data(), ar.data(), ac.data(), pattern_.put()) != SFB_OK) {
         throw std::runtime_error(std::string("sfb_qp_sparse_analyze: ") + sfb_last_error_message(handle_.get()));
       }
-      pat_P_ = std::move(pr); pat_A_ = std::move(ac);
+      pat_P_ = std::move(pr); pat_A_ = std::move(ac); pat_Po_ = std::move(pc); pat_Ao_ = std::move(ar);
     }
     P_.resize(B * nnzP); q_.resize(B * n); A_.resize(B * nnzA); l_.resize(B * m); u_.resize(B * m);
     x_.resize(B * n); y_.resize(B * m); obj_.resize(B); st_.resize(B); it_.resize(B);
@@ -270,7 +259,11 @@ private:
     if (has_warm) { wx_.resize(B * n); wy_.resize(B * m); }
     for (int64_t b = 0; b < B; ++b) {
       const Pbm & p = pbms[b];
+      if (!p.P.isCompressed() || !p.A.isCompressed()) {
+        throw std::invalid_argument("smooth::feedback (B200 engine): sparse problems must be in compressed storage (makeCompressed)");
+      }
       if (static_cast<int64_t>(p.P.nonZeros()) != nnzP || static_cast<int64_t>(p.A.nonZeros()) != nnzA ||
+          !std::equal(pat_Po_.begin(), pat_Po_.end(), p.P.outerIndexPtr()) || !std::equal(pat_Ao_.begin(), pat_Ao_.end(), p.A.outerIndexPtr()) ||
           !std::equal(pat_P_.begin(), pat_P_.end(), p.P.innerIndexPtr()) || !std::equal(pat_A_.begin(), pat_A_.end(), p.A.innerIndexPtr())) {
         throw std::invalid_argument("smooth::feedback (B200 engine): problems of one batch must share the analysed sparsity pattern");
       }
@@ -315,7 +308,7 @@ private:
   int n_{0}, m_{0};
   detail::Handle handle_{};
   detail::Pattern pattern_{};
-  std::vector<int32_t> pat_P_, pat_A_;
+  std::vector<int32_t> pat_P_, pat_A_, pat_Po_, pat_Ao_;
   std::vector<Scalar> P_, q_, A_, l_, u_, wx_, wy_, x_, y_, obj_;
   std::vector<int32_t> st_;
   std::vector<uint32_t> it_;
@@ -323,10 +316,10 @@ private:
 
 /// One-off solve (qp_solver.hpp:779-787): fresh solver per call
 template<typename Pbm>
-typename QPSolver<Pbm>::Solution solve_qp(
+detail::qp_solution_t<Pbm> solve_qp(
   const Pbm & pbm,
   const QPSolverParams & prm,
-  std::optional<std::reference_wrapper<const typename QPSolver<Pbm>::Solution>> warmstart = {})
+  std::optional<std::reference_wrapper<const detail::qp_solution_t<Pbm>>> warmstart = {})
 {
   QPSolver<Pbm> solver(pbm, prm);
   return solver.solve(pbm, warmstart);

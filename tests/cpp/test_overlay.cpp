@@ -1,17 +1,16 @@
 // The reference's own BasicDynamic / Portfolio / SolverAPI unit tests (tests/test_qp.cpp:75-98, :244-272, :338-372) written
-// against the overlay header, with mock matrices instead of Eigen.  Needs a GPU to run; compiles anywhere.
+// against the overlay header and the reference's own QuadraticProgram / QPSolution templates (Eigen stand-in: tests/cpp/mock_include).  Needs a GPU to run; compiles anywhere.
 #include <cmath>
 #include <cstdio>
 #include <limits>
-#include "../../include/smooth_feedback_b200/qp_solver_b200.hpp"
-#include "mock_eigen.hpp"
+#include <smooth_feedback_b200/qp_solver.hpp>
 
 #define CHECK(c) do { if (!(c)) { std::printf("FAILED %s:%d %s\n", __FILE__, __LINE__, #c); return 1; } } while (0)
 
 int main()
 {
   using namespace smooth::feedback;
-  using Pbm = mock::QuadraticProgram<double>;
+  using Pbm = QuadraticProgram<-1, -1, double>;
   constexpr double inf = std::numeric_limits<double>::infinity();
   const QPSolverParams test_prm{.verbose = false, .polish = true};
 
@@ -26,7 +25,8 @@ int main()
   CHECK(sol.code == QPSolutionStatus::Optimal);
   CHECK(std::fabs(sol.primal(0) - 1) < 1e-4 && std::fabs(sol.primal(1) + 0.25) < 1e-4);
   CHECK(std::fabs(sol.objective - (0.5 - 4 - 1. / 32)) < 1e-4);
-  auto sol_hs = solve_qp(basic, test_prm, sol);  // warm start with own solution
+  auto sol_hs = solve_qp(basic, test_prm, sol);  // warm start with own solution (tests/test_qp.cpp:92-97)
+  static_assert(std::is_same_v<decltype(sol), QPSolution<-1, -1, double>>);
   CHECK(sol_hs.code == QPSolutionStatus::Optimal && sol_hs.iter == 2);
 
   // SolverAPI: copies and moved-from solvers give the same primal
@@ -50,10 +50,10 @@ int main()
   for (int i = 0; i < 100; ++i) { CHECK(sols[i].code == QPSolutionStatus::Optimal && std::fabs(sols[i].primal(0) - 1) < 1e-4); }
   // BasicSparse (tests/test_qp.cpp:100-122): the same QP as QuadraticProgramSparse -- the problem type MPC instantiates
   {
-    using SPbm = mock::QuadraticProgramSparse<double>;
+    using SPbm = QuadraticProgramSparse<double>;
     SPbm sp;
-    sp.P.r = sp.P.c = 2; sp.P.outer = {0, 1, 2}; sp.P.inner = {0, 1}; sp.P.vals = {1, 1};
-    sp.A.r = sp.A.c = 2; sp.A.outer = {0, 1, 2}; sp.A.inner = {0, 1}; sp.A.vals = {1, 1};
+    sp.P.set(2, 2, {0, 1, 2}, {0, 1}, {1, 1});
+    sp.A.set(2, 2, {0, 1, 2}, {0, 1}, {1, 1});
     sp.q.resize(2); sp.q(0) = -4; sp.q(1) = 0.25;
     sp.l.resize(2); sp.l(0) = -1; sp.l(1) = -1;
     sp.u.resize(2); sp.u(0) = 1; sp.u(1) = 1;
@@ -76,6 +76,17 @@ int main()
     bool threw = false;
     try { ss.solve_batch(sbatch, ssols); } catch (const std::invalid_argument &) { threw = true; }
     CHECK(threw);
+    sbatch[7].A.inner = {0, 1};
+    sbatch[7].A.outer = {0, 2, 2};  // same inner indices, different row partition: also a different pattern
+    threw = false;
+    try { ss.solve_batch(sbatch, ssols); } catch (const std::invalid_argument &) { threw = true; }
+    CHECK(threw);
+    // BasicStatic (tests/test_qp.cpp:54-73): statically sized problem and solution types
+    QuadraticProgram<2, 2, double> st;
+    st.P(0, 0) = 1; st.P(1, 1) = 1; st.A(0, 0) = 1; st.A(1, 1) = 1;
+    st.q(0) = -4; st.q(1) = 0.25; st.l(0) = -1; st.l(1) = -1; st.u(0) = 1; st.u(1) = 1;
+    const QPSolution<2, 2, double> sts = solve_qp(st, test_prm);
+    CHECK(sts.code == QPSolutionStatus::Optimal && std::fabs(sts.primal(0) - 1) < 1e-4);
   }
   (void)inf;
   std::printf("overlay ok\n");
