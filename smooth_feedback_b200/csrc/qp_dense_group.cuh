@@ -1195,6 +1195,172 @@ template <typename T, int G, int NS, int MS> struct QpGroup
     return code;
   }
 
+
+  // ---------------------------------------------------------------- main ADMM loop, REGISTER-RESIDENT Abar
+  // For compile-time shapes with n <= 56, m <= 112 and G = 4 (the headline n = 50, m = 100) every thread keeps a 7 x 7
+  // block of Abar in registers for the whole loop: threads form a 16 x 8 grid (row group rg = 4 warp + lane / 8 owns rows
+  // rg + 16 a, column group cg = lane % 8 owns columns cg + 8 b).  Per iteration
+  //   Abar^T w : 49 FMAs on registers, reduce-scatter over the 4 row groups of the warp (6 shuffles), 4 warp partials
+  //              through shared memory;
+  //   Minv rhs : two threads per row of Minv (shared memory), one shuffle;
+  //   Abar xt  : 49 FMAs on registers, reduce-scatter over the 8 column groups (7 shuffles) -- lane (rl, cg) ends up with
+  //              row rg + 16 cg, whose z, y, rho, bounds live in ITS registers, so the z / y update touches no memory.
+  // The shared-memory version above streams Abar twice per iteration (10 000 of its 12 500 operand loads); this one loads
+  // it once per solve.  Same arithmetic, different summation order (parity with the oracle is unaffected: tests).
+  static constexpr bool kRegLoop = (G == 4) && (NS > 0) && (NS <= 56) && (MS > 0) && (MS <= 112);
+  template <typename TIO> __device__ int admm_loop_reg(const QpArgs<T, TIO>& a, long long b, unsigned long long t0, int code, unsigned* iter_out)
+  {
+    constexpr int RA = 7, CBK = 7;
+    const T alpha = T(a.prm.alpha), alpha_comp = T(1) - alpha, sigma = T(a.prm.sigma);
+    const unsigned sci = a.prm.stop_check_iter;
+    const int cg = lane & 7, rl = lane >> 3, rg = warp * 4 + rl;
+    T Ar[RA][CBK];
+#pragma unroll
+    for (int ia = 0; ia < RA; ++ia)
+#pragma unroll
+      for (int jb = 0; jb < CBK; ++jb) {
+        const int i = rg + 16 * ia, j = cg + 8 * jb;
+        Ar[ia][jb] = (i < m && j < n) ? As[i + ldA * j] : T(0);
+      }
+    // the row whose iterate this thread owns: a == cg after the reduce-scatter of Abar xt
+    const int myrow = rg + 16 * cg;
+    const bool has_row = (cg < RA) && (myrow < m);
+    T zr = T(0), yr = T(0), rr = T(0), rinvr = T(0), lor = T(0), hir = T(0), yoldr = T(0);
+    if (has_row) {
+      zr = z[myrow]; yr = y[myrow]; rr = rho[myrow]; rinvr = rinv[myrow];
+      lor = sy[myrow] * l[myrow]; hir = sy[myrow] * u[myrow];
+    }
+    T* part4 = gjbuf;  // 4 warps x kGjPad column partials (the inverse's scratch is idle during the loop)
+    const int r2 = tid >> 1, h2 = tid & 1;
+    const bool has2 = r2 < n;
+    const int c0 = cg + 16 * rl, c1 = c0 + 8;  // the two columns this lane holds after the reduce-scatter of Abar^T w
+    unsigned iter = 0;
+#pragma unroll 1
+    for (; iter != a.max_iter_eff && code == kStatusUnset; ++iter) {
+      // ---- rhs_x = sigma x - qb + Abar^T w,  w = R z - y
+      {
+        T wv[RA];
+#pragma unroll
+        for (int ia = 0; ia < RA; ++ia) {
+          const int i = rg + 16 * ia;
+          wv[ia] = (i < m) ? w[i] : T(0);
+        }
+        T pc[8];
+#pragma unroll
+        for (int jb = 0; jb < CBK; ++jb) {
+          T acc = T(0);
+#pragma unroll
+          for (int ia = 0; ia < RA; ++ia) acc += Ar[ia][jb] * wv[ia];
+          pc[jb] = acc;
+        }
+        pc[7] = T(0);
+        const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const T keep = up16 ? pc[4 + k] : pc[k], send = up16 ? pc[k] : pc[4 + k];
+          pc[k] = keep + __shfl_xor_sync(kFullMask, send, 16);
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const T keep = up8 ? pc[2 + k] : pc[k], send = up8 ? pc[k] : pc[2 + k];
+          pc[k] = keep + __shfl_xor_sync(kFullMask, send, 8);
+        }
+        if (c0 < n) part4[warp * kGjPad + c0] = pc[0];
+        if (c1 < n) part4[warp * kGjPad + c1] = pc[1];
+      }
+      gsync();
+      if (tid < n) {
+        const T t = (part4[tid] + part4[kGjPad + tid]) + (part4[2 * kGjPad + tid] + part4[3 * kGjPad + tid]);
+        xt[tid] = sigma * x[tid] - qb[tid] + t;
+      }
+      gsync();
+      // ---- xtilde = Minv rhs_x ; x <- alpha xtilde + (1 - alpha) x   :470   (two threads per row: columns h2, h2 + 2, ...)
+      const bool chk = (iter % sci == 1u);
+      {
+        T a0 = T(0), a1 = T(0);
+        if (has2) {
+          const T* pr = Ms + r2 + ldN * h2;
+          int k = 0;
+#pragma unroll 6
+          for (; k + 1 < (n - h2 + 1) / 2; k += 2) {
+            a0 += pr[ldN * (2 * k)] * xt[h2 + 2 * k];
+            a1 += pr[ldN * (2 * k + 2)] * xt[h2 + 2 * k + 2];
+          }
+          if (k < (n - h2 + 1) / 2) a0 += pr[ldN * (2 * k)] * xt[h2 + 2 * k];
+        }
+        T xti = a0 + a1;
+        xti += __shfl_xor_sync(kFullMask, xti, 1);
+        if (has2 && h2 == 0) {
+          nv1[r2] = xti;
+          const T xi = x[r2];
+          if (chk) xold[r2] = xi;  // :465-468
+          x[r2] = alpha * xti + alpha_comp * xi;
+        }
+      }
+      gsync();
+      // ---- nu = R (Abar xtilde - z) + y ; z, y updates  :471-477 ; next w
+      {
+        T xv[CBK];
+#pragma unroll
+        for (int jb = 0; jb < CBK; ++jb) {
+          const int j = cg + 8 * jb;
+          xv[jb] = (j < n) ? nv1[j] : T(0);
+        }
+        T zp[8];
+#pragma unroll
+        for (int ia = 0; ia < RA; ++ia) {
+          T acc = T(0);
+#pragma unroll
+          for (int jb = 0; jb < CBK; ++jb) acc += Ar[ia][jb] * xv[jb];
+          zp[ia] = acc;
+        }
+        zp[7] = T(0);
+        const bool up4 = (lane & 4) != 0, up2 = (lane & 2) != 0, up1 = (lane & 1) != 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const T keep = up4 ? zp[4 + k] : zp[k], send = up4 ? zp[k] : zp[4 + k];
+          zp[k] = keep + __shfl_xor_sync(kFullMask, send, 4);
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const T keep = up2 ? zp[2 + k] : zp[k], send = up2 ? zp[k] : zp[2 + k];
+          zp[k] = keep + __shfl_xor_sync(kFullMask, send, 2);
+        }
+        {
+          const T keep = up1 ? zp[1] : zp[0], send = up1 ? zp[0] : zp[1];
+          zp[0] = keep + __shfl_xor_sync(kFullMask, send, 1);
+        }
+        if (has_row) {
+          const T zt = zp[0];
+          if (chk) yoldr = yr;
+          const T nu = rr * (zt - zr) + yr;
+          T v = alpha * (rinvr * nu) + alpha_comp * (rinvr * yr) + zr;
+          v = fmax(v, lor);
+          v = fmin(v, hir);
+          const T yn = alpha_comp * yr + alpha * nu + rr * zr - rr * v;
+          yr = yn;
+          zr = v;
+          w[myrow] = rr * v - yn;
+        }
+      }
+      if (chk) {
+        if (has_row) { z[myrow] = zr; y[myrow] = yr; yold[myrow] = yoldr; }
+        gsync();
+        code = qp_stage_check<T, G, NS, MS>(&a, b, c);  // :488  (clobbers w)
+        if (code == kStatusUnset && a.prm.has_max_time) {
+          const bool late = (tid == 0) && ((long long)(global_timer_ns() - t0) > a.prm.max_time_ns);
+          if (gany(late)) code = SFB_QP_MAX_TIME;
+        }
+        if (has_row) w[myrow] = rr * zr - yr;
+      }
+      gsync();
+    }
+    if (has_row) { z[myrow] = zr; y[myrow] = yr; }
+    gsync();
+    *iter_out = iter;
+    return code;
+  }
+
   // ---------------------------------------------------------------- QPSolver::solve, qp_solver.hpp:343-568
   template <typename TIO> __device__ void solve(const QpArgs<T, TIO>& a, long long b, T* gscratch)
   {
@@ -1409,7 +1575,9 @@ template <typename T, int G, int NS, int MS, typename TIO>
 __device__ __noinline__ int qp_stage_loop(const QpArgs<T, TIO>* a, long long b, T c, unsigned long long t0, int code, unsigned* iter_out)
 {
   QpGroup<T, G, NS, MS> s = qp_view<T, G, NS, MS>(a->n, a->m, c);
-  const int r = s.admm_loop(*a, b, t0, code, iter_out);
+  int r;
+  if constexpr (QpGroup<T, G, NS, MS>::kRegLoop) r = s.admm_loop_reg(*a, b, t0, code, iter_out);
+  else r = s.admm_loop(*a, b, t0, code, iter_out);
   s.gsync();
   return r;
 }
