@@ -1231,8 +1231,13 @@ template <typename T, int G, int NS, int MS> struct QpGroup
       lor = sy[myrow] * l[myrow]; hir = sy[myrow] * u[myrow];
     }
     T* part4 = gjbuf;  // 4 warps x kGjPad column partials (the inverse's scratch is idle during the loop)
-    const int r2 = tid >> 1, h2 = tid & 1;
+    // Minv rows: lanes 0-15 of a warp take columns 0, 2, 4, ... of rows 16 warp + lane, lanes 16-31 the odd columns of the
+    // same rows (each half-warp then reads 16 consecutive scalars: conflict-free; tid / 2, tid % 2 put rows r and r + 51 into
+    // one half-warp and measured 35 % excess wavefronts)
+    const int r2 = warp * 16 + (lane & 15), h2 = lane >> 4;
     const bool has2 = r2 < n;
+    // iterations until the next stop check (iter % sci == 1) without a division per iteration; sci == 1 never checks (x % 1 != 1)
+    unsigned until_check = (sci == 1u) ? 0xffffffffu : 1u;
     const int c0 = cg + 16 * rl, c1 = c0 + 8;  // the two columns this lane holds after the reduce-scatter of Abar^T w
     unsigned iter = 0;
 #pragma unroll 1
@@ -1275,7 +1280,8 @@ template <typename T, int G, int NS, int MS> struct QpGroup
       }
       gsync();
       // ---- xtilde = Minv rhs_x ; x <- alpha xtilde + (1 - alpha) x   :470   (two threads per row: columns h2, h2 + 2, ...)
-      const bool chk = (iter % sci == 1u);
+      const bool chk = (until_check == 0u);
+      until_check = chk ? sci - 1u : until_check - 1u;
       {
         T a0 = T(0), a1 = T(0);
         if (has2) {
@@ -1289,7 +1295,7 @@ template <typename T, int G, int NS, int MS> struct QpGroup
           if (k < (n - h2 + 1) / 2) a0 += pr[ldN * (2 * k)] * xt[h2 + 2 * k];
         }
         T xti = a0 + a1;
-        xti += __shfl_xor_sync(kFullMask, xti, 1);
+        xti += __shfl_xor_sync(kFullMask, xti, 16);
         if (has2 && h2 == 0) {
           nv1[r2] = xti;
           const T xi = x[r2];

@@ -9,11 +9,12 @@ pat = [("load", "__device__ void load("), ("scale", "__device__ void scale("), (
        ("gj_misc", "__device__ __forceinline__ bool gj_invert_at("), ("colpass", "__device__ __forceinline__ void colpass("),
        ("colpass_skinny", "__device__ void colpass_skinny("), ("At_vec", "__device__ void At_vec("), ("rowdot", "T rowdot("),
        ("check", "__device__ int check_stopping("), ("pbar", "T pbar("), ("polish", "__device__ unsigned polish("),
-       ("form_kkt", "__device__ void form_reduced_kkt("), ("setup", "__device__ int setup("), ("solve(loop etc)", "__device__ void solve("),
+       ("form_kkt", "__device__ void form_reduced_kkt("), ("setup", "__device__ int setup("), ("admm_loop(smem)", "__device__ int admm_loop("),
+       ("admm_loop_reg", "__device__ int admm_loop_reg("), ("solve(load..store)", "__device__ void solve("),
        ("stages", "// out-of-line stages\n")]
 for name, p in pat:
     for i, l in enumerate(lines):
-        if p.strip() in l and "template <typename T, int G> __device__" not in l:
+        if p.strip() in l and "template <typename T, int G> __device__" not in l and "__noinline__" not in l:
             marks.append((name, i + 1)); break
 marks.sort(key=lambda t: t[1])
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
