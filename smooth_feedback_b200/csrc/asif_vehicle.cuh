@@ -9,12 +9,13 @@
 // for the model family of examples/mpc_asif_vehicle.cpp:42-52 (dynamics), :96-100 (safe set), :103 (backup controller).
 // The reference differentiates user lambdas on the host with autodiff; here the family's derivatives are closed forms.
 //
-// Structure: a warp owns a tile of 32 agents.
-//   phase 1 (lane = agent): the backup trajectory x(t) and its 6 x 6 sensitivity S(t) are integrated in registers (fp64
+// Structure: one launch, two work queues.
+//   phase 1 (a warp takes a tile of 32 agents, lane = agent): the backup trajectory x(t) and its 6 x 6 sensitivity S(t) are integrated in registers (fp64
 //     whatever the QP precision) along the step schedule the host computed with the reference's exact time arithmetic
 //     (asif_func.hpp:139-143,170-176 -- it does not depend on the state).  Per constraint k the only agent-dependent QP
 //     entries are (A_k0, A_k1, l_k); they go to a [3][K] block per agent.
-//   phase 2 (warp = agent, 32 times): rows are re-read lane-strided (coalesced), the remaining rows / P / q are
+//   phase 2 (a warp takes ONE agent at a time from a queue over the whole batch; tiles are published through a ready flag):
+//     rows are re-read lane-strided (coalesced), the remaining rows / P / q are
 //     constants of the parameter set, and the register-resident tall-skinny ADMM solver of qp_dense_skinny.cuh runs
 //     (n = 3, m = K + 3; polish off like mpc_asif_vehicle.cpp:127).  Warm starts stay resident in device memory.
 #pragma once
@@ -54,7 +55,9 @@ template <typename T> struct AsifArgs
   uint32_t* out_iter;
   // transcription-only mode (asif_to_qp, asif_func.hpp:246-261): dense QP in the reference's column-major storage
   T *qp_P, *qp_q, *qp_A, *qp_l, *qp_u;
-  unsigned long long* work_counter;
+  unsigned long long* work_counter;   // tiles of 32 agents to transcribe
+  unsigned long long* solve_counter;  // agents to solve
+  unsigned* tile_ready;               // [ceil(batch / 32)] 0 until the tile's rows are in memory (zeroed before every launch)
 };
 
 // phase 1 for one agent.  All arithmetic in double, in the operation order of oracle/transcribe.py::asif_to_qp.
@@ -133,24 +136,38 @@ __global__ void __launch_bounds__(32 * kSkinnyWarps, sizeof(T) == 4 ? 3 : 2) asi
   const int lane = threadIdx.x & 31;
   const AsifVehicleDev& M = a.mdl;
   const int K = M.K, m = K + 3;
+  const long long ntiles = (a.batch + 31) / 32;
+  // ---- phase 1: warps pull tiles of 32 agents (lane = agent) until none is left, publishing each finished tile
 #pragma unroll 1
   for (;;) {
     unsigned long long tile = 0;
     if (lane == 0) tile = atomicAdd(a.work_counter, 1ull);
     tile = __shfl_sync(kFullMask, tile, 0);
-    const long long b0 = (long long)tile * 32;
-    if (b0 >= a.batch) break;
-    // ---- phase 1: lane = agent
-    {
-      const long long b = b0 + lane;
-      if (b < a.batch) asif_vehicle_rows<T>(M, a.x + b * 7, a.u_des + b * 2, a.rows + b * 3 * (long long)K);
-    }
+    if ((long long)tile >= ntiles) break;
+    const long long b = (long long)tile * 32 + lane;
+    if (b < a.batch) asif_vehicle_rows<T>(M, a.x + b * 7, a.u_des + b * 2, a.rows + b * 3 * (long long)K);
+    __threadfence();  // every lane's rows are visible device-wide before the tile is published
     __syncwarp();
-    // ---- phase 2: the warp solves the tile's QPs one after the other
-    const int cnt = (int)min((long long)32, a.batch - b0);
+    if (lane == 0) atomicExch(a.tile_ready + tile, 1u);
+  }
+  // ---- phase 2: warps pull single agents from ONE queue over the whole batch (iteration counts are heavy-tailed: median 2,
+  // mean ~300, max > 2500 on the vehicle workload), whichever tile they came from.  A warp gets here only after every tile has
+  // been claimed by a running warp, and a warp transcribing a tile never waits, so the spin below always terminates.
 #pragma unroll 1
-    for (int t = 0; t < cnt; ++t) {
-      const long long b = b0 + t;
+  for (;;) {
+    unsigned long long bb = 0;
+    if (lane == 0) {
+      bb = atomicAdd(a.solve_counter, 1ull);
+      if ((long long)bb < a.batch) {
+        const volatile unsigned* flag = a.tile_ready + (bb >> 5);
+        while (*flag == 0u) {}
+        __threadfence();
+      }
+    }
+    bb = __shfl_sync(kFullMask, bb, 0);
+    if ((long long)bb >= a.batch) break;
+    {
+      const long long b = (long long)bb;
       QpSkinny<T, 3, R> s;
       s.lane = lane;
       s.m = m;
@@ -163,7 +180,7 @@ __global__ void __launch_bounds__(32 * kSkinnyWarps, sizeof(T) == 4 ? 3 : 2) asi
         const int i = lane + 32 * k;
         s.valid[k] = i < m;
         T a0 = T(0), a1 = T(0), a2 = T(0), lo = -inf, hi = inf;
-        if (i < K) { a0 = rw[i]; a1 = rw[K + i]; a2 = T(1); lo = rw[2 * K + i]; }                       // :160-162,180
+        if (i < K) { a0 = __ldcg(rw + i); a1 = __ldcg(rw + K + i); a2 = T(1); lo = __ldcg(rw + 2 * K + i); }                       // :160-162,180
         else if (i == K) { a0 = T(1); lo = (T)(M.ulim_l[0] - ud0); hi = (T)(M.ulim_u[0] - ud0); }          // :183-185 (ulim.A = I, c = 0)
         else if (i == K + 1) { a1 = T(1); lo = (T)(M.ulim_l[1] - ud1); hi = (T)(M.ulim_u[1] - ud1); }
         else if (i == K + 2) { a2 = T(1); lo = T(0); }                                                     // :188-190

@@ -23,6 +23,7 @@ struct sfb_asif_fleet
   void* d_warm_x = nullptr;      // [batch][3]
   void* d_warm_y = nullptr;      // [batch][m]
   uint8_t* d_warm_valid = nullptr;
+  unsigned* d_tile_ready = nullptr;  // [ceil(batch / 32)] per-launch publication flags of the transcription tiles
   // staging of host buffers
   void* d_x = nullptr;
   void* d_ud = nullptr;
@@ -106,10 +107,14 @@ int asif_launch(sfb_asif_fleet* f, const T* x, const T* ud, T* out_u, int32_t* o
   a.warm_valid = f->d_warm_valid;
   a.out_u = out_u; a.out_status = out_status; a.out_iter = out_iter;
   a.qp_P = qP; a.qp_q = qq; a.qp_A = qA; a.qp_l = ql; a.qp_u = qu;
-  a.work_counter = next_counter(h, kNumSlots);
-  SFB_CUDA(h, cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), h->stream));
   const long long tiles = (f->batch + 31) / 32;
-  const long long ctas = (tiles + sfb::kSkinnyWarps - 1) / sfb::kSkinnyWarps;
+  a.work_counter = next_counter(h, kNumSlots);
+  a.solve_counter = next_counter(h, kNumSlots);
+  a.tile_ready = f->d_tile_ready;
+  SFB_CUDA(h, cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), h->stream));
+  SFB_CUDA(h, cudaMemsetAsync(a.solve_counter, 0, sizeof(unsigned long long), h->stream));
+  SFB_CUDA(h, cudaMemsetAsync(a.tile_ready, 0, sizeof(unsigned) * (size_t)tiles, h->stream));
+  const long long ctas = (f->batch + sfb::kSkinnyWarps - 1) / sfb::kSkinnyWarps;  // phase 2 hands out single agents
   auto go = [&](auto kern) -> int {
     int nb = 0;
     SFB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 32 * sfb::kSkinnyWarps, 0));
@@ -193,6 +198,7 @@ int sfb_asif_fleet_create(sfb_handle_t h, const sfb_asif_vehicle_params* p, int6
   bool ok = cudaMalloc(&f->d_nsteps, sizeof(int) * p->K) == cudaSuccess && cudaMalloc(&f->d_dt, sizeof(double) * p->K) == cudaSuccess &&
             cudaMalloc(&f->d_rows, sb * 3 * p->K * B) == cudaSuccess && cudaMalloc(&f->d_warm_x, sb * 3 * B) == cudaSuccess &&
             cudaMalloc(&f->d_warm_y, sb * f->m * B) == cudaSuccess && cudaMalloc(&f->d_warm_valid, B) == cudaSuccess &&
+            cudaMalloc(&f->d_tile_ready, sizeof(unsigned) * ((B + 31) / 32)) == cudaSuccess &&
             cudaMalloc(&f->d_x, sb * 7 * B) == cudaSuccess && cudaMalloc(&f->d_ud, sb * 2 * B) == cudaSuccess &&
             cudaMalloc(&f->d_u, sb * 2 * B) == cudaSuccess && cudaMalloc(&f->d_status, 4 * B) == cudaSuccess &&
             cudaMalloc(&f->d_iter, 4 * B) == cudaSuccess;
@@ -213,7 +219,7 @@ int sfb_asif_fleet_destroy(sfb_asif_fleet_t f)
   if (!f) return SFB_OK;
   cudaSetDevice(f->h->device);
   cudaStreamSynchronize(f->h->stream);
-  void* ptrs[] = {f->d_nsteps, f->d_dt, f->d_rows, f->d_warm_x, f->d_warm_y, f->d_warm_valid, f->d_x, f->d_ud, f->d_u, f->d_status, f->d_iter};
+  void* ptrs[] = {f->d_nsteps, f->d_dt, f->d_rows, f->d_warm_x, f->d_warm_y, f->d_warm_valid, f->d_tile_ready, f->d_x, f->d_ud, f->d_u, f->d_status, f->d_iter};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete f;

@@ -32,5 +32,25 @@ for tw in (4, 8, 32):
 pat2, Pv, q, Av, l, u = random_sparse_qp_numpy(9, 20, 30, density=0.2, seed=3)
 sp = sfb.SparsePattern(pat2["n"], pat2["m"], pat2["P_colptr"], pat2["P_rowidx"], pat2["A_rowptr"], pat2["A_colidx"], handle=h)
 sfb.solve_sparse_batch(sp, t(Pv), t(q), t(Av), t(l), t(u), prm)
+# round 2: fp32 + polish (mixed-precision second pass), the ASIF / MPC fleets (transcription, fused filter, epilogue) and the
+# library's own all-gather (world size 1)
+from smooth_feedback_b200.generators import vehicle_fleet_numpy
+P, q, A, l, u = random_qp_numpy(24, 10, 20, seed=4)
+f = lambda a: t(a).float()
+sfb.solve_dense_batch(f(cm(P)), f(q), f(cm(A)), f(l), f(u), sfb.QPSolverParams(max_iter=200))
+t0, x0, ud = vehicle_fleet_numpy(70, seed=3)
+for dt in (np.float64, np.float32):
+    fl = sfb.ASIFVehicleFleet(70, sfb.ASIFVehicleParams(qp=sfb.QPSolverParams(polish=False, max_iter=120)), dtype=dt)
+    fl(x0.astype(dt), ud.astype(dt)); fl(x0.astype(dt), ud.astype(dt))
+    if dt == np.float64:
+        fl.to_qp(x0, ud)
+    fl.close()
+    mf = sfb.MPCVehicleFleet(9, sfb.MPCVehicleParams(K=10, tf=2.0, qp=sfb.QPSolverParams(max_iter=120)), dtype=dt)
+    mf(t0[:9].astype(dt), x0[:9].astype(dt)); mf(t0[:9].astype(dt), x0[:9].astype(dt))
+    mf.close()
+hc = sfb.Handle(0)
+comm = sfb.Communicator(hc, 1, 0, sfb.Communicator.unique_id())
+r = sfb.solve_dense_batch(t(cm(P)), t(q), t(cm(A)), t(l), t(u), prm, handle=hc)
+comm.all_gather([r.x, r.y, r.status]); comm.wait(host=True); comm.close()
 torch.cuda.synchronize()
 print("sanitize workload done")
