@@ -154,7 +154,9 @@ int sfb_qp_solve_dense_batch_f64(sfb_handle_t h, const sfb_qp_params* prm, int64
                                  double* out_y, double* out_obj, int32_t* out_status, uint32_t* out_iter,
                                  int8_t* out_active, uint32_t* out_flags);
 
-/* Same in single precision (new functionality: the reference has no float instantiation). */
+/* Same in single precision (new functionality: the reference has no float instantiation): ADMM iterations in
+ * fp32; polish_qp (delta = 1e-6 is 8 ulp in fp32) runs as a mixed-precision second pass in fp64 on the fp32 iterate and active
+ * set (SFB_QP_FLAG_POLISHED); shapes whose fp64 working set does not fit in shared memory keep SFB_QP_FLAG_POLISH_SKIPPED. */
 int sfb_qp_solve_dense_batch_f32(sfb_handle_t h, const sfb_qp_params* prm, int64_t batch, int n, int m,
                                  const float* P, const float* q, const float* A, const float* l, const float* u,
                                  const float* warm_x, const float* warm_y, float* out_x, float* out_y,
@@ -237,7 +239,19 @@ int sfb_qp_solve_sparse_batch_f64(sfb_handle_t h, sfb_qp_sparse_pattern_t patter
                                   const double* l, const double* u, const double* warm_x, const double* warm_y,
                                   double* out_x, double* out_y, double* out_obj, int32_t* out_status,
                                   uint32_t* out_iter, int8_t* out_active, uint32_t* out_flags);
-/* single precision (new functionality; polish is reported as skipped, as in the dense f32 entry point) */
+/*
+ * OSQP-style ingestion (compat/osqp.hpp:36-49 hands OSQP both matrices in CSC): the same problems with A
+ * given column-compressed -- A_colptr [n+1], A_rowidx [nnzA], values per instance in that order.  The analysis converts the
+ * pattern to the solver's CSR order once and keeps the value permutation; results are identical to the CSR entry point.
+ */
+int sfb_qp_sparse_analyze_csc(sfb_handle_t h, int n, int m, const int32_t* P_colptr, const int32_t* P_rowidx,
+                              const int32_t* A_colptr, const int32_t* A_rowidx, sfb_qp_sparse_pattern_t* out);
+int sfb_qp_solve_sparse_batch_csc_f64(sfb_handle_t h, sfb_qp_sparse_pattern_t pattern, const sfb_qp_params* prm,
+                                      int64_t batch, const double* P_vals, const double* q, const double* A_vals_csc,
+                                      const double* l, const double* u, const double* warm_x, const double* warm_y,
+                                      double* out_x, double* out_y, double* out_obj, int32_t* out_status,
+                                      uint32_t* out_iter, int8_t* out_active, uint32_t* out_flags);
+/* single precision (new functionality): ADMM iterations in fp32, polish_qp as a mixed-precision second pass in fp64 */
 int sfb_qp_solve_sparse_batch_f32(sfb_handle_t h, sfb_qp_sparse_pattern_t pattern, const sfb_qp_params* prm,
                                   int64_t batch, const float* P_vals, const float* q, const float* A_vals,
                                   const float* l, const float* u, const float* warm_x, const float* warm_y, float* out_x,

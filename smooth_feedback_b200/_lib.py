@@ -52,7 +52,7 @@ EXPORTED_SYMBOLS = [
     "sfb_qp_solve_dense_batch_f32", "sfb_qp_dense_max_m", "sfb_qp_scale_dense_batch_f64",
     "sfb_ekf_predict_batch_f64", "sfb_ekf_update_batch_f64", "sfb_ekf_step_batch_f64",
     "sfb_qp_sparse_analyze", "sfb_qp_sparse_symbolic", "sfb_qp_sparse_pattern_destroy", "sfb_qp_sparse_pattern_info",
-    "sfb_qp_solve_sparse_batch_f64", "sfb_qp_solve_sparse_batch_f32",
+    "sfb_qp_solve_sparse_batch_f64", "sfb_qp_solve_sparse_batch_f32", "sfb_qp_sparse_analyze_csc", "sfb_qp_solve_sparse_batch_csc_f64",
     "sfb_asif_vehicle_params_default", "sfb_asif_fleet_create", "sfb_asif_fleet_destroy", "sfb_asif_fleet_reset_warmstart",
     "sfb_asif_fleet_set_warmstart", "sfb_asif_fleet_filter_f64", "sfb_asif_fleet_filter_f32", "sfb_asif_fleet_to_qp_f64",
     "sfb_mpc_vehicle_params_default", "sfb_mpc_fleet_create", "sfb_mpc_fleet_destroy", "sfb_mpc_fleet_reset_warmstart",
@@ -130,6 +130,8 @@ def lib() -> C.CDLL:
     sp_sig = [vp, vp, C.POINTER(SfbQpParams), i64] + [vp] * 14
     L.sfb_qp_solve_sparse_batch_f64.argtypes = sp_sig
     L.sfb_qp_solve_sparse_batch_f32.argtypes = sp_sig
+    L.sfb_qp_sparse_analyze_csc.argtypes = [vp, i32, i32, vp, vp, vp, vp, C.POINTER(vp)]
+    L.sfb_qp_solve_sparse_batch_csc_f64.argtypes = sp_sig
     L.sfb_asif_vehicle_params_default.argtypes = [vp]
     L.sfb_asif_vehicle_params_default.restype = None
     L.sfb_asif_fleet_create.argtypes = [vp, vp, i64, i32, C.POINTER(vp)]

@@ -495,6 +495,7 @@ int sfb_destroy(sfb_handle_t h)
   if (h->sparse_ws.dev) cudaFree(h->sparse_ws.dev);
   if (h->sparse_stage.dev) cudaFree(h->sparse_stage.dev);
   if (h->act_tmp.dev) cudaFree(h->act_tmp.dev);
+  if (h->csc_tmp.dev) cudaFree(h->csc_tmp.dev);
   if (h->counters) cudaFree(h->counters);
   delete h;
   return SFB_OK;

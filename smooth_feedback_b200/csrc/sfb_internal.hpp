@@ -59,6 +59,7 @@ struct sfb_context
   int sparse_tw = 0;     // SFB_SPARSE_TW=4|8|32 overrides the tile-width heuristic of the sparse QP path (A/B measurements)
   sfbi::Scratch sparse_ws;     // tiled working set of the sparse QP path
   sfbi::Scratch sparse_stage;  // device copies of host buffers (sparse path)
+  sfbi::Scratch csc_tmp;       // CSC -> CSR permuted A values (sfb_qp_solve_sparse_batch_csc_f64)
   sfbi::Scratch act_tmp;       // active sets of an fp32 solve when the caller did not ask for them (mixed-precision polish)
 };
 

@@ -14,6 +14,9 @@ struct sfb_qp_sparse_pattern
   sfb::SparseSymbolic sym;
   int* dev = nullptr;  // one allocation holding all index arrays
   sfb::SpPattern pat{};
+  // sfb_qp_sparse_analyze_csc: CSR slot e of A takes the caller's CSC value csc2csr[e]
+  std::vector<int> csc2csr;
+  int* d_csc2csr = nullptr;
 };
 
 namespace {
@@ -179,6 +182,21 @@ int qp_sparse_solve_impl(sfb_context* h, const sfb_qp_sparse_pattern* pt, const 
 
 }  // namespace
 
+
+namespace {
+// A_vals in the caller's CSC order -> the CSR order the solver ingests (per instance gather through the pattern's map)
+template <typename T> __global__ void csc_to_csr_values_kernel(const T* __restrict__ in, T* __restrict__ out, const int* __restrict__ map,
+                                                             int nnz, long long batch)
+{
+  const long long total = batch * (long long)nnz;
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
+    const long long b = k / nnz;
+    const int e = (int)(k - b * nnz);
+    out[k] = in[b * (long long)nnz + map[e]];
+  }
+}
+}  // namespace
+
 extern "C" {
 
 int sfb_qp_sparse_analyze(sfb_handle_t h, int n, int m, const int32_t* P_colptr, const int32_t* P_rowidx,
@@ -258,6 +276,7 @@ int sfb_qp_sparse_pattern_destroy(sfb_qp_sparse_pattern_t p)
   if (!p) return SFB_OK;
   cudaSetDevice(p->device);
   if (p->dev) cudaFree(p->dev);
+  if (p->d_csc2csr) cudaFree(p->d_csc2csr);
   delete p;
   return SFB_OK;
 }
@@ -289,6 +308,81 @@ int sfb_qp_solve_sparse_batch_f32(sfb_handle_t h, sfb_qp_sparse_pattern_t patter
 {
   return qp_sparse_solve_impl<float>(h, pattern, prm, batch, P_vals, q, A_vals, l, u, warm_x, warm_y, out_x, out_y,
                                      out_obj, out_status, out_iter, out_active, out_flags);
+}
+
+int sfb_qp_sparse_analyze_csc(sfb_handle_t h, int n, int m, const int32_t* P_colptr, const int32_t* P_rowidx,
+                              const int32_t* A_colptr, const int32_t* A_rowidx, sfb_qp_sparse_pattern_t* out)
+{
+  if (!h) return SFB_ERR_INVALID_ARGUMENT;
+  if (!out) return fail(h, SFB_ERR_INVALID_ARGUMENT, "out is NULL");
+  *out = nullptr;
+  if (n <= 0 || m < 0 || !P_colptr || !A_colptr) return fail(h, SFB_ERR_INVALID_ARGUMENT, "bad pattern arguments");
+  if (A_colptr[0] != 0) return fail(h, SFB_ERR_INVALID_ARGUMENT, "pattern pointers must start at 0");
+  for (int j = 0; j < n; ++j)
+    if (A_colptr[j + 1] < A_colptr[j]) return fail(h, SFB_ERR_INVALID_ARGUMENT, "A_colptr not monotone");
+  const int nnz = A_colptr[n];
+  if (nnz > 0 && !A_rowidx) return fail(h, SFB_ERR_INVALID_ARGUMENT, "index array is NULL");
+  // CSC -> CSR: counting sort by row; within a row the columns come out ascending because columns are visited in order
+  std::vector<int32_t> rowptr(m + 1, 0), colidx(nnz);
+  std::vector<int> map(nnz);
+  for (int k = 0; k < nnz; ++k) {
+    if (A_rowidx[k] < 0 || A_rowidx[k] >= m) return fail(h, SFB_ERR_INVALID_ARGUMENT, "A row index out of range");
+    rowptr[A_rowidx[k] + 1] += 1;
+  }
+  for (int i = 0; i < m; ++i) rowptr[i + 1] += rowptr[i];
+  std::vector<int32_t> fill(rowptr.begin(), rowptr.end() - 1);
+  for (int j = 0; j < n; ++j)
+    for (int k = A_colptr[j]; k < A_colptr[j + 1]; ++k) {
+      const int e = fill[A_rowidx[k]]++;
+      colidx[e] = j;
+      map[e] = k;
+    }
+  int rc = sfb_qp_sparse_analyze(h, n, m, P_colptr, P_rowidx, rowptr.data(), colidx.data(), out);
+  if (rc != SFB_OK) return rc;
+  sfb_qp_sparse_pattern* p = *out;
+  p->csc2csr = map;
+  if (nnz > 0 && (cudaMalloc(&p->d_csc2csr, sizeof(int) * nnz) != cudaSuccess ||
+                  cudaMemcpy(p->d_csc2csr, map.data(), sizeof(int) * nnz, cudaMemcpyHostToDevice) != cudaSuccess)) {
+    const char* msg = cudaGetErrorString(cudaGetLastError());
+    sfb_qp_sparse_pattern_destroy(p);
+    *out = nullptr;
+    return fail(h, SFB_ERR_CUDA, "uploading the CSC map failed: %s", msg);
+  }
+  return SFB_OK;
+}
+
+int sfb_qp_solve_sparse_batch_csc_f64(sfb_handle_t h, sfb_qp_sparse_pattern_t pattern, const sfb_qp_params* prm,
+                                      int64_t batch, const double* P_vals, const double* q, const double* A_vals_csc,
+                                      const double* l, const double* u, const double* warm_x, const double* warm_y,
+                                      double* out_x, double* out_y, double* out_obj, int32_t* out_status,
+                                      uint32_t* out_iter, int8_t* out_active, uint32_t* out_flags)
+{
+  if (!h) return SFB_ERR_INVALID_ARGUMENT;
+  if (!pattern) return fail(h, SFB_ERR_INVALID_ARGUMENT, "pattern is NULL");
+  const int nnz = pattern->sym.nnzA;
+  if (nnz == 0 || batch <= 0)
+    return sfb_qp_solve_sparse_batch_f64(h, pattern, prm, batch, P_vals, q, A_vals_csc, l, u, warm_x, warm_y, out_x, out_y, out_obj,
+                                         out_status, out_iter, out_active, out_flags);
+  if ((int)pattern->csc2csr.size() != nnz) return fail(h, SFB_ERR_INVALID_ARGUMENT, "pattern was not analysed with sfb_qp_sparse_analyze_csc");
+  if (!A_vals_csc) return fail(h, SFB_ERR_INVALID_ARGUMENT, "required pointer is NULL");
+  SFB_CUDA(h, cudaSetDevice(h->device));
+  if (mem_space(A_vals_csc) == 1) {  // device: gather kernel into a workspace, then the CSR entry point
+    int rc = ensure_scratch(h, h->csc_tmp, sizeof(double) * (size_t)nnz * (size_t)batch, h->stream);
+    if (rc != SFB_OK) return rc;
+    double* tmp = static_cast<double*>(h->csc_tmp.dev);
+    const long long total = (long long)batch * nnz;
+    const int grid = (int)std::min<long long>((total + 255) / 256, (long long)h->prop.multiProcessorCount * 16);
+    csc_to_csr_values_kernel<double><<<grid, 256, 0, h->stream>>>(A_vals_csc, tmp, pattern->d_csc2csr, nnz, batch);
+    SFB_CUDA(h, cudaGetLastError());
+    h->launches += 1;
+    return sfb_qp_solve_sparse_batch_f64(h, pattern, prm, batch, P_vals, q, tmp, l, u, warm_x, warm_y, out_x, out_y, out_obj, out_status,
+                                         out_iter, out_active, out_flags);
+  }
+  std::vector<double> tmp((size_t)nnz * (size_t)batch);  // host: permute in place of the staging copy's source
+  for (int64_t b = 0; b < batch; ++b)
+    for (int e = 0; e < nnz; ++e) tmp[(size_t)b * nnz + e] = A_vals_csc[(size_t)b * nnz + pattern->csc2csr[e]];
+  return sfb_qp_solve_sparse_batch_f64(h, pattern, prm, batch, P_vals, q, tmp.data(), l, u, warm_x, warm_y, out_x, out_y, out_obj,
+                                       out_status, out_iter, out_active, out_flags);
 }
 
 }  // extern "C"

@@ -48,17 +48,21 @@ class QuadraticProgramSparse:
 class SparsePattern:
     """Owns one sfb_qp_sparse_pattern_t: ordering, symbolic L D L^T factor and assembly schedules on the device."""
 
-    def __init__(self, n: int, m: int, P_colptr, P_rowidx, A_rowptr, A_colidx, handle: Handle | None = None):
+    def __init__(self, n: int, m: int, P_colptr, P_rowidx, A_rowptr, A_colidx, handle: Handle | None = None, a_csc: bool = False):
+        """a_csc = True: A is given column-compressed like OSQP's csc_matrix (compat/osqp.hpp:36-49): A_rowptr / A_colidx then
+        hold A's COLUMN pointers [n+1] / ROW indices, and solve_sparse_batch expects A_vals in that order."""
         self.n, self.m = int(n), int(m)
+        self.a_csc = bool(a_csc)
         i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
         self.P_colptr, self.P_rowidx, self.A_rowptr, self.A_colidx = i32(P_colptr), i32(P_rowidx), i32(A_rowptr), i32(A_colidx)
-        assert self.P_colptr.shape == (n + 1,) and self.A_rowptr.shape == (m + 1,)
+        assert self.P_colptr.shape == (n + 1,) and self.A_rowptr.shape == ((n if a_csc else m) + 1,)
         self.nnzP, self.nnzA = int(self.P_colptr[-1]), int(self.A_rowptr[-1])
         self.handle = handle or default_handle(0)
         self._p = C.c_void_p()
         ip = lambda a: a.ctypes.data_as(C.c_void_p)
-        self.handle.check(_lib.lib().sfb_qp_sparse_analyze(self.handle.raw, self.n, self.m, ip(self.P_colptr), ip(self.P_rowidx),
-                                                            ip(self.A_rowptr), ip(self.A_colidx), C.byref(self._p)))
+        analyze = _lib.lib().sfb_qp_sparse_analyze_csc if a_csc else _lib.lib().sfb_qp_sparse_analyze
+        self.handle.check(analyze(self.handle.raw, self.n, self.m, ip(self.P_colptr), ip(self.P_rowidx),
+                                  ip(self.A_rowptr), ip(self.A_colidx), C.byref(self._p)))
         nnzL, flops = C.c_int64(), C.c_int64()
         self.perm = np.empty(n, np.int32)
         _lib.lib().sfb_qp_sparse_pattern_info(self._p, C.byref(nnzL), C.byref(flops), ip(self.perm))
@@ -144,6 +148,9 @@ def solve_sparse_batch(pattern: SparsePattern, P_vals, q, A_vals, l, u, prm: QPS
                                 status=np.empty((B,), np.int32), iter=np.empty((B,), np.uint32),
                                 active=np.empty((B, m), np.int8), flags=np.empty((B,), np.uint32))
     fn = _lib.lib().sfb_qp_solve_sparse_batch_f64 if f64 else _lib.lib().sfb_qp_solve_sparse_batch_f32
+    if pattern.a_csc:
+        assert f64, "the CSC ingestion entry point is fp64 (OSQP's c_float)"
+        fn = _lib.lib().sfb_qp_solve_sparse_batch_csc_f64
     rc = fn(h.raw, pattern.raw, C.byref(cprm), B, _ptr(P_vals), _ptr(q), _ptr(A_vals), _ptr(l), _ptr(u), _ptr(warm_x),
             _ptr(warm_y), _ptr(out.x), _ptr(out.y), _ptr(out.obj), _ptr(out.status), _ptr(out.iter), _ptr(out.active),
             _ptr(out.flags))
