@@ -407,7 +407,9 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --batch instances per GPU (default); strong: --batch instances in total, sharded over the GPUs")
     ap.add_argument("--config", default="dense", choices=["dense", "ekf", "asif", "mpc"])
-    ap.add_argument("--chunks", type=int, default=8, help="--config ekf: chunks of the compute / exchange pipeline")
+    ap.add_argument("--chunks", type=int, default=1,
+                    help="--config ekf: chunks of the compute / exchange pipeline (measured on 8 GPUs: 1 chunk 0.60 ms, 2: 0.68, 4: 0.92, "
+                         "8: 1.01 -- the kernel is 7 %% of the exchange, splitting only adds latency; profiles/r02_bench_8gpu_ekf_chunks.jsonl)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
