@@ -1,6 +1,6 @@
 """Pins the CPU oracle's EKF algebra with the reference's closed-form tests (tests/test_ekf.cpp:50-180).
 
-CPU only.  State propagation (g_hat (+) tau*f) is host-side group arithmetic and is covered in test_ekf_host.py.
+CPU only.  State propagation (g_hat (+) tau*f) is host-side group arithmetic and is covered in tests/cpp/test_ekf_overlay.cpp (the same tests through the C++ EKF overlay).
 """
 import numpy as np
 import pytest
