@@ -224,6 +224,13 @@ int sfb_qp_sparse_pattern_destroy(sfb_qp_sparse_pattern_t p);
 int sfb_qp_sparse_symbolic(int n, int m, const int32_t* P_colptr, const int32_t* P_rowidx, const int32_t* A_rowptr,
                            const int32_t* A_colidx, int64_t* nnz_L, int64_t* factor_flops, int32_t* perm_out,
                            int32_t* L_colptr_out);
+/* Host-only self-check of the schedules of the on-chip (one CTA per instance) sparse kernel: analyses the pattern with
+ * ordering = -1 (cost model picks), 0 (minimum degree) or 1 (nested dissection), executes assembly, supernodal
+ * factorisation, diagonal-block inversion and the staged triangular sweeps on the host on seeded random values and compares
+ * the solution of (L D L^T) x = b with a dense Cholesky solve.  info_out [8] = {supernodes, levels, factor slots nW,
+ * structural nnz(L), multiply-adds, largest supernode, sweep stages, ordering used}; max_rel_err_out = the largest relative error. */
+int sfb_qp_sparse_cta_selfcheck(int n, int m, const int32_t* P_colptr, const int32_t* P_rowidx, const int32_t* A_rowptr,
+                                const int32_t* A_colidx, int ordering, int64_t* info_out, double* max_rel_err_out);
 /* nnz of the strictly lower factor L, multiply-adds of one numeric factorisation, ordering (perm_out [n], may be NULL) */
 int sfb_qp_sparse_pattern_info(sfb_qp_sparse_pattern_t p, int64_t* nnz_L, int64_t* factor_flops, int32_t* perm_out);
 

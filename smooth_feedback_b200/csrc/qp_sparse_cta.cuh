@@ -1,0 +1,875 @@
+// qp_sparse_cta.cuh -- ON-CHIP batched sparse operator-splitting QP solver for sm_100a: one CTA per instance, the
+// supernodal L D L^T factor, Abar, P, the vectors of the iteration and every index table of the hot loops resident in
+// shared memory.
+//
+// Replaces the sparse branches of (pettni/smooth_feedback @ 9a08971)
+//   QPSolver<QuadraticProgramSparse>::solve   include/smooth/feedback/qp_solver.hpp:343-568 (fill :380-397,
+//                                             SimplicialLDLT factorize :424-426, permuted solve :456-460)
+//   QPSolver::scale / check_stopping          :673-730 / :574-644
+//   detail::polish_qp                         :92-204
+// i.e. the call MPC::operator() makes at mpc.hpp:491 -- same algorithm and arithmetic as qp_sparse_tiled.cuh (which
+// stays as the fallback for patterns whose working set does not fit in shared memory), different machine mapping:
+//   * HBM traffic is the compulsory bytes only (inputs once, outputs once); the tiled kernel re-streamed Abar and the
+//     factor from HBM in every iteration (27 MB per solve at n = m = 422);
+//   * the triangular sweeps are 4 x (supernode levels) barrier-separated stages of independent dot products over dense
+//     supernodal blocks with INVERTED diagonal blocks (qp_sparse_cta_host.hpp) instead of ~850 dependent steps;
+//   * the numeric factorisation advances all supernodes of one level column by column together (each with its own
+//     warps), then pushes their rank-s updates into the levels above;
+//   * assembly of Abar^T R Abar runs colour by colour (rows of one colour touch disjoint columns): deterministic, no atomics;
+//   * nothing on a dependent chain is fetched from global memory: the first version kept the schedules in global memory
+//     and spent 2.7 k cycles per sweep stage on chains of L2 round trips (profiles/r02_cta_phases.txt).
+// The reduced system (Pbar + sigma I + Abar^T R Abar) xt = sigma x - qbar + Abar^T (R z - y) is the tiled / dense kernels'.
+// CTAs are persistent and pull instances from a work counter (iteration counts differ between instances).
+
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sfb.h"
+#include "qp_dense_group.cuh"  // Num<T>, kStatusUnset, global_timer_ns
+#include "qp_sparse_cta_host.hpp"
+
+namespace sfb {
+
+struct CtaPattern
+{
+  int n, m, nnzP, nnzA, nW, ns, smax, nstages, nrounds, nfacrounds, nints;
+  unsigned tscalars;  // scalars of type T in front of the integer tables (cta_smem_scalars)
+  int ioff[kI_count];
+  const int *ints;    // the tables copied into shared memory (CtaSymbolic::smem_ints)
+  const int *perm, *iperm, *P_rowp, *P_colp, *P_tgt, *PR_ptr, *PR_col, *PR_slot, *PS_ptr, *PS_col, *PS_slot, *PC_ptr, *PC_slot, *asm_sync;
+  const int2* asm_desc;
+};
+
+template <typename T, typename TIO = T> struct CtaArgs
+{
+  CtaPattern pat;
+  const TIO *P, *q, *A, *l, *u, *warm_x, *warm_y;
+  TIO *out_x, *out_y, *out_obj;
+  int32_t* out_status;
+  uint32_t* out_iter;
+  int8_t* out_active;
+  uint32_t* out_flags;
+  T* ws;  // per CTA: n + m scalars (x and y of the previous stop check)
+  unsigned long long* work_counter;
+  long long batch;
+  sfb_qp_params prm;
+  unsigned max_iter_eff;
+  int dinf_guard;
+  int mode;  // 0 = solve, 2 = polish only (see SpArgs::mode)
+  unsigned long long* prof;  // dev instrumentation (SFB_CTA_PROF=1): cycles per phase summed over CTAs, nullptr otherwise
+};
+
+enum CtaPhase { kPhLoad = 0, kPhScale, kPhPrep, kPhAssemble, kPhFactorCols, kPhFactorExt, kPhFactorInv, kPhRhs, kPhSolve, kPhUpdate,
+                kPhCheck, kPhPolish, kPhOut, kPhCount };
+
+// a vector in shared memory, addressed through the extern symbol (LDS / STS with 32-bit addresses)
+template <typename T> struct SV
+{
+  unsigned off;
+  __device__ __forceinline__ T& operator[](int i) const
+  {
+    extern __shared__ __align__(16) unsigned char cta_smem_raw[];
+    return reinterpret_cast<T*>(cta_smem_raw)[off + (unsigned)i];
+  }
+};
+
+__device__ __forceinline__ int lo16(int x) { return (int)((unsigned)x & 0xffffu); }
+__device__ __forceinline__ int hi16(int x) { return (int)((unsigned)x >> 16); }
+
+template <typename T, typename TIO, int NT> struct CtaSolver
+{
+  static constexpr int NW = NT / 32;
+  using V = SV<T>;
+  const CtaArgs<T, TIO>& a;
+  const CtaPattern& S;
+  const int n, m, nW, tid, lane, warp;
+  V W, A, P;                          // factor slots (+ D, 1/D), Abar (CSR order), P as given
+  V qb, x, v, sv, sx, t1, t2;         // n-vectors (permuted order); v / sv: the two buffers of the sweeps, sv = result
+  V sy, rho, rinv, z, y, w, lo, hi;   // m-vectors
+  V red;
+  T *xold, *yold;                     // global: iterate at the previous stop check
+  unsigned ibase;                     // byte offset of the integer tables
+  T c;
+  T qn_us;                            // max |q| (unscaled)
+  long long b = 0;                    // current instance
+  unsigned long long* prof = nullptr;
+  long long tlast = 0;
+
+  __device__ CtaSolver(const CtaArgs<T, TIO>& args)
+      : a(args), S(args.pat), n(args.pat.n), m(args.pat.m), nW(args.pat.nW), tid(threadIdx.x), lane(threadIdx.x & 31), warp(threadIdx.x >> 5)
+  {
+    unsigned o = 0;
+    auto take = [&](unsigned len) { V r{o}; o += len; return r; };
+    W = take(nW + 2 * n); A = take(S.nnzA); P = take(S.nnzP);
+    qb = take(n + 1); x = take(n + 1); v = take(n + 1); sv = take(n + 1); sx = take(n + 1); t1 = take(n + 1); t2 = take(n + 1);
+    sy = take(m + 1); rho = take(m + 1); rinv = take(m + 1); z = take(m + 1); y = take(m + 1); w = take(m + 1); lo = take(m + 1); hi = take(m + 1);
+    red = take(kCtaRed);
+    ibase = S.tscalars * (unsigned)sizeof(T);
+    xold = a.ws + (size_t)blockIdx.x * (size_t)(n + m);
+    yold = xold + n;
+    c = T(1);
+    qn_us = T(0);
+  }
+
+  __device__ __forceinline__ const int* itab(int which) const
+  {
+    extern __shared__ __align__(16) unsigned char cta_smem_raw[];
+    return reinterpret_cast<const int*>(cta_smem_raw + ibase) + S.ioff[which];
+  }
+  __device__ __forceinline__ const unsigned short* htab(int which) const { return reinterpret_cast<const unsigned short*>(itab(which)); }
+  __device__ void load_tables()
+  {
+    extern __shared__ __align__(16) unsigned char cta_smem_raw[];
+    int* dst = reinterpret_cast<int*>(cta_smem_raw + ibase);
+    for (int k = tid; k < S.nints; k += NT) dst[k] = __ldg(S.ints + k);
+    __syncthreads();
+  }
+  // inputs of the current instance, read in place (global, read-only)
+  __device__ __forceinline__ T qg(int pj) const { return (T)__ldg(a.q + b * (long long)n + __ldg(S.perm + pj)); }
+  __device__ __forceinline__ T lg(int i) const { return (T)__ldg(a.l + b * (long long)m + i); }
+  __device__ __forceinline__ T ug(int i) const { return (T)__ldg(a.u + b * (long long)m + i); }
+
+  __device__ __forceinline__ void mark(int phase)
+  {
+    if (prof != nullptr && tid == 0) {
+      const long long t = clock64();
+      atomicAdd(prof + phase, (unsigned long long)(t - tlast));
+      tlast = t;
+    }
+  }
+
+  // ---------------------------------------------------------------- CTA reductions (results on every thread, fixed order)
+  // K values at once; bit k of MAXMASK: maximum instead of sum
+  template <int K, unsigned MAXMASK> __device__ __forceinline__ void reduce(T (&val)[K])
+  {
+    static_assert(K * NW <= kCtaRed, "reduction scratch too small");
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const T other = __shfl_xor_sync(0xffffffffu, val[k], o);
+        val[k] = ((MAXMASK >> k) & 1u) ? fmax(val[k], other) : val[k] + other;
+      }
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) red[warp * K + k] = val[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      T acc = red[k];
+#pragma unroll
+      for (int wv = 1; wv < NW; ++wv) acc = ((MAXMASK >> k) & 1u) ? fmax(acc, red[wv * K + k]) : acc + red[wv * K + k];
+      val[k] = acc;
+    }
+    __syncthreads();
+  }
+  __device__ __forceinline__ T bmax(T val) { T r[1] = {val}; reduce<1, 1u>(r); return r[0]; }
+  __device__ __forceinline__ T bsum(T val) { T r[1] = {val}; reduce<1, 0u>(r); return r[0]; }
+  __device__ __forceinline__ bool bany(bool pr) { return __syncthreads_or(pr ? 1 : 0) != 0; }
+
+  // ---------------------------------------------------------------- QPSolver::scale, qp_solver.hpp:673-730
+  // Same evaluation as qp_sparse_tiled.cuh::scale (bit-exact against the CPU restatement: max / abs / mul / div / sqrt only,
+  // products in the reference's order, the column mean summed sequentially in the original column order).
+  __device__ void scale()
+  {
+    const unsigned short *arp = htab(kI_Arowptr), *acol = htab(kI_Acol), *atp = htab(kI_ATptr), *atr = htab(kI_ATrow), *ats = htab(kI_ATslot);
+    for (int j = tid; j < n; j += NT) sx[j] = T(1);
+    for (int i = tid; i < m; i += NT) sy[i] = T(1);
+    for (int pj = tid; pj < n; pj += NT) {
+      T g = T(0);
+      for (int e = S.PC_ptr[pj]; e < S.PC_ptr[pj + 1]; ++e) g = fmax(g, fabs(P[__ldg(S.PC_slot + e)]));
+      t1[pj] = g;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      T mean = T(0);
+      for (int j = 0; j < n; ++j) {
+        T g = t1[__ldg(S.iperm + j)];
+        if (g == T(0)) g = T(1);
+        mean += g;
+      }
+      mean /= T(n);
+      red[0] = T(1) / fmax(fmax(T(1e-6), mean), qn_us);
+    }
+    __syncthreads();
+    c = red[0];
+    __syncthreads();
+    const T cc = c;
+    int it = 0;
+    T dev;
+    do {
+      for (int pj = tid; pj < n; pj += NT) {
+        const T sxj = sx[pj];
+        T g = T(0);
+        for (int e = S.PC_ptr[pj]; e < S.PC_ptr[pj + 1]; ++e) {
+          const int sl = __ldg(S.PC_slot + e);
+          g = fmax(g, fabs(((cc * sx[__ldg(S.P_rowp + sl)]) * sxj) * P[sl]));
+        }
+        const int e1 = atp[pj + 1];
+#pragma unroll 4
+        for (int e = atp[pj]; e < e1; ++e) g = fmax(g, fabs((sy[atr[e]] * sxj) * A[ats[e]]));
+        t1[pj] = g;
+      }
+      for (int i = tid; i < m; i += NT) {
+        const T syi = sy[i];
+        T g = T(0);
+        const int e1 = arp[i + 1];
+#pragma unroll 4
+        for (int e = arp[i]; e < e1; ++e) g = fmax(g, fabs((syi * sx[acol[e]]) * A[e]));
+        w[i] = g;
+      }
+      __syncthreads();  // every maximum is formed before any scale factor changes
+      dev = T(0);
+      for (int j = tid; j < n; j += NT) {
+        T g = t1[j];
+        if (g == T(0)) g = T(1);
+        sx[j] = sqrt(T(1) / fmax(g, T(1e-8))) * sx[j];
+        dev = fmax(dev, fabs(g - T(1)));
+      }
+      for (int i = tid; i < m; i += NT) {
+        T g = w[i];
+        if (g == T(0)) g = T(1);
+        sy[i] = sqrt(T(1) / fmax(g, T(1e-8))) * sy[i];
+        dev = fmax(dev, fabs(g - T(1)));
+      }
+      dev = bmax(dev);
+    } while (it++ < 10 && dev > T(0.1));
+  }
+
+  // ---------------------------------------------------------------- W <- shift I + c Sx triu(P) Sx + Abar^T diag(wt) Abar
+  __device__ void assemble(T shift, const V& wt)
+  {
+    for (int e = tid; e < nW; e += NT) W[e] = T(0);
+    for (int k = tid; k < n; k += NT) W[nW + k] = shift;
+    __syncthreads();
+    for (int e = tid; e < S.nnzP; e += NT) {  // compressed P: distinct targets
+      const int t = __ldg(S.P_tgt + e);
+      if (t >= 0) W[t] += ((c * sx[__ldg(S.P_rowp + e)]) * sx[__ldg(S.P_colp + e)]) * P[e];  // qp_solver.hpp:386
+    }
+    __syncthreads();
+    // colour by colour; the descriptors of four rounds are requested together (one L2 round trip per four rounds)
+    constexpr int U = 4;
+    for (int r0 = 0; r0 < S.nrounds; r0 += U) {
+      int2 d[U];
+      int fl[U];
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const bool in = r0 + k < S.nrounds;
+        d[k] = in ? __ldg(S.asm_desc + (size_t)(r0 + k) * NT + tid) : make_int2(0, -1);
+        fl[k] = in ? __ldg(S.asm_sync + r0 + k) : 0;
+      }
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        if (d[k].y != -1) {
+          const T wr = wt[hi16(d[k].y)];
+          if (wr != T(0)) W[lo16(d[k].y)] += (wr * A[lo16(d[k].x)]) * A[hi16(d[k].x)];
+        }
+        if (fl[k]) __syncthreads();
+      }
+    }
+  }
+
+  // ---------------------------------------------------------------- supernodal right-looking L D L^T in place
+  // Afterwards: below blocks hold L, diagonal blocks hold X' = -(strict lower part of L_SS^-1), W[nW + k] = D_k,
+  // W[nW + n + k] = 1 / D_k.  False on a non-positive pivot.
+  __device__ bool factor()
+  {
+    const T inf = Num<T>::inf();
+    bool ok = true;
+    const int *rounds = itab(kI_facrounds), *fext = itab(kI_facext), *fwarp = itab(kI_facwarp), *sn = itab(kI_sntab), *extptr = itab(kI_extptr),
+              *extw = itab(kI_extword);
+    for (int r = 0; r < S.nfacrounds; ++r) {
+      const int maxs = rounds[4 * r], cnt = lo16(rounds[4 * r + 1]), totw = hi16(rounds[4 * r + 1]), e0 = rounds[4 * r + 2], w0 = rounds[4 * r + 3];
+      int q = -1, rank = 0, nw = 1;
+      if (warp < totw) {
+        const unsigned wd = (unsigned)fwarp[w0 + warp];
+        q = (int)(wd & 0xffffu); rank = (int)((wd >> 16) & 0xffu); nw = (int)(wd >> 24);
+      }
+      int c0 = 0, s = 0, t = 0, db = 0, bb = 0;
+      if (q >= 0) {
+        const int4 h = *reinterpret_cast<const int4*>(sn + 8 * q);
+        c0 = h.x; s = h.y; t = h.z; db = h.w; bb = sn[8 * q + 4];
+      }
+      const int gsize = nw * 32, gtid = rank * 32 + lane;
+      __syncthreads();  // the external updates of the previous round are complete
+      if (q >= 0 && gtid == 0) W[nW + n + c0] = T(1) / W[nW + c0];
+      for (int kc = 0; kc <= maxs; ++kc) {
+        __syncthreads();
+        if (q < 0 || kc > s) continue;
+        if (kc > 0) {  // column kc - 1 is final: scale it (nobody reads it during this step)
+          const T dprev = W[nW + n + c0 + kc - 1];
+          const int nd = s - kc, nsc = nd + t;
+          for (int p = gtid; p < nsc; p += gsize) {
+            const int i = kc + p;
+            const int slot = (p < nd) ? db + i * (i - 1) / 2 + kc - 1 : bb + (p - nd) * s + kc - 1;
+            W[slot] *= dprev;
+          }
+        }
+        if (kc == s) continue;
+        const T d = W[nW + c0 + kc];
+        if (!(d > T(0)) || !(d < inf)) ok = false;
+        const T dinv = W[nW + n + c0 + kc];
+        const int ndiag = s - kc - 1, nrows = ndiag + t;
+        int nch = 1;
+        while (nch < 32 && 2 * nch * nrows <= gsize) nch <<= 1;
+        const int prow = gtid / nch, ch = gtid % nch, rstep = gsize / nch;
+        const int colk = db + kc;  // entry (j, kc) of the diagonal block: colk + j (j - 1) / 2
+        for (int p = prow; p < nrows; p += rstep) {
+          const bool diag = p < ndiag;
+          const int i = kc + 1 + p;
+          const int rb = diag ? db + i * (i - 1) / 2 : bb + (p - ndiag) * s;
+          const int jmax = diag ? i : s - 1;
+          const T vi = W[rb + kc] * dinv;
+          constexpr int U = 4;
+          for (int j0 = kc + 1 + ch; j0 <= jmax; j0 += U * nch) {
+            T vj[U], old[U];
+            int tg[U];
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+              const int j = j0 + k * nch;
+              tg[k] = -1;
+              if (j <= jmax) {
+                vj[k] = W[colk + j * (j - 1) / 2];
+                tg[k] = (diag && j == i) ? nW + c0 + j : rb + j;
+                old[k] = W[tg[k]];
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+              if (tg[k] >= 0) {
+                const T nv = old[k] - vi * vj[k];
+                W[tg[k]] = nv;
+                if (tg[k] == nW + c0 + kc + 1) W[nW + n + c0 + kc + 1] = T(1) / nv;  // the next pivot's reciprocal, off everyone else's path
+              }
+            }
+          }
+        }
+      }
+      __syncthreads();
+      mark(kPhFactorCols);
+      // external updates, one supernode after the other (supernodes of one round may share targets): L D L^T of the below block
+      for (int k = 0; k < cnt; ++k) {
+        const int qe = fext[e0 + k];
+        const int ec0 = sn[8 * qe], es = sn[8 * qe + 1], ebb = sn[8 * qe + 4];
+        const int p1 = extptr[qe + 1];
+        for (int p = extptr[qe] + tid; p < p1; p += NT) {
+          const unsigned wd = (unsigned)extw[p];
+          const int ra = ebb + (int)(wd & 0xffu) * es, rb = ebb + (int)((wd >> 8) & 0xffu) * es, tg = (int)(wd >> 16);
+          T acc0 = T(0), acc1 = T(0);
+          int cc = 0;
+          for (; cc + 1 < es; cc += 2) {
+            acc0 += (W[ra + cc] * W[nW + ec0 + cc]) * W[rb + cc];
+            acc1 += (W[ra + cc + 1] * W[nW + ec0 + cc + 1]) * W[rb + cc + 1];
+          }
+          if (cc < es) acc0 += (W[ra + cc] * W[nW + ec0 + cc]) * W[rb + cc];
+          W[tg] -= acc0 + acc1;
+        }
+        __syncthreads();
+      }
+      mark(kPhFactorExt);
+    }
+    // invert the unit-lower diagonal blocks in place, row step by row step for all supernodes at once; a thread owns
+    // columns.  Row i of every block is read (as L) by all threads before anyone overwrites it (as X').
+    {
+      constexpr int KS = 4;  // n <= KS * NT (checked on the host)
+      int cdb[KS], cs[KS], ckc[KS];
+      const unsigned short* colsn = htab(kI_colsn);
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const int k = tid + ks * NT;
+        cs[ks] = 0; cdb[ks] = 0; ckc[ks] = 0;
+        if (k < n) {
+          const int q = colsn[k];
+          cs[ks] = sn[8 * q + 1]; cdb[ks] = sn[8 * q + 3]; ckc[ks] = k - sn[8 * q];
+        }
+      }
+      for (int i = 1; i < S.smax; ++i) {
+        T res[KS];
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          if (ckc[ks] < i && i < cs[ks]) {
+            const int ri = cdb[ks] + i * (i - 1) / 2, kc = ckc[ks];
+            T acc0 = W[ri + kc], acc1 = T(0);
+            int j = kc + 1;
+            for (; j + 1 < i; j += 2) {
+              acc0 -= W[ri + j] * W[cdb[ks] + j * (j - 1) / 2 + kc];
+              acc1 -= W[ri + j + 1] * W[cdb[ks] + (j + 1) * j / 2 + kc];
+            }
+            if (j < i) acc0 -= W[ri + j] * W[cdb[ks] + j * (j - 1) / 2 + kc];
+            res[ks] = acc0 + acc1;
+          }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+          if (ckc[ks] < i && i < cs[ks]) W[cdb[ks] + i * (i - 1) / 2 + ckc[ks]] = res[ks];
+      }
+    }
+    ok = !bany(!ok);
+    mark(kPhFactorInv);
+    return ok;
+  }
+
+  // ---------------------------------------------------------------- v <- (L D L^T)^-1 v, result in sv
+  // Stage list of qp_sparse_cta_host.hpp; G lanes cooperate on one output (G = the largest power of two that keeps every
+  // output of the stage in one round).  Ends with a barrier.
+  __device__ void solve()
+  {
+    const int *stages = itab(kI_stages), *sn = itab(kI_sntab), *pout = itab(kI_pushout), *ptask = itab(kI_pushtask);
+    const unsigned short *levcols = htab(kI_levcols), *colsn = htab(kI_colsn), *rl = htab(kI_rlist);
+    for (int st = 0; st < S.nstages; ++st) {
+      const int kind = stages[4 * st], first = stages[4 * st + 1], count = stages[4 * st + 2];
+      int G = 1;
+      while (G < 32 && 2 * G * count <= NT) G <<= 1;
+      const int ngroups = NT / G;
+      if (kind == kStageFwdPush) {
+        const int group = tid / G, g = tid % G;
+        for (int o0 = 0; o0 < count; o0 += ngroups) {
+          const int o = o0 + group;
+          const bool valid = o < count;
+          T acc = T(0);
+          int dst = 0;
+          if (valid) {
+            const int w0 = pout[first + o], w1 = pout[first + o + 1];
+            dst = lo16(w0);
+            for (int k = hi16(w0); k < hi16(w1); ++k) {
+              const int tw = ptask[k];
+              const int q = lo16(tw);
+              const int c0 = sn[8 * q], s = sn[8 * q + 1], slot0 = sn[8 * q + 4] + hi16(tw) * s;
+#pragma unroll 4
+              for (int cc = g; cc < s; cc += G) acc += W[slot0 + cc] * sv[c0 + cc];
+            }
+          }
+          for (int off = G >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+          if (valid && g == 0) v[dst] -= acc;
+        }
+      } else if (kind == kStageFwdDiag) {
+        const int group = tid / G, g = tid % G;  // lanes of a group are adjacent: contiguous reads of a row
+        for (int o0 = 0; o0 < count; o0 += ngroups) {
+          const int o = o0 + group;
+          const bool valid = o < count;
+          T acc = T(0);
+          int k = 0;
+          if (valid) {
+            k = levcols[first + o];
+            const int q = colsn[k];
+            const int c0 = sn[8 * q], i = k - c0, slot0 = sn[8 * q + 3] + i * (i - 1) / 2;
+#pragma unroll 4
+            for (int cc = g; cc < i; cc += G) acc += W[slot0 + cc] * v[c0 + cc];
+          }
+          for (int off = G >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+          if (valid && g == 0) sv[k] = v[k] - acc;
+        }
+      } else {
+        const int OPW = 32 / G;  // outputs per warp; lanes of adjacent outputs are adjacent: contiguous reads across columns
+        const int g = lane / OPW, ow = lane % OPW;
+        for (int o0 = 0; o0 < count; o0 += ngroups) {
+          const int o = o0 + warp * OPW + ow;
+          const bool valid = o < count;
+          T acc = T(0);
+          int k = 0;
+          if (valid) {
+            k = levcols[first + o];
+            const int q = colsn[k];
+            const int4 h = *reinterpret_cast<const int4*>(sn + 8 * q);  // c0, s, t, dbase
+            const int kc = k - h.x;
+            if (kind == kStageBwdPull) {
+              const int slot0 = sn[8 * q + 4] + kc, rb = sn[8 * q + 5];
+#pragma unroll 4
+              for (int r = g; r < h.z; r += G) acc += W[slot0 + r * h.y] * sv[rl[rb + r]];
+            } else {
+              const int base = h.w + kc;
+#pragma unroll 4
+              for (int i = kc + 1 + g; i < h.y; i += G) acc += W[base + i * (i - 1) / 2] * v[h.x + i];
+            }
+          }
+          for (int off = 16; off >= OPW; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+          if (valid && g == 0) {
+            if (kind == kStageBwdPull) v[k] = W[nW + n + k] * sv[k] - acc;
+            else sv[k] = v[k] - acc;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  // sum_i Abar_ij in_i for column j
+  __device__ __forceinline__ T At_col_dot(int j, const V& in) const
+  {
+    const unsigned short *atp = htab(kI_ATptr), *atr = htab(kI_ATrow), *ats = htab(kI_ATslot);
+    const int e1 = atp[j + 1];
+    T acc = T(0);
+#pragma unroll 4
+    for (int e = atp[j]; e < e1; ++e) acc += A[ats[e]] * in[atr[e]];
+    return acc;
+  }
+  // out[j] = fin(j, sum_i Abar_ij in_i)
+  template <class FIN> __device__ __forceinline__ void At_gather(const V& in, const V& out, FIN fin)
+  {
+    for (int j = tid; j < n; j += NT) out[j] = fin(j, At_col_dot(j, in));
+    __syncthreads();
+  }
+  // sum_k sym(Pbar)_jk in_k  (upper triangle of c Sx P Sx mirrored)
+  __device__ __forceinline__ T Psym_row_dot(int j, const V& in) const
+  {
+    T acc = T(0);
+    for (int e = S.PS_ptr[j]; e < S.PS_ptr[j + 1]; ++e) {
+      const int sl = __ldg(S.PS_slot + e);
+      acc += (((c * sx[__ldg(S.P_rowp + sl)]) * sx[__ldg(S.P_colp + sl)]) * P[sl]) * in[__ldg(S.PS_col + e)];
+    }
+    return acc;
+  }
+  __device__ __forceinline__ T A_row_dot(int i, const V& vec) const
+  {
+    const unsigned short *arp = htab(kI_Arowptr), *acol = htab(kI_Acol);
+    const int e1 = arp[i + 1];
+    T acc = T(0);
+#pragma unroll 4
+    for (int e = arp[i]; e < e1; ++e) acc += A[e] * vec[acol[e]];
+    return acc;
+  }
+
+  // ---------------------------------------------------------------- check_stopping, qp_solver.hpp:574-644
+  // Same evaluation as qp_sparse_tiled.cuh::check_stopping.  Clobbers v, w, t1, t2.
+  __device__ int check_stopping(const sfb_qp_params& prm, bool dinf_guard)
+  {
+    const T eps_abs = T(prm.eps_abs), eps_rel = T(prm.eps_rel);
+    const T eps_pinf = T(prm.eps_primal_inf), eps_dinf = T(prm.eps_dual_inf);
+    const T inf = Num<T>::inf();
+    T r1[3] = {T(0), T(0), T(0)};  // dxn, Edy (max), qdx (sum)
+    for (int j = tid; j < n; j += NT) {
+      const T xj = x[j];
+      const T d = xj - xold[j];
+      t1[j] = sx[j] * xj;       // x_us   :481
+      t2[j] = d;                // scaled dx
+      const T dus = sx[j] * d;  // dx_us  :484
+      v[j] = dus;
+      r1[0] = fmax(r1[0], fabs(dus));
+      r1[2] += qg(j) * dus;
+    }
+    for (int i = tid; i < m; i += NT) {
+      const T d = y[i] - yold[i];
+      w[i] = d;
+      r1[1] = fmax(r1[1], fabs(sy[i] * d / c));  // :485
+    }
+    reduce<3, 0x3u>(r1);
+    const T qn = qn_us, dxn = r1[0], Edy = r1[1], qdx = r1[2];
+    T r2[4] = {T(0), T(0), T(0), T(0)};  // n_Ax, n_r, n_z (max), s_pinf (sum)
+    bool pinf_blocked = false, dinf_rows_bad = false;
+    for (int i = tid; i < m; i += NT) {
+      T ax = A_row_dot(i, x), adx = A_row_dot(i, t2);
+      const T syinv = T(1) / sy[i];
+      ax *= syinv;
+      adx *= syinv;
+      const T zus = syinv * z[i];  // :483
+      r2[0] = fmax(r2[0], fabs(ax));
+      r2[1] = fmax(r2[1], fabs(ax - zus));
+      r2[2] = fmax(r2[2], fabs(zus));
+      const T dyus = sy[i] * w[i] / c;
+      const T li = lg(i), ui = ug(i);
+      if (ui != inf) r2[3] += ui * fmax(T(0), dyus);  // :602-617
+      else if (dyus > eps_pinf * Edy) pinf_blocked = true;
+      if (li != -inf) r2[3] += li * fmin(T(0), dyus);
+      else if (dyus < -eps_pinf * Edy) pinf_blocked = true;
+      bool okrow;
+      if (ui == inf) okrow = (adx >= -eps_dinf * dxn);  // :631-639
+      else if (li == -inf) okrow = (adx <= eps_dinf * dxn);
+      else okrow = (fabs(adx) < eps_dinf * dxn);
+      dinf_rows_bad = dinf_rows_bad || !okrow;
+    }
+    reduce<4, 0x7u>(r2);
+    const T n_Ax = r2[0], n_r = r2[1], n_z = r2[2];
+    T s_pinf = r2[3];
+    pinf_blocked = bany(pinf_blocked);
+    const bool dinf_rows_ok = !bany(dinf_rows_bad);
+    if (pinf_blocked) s_pinf = inf;
+    // Abar^T y, Abar^T dy; P x_us, P dx_us with the entries as stored -- all consumed by the thread that forms them
+    T r3[5] = {T(0), T(0), T(0), T(0), T(0)};  // n_Px, n_Aty, n_res, n_Atdy, n_Pdx
+    {
+      const unsigned short *atp = htab(kI_ATptr), *atr = htab(kI_ATrow), *ats = htab(kI_ATslot);
+      for (int j = tid; j < n; j += NT) {
+        const int e1 = atp[j + 1];
+        T a1 = T(0), a2 = T(0);
+        for (int e = atp[j]; e < e1; ++e) {
+          const T av = A[ats[e]];
+          const int i = atr[e];
+          a1 += av * y[i];
+          a2 += av * w[i];
+        }
+        T px = T(0), pdx = T(0);
+        for (int e = S.PR_ptr[j]; e < S.PR_ptr[j + 1]; ++e) {
+          const T pv = P[__ldg(S.PR_slot + e)];
+          const int k = __ldg(S.PR_col + e);
+          px += pv * t1[k];
+          pdx += pv * v[k];
+        }
+        const T sc = T(1) / (sx[j] * c);
+        const T aty = a1 * sc, atdy = a2 * sc;
+        r3[0] = fmax(r3[0], fabs(px));
+        r3[1] = fmax(r3[1], fabs(aty));
+        r3[2] = fmax(r3[2], fabs(px + qg(j) + aty));
+        r3[3] = fmax(r3[3], fabs(atdy));
+        r3[4] = fmax(r3[4], fabs(pdx));
+      }
+    }
+    reduce<5, 0x1fu>(r3);
+    const T n_Px = r3[0], n_Aty = r3[1], n_res = r3[2], n_Atdy = r3[3], n_Pdx = r3[4];
+    if (n_r <= eps_abs + eps_rel * fmax(n_Ax, n_z)) {  // :584-594
+      const T dual_scale = fmax(fmax(n_Px, qn), n_Aty);
+      if (n_res <= eps_abs + eps_rel * dual_scale) return SFB_QP_OPTIMAL;
+    }
+    if (fmax(n_Atdy, s_pinf) < eps_pinf * Edy) return SFB_QP_PRIMAL_INFEASIBLE;  // :619
+    if ((dxn > T(0) || !dinf_guard) && (n_Pdx <= eps_dinf * dxn) && (qdx <= eps_dinf * dxn) && dinf_rows_ok) return SFB_QP_DUAL_INFEASIBLE;
+    return kStatusUnset;
+  }
+
+  // ---------------------------------------------------------------- detail::polish_qp, qp_solver.hpp:92-204
+  // As in qp_sparse_tiled.cuh::polish: the regularised system is solved through the SAME symbolic factor,
+  // (Pbar + delta I + Aa^T Aa / delta) s1 = r1 + Aa^T r2 / delta, s2 = (Aa s1 - r2) / delta; the reference's outer iteration
+  // t += Hp^-1 (h - H t) absorbs the error of the ill-conditioned reduced solve.  On entry: w[i] = 1 on active rows else 0,
+  // yold = scaled active bound.  Row-space vectors are kept exactly zero on inactive rows.  t = (t1, rinv), h = (-qb, yold).
+  __device__ unsigned polish(const sfb_qp_params& prm)
+  {
+    const T delta = T(prm.delta), dinv = T(1) / delta;
+    for (int i = tid; i < m; i += NT) rho[i] = (w[i] != T(0)) ? dinv : T(0);
+    __syncthreads();
+    assemble(delta, rho);
+    if (!factor()) return SFB_QP_FLAG_POLISH_FAILED;
+    for (int j = tid; j < n; j += NT) t1[j] = T(0);
+    for (int i = tid; i < m; i += NT) rinv[i] = T(0);
+    __syncthreads();
+    for (unsigned it = 0; it < prm.polish_iter; ++it) {
+      // r = h - H t -> (t2, z):  r1 = -qb - sym(Pbar) t1 - Aa^T rinv,  r2 = bnd - Aa t1 on active rows
+      for (int j = tid; j < n; j += NT) t2[j] = -qb[j] - Psym_row_dot(j, t1) - At_col_dot(j, rinv);
+      for (int i = tid; i < m; i += NT) z[i] = (w[i] != T(0)) ? yold[i] - A_row_dot(i, t1) : T(0);
+      __syncthreads();
+      // s = Hp^-1 r -> (sv, s2):  (..) s1 = r1 + Aa^T r2 / delta,  s2 = (Aa s1 - r2) / delta
+      for (int j = tid; j < n; j += NT) v[j] = t2[j] + dinv * At_col_dot(j, z);
+      __syncthreads();
+      solve();
+      T dm[2] = {T(0), T(0)};
+      for (int i = tid; i < m; i += NT) {
+        const T s2 = (w[i] != T(0)) ? (A_row_dot(i, sv) - z[i]) * dinv : T(0);
+        const T tn = rinv[i] + s2;
+        dm[0] = fmax(dm[0], fabs(s2));
+        dm[1] = fmax(dm[1], fabs(tn));
+        rinv[i] = tn;  // read by its own thread only in this loop
+      }
+      for (int j = tid; j < n; j += NT) {
+        const T s1 = sv[j], tn = t1[j] + s1;
+        dm[0] = fmax(dm[0], fabs(s1));
+        dm[1] = fmax(dm[1], fabs(tn));
+        t1[j] = tn;
+      }
+      reduce<2, 0x3u>(dm);
+      if (dm[0] <= T(1e-12) * dm[1]) break;  // see qp_sparse_tiled.cuh::polish
+    }
+    bool bad = false;
+    for (int j = tid; j < n; j += NT) bad = bad || !(fabs(t1[j]) < Num<T>::inf());
+    if (bany(bad)) return SFB_QP_FLAG_POLISH_FAILED;
+    for (int j = tid; j < n; j += NT) x[j] = t1[j];  // :199
+    for (int i = tid; i < m; i += NT)
+      if (w[i] != T(0)) y[i] = rinv[i];  // :200-201
+    __syncthreads();
+    return SFB_QP_FLAG_POLISHED;
+  }
+
+  // ---------------------------------------------------------------- QPSolver::solve, qp_solver.hpp:343-568
+  __device__ void run(long long inst)
+  {
+    b = inst;
+    const T inf = Num<T>::inf();
+    const sfb_qp_params& prm = a.prm;
+    const unsigned long long t0 = prm.has_max_time ? global_timer_ns() : 0ull;
+    const unsigned short *arp = htab(kI_Arowptr), *acol = htab(kI_Acol);
+    prof = a.prof;
+    if (prof != nullptr && tid == 0) tlast = clock64();
+    {
+      const TIO* gA = a.A + b * (long long)S.nnzA;
+      const TIO* gP = a.P + b * (long long)S.nnzP;
+      for (int e = tid; e < S.nnzA; e += NT) A[e] = (T)__ldg(gA + e);
+      for (int e = tid; e < S.nnzP; e += NT) P[e] = (T)__ldg(gP + e);
+      T qn = T(0);
+      for (int j = tid; j < n; j += NT) qn = fmax(qn, fabs((T)__ldg(a.q + b * (long long)n + j)));
+      qn_us = bmax(qn);
+    }
+    mark(kPhLoad);
+    if (prm.scaling) scale();  // :347
+    else {
+      c = T(1);
+      for (int j = tid; j < n; j += NT) sx[j] = T(1);
+      for (int i = tid; i < m; i += NT) sy[i] = T(1);
+      __syncthreads();
+    }
+    mark(kPhScale);
+    // ---- rho classes + trivially empty feasible set  :361-374
+    int code = kStatusUnset;
+    const T rho_bar = T(prm.rho), sigma = T(prm.sigma), alpha = T(prm.alpha), alpha_comp = T(1) - alpha;
+    bool triv = false;
+    for (int i = tid; i < m; i += NT) {
+      const T li = lg(i), ui = ug(i);
+      if (li == inf || ui == -inf || ui - li < T(0)) triv = true;
+      T rr;
+      if (li == -inf && ui == inf) rr = T(1e-6);
+      else if (sy[i] * fabs(li - ui) < T(1e-5)) rr = T(1e3) * rho_bar;
+      else rr = rho_bar;
+      rho[i] = rr;
+      rinv[i] = T(1) / rr;
+      lo[i] = sy[i] * li;
+      hi[i] = sy[i] * ui;
+    }
+    if (bany(triv)) code = SFB_QP_PRIMAL_INFEASIBLE;
+    // ---- scaled data: qb = c Sx q, Abar = Sy A Sx  (:401-403, :450)
+    for (int j = tid; j < n; j += NT) qb[j] = (c * sx[j]) * qg(j);
+    for (int i = tid; i < m; i += NT) {
+      const T syi = sy[i];
+      const int e1 = arp[i + 1];
+      for (int e = arp[i]; e < e1; ++e) A[e] = (syi * sx[acol[e]]) * A[e];
+    }
+    __syncthreads();
+    const bool polish_only = a.mode == 2;
+    const bool skip = polish_only && a.out_status[b] != (int32_t)SFB_QP_OPTIMAL;
+    mark(kPhPrep);
+    if (!polish_only) {
+      assemble(sigma, rho);
+      mark(kPhAssemble);
+      if (!factor()) code = SFB_QP_UNKNOWN;  // :433
+    }
+    // ---- initial iterate  :436-445
+    if (polish_only) {
+      for (int pj = tid; pj < n; pj += NT) x[pj] = (T(1) / sx[pj]) * (T)a.out_x[b * (long long)n + __ldg(S.perm + pj)];
+      for (int i = tid; i < m; i += NT) {
+        y[i] = c * ((T(1) / sy[i]) * (T)a.out_y[b * (long long)m + i]);
+        z[i] = T(0);
+      }
+    } else if (a.warm_x != nullptr) {
+      for (int pj = tid; pj < n; pj += NT) x[pj] = (T(1) / sx[pj]) * (T)__ldg(a.warm_x + b * (long long)n + __ldg(S.perm + pj));
+      __syncthreads();
+      for (int i = tid; i < m; i += NT) {
+        y[i] = c * ((T(1) / sy[i]) * (T)__ldg(a.warm_y + b * (long long)m + i));
+        z[i] = A_row_dot(i, x);
+      }
+    } else {
+      for (int j = tid; j < n; j += NT) x[j] = T(0);
+      for (int i = tid; i < m; i += NT) { y[i] = T(0); z[i] = T(0); }
+    }
+    __syncthreads();
+    for (int i = tid; i < m; i += NT) w[i] = rho[i] * z[i] - y[i];
+    __syncthreads();
+    mark(kPhPrep);
+
+    // ---- main loop  :449-510
+    const unsigned sci = prm.stop_check_iter;
+    unsigned iter = 0;
+    if (polish_only) { code = skip ? kStatusUnset - 1 : (int)SFB_QP_OPTIMAL; iter = a.out_iter[b]; }
+    for (; iter != a.max_iter_eff && code == kStatusUnset; ++iter) {
+      // rhs = sigma x - qb + Abar^T w   (reduced system)
+      At_gather(w, v, [&](int j, T sum) { return sigma * x[j] - qb[j] + sum; });
+      mark(kPhRhs);
+      solve();
+      mark(kPhSolve);
+      const bool chk = (iter % sci == 1u);
+      for (int j = tid; j < n; j += NT) {
+        const T xi = x[j];
+        if (chk) xold[j] = xi;  // :465-468
+        x[j] = alpha * sv[j] + alpha_comp * xi;  // :470
+      }
+      for (int i = tid; i < m; i += NT) {
+        const T zi = z[i], yi = y[i], ri = rho[i], rinvi = rinv[i];
+        const T lob = lo[i], hib = hi[i];
+        const T zt = A_row_dot(i, sv);
+        if (chk) yold[i] = yi;
+        const T nu = ri * (zt - zi) + yi;
+        T zn = alpha * (rinvi * nu) + alpha_comp * (rinvi * yi) + zi;  // :471-474
+        zn = fmax(zn, lob);
+        zn = fmin(zn, hib);
+        const T yn = alpha_comp * yi + alpha * nu + ri * zi - ri * zn;  // :475-477
+        y[i] = yn;
+        z[i] = zn;
+        w[i] = ri * zn - yn;
+      }
+      __syncthreads();
+      mark(kPhUpdate);
+      if (chk) {
+        code = check_stopping(prm, a.dinf_guard != 0);  // :488 (clobbers w, v, t1, t2)
+        if (code == kStatusUnset && prm.has_max_time) {
+          const bool late = (long long)(global_timer_ns() - t0) > prm.max_time_ns;  // :504-508
+          if (bany(late)) code = SFB_QP_MAX_TIME;
+        }
+        __syncthreads();
+        for (int i = tid; i < m; i += NT) w[i] = rho[i] * z[i] - y[i];
+        __syncthreads();
+        mark(kPhCheck);
+      }
+    }
+
+    // ---- active sets as polish_qp builds them (:113-123) on the scaled dual; yold <- scaled active bound
+    const T thr = T(100) * Num<T>::eps();
+    for (int i = tid; i < m; i += NT) {
+      int act = 0;
+      T bv = T(0);
+      const T li = lg(i), ui = ug(i);
+      if (polish_only) {
+        act = a.out_active[b * (long long)m + i];
+        if (act < 0) bv = sy[i] * li;
+        if (act > 0) bv = sy[i] * ui;
+      } else {
+        if (y[i] < -thr && li != -inf) { act = -1; bv = sy[i] * li; }
+        if (y[i] > thr && ui != inf) { act = 1; bv = sy[i] * ui; }
+        if (a.out_active) a.out_active[b * (long long)m + i] = (int8_t)act;
+      }
+      w[i] = (act != 0) ? T(1) : T(0);
+      yold[i] = bv;
+    }
+    __syncthreads();
+    unsigned flags = 0;
+    if (code == SFB_QP_OPTIMAL && prm.polish) {
+      if (sizeof(T) == 4) flags = SFB_QP_FLAG_POLISH_SKIPPED;  // delta = 1e-6 is not resolvable in fp32: second pass in fp64 (mode 2)
+      else flags = polish(prm);
+    }
+    mark(kPhPolish);
+    if (skip) return;
+    // ---- unscale + objective  :544-548
+    for (int j = tid; j < n; j += NT) t1[j] = sx[j] * x[j];
+    __syncthreads();
+    T obj = T(0);
+    for (int j = tid; j < n; j += NT) {
+      T px = T(0);
+      for (int e = S.PR_ptr[j]; e < S.PR_ptr[j + 1]; ++e) px += (T(0.5) * P[__ldg(S.PR_slot + e)]) * t1[__ldg(S.PR_col + e)];
+      const T xv = t1[j];
+      a.out_x[b * (long long)n + __ldg(S.perm + j)] = (TIO)xv;
+      obj += xv * (px + qg(j));
+    }
+    obj = bsum(obj);
+    for (int i = tid; i < m; i += NT) a.out_y[b * (long long)m + i] = (TIO)(sy[i] * y[i] / c);
+    if (tid == 0) {
+      a.out_obj[b] = (TIO)obj;
+      a.out_status[b] = (code == kStatusUnset) ? (int32_t)SFB_QP_MAX_ITERATIONS : (int32_t)code;
+      a.out_iter[b] = iter;
+      if (a.out_flags) a.out_flags[b] = flags;
+    }
+    mark(kPhOut);
+  }
+};
+
+template <typename T, typename TIO> __global__ void __launch_bounds__(kCtaNT, 1) qp_sparse_cta_kernel(const CtaArgs<T, TIO> a)
+{
+  __shared__ long long next_inst;
+  CtaSolver<T, TIO, kCtaNT> s(a);
+  s.load_tables();
+  for (;;) {
+    if (threadIdx.x == 0) next_inst = (long long)atomicAdd(a.work_counter, 1ull);
+    __syncthreads();
+    const long long b = next_inst;
+    __syncthreads();
+    if (b >= a.batch) break;
+    s.run(b);
+  }
+}
+
+}  // namespace sfb

@@ -451,6 +451,8 @@ int sfb_create(int device, void* stream, sfb_handle_t* out)
   h->device = device;
   { const char* e = getenv("SFB_EKF_FORCE_GENERIC"); h->ekf_force_generic = e && e[0] == '1'; }
   { const char* e = getenv("SFB_SPARSE_TW"); h->sparse_tw = e ? atoi(e) : 0; }
+  { const char* e = getenv("SFB_SPARSE_KERNEL"); h->sparse_kernel = (e && !strcmp(e, "tiled")) ? 1 : ((e && !strcmp(e, "cta")) ? 2 : 0); }
+  if (h->sparse_tw == 4 || h->sparse_tw == 8 || h->sparse_tw == 32) h->sparse_kernel = 1;  // a forced tile width means the tiled kernel
   { const char* e = getenv("SFB_DENSE_FORCE_GENERIC"); h->dense_force_generic = e && e[0] == '1'; }
   h->stream = static_cast<cudaStream_t>(stream);
   if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&h->prop, device) != cudaSuccess) {
@@ -493,6 +495,7 @@ int sfb_destroy(sfb_handle_t h)
   for (auto& sc : h->scratch)
     if (sc.dev) cudaFree(sc.dev);
   if (h->sparse_ws.dev) cudaFree(h->sparse_ws.dev);
+  if (h->sparse_cta_ws.dev) cudaFree(h->sparse_cta_ws.dev);
   if (h->sparse_stage.dev) cudaFree(h->sparse_stage.dev);
   if (h->act_tmp.dev) cudaFree(h->act_tmp.dev);
   if (h->csc_tmp.dev) cudaFree(h->csc_tmp.dev);

@@ -57,6 +57,8 @@ struct sfb_context
   bool ekf_force_generic = false;
   bool dense_force_generic = false;  // SFB_DENSE_FORCE_GENERIC=1: bypass the tall-skinny register kernel (A/B measurements)
   int sparse_tw = 0;     // SFB_SPARSE_TW=4|8|32 overrides the tile-width heuristic of the sparse QP path (A/B measurements)
+  int sparse_kernel = 0; // SFB_SPARSE_KERNEL=tiled (1) forces the HBM-tiled kernel, =cta (2) / unset: the on-chip kernel when the instance fits in shared memory
+  sfbi::Scratch sparse_cta_ws; // per-CTA global vectors of the on-chip sparse kernel
   sfbi::Scratch sparse_ws;     // tiled working set of the sparse QP path
   sfbi::Scratch sparse_stage;  // device copies of host buffers (sparse path)
   sfbi::Scratch csc_tmp;       // CSC -> CSR permuted A values (sfb_qp_solve_sparse_batch_csc_f64)

@@ -54,7 +54,8 @@ def run(batch=8192, dtype="f64", steps=3, small=False, tw=0):
     t0 = time.perf_counter()
     sp = sfb.SparsePattern(pat["n"], pat["m"], pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], pat["A_colidx"], handle=handle)
     t_analyze = time.perf_counter() - t0
-    prm = sfb.QPSolverParams(max_iter=4000)
+    prm = sfb.QPSolverParams(max_iter=4000, polish=os.environ.get("SFB_BENCH_POLISH", "1") != "0",
+                             scaling=os.environ.get("SFB_BENCH_SCALING", "1") != "0")
     out = None
     for _ in range(2):
         out = sfb.solve_sparse_batch(sp, Pv, q, Av, l, u, prm, out=out)
