@@ -231,6 +231,12 @@ int sfb_qp_sparse_symbolic(int n, int m, const int32_t* P_colptr, const int32_t*
  * structural nnz(L), multiply-adds, largest supernode, sweep stages, ordering used}; max_rel_err_out = the largest relative error. */
 int sfb_qp_sparse_cta_selfcheck(int n, int m, const int32_t* P_colptr, const int32_t* P_rowidx, const int32_t* A_rowptr,
                                 const int32_t* A_colidx, int ordering, int64_t* info_out, double* max_rel_err_out);
+/* 1 if sfb_qp_solve_sparse_batch_* on this handle runs the on-chip kernel (one CTA per instance, working set in shared memory)
+ * for problems of scalar_bytes = 4 (fp32) or 8 (fp64) with this pattern, 0 if it runs the HBM-tiled kernel (working set too large for
+ * shared memory, or SFB_SPARSE_KERNEL=tiled in the environment when the handle was created).  info_out [8] (may be NULL) = the
+ * on-chip analysis: {supernodes, levels, factor slots, structural nnz(L), multiply-adds, largest supernode, sweep stages,
+ * shared-memory bytes per CTA}. */
+int sfb_qp_sparse_uses_onchip(sfb_handle_t h, sfb_qp_sparse_pattern_t p, int scalar_bytes, int64_t* info_out);
 /* nnz of the strictly lower factor L, multiply-adds of one numeric factorisation, ordering (perm_out [n], may be NULL) */
 int sfb_qp_sparse_pattern_info(sfb_qp_sparse_pattern_t p, int64_t* nnz_L, int64_t* factor_flops, int32_t* perm_out);
 

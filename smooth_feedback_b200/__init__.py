@@ -8,7 +8,8 @@ from .qp import (  # noqa: F401
     QPBatchResult, QPSolution, QPSolutionStatus, QPSolver, QPSolverParams, QuadraticProgram, solve_dense_batch,
     solve_qp, to_colmajor,
 )
-from .qp_sparse import QuadraticProgramSparse, SparsePattern, solve_sparse_batch, sparse_symbolic  # noqa: F401
+from .qp_sparse import (QuadraticProgramSparse, SparsePattern, solve_sparse_batch, sparse_onchip_selfcheck,  # noqa: F401
+                        sparse_symbolic)
 from .asif import ASIFVehicleFleet, ASIFVehicleParams  # noqa: F401
 from .comm import Communicator  # noqa: F401
 from .mpc import MPCVehicleFleet, MPCVehicleParams  # noqa: F401

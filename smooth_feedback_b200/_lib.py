@@ -51,7 +51,7 @@ EXPORTED_SYMBOLS = [
     "sfb_synchronize", "sfb_set_option", "sfb_kernel_launch_count", "sfb_qp_params_default", "sfb_qp_solve_dense_batch_f64",
     "sfb_qp_solve_dense_batch_f32", "sfb_qp_dense_max_m", "sfb_qp_scale_dense_batch_f64",
     "sfb_ekf_predict_batch_f64", "sfb_ekf_update_batch_f64", "sfb_ekf_step_batch_f64",
-    "sfb_qp_sparse_analyze", "sfb_qp_sparse_symbolic", "sfb_qp_sparse_cta_selfcheck", "sfb_qp_sparse_pattern_destroy", "sfb_qp_sparse_pattern_info",
+    "sfb_qp_sparse_analyze", "sfb_qp_sparse_symbolic", "sfb_qp_sparse_cta_selfcheck", "sfb_qp_sparse_uses_onchip", "sfb_qp_sparse_pattern_destroy", "sfb_qp_sparse_pattern_info",
     "sfb_qp_solve_sparse_batch_f64", "sfb_qp_solve_sparse_batch_f32", "sfb_qp_sparse_analyze_csc", "sfb_qp_solve_sparse_batch_csc_f64",
     "sfb_asif_vehicle_params_default", "sfb_asif_fleet_create", "sfb_asif_fleet_destroy", "sfb_asif_fleet_reset_warmstart",
     "sfb_asif_fleet_set_warmstart", "sfb_asif_fleet_filter_f64", "sfb_asif_fleet_filter_f32", "sfb_asif_fleet_to_qp_f64",
@@ -126,6 +126,7 @@ def lib() -> C.CDLL:
     L.sfb_qp_sparse_analyze.argtypes = [vp, i32, i32, vp, vp, vp, vp, C.POINTER(vp)]
     L.sfb_qp_sparse_symbolic.argtypes = [i32, i32, vp, vp, vp, vp, C.POINTER(i64), C.POINTER(i64), vp, vp]
     L.sfb_qp_sparse_cta_selfcheck.argtypes = [i32, i32, vp, vp, vp, vp, i32, vp, C.POINTER(C.c_double)]
+    L.sfb_qp_sparse_uses_onchip.argtypes = [vp, vp, i32, vp]
     L.sfb_qp_sparse_pattern_destroy.argtypes = [vp]
     L.sfb_qp_sparse_pattern_info.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), vp]
     sp_sig = [vp, vp, C.POINTER(SfbQpParams), i64] + [vp] * 14

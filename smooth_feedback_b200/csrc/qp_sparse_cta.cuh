@@ -34,12 +34,13 @@ namespace sfb {
 
 struct CtaPattern
 {
-  int n, m, nnzP, nnzA, nW, ns, smax, nstages, nrounds, nfacrounds, nints;
+  int n, m, np, nnzP, nnzA, nW, ns, smax, nstages, nrounds, nfacrounds, nints;
   unsigned tscalars;  // scalars of type T in front of the integer tables (cta_smem_scalars)
   int ioff[kI_count];
   const int *ints;    // the tables copied into shared memory (CtaSymbolic::smem_ints)
   const int *perm, *iperm, *P_rowp, *P_colp, *P_tgt, *PR_ptr, *PR_col, *PR_slot, *PS_ptr, *PS_col, *PS_slot, *PC_ptr, *PC_slot, *asm_sync;
   const int2* asm_desc;
+  const int *ATword_g, *extword_g;  // the two big tables in global memory (kernels instantiated with GT = true read them there)
 };
 
 template <typename T, typename TIO = T> struct CtaArgs
@@ -51,7 +52,7 @@ template <typename T, typename TIO = T> struct CtaArgs
   uint32_t* out_iter;
   int8_t* out_active;
   uint32_t* out_flags;
-  T* ws;  // per CTA: n + m scalars (x and y of the previous stop check)
+  T* ws;  // per CTA: np + m scalars (x and y of the previous stop check)
   unsigned long long* work_counter;
   long long batch;
   sfb_qp_params prm;
@@ -62,7 +63,7 @@ template <typename T, typename TIO = T> struct CtaArgs
 };
 
 enum CtaPhase { kPhLoad = 0, kPhScale, kPhPrep, kPhAssemble, kPhFactorCols, kPhFactorExt, kPhFactorInv, kPhRhs, kPhSolve, kPhUpdate,
-                kPhCheck, kPhPolish, kPhOut, kPhCount };
+                kPhCheck, kPhPolish, kPhOut, kPhCount, kPhStage0 = kPhCount, kPhTotal = kPhCount + 32 };
 
 // a vector in shared memory, addressed through the extern symbol (LDS / STS with 32-bit addresses)
 template <typename T> struct SV
@@ -78,15 +79,34 @@ template <typename T> struct SV
 __device__ __forceinline__ int lo16(int x) { return (int)((unsigned)x & 0xffffu); }
 __device__ __forceinline__ int hi16(int x) { return (int)((unsigned)x >> 16); }
 
-template <typename T, typename TIO, int NT> struct CtaSolver
+// 16-byte vectors of the compute type: block rows of the factor are padded to whole vectors (qp_sparse_cta_host.hpp)
+template <typename T> struct VecOf;
+template <> struct VecOf<float>
 {
+  using type = float4;
+  static constexpr int PAD = 4, LPAD = 2;
+  static __device__ __forceinline__ void unpack(const float4& v, float (&o)[4]) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+  static __device__ __forceinline__ float4 pack(const float (&o)[4]) { return make_float4(o[0], o[1], o[2], o[3]); }
+};
+template <> struct VecOf<double>
+{
+  using type = double2;
+  static constexpr int PAD = 2, LPAD = 1;
+  static __device__ __forceinline__ void unpack(const double2& v, double (&o)[2]) { o[0] = v.x; o[1] = v.y; }
+  static __device__ __forceinline__ double2 pack(const double (&o)[2]) { return make_double2(o[0], o[1]); }
+};
+
+template <typename T, typename TIO, int NT, bool GT> struct CtaSolver
+{
+  static constexpr int PAD = VecOf<T>::PAD, LPAD = VecOf<T>::LPAD;
+  using VT = typename VecOf<T>::type;
   static constexpr int NW = NT / 32;
   using V = SV<T>;
   const CtaArgs<T, TIO>& a;
   const CtaPattern& S;
-  const int n, m, nW, tid, lane, warp;
-  V W, A, P;                          // factor slots (+ D, 1/D), Abar (CSR order), P as given
-  V qb, x, v, sv, sx, t1, t2;         // n-vectors (permuted order); v / sv: the two buffers of the sweeps, sv = result
+  const int n, m, np, nW, tid, lane, warp;
+  V W, A;                             // factor slots (+ 1/D), Abar (CSR order)
+  V qb, x, v, sv, sx, t1;             // n-vectors over the padded ids (holes stay zero); v / sv: the two buffers of the sweeps, sv = result
   V sy, rho, rinv, z, y, w, lo, hi;   // m-vectors
   V red;
   T *xold, *yold;                     // global: iterate at the previous stop check
@@ -98,17 +118,19 @@ template <typename T, typename TIO, int NT> struct CtaSolver
   long long tlast = 0;
 
   __device__ CtaSolver(const CtaArgs<T, TIO>& args)
-      : a(args), S(args.pat), n(args.pat.n), m(args.pat.m), nW(args.pat.nW), tid(threadIdx.x), lane(threadIdx.x & 31), warp(threadIdx.x >> 5)
+      : a(args), S(args.pat), n(args.pat.n), m(args.pat.m), np(args.pat.np), nW(args.pat.nW), tid(threadIdx.x), lane(threadIdx.x & 31),
+        warp(threadIdx.x >> 5)
   {
     unsigned o = 0;
-    auto take = [&](unsigned len) { V r{o}; o += len; return r; };
-    W = take(nW + 2 * n); A = take(S.nnzA); P = take(S.nnzP);
-    qb = take(n + 1); x = take(n + 1); v = take(n + 1); sv = take(n + 1); sx = take(n + 1); t1 = take(n + 1); t2 = take(n + 1);
-    sy = take(m + 1); rho = take(m + 1); rinv = take(m + 1); z = take(m + 1); y = take(m + 1); w = take(m + 1); lo = take(m + 1); hi = take(m + 1);
+    auto r4 = [](unsigned k) { return (k + 3u) & ~3u; };
+    auto take = [&](unsigned len) { V r{o}; o += r4(len); return r; };  // same carving as cta_smem_scalars
+    W = take(nW + np); A = take(S.nnzA);
+    qb = take(np); x = take(np); v = take(np); sv = take(np); sx = take(np); t1 = take(np);
+    sy = take(m); rho = take(m); rinv = take(m); z = take(m); y = take(m); w = take(m); lo = take(m); hi = take(m);
     red = take(kCtaRed);
     ibase = S.tscalars * (unsigned)sizeof(T);
-    xold = a.ws + (size_t)blockIdx.x * (size_t)(n + m);
-    yold = xold + n;
+    xold = a.ws + (size_t)blockIdx.x * (size_t)(np + m);
+    yold = xold + np;
     c = T(1);
     qn_us = T(0);
   }
@@ -119,15 +141,26 @@ template <typename T, typename TIO, int NT> struct CtaSolver
     return reinterpret_cast<const int*>(cta_smem_raw + ibase) + S.ioff[which];
   }
   __device__ __forceinline__ const unsigned short* htab(int which) const { return reinterpret_cast<const unsigned short*>(itab(which)); }
+  // once per CTA: schedules into shared memory, every scalar zero (holes of the padded vectors and 1 / D of the holes stay zero)
   __device__ void load_tables()
   {
     extern __shared__ __align__(16) unsigned char cta_smem_raw[];
     int* dst = reinterpret_cast<int*>(cta_smem_raw + ibase);
     for (int k = tid; k < S.nints; k += NT) dst[k] = __ldg(S.ints + k);
+    T* sc = reinterpret_cast<T*>(cta_smem_raw);
+    for (unsigned k = tid; k < S.tscalars; k += NT) sc[k] = T(0);
     __syncthreads();
   }
-  // inputs of the current instance, read in place (global, read-only)
-  __device__ __forceinline__ T qg(int pj) const { return (T)__ldg(a.q + b * (long long)n + __ldg(S.perm + pj)); }
+  // 16-byte accesses (slot a multiple of PAD)
+  __device__ __forceinline__ void ldv(const V& vec, int slot, T (&o)[PAD]) const { VecOf<T>::unpack(*reinterpret_cast<const VT*>(&vec[slot]), o); }
+  __device__ __forceinline__ void stv(const V& vec, int slot, const T (&o)[PAD]) const { *reinterpret_cast<VT*>(&vec[slot]) = VecOf<T>::pack(o); }
+  // inputs of the current instance, read in place (global, read-only); pj: padded id
+  __device__ __forceinline__ T qg(int pj) const
+  {
+    const int jo = __ldg(S.perm + pj);
+    return jo >= 0 ? (T)__ldg(a.q + b * (long long)n + jo) : T(0);
+  }
+  __device__ __forceinline__ T Pg(int e) const { return (T)__ldg(a.P + b * (long long)S.nnzP + e); }  // P as given (only cold paths read it)
   __device__ __forceinline__ T lg(int i) const { return (T)__ldg(a.l + b * (long long)m + i); }
   __device__ __forceinline__ T ug(int i) const { return (T)__ldg(a.u + b * (long long)m + i); }
 
@@ -171,17 +204,88 @@ template <typename T, typename TIO, int NT> struct CtaSolver
   __device__ __forceinline__ T bsum(T val) { T r[1] = {val}; reduce<1, 0u>(r); return r[0]; }
   __device__ __forceinline__ bool bany(bool pr) { return __syncthreads_or(pr ? 1 : 0) != 0; }
 
+  // ---------------------------------------------------------------- gathers over A (index tables in shared memory)
+  // sum_i Abar_ij in_i for column j (padded id); one word per entry: slot | row << 16
+  __device__ __forceinline__ T At_col_dot(int j, const V& in) const
+  {
+    const unsigned short* atp = htab(kI_ATptr);
+    const int* atw = GT ? S.ATword_g : itab(kI_ATword);
+    const int e0 = atp[j], e1 = atp[j + 1];
+    T acc = T(0);
+    for (int e = e0; e < e1; e += 4) {
+      int wd[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) wd[k] = (e + k < e1) ? atw[e + k] : -1;
+      T av[4], iv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        av[k] = (wd[k] != -1) ? A[lo16(wd[k])] : T(0);
+        iv[k] = (wd[k] != -1) ? in[hi16(wd[k])] : T(0);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc += av[k] * iv[k];
+    }
+    return acc;
+  }
+  // two column dots at once (check_stopping)
+  __device__ __forceinline__ void At_col_dot2(int j, const V& in1, const V& in2, T& o1, T& o2) const
+  {
+    const unsigned short* atp = htab(kI_ATptr);
+    const int* atw = GT ? S.ATword_g : itab(kI_ATword);
+    const int e1 = atp[j + 1];
+    T a1 = T(0), a2 = T(0);
+#pragma unroll 2
+    for (int e = atp[j]; e < e1; ++e) {
+      const int wd = atw[e];
+      const T av = A[lo16(wd)];
+      a1 += av * in1[hi16(wd)];
+      a2 += av * in2[hi16(wd)];
+    }
+    o1 = a1; o2 = a2;
+  }
+  __device__ __forceinline__ T A_row_dot(int i, const V& vec) const
+  {
+    const unsigned short *arp = htab(kI_Arowptr), *acol = htab(kI_Acol);
+    const int e0 = arp[i], e1 = arp[i + 1];
+    T acc = T(0);
+    for (int e = e0; e < e1; e += 4) {
+      int cj[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) cj[k] = (e + k < e1) ? (int)acol[e + k] : -1;
+      T av[4], xv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        av[k] = (cj[k] >= 0) ? A[e + k] : T(0);
+        xv[k] = (cj[k] >= 0) ? vec[cj[k]] : T(0);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc += av[k] * xv[k];
+    }
+    return acc;
+  }
+  // sum_k sym(Pbar)_jk in_k  (upper triangle of c Sx P Sx mirrored)
+  __device__ __forceinline__ T Psym_row_dot(int j, const V& in) const
+  {
+    T acc = T(0);
+    for (int e = S.PS_ptr[j]; e < S.PS_ptr[j + 1]; ++e) {
+      const int sl = __ldg(S.PS_slot + e);
+      acc += (((c * sx[__ldg(S.P_rowp + sl)]) * sx[__ldg(S.P_colp + sl)]) * Pg(sl)) * in[__ldg(S.PS_col + e)];
+    }
+    return acc;
+  }
+
   // ---------------------------------------------------------------- QPSolver::scale, qp_solver.hpp:673-730
   // Same evaluation as qp_sparse_tiled.cuh::scale (bit-exact against the CPU restatement: max / abs / mul / div / sqrt only,
   // products in the reference's order, the column mean summed sequentially in the original column order).
   __device__ void scale()
   {
-    const unsigned short *arp = htab(kI_Arowptr), *acol = htab(kI_Acol), *atp = htab(kI_ATptr), *atr = htab(kI_ATrow), *ats = htab(kI_ATslot);
-    for (int j = tid; j < n; j += NT) sx[j] = T(1);
+    const unsigned short *arp = htab(kI_Arowptr), *acol = htab(kI_Acol), *atp = htab(kI_ATptr);
+    const int* atw = GT ? S.ATword_g : itab(kI_ATword);
+    for (int j = tid; j < np; j += NT) sx[j] = T(1);
     for (int i = tid; i < m; i += NT) sy[i] = T(1);
-    for (int pj = tid; pj < n; pj += NT) {
+    for (int pj = tid; pj < np; pj += NT) {
       T g = T(0);
-      for (int e = S.PC_ptr[pj]; e < S.PC_ptr[pj + 1]; ++e) g = fmax(g, fabs(P[__ldg(S.PC_slot + e)]));
+      for (int e = S.PC_ptr[pj]; e < S.PC_ptr[pj + 1]; ++e) g = fmax(g, fabs(Pg(__ldg(S.PC_slot + e))));
       t1[pj] = g;
     }
     __syncthreads();
@@ -202,16 +306,19 @@ template <typename T, typename TIO, int NT> struct CtaSolver
     int it = 0;
     T dev;
     do {
-      for (int pj = tid; pj < n; pj += NT) {
+      for (int pj = tid; pj < np; pj += NT) {
         const T sxj = sx[pj];
         T g = T(0);
         for (int e = S.PC_ptr[pj]; e < S.PC_ptr[pj + 1]; ++e) {
           const int sl = __ldg(S.PC_slot + e);
-          g = fmax(g, fabs(((cc * sx[__ldg(S.P_rowp + sl)]) * sxj) * P[sl]));
+          g = fmax(g, fabs(((cc * sx[__ldg(S.P_rowp + sl)]) * sxj) * Pg(sl)));
         }
         const int e1 = atp[pj + 1];
 #pragma unroll 4
-        for (int e = atp[pj]; e < e1; ++e) g = fmax(g, fabs((sy[atr[e]] * sxj) * A[ats[e]]));
+        for (int e = atp[pj]; e < e1; ++e) {
+          const int wd = atw[e];
+          g = fmax(g, fabs((sy[hi16(wd)] * sxj) * A[lo16(wd)]));
+        }
         t1[pj] = g;
       }
       for (int i = tid; i < m; i += NT) {
@@ -224,7 +331,7 @@ template <typename T, typename TIO, int NT> struct CtaSolver
       }
       __syncthreads();  // every maximum is formed before any scale factor changes
       dev = T(0);
-      for (int j = tid; j < n; j += NT) {
+      for (int j = tid; j < np; j += NT) {
         T g = t1[j];
         if (g == T(0)) g = T(1);
         sx[j] = sqrt(T(1) / fmax(g, T(1e-8))) * sx[j];
@@ -244,11 +351,19 @@ template <typename T, typename TIO, int NT> struct CtaSolver
   __device__ void assemble(T shift, const V& wt)
   {
     for (int e = tid; e < nW; e += NT) W[e] = T(0);
-    for (int k = tid; k < n; k += NT) W[nW + k] = shift;
+    __syncthreads();
+    {  // the diagonal of every real column lives in its row of the diagonal block
+      const int *fd = itab(kI_fdiag), *sn = itab(kI_sntab);
+      const unsigned short* prow = htab(kI_prow);
+      for (int e = tid; e < n; e += NT) {
+        const int wd = fd[e], q = hi16(wd), i = lo16(wd) - sn[8 * q];
+        W[prow[sn[8 * q + 7] + i] + i] = shift;
+      }
+    }
     __syncthreads();
     for (int e = tid; e < S.nnzP; e += NT) {  // compressed P: distinct targets
       const int t = __ldg(S.P_tgt + e);
-      if (t >= 0) W[t] += ((c * sx[__ldg(S.P_rowp + e)]) * sx[__ldg(S.P_colp + e)]) * P[e];  // qp_solver.hpp:386
+      if (t >= 0) W[t] += ((c * sx[__ldg(S.P_rowp + e)]) * sx[__ldg(S.P_colp + e)]) * Pg(e);  // qp_solver.hpp:386
     }
     __syncthreads();
     // colour by colour; the descriptors of four rounds are requested together (one L2 round trip per four rounds)
@@ -274,14 +389,20 @@ template <typename T, typename TIO, int NT> struct CtaSolver
   }
 
   // ---------------------------------------------------------------- supernodal right-looking L D L^T in place
-  // Afterwards: below blocks hold L, diagonal blocks hold X' = -(strict lower part of L_SS^-1), W[nW + k] = D_k,
-  // W[nW + n + k] = 1 / D_k.  False on a non-positive pivot.
+  // Afterwards: below blocks hold L, diagonal blocks hold X' = -(strict lower part of L_SS^-1) (diagonal and padding zero),
+  // W[nW + k] = 1 / D_k.  False on a non-positive pivot.
+  // Rounds (qp_sparse_cta_host.hpp): the supernodes of a round advance column by column together, each with its own warps.
+  // The diagonal D_i lives IN row i of its block during the factorisation, so a column step is one uniform update of the
+  // trailing panel: a thread owns a group of PAD adjacent columns (their pivot-column entries are loaded once) and walks panel
+  // rows with 16-byte read-modify-writes; the padding of a row (columns > i) collects garbage that the scaling pass clears.
   __device__ bool factor()
   {
     const T inf = Num<T>::inf();
     bool ok = true;
     const int *rounds = itab(kI_facrounds), *fext = itab(kI_facext), *fwarp = itab(kI_facwarp), *sn = itab(kI_sntab), *extptr = itab(kI_extptr),
-              *extw = itab(kI_extword);
+              *extw = GT ? S.extword_g : itab(kI_extword);
+    const unsigned short* prow = htab(kI_prow);
+    const int Di = nW;  // 1 / D
     for (int r = 0; r < S.nfacrounds; ++r) {
       const int maxs = rounds[4 * r], cnt = lo16(rounds[4 * r + 1]), totw = hi16(rounds[4 * r + 1]), e0 = rounds[4 * r + 2], w0 = rounds[4 * r + 3];
       int q = -1, rank = 0, nw = 1;
@@ -289,124 +410,166 @@ template <typename T, typename TIO, int NT> struct CtaSolver
         const unsigned wd = (unsigned)fwarp[w0 + warp];
         q = (int)(wd & 0xffffu); rank = (int)((wd >> 16) & 0xffu); nw = (int)(wd >> 24);
       }
-      int c0 = 0, s = 0, t = 0, db = 0, bb = 0;
+      int c0 = 0, s = 0, t = 0, sp = 0;
+      const unsigned short* pr = prow;
       if (q >= 0) {
         const int4 h = *reinterpret_cast<const int4*>(sn + 8 * q);
-        c0 = h.x; s = h.y; t = h.z; db = h.w; bb = sn[8 * q + 4];
+        c0 = h.x; s = h.y; t = h.z; sp = sn[8 * q + 6]; pr = prow + sn[8 * q + 7];
       }
+      // thread -> (column group cg of NCG = sp / PAD, row chunk rc of RC); NCG rounded up to a power of two (<= 32 <= group size)
       const int gsize = nw * 32, gtid = rank * 32 + lane;
+      const int NCG = sp >> LPAD;
+      int lcg = 0;
+      while ((1 << lcg) < NCG) ++lcg;
+      const int cg = gtid & ((1 << lcg) - 1), rc = gtid >> lcg, RC = gsize >> lcg;
+      const bool active = q >= 0 && cg < NCG && rc < RC;
+      const int j0 = cg << LPAD;
+      const int nrows = s + t;
       __syncthreads();  // the external updates of the previous round are complete
-      if (q >= 0 && gtid == 0) W[nW + n + c0] = T(1) / W[nW + c0];
-      for (int kc = 0; kc <= maxs; ++kc) {
+      if (q >= 0 && gtid == 0) {
+        const T d0 = W[pr[0]];
+        if (!(d0 > T(0)) || !(d0 < inf)) ok = false;
+        W[Di + c0] = T(1) / d0;
+      }
+      for (int kc = 0; kc + 1 < maxs; ++kc) {
         __syncthreads();
-        if (q < 0 || kc > s) continue;
-        if (kc > 0) {  // column kc - 1 is final: scale it (nobody reads it during this step)
-          const T dprev = W[nW + n + c0 + kc - 1];
-          const int nd = s - kc, nsc = nd + t;
-          for (int p = gtid; p < nsc; p += gsize) {
-            const int i = kc + p;
-            const int slot = (p < nd) ? db + i * (i - 1) / 2 + kc - 1 : bb + (p - nd) * s + kc - 1;
-            W[slot] *= dprev;
-          }
+        if (!active || kc + 1 >= s || j0 + PAD - 1 <= kc) continue;  // (a group entirely left of / at the pivot column has nothing to update)
+        const T dinv = W[Di + c0 + kc];
+        T vjs[PAD];
+#pragma unroll
+        for (int cc = 0; cc < PAD; ++cc) {
+          const int j = j0 + cc;
+          vjs[cc] = (j > kc && j < s) ? W[pr[j] + kc] * dinv : T(0);
         }
-        if (kc == s) continue;
-        const T d = W[nW + c0 + kc];
-        if (!(d > T(0)) || !(d < inf)) ok = false;
-        const T dinv = W[nW + n + c0 + kc];
-        const int ndiag = s - kc - 1, nrows = ndiag + t;
-        int nch = 1;
-        while (nch < 32 && 2 * nch * nrows <= gsize) nch <<= 1;
-        const int prow = gtid / nch, ch = gtid % nch, rstep = gsize / nch;
-        const int colk = db + kc;  // entry (j, kc) of the diagonal block: colk + j (j - 1) / 2
-        for (int p = prow; p < nrows; p += rstep) {
-          const bool diag = p < ndiag;
-          const int i = kc + 1 + p;
-          const int rb = diag ? db + i * (i - 1) / 2 : bb + (p - ndiag) * s;
-          const int jmax = diag ? i : s - 1;
-          const T vi = W[rb + kc] * dinv;
-          constexpr int U = 4;
-          for (int j0 = kc + 1 + ch; j0 <= jmax; j0 += U * nch) {
-            T vj[U], old[U];
-            int tg[U];
+        const bool pivot_group = j0 <= kc;                     // its columns <= kc are being read by everybody: not rewritten
+        const int nextc = kc + 1 - j0;                          // 0 .. PAD - 1: this group holds the next pivot's diagonal
+        constexpr int U = 2;
+        for (int p0 = max(kc + 1, j0) + rc; p0 < nrows; p0 += U * RC) {  // rows of the diagonal block from j0 on (they hold the group), then the rows below
+          T vi[U], old[U][PAD];
+          int base[U];
 #pragma unroll
-            for (int k = 0; k < U; ++k) {
-              const int j = j0 + k * nch;
-              tg[k] = -1;
-              if (j <= jmax) {
-                vj[k] = W[colk + j * (j - 1) / 2];
-                tg[k] = (diag && j == i) ? nW + c0 + j : rb + j;
-                old[k] = W[tg[k]];
-              }
+          for (int k = 0; k < U; ++k) {
+            const int p = p0 + k * RC;
+            base[k] = -1;
+            if (p < nrows) {
+              base[k] = pr[p];
+              vi[k] = W[base[k] + kc];
+              ldv(W, base[k] + j0, old[k]);
             }
+          }
 #pragma unroll
-            for (int k = 0; k < U; ++k) {
-              if (tg[k] >= 0) {
-                const T nv = old[k] - vi * vj[k];
-                W[tg[k]] = nv;
-                if (tg[k] == nW + c0 + kc + 1) W[nW + n + c0 + kc + 1] = T(1) / nv;  // the next pivot's reciprocal, off everyone else's path
-              }
+          for (int k = 0; k < U; ++k) {
+            if (base[k] < 0) continue;
+            T nv[PAD];
+#pragma unroll
+            for (int cc = 0; cc < PAD; ++cc) nv[cc] = old[k][cc] - vi[k] * vjs[cc];
+            if (!pivot_group) stv(W, base[k] + j0, nv);
+            else {
+#pragma unroll
+              for (int cc = 1; cc < PAD; ++cc)
+                if (j0 + cc > kc) W[base[k] + j0 + cc] = nv[cc];
+            }
+            if (p0 + k * RC == kc + 1 && nextc >= 0 && nextc < PAD) {  // the next pivot: its reciprocal, off everyone else's path
+              T dn = nv[0];
+#pragma unroll
+              for (int cc = 1; cc < PAD; ++cc) dn = (nextc == cc) ? nv[cc] : dn;
+              if (!(dn > T(0)) || !(dn < inf)) ok = false;
+              W[Di + c0 + kc + 1] = T(1) / dn;
             }
           }
         }
       }
       __syncthreads();
       mark(kPhFactorCols);
-      // external updates, one supernode after the other (supernodes of one round may share targets): L D L^T of the below block
+      // external updates, one supernode after the other (supernodes of one round may share targets): U D^-1 U^T of the below block
       for (int k = 0; k < cnt; ++k) {
         const int qe = fext[e0 + k];
-        const int ec0 = sn[8 * qe], es = sn[8 * qe + 1], ebb = sn[8 * qe + 4];
+        const int ec0 = sn[8 * qe], ebb = sn[8 * qe + 4], esp = sn[8 * qe + 6];
         const int p1 = extptr[qe + 1];
         for (int p = extptr[qe] + tid; p < p1; p += NT) {
           const unsigned wd = (unsigned)extw[p];
-          const int ra = ebb + (int)(wd & 0xffu) * es, rb = ebb + (int)((wd >> 8) & 0xffu) * es, tg = (int)(wd >> 16);
-          T acc0 = T(0), acc1 = T(0);
-          int cc = 0;
-          for (; cc + 1 < es; cc += 2) {
-            acc0 += (W[ra + cc] * W[nW + ec0 + cc]) * W[rb + cc];
-            acc1 += (W[ra + cc + 1] * W[nW + ec0 + cc + 1]) * W[rb + cc + 1];
+          const int ra = ebb + (int)(wd & 0xffu) * esp, rb = ebb + (int)((wd >> 8) & 0xffu) * esp, tg = (int)(wd >> 16);
+          T acc[PAD];
+#pragma unroll
+          for (int cc = 0; cc < PAD; ++cc) acc[cc] = T(0);
+          for (int ch = 0; ch < esp; ch += PAD) {  // whole padded rows: the padding columns hold zeros (and 1 / D of the holes is zero)
+            T ua[PAD], ub[PAD], di[PAD];
+            ldv(W, ra + ch, ua); ldv(W, rb + ch, ub); ldv(W, Di + ec0 + ch, di);
+#pragma unroll
+            for (int cc = 0; cc < PAD; ++cc) acc[cc] += (ua[cc] * di[cc]) * ub[cc];
           }
-          if (cc < es) acc0 += (W[ra + cc] * W[nW + ec0 + cc]) * W[rb + cc];
-          W[tg] -= acc0 + acc1;
+          T tot = acc[0];
+#pragma unroll
+          for (int cc = 1; cc < PAD; ++cc) tot += acc[cc];
+          W[tg] -= tot;
         }
         __syncthreads();
       }
       mark(kPhFactorExt);
     }
-    // invert the unit-lower diagonal blocks in place, row step by row step for all supernodes at once; a thread owns
-    // columns.  Row i of every block is read (as L) by all threads before anyone overwrites it (as X').
+    // scale the panels, L = (unscaled columns) D^-1, and clear the diagonal and the padding of the rows of the diagonal blocks:
+    // a thread owns (panel row, column group); 1 / D as a vector (zero in the holes)
+    for (int sq = 0; sq < S.ns; ++sq) {
+      const int4 h = *reinterpret_cast<const int4*>(sn + 8 * sq);  // c0, s, t, dbase
+      const int sp = sn[8 * sq + 6];
+      const unsigned short* pr = prow + sn[8 * sq + 7];
+      const int NCG = sp >> LPAD, tasks = (h.y + h.z) * NCG;
+      for (int e = tid; e < tasks; e += NT) {
+        const int p = e / NCG, j0 = (e - p * NCG) << LPAD;
+        if (p < h.y && j0 > p) continue;  // row p of the diagonal block holds the columns <= p
+        T lw[PAD], di[PAD];
+        const int slot = pr[p] + j0;
+        ldv(W, slot, lw); ldv(W, Di + h.x + j0, di);
+#pragma unroll
+        for (int cc = 0; cc < PAD; ++cc) lw[cc] = (p < h.y && j0 + cc >= p) ? T(0) : lw[cc] * di[cc];
+        stv(W, slot, lw);
+      }
+    }
+    __syncthreads();
+    // invert the unit-lower diagonal blocks in place: L^-1 = (I - l_{s-1} e^T) ... (I - l_0 e^T), applied right-looking.  With
+    // X' = -(strict lower part of L^-1) stored, step k is X'(i, c) -= L(i, k) X'(k, c) for i > k, c < k (column k itself is already
+    // X').  A thread owns a row i of a diagonal block and updates it with 16-byte vectors; row k is final after step k - 1 and its
+    // diagonal and padding are zero, so whole vectors are exact.  One barrier per step, all supernodes at once.
     {
-      constexpr int KS = 4;  // n <= KS * NT (checked on the host)
-      int cdb[KS], cs[KS], ckc[KS];
-      const unsigned short* colsn = htab(kI_colsn);
+      constexpr int KS = 2;  // n <= KS * NT (checked on the host)
+      int rbase[KS], ri[KS];
+      const unsigned short* rq[KS];
+      const int* fd = itab(kI_fdiag);
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
-        const int k = tid + ks * NT;
-        cs[ks] = 0; cdb[ks] = 0; ckc[ks] = 0;
-        if (k < n) {
-          const int q = colsn[k];
-          cs[ks] = sn[8 * q + 1]; cdb[ks] = sn[8 * q + 3]; ckc[ks] = k - sn[8 * q];
+        const int e = tid + ks * NT;
+        ri[ks] = 0; rbase[ks] = 0; rq[ks] = prow;
+        if (e < n) {
+          const int wd = fd[e];  // column | supernode << 16, every real column once
+          const int q = hi16(wd);
+          ri[ks] = lo16(wd) - sn[8 * q];
+          rq[ks] = prow + sn[8 * q + 7];
+          rbase[ks] = rq[ks][ri[ks]];
         }
       }
-      for (int i = 1; i < S.smax; ++i) {
-        T res[KS];
+      for (int k = 1; k + 1 < S.smax; ++k) {
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
-          if (ckc[ks] < i && i < cs[ks]) {
-            const int ri = cdb[ks] + i * (i - 1) / 2, kc = ckc[ks];
-            T acc0 = W[ri + kc], acc1 = T(0);
-            int j = kc + 1;
-            for (; j + 1 < i; j += 2) {
-              acc0 -= W[ri + j] * W[cdb[ks] + j * (j - 1) / 2 + kc];
-              acc1 -= W[ri + j + 1] * W[cdb[ks] + (j + 1) * j / 2 + kc];
+          if (k < ri[ks]) {
+            const T lik = W[rbase[ks] + k];
+            const int rowk = rq[ks][k];
+            for (int ch = 0; ch < k; ch += 2 * PAD) {  // two vectors per trip: the loads of the second do not wait for the store of the first
+              T x0[PAD], r0[PAD], x1[PAD], r1[PAD];
+              const bool two = ch + PAD < k;
+              ldv(W, rbase[ks] + ch, x0); ldv(W, rowk + ch, r0);
+              if (two) { ldv(W, rbase[ks] + ch + PAD, x1); ldv(W, rowk + ch + PAD, r1); }
+#pragma unroll
+              for (int cc = 0; cc < PAD; ++cc) x0[cc] -= lik * r0[cc];
+              stv(W, rbase[ks] + ch, x0);
+              if (two) {
+#pragma unroll
+                for (int cc = 0; cc < PAD; ++cc) x1[cc] -= lik * r1[cc];
+                stv(W, rbase[ks] + ch + PAD, x1);
+              }
             }
-            if (j < i) acc0 -= W[ri + j] * W[cdb[ks] + j * (j - 1) / 2 + kc];
-            res[ks] = acc0 + acc1;
           }
         }
         __syncthreads();
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks)
-          if (ckc[ks] < i && i < cs[ks]) W[cdb[ks] + i * (i - 1) / 2 + ckc[ks]] = res[ks];
       }
     }
     ok = !bany(!ok);
@@ -415,138 +578,166 @@ template <typename T, typename TIO, int NT> struct CtaSolver
   }
 
   // ---------------------------------------------------------------- v <- (L D L^T)^-1 v, result in sv
-  // Stage list of qp_sparse_cta_host.hpp; G lanes cooperate on one output (G = the largest power of two that keeps every
-  // output of the stage in one round).  Ends with a barrier.
-  __device__ void solve()
+  // Stage list of qp_sparse_cta_host.hpp.  G = 1 << lg lanes cooperate on one output; every inner loop moves whole 16-byte
+  // vectors of the factor (block rows are padded with zeros).  Each stage ends with a barrier.  The stage bodies are kept SMALL
+  // (run-time lane-group size, no unrolling): the ADMM loop runs 15 of them per iteration and must stay inside the instruction
+  // cache -- templated on the group size the sweeps alone were 72 KB of SASS and every stage started with instruction-fetch misses.
+  __device__ void stage_fwd_diag(int first, int count, int lg)
   {
-    const int *stages = itab(kI_stages), *sn = itab(kI_sntab), *pout = itab(kI_pushout), *ptask = itab(kI_pushtask);
-    const unsigned short *levcols = htab(kI_levcols), *colsn = htab(kI_colsn), *rl = htab(kI_rlist);
-    for (int st = 0; st < S.nstages; ++st) {
-      const int kind = stages[4 * st], first = stages[4 * st + 1], count = stages[4 * st + 2];
-      int G = 1;
-      while (G < 32 && 2 * G * count <= NT) G <<= 1;
-      const int ngroups = NT / G;
-      if (kind == kStageFwdPush) {
-        const int group = tid / G, g = tid % G;
-        for (int o0 = 0; o0 < count; o0 += ngroups) {
-          const int o = o0 + group;
-          const bool valid = o < count;
-          T acc = T(0);
-          int dst = 0;
-          if (valid) {
-            const int w0 = pout[first + o], w1 = pout[first + o + 1];
-            dst = lo16(w0);
-            for (int k = hi16(w0); k < hi16(w1); ++k) {
-              const int tw = ptask[k];
-              const int q = lo16(tw);
-              const int c0 = sn[8 * q], s = sn[8 * q + 1], slot0 = sn[8 * q + 4] + hi16(tw) * s;
-#pragma unroll 4
-              for (int cc = g; cc < s; cc += G) acc += W[slot0 + cc] * sv[c0 + cc];
-            }
-          }
-          for (int off = G >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-          if (valid && g == 0) v[dst] -= acc;
+    const int G = 1 << lg;
+    const int *fd = itab(kI_fdiag), *sn = itab(kI_sntab);
+    const unsigned short* doff = htab(kI_diagoff);
+    const int group = tid >> lg, g = tid & (G - 1);  // lanes of a group are adjacent: contiguous reads of a row
+    for (int o0 = 0; o0 < count; o0 += NT >> lg) {
+      const int o = o0 + group;
+      const bool valid = o < count;
+      T acc = T(0);
+      int k = 0;
+      if (valid) {
+        const int wd = fd[first + o];
+        k = lo16(wd);
+        const int q = hi16(wd);
+        const int c0 = sn[8 * q], i = k - c0, row = sn[8 * q + 3] + doff[i];
+#pragma unroll 2
+        for (int ch = g << LPAD; ch < i; ch += G << LPAD) {
+          T lw[PAD], vv[PAD];
+          ldv(W, row + ch, lw); ldv(v, c0 + ch, vv);
+#pragma unroll
+          for (int cc = 0; cc < PAD; ++cc) acc += lw[cc] * vv[cc];
         }
-      } else if (kind == kStageFwdDiag) {
-        const int group = tid / G, g = tid % G;  // lanes of a group are adjacent: contiguous reads of a row
-        for (int o0 = 0; o0 < count; o0 += ngroups) {
-          const int o = o0 + group;
-          const bool valid = o < count;
-          T acc = T(0);
-          int k = 0;
-          if (valid) {
-            k = levcols[first + o];
-            const int q = colsn[k];
-            const int c0 = sn[8 * q], i = k - c0, slot0 = sn[8 * q + 3] + i * (i - 1) / 2;
-#pragma unroll 4
-            for (int cc = g; cc < i; cc += G) acc += W[slot0 + cc] * v[c0 + cc];
-          }
-          for (int off = G >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-          if (valid && g == 0) sv[k] = v[k] - acc;
-        }
-      } else {
-        const int OPW = 32 / G;  // outputs per warp; lanes of adjacent outputs are adjacent: contiguous reads across columns
-        const int g = lane / OPW, ow = lane % OPW;
-        for (int o0 = 0; o0 < count; o0 += ngroups) {
-          const int o = o0 + warp * OPW + ow;
-          const bool valid = o < count;
-          T acc = T(0);
-          int k = 0;
-          if (valid) {
-            k = levcols[first + o];
-            const int q = colsn[k];
-            const int4 h = *reinterpret_cast<const int4*>(sn + 8 * q);  // c0, s, t, dbase
-            const int kc = k - h.x;
-            if (kind == kStageBwdPull) {
-              const int slot0 = sn[8 * q + 4] + kc, rb = sn[8 * q + 5];
-#pragma unroll 4
-              for (int r = g; r < h.z; r += G) acc += W[slot0 + r * h.y] * sv[rl[rb + r]];
-            } else {
-              const int base = h.w + kc;
-#pragma unroll 4
-              for (int i = kc + 1 + g; i < h.y; i += G) acc += W[base + i * (i - 1) / 2] * v[h.x + i];
-            }
-          }
-          for (int off = 16; off >= OPW; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-          if (valid && g == 0) {
-            if (kind == kStageBwdPull) v[k] = W[nW + n + k] * sv[k] - acc;
-            else sv[k] = v[k] - acc;
+      }
+      for (int off = G >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+      if (valid && g == 0) sv[k] = v[k] - acc;
+    }
+  }
+  __device__ void stage_fwd_push(int first, int count, int lg)
+  {
+    const int G = 1 << lg;
+    const int *pout = itab(kI_pushout), *ptask = itab(kI_pushtask), *sn = itab(kI_sntab);
+    const int group = tid >> lg, g = tid & (G - 1);
+    for (int o0 = 0; o0 < count; o0 += NT >> lg) {
+      const int o = o0 + group;
+      const bool valid = o < count;
+      T acc = T(0);
+      int dst = 0;
+      if (valid) {
+        const int w0 = pout[first + o], w1 = pout[first + o + 1];
+        dst = lo16(w0);
+        for (int k = hi16(w0); k < hi16(w1); ++k) {
+          const int tw = ptask[k];
+          const int q = lo16(tw);
+          const int c0 = sn[8 * q], sp = sn[8 * q + 6], row = sn[8 * q + 4] + hi16(tw) * sp;
+#pragma unroll 2
+          for (int ch = g << LPAD; ch < sp; ch += G << LPAD) {
+            T lw[PAD], yv[PAD];
+            ldv(W, row + ch, lw); ldv(sv, c0 + ch, yv);
+#pragma unroll
+            for (int cc = 0; cc < PAD; ++cc) acc += lw[cc] * yv[cc];
           }
         }
       }
+      for (int off = G >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+      if (valid && g == 0) v[dst] -= acc;
+    }
+  }
+  // backward stages: an output is a group of PAD adjacent columns; lanes of adjacent outputs are adjacent
+  template <bool PULL> __device__ void stage_bwd(int first, int count, int lg)
+  {
+    const int G = 1 << lg, lopw = 5 - lg, OPW = 1 << lopw;
+    const int *bo = itab(kI_bwd), *sn = itab(kI_sntab);
+    const unsigned short *doff = htab(kI_diagoff), *rl = htab(kI_rlist);
+    const int g = lane >> lopw, ow = lane & (OPW - 1);
+    for (int o0 = 0; o0 < count; o0 += NT >> lg) {
+      const int o = o0 + (warp << lopw) + ow;
+      const bool valid = o < count;
+      T acc[PAD];
+#pragma unroll
+      for (int cc = 0; cc < PAD; ++cc) acc[cc] = T(0);
+      int k0 = 0;
+      if (valid) {
+        const int wd = bo[first + o];
+        k0 = lo16(wd);
+        const int q = hi16(wd);
+        const int4 h = *reinterpret_cast<const int4*>(sn + 8 * q);  // c0, s, t, dbase
+        const int kc = k0 - h.x;
+        if (PULL) {
+          const int sp = sn[8 * q + 6], base = sn[8 * q + 4] + kc, rb = sn[8 * q + 5];
+#pragma unroll 2
+          for (int r = g; r < h.z; r += G) {
+            T lw[PAD];
+            ldv(W, base + r * sp, lw);
+            const T xr = sv[rl[rb + r]];
+#pragma unroll
+            for (int cc = 0; cc < PAD; ++cc) acc[cc] += lw[cc] * xr;
+          }
+        } else {
+          const int base = h.w + kc;
+#pragma unroll 2
+          for (int i = kc + 1 + g; i < h.y; i += G) {  // columns >= i of row i are zeros
+            T lw[PAD];
+            ldv(W, base + doff[i], lw);
+            const T vi = v[h.x + i];
+#pragma unroll
+            for (int cc = 0; cc < PAD; ++cc) acc[cc] += lw[cc] * vi;
+          }
+        }
+      }
+      for (int off = 16; off >= OPW; off >>= 1) {
+#pragma unroll
+        for (int cc = 0; cc < PAD; ++cc) acc[cc] += __shfl_xor_sync(0xffffffffu, acc[cc], off);
+      }
+      if (valid && g == 0) {  // whole vectors: the holes come out as zero (1 / D of a hole and every padding entry are zero)
+        T o4[PAD];
+        if (PULL) {
+          T di[PAD], yv[PAD];
+          ldv(W, nW + k0, di); ldv(sv, k0, yv);
+#pragma unroll
+          for (int cc = 0; cc < PAD; ++cc) o4[cc] = di[cc] * yv[cc] - acc[cc];
+          stv(v, k0, o4);
+        } else {
+          T vv[PAD];
+          ldv(v, k0, vv);
+#pragma unroll
+          for (int cc = 0; cc < PAD; ++cc) o4[cc] = vv[cc] - acc[cc];
+          stv(sv, k0, o4);
+        }
+      }
+    }
+  }
+  __device__ void solve()
+  {
+    const int4* stages = reinterpret_cast<const int4*>(itab(kI_stages));
+    long long tstage = (prof != nullptr && tid == 0) ? clock64() : 0;
+    int4 nxt = stages[0];  // kind, first, count, log2(lanes per output); the next descriptor is fetched a stage ahead
+    for (int st = 0; st < S.nstages; ++st) {
+      const int4 sd = nxt;
+      if (st + 1 < S.nstages) nxt = stages[st + 1];
+      if (sd.x == kStageFwdDiag) stage_fwd_diag(sd.y, sd.z, sd.w);
+      else if (sd.x == kStageFwdPush) stage_fwd_push(sd.y, sd.z, sd.w);
+      else if (sd.x == kStageBwdPull) stage_bwd<true>(sd.y, sd.z, sd.w);
+      else stage_bwd<false>(sd.y, sd.z, sd.w);
       __syncthreads();
+      if (prof != nullptr && tid == 0 && st < 32) {  // per-stage split of the solve phase (the phase total is accumulated by mark() as well)
+        const long long t = clock64();
+        atomicAdd(prof + kPhStage0 + st, (unsigned long long)(t - tstage));
+        tstage = t;
+      }
     }
-  }
-
-  // sum_i Abar_ij in_i for column j
-  __device__ __forceinline__ T At_col_dot(int j, const V& in) const
-  {
-    const unsigned short *atp = htab(kI_ATptr), *atr = htab(kI_ATrow), *ats = htab(kI_ATslot);
-    const int e1 = atp[j + 1];
-    T acc = T(0);
-#pragma unroll 4
-    for (int e = atp[j]; e < e1; ++e) acc += A[ats[e]] * in[atr[e]];
-    return acc;
-  }
-  // out[j] = fin(j, sum_i Abar_ij in_i)
-  template <class FIN> __device__ __forceinline__ void At_gather(const V& in, const V& out, FIN fin)
-  {
-    for (int j = tid; j < n; j += NT) out[j] = fin(j, At_col_dot(j, in));
-    __syncthreads();
-  }
-  // sum_k sym(Pbar)_jk in_k  (upper triangle of c Sx P Sx mirrored)
-  __device__ __forceinline__ T Psym_row_dot(int j, const V& in) const
-  {
-    T acc = T(0);
-    for (int e = S.PS_ptr[j]; e < S.PS_ptr[j + 1]; ++e) {
-      const int sl = __ldg(S.PS_slot + e);
-      acc += (((c * sx[__ldg(S.P_rowp + sl)]) * sx[__ldg(S.P_colp + sl)]) * P[sl]) * in[__ldg(S.PS_col + e)];
-    }
-    return acc;
-  }
-  __device__ __forceinline__ T A_row_dot(int i, const V& vec) const
-  {
-    const unsigned short *arp = htab(kI_Arowptr), *acol = htab(kI_Acol);
-    const int e1 = arp[i + 1];
-    T acc = T(0);
-#pragma unroll 4
-    for (int e = arp[i]; e < e1; ++e) acc += A[e] * vec[acol[e]];
-    return acc;
   }
 
   // ---------------------------------------------------------------- check_stopping, qp_solver.hpp:574-644
-  // Same evaluation as qp_sparse_tiled.cuh::check_stopping.  Clobbers v, w, t1, t2.
+  // Same evaluation as qp_sparse_tiled.cuh::check_stopping.  Clobbers v, sv, w, t1.
   __device__ int check_stopping(const sfb_qp_params& prm, bool dinf_guard)
   {
     const T eps_abs = T(prm.eps_abs), eps_rel = T(prm.eps_rel);
     const T eps_pinf = T(prm.eps_primal_inf), eps_dinf = T(prm.eps_dual_inf);
     const T inf = Num<T>::inf();
     T r1[3] = {T(0), T(0), T(0)};  // dxn, Edy (max), qdx (sum)
-    for (int j = tid; j < n; j += NT) {
+    for (int j = tid; j < np; j += NT) {
       const T xj = x[j];
       const T d = xj - xold[j];
       t1[j] = sx[j] * xj;       // x_us   :481
-      t2[j] = d;                // scaled dx
+      sv[j] = d;                // scaled dx
       const T dus = sx[j] * d;  // dx_us  :484
       v[j] = dus;
       r1[0] = fmax(r1[0], fabs(dus));
@@ -562,7 +753,7 @@ template <typename T, typename TIO, int NT> struct CtaSolver
     T r2[4] = {T(0), T(0), T(0), T(0)};  // n_Ax, n_r, n_z (max), s_pinf (sum)
     bool pinf_blocked = false, dinf_rows_bad = false;
     for (int i = tid; i < m; i += NT) {
-      T ax = A_row_dot(i, x), adx = A_row_dot(i, t2);
+      T ax = A_row_dot(i, x), adx = A_row_dot(i, sv);
       const T syinv = T(1) / sy[i];
       ax *= syinv;
       adx *= syinv;
@@ -590,32 +781,23 @@ template <typename T, typename TIO, int NT> struct CtaSolver
     if (pinf_blocked) s_pinf = inf;
     // Abar^T y, Abar^T dy; P x_us, P dx_us with the entries as stored -- all consumed by the thread that forms them
     T r3[5] = {T(0), T(0), T(0), T(0), T(0)};  // n_Px, n_Aty, n_res, n_Atdy, n_Pdx
-    {
-      const unsigned short *atp = htab(kI_ATptr), *atr = htab(kI_ATrow), *ats = htab(kI_ATslot);
-      for (int j = tid; j < n; j += NT) {
-        const int e1 = atp[j + 1];
-        T a1 = T(0), a2 = T(0);
-        for (int e = atp[j]; e < e1; ++e) {
-          const T av = A[ats[e]];
-          const int i = atr[e];
-          a1 += av * y[i];
-          a2 += av * w[i];
-        }
-        T px = T(0), pdx = T(0);
-        for (int e = S.PR_ptr[j]; e < S.PR_ptr[j + 1]; ++e) {
-          const T pv = P[__ldg(S.PR_slot + e)];
-          const int k = __ldg(S.PR_col + e);
-          px += pv * t1[k];
-          pdx += pv * v[k];
-        }
-        const T sc = T(1) / (sx[j] * c);
-        const T aty = a1 * sc, atdy = a2 * sc;
-        r3[0] = fmax(r3[0], fabs(px));
-        r3[1] = fmax(r3[1], fabs(aty));
-        r3[2] = fmax(r3[2], fabs(px + qg(j) + aty));
-        r3[3] = fmax(r3[3], fabs(atdy));
-        r3[4] = fmax(r3[4], fabs(pdx));
+    for (int j = tid; j < np; j += NT) {
+      T a1, a2;
+      At_col_dot2(j, y, w, a1, a2);
+      T px = T(0), pdx = T(0);
+      for (int e = S.PR_ptr[j]; e < S.PR_ptr[j + 1]; ++e) {
+        const T pv = Pg(__ldg(S.PR_slot + e));
+        const int k = __ldg(S.PR_col + e);
+        px += pv * t1[k];
+        pdx += pv * v[k];
       }
+      const T sc = T(1) / (sx[j] * c);
+      const T aty = a1 * sc, atdy = a2 * sc;
+      r3[0] = fmax(r3[0], fabs(px));
+      r3[1] = fmax(r3[1], fabs(aty));
+      r3[2] = fmax(r3[2], fabs(px + qg(j) + aty));
+      r3[3] = fmax(r3[3], fabs(atdy));
+      r3[4] = fmax(r3[4], fabs(pdx));
     }
     reduce<5, 0x1fu>(r3);
     const T n_Px = r3[0], n_Aty = r3[1], n_res = r3[2], n_Atdy = r3[3], n_Pdx = r3[4];
@@ -640,16 +822,16 @@ template <typename T, typename TIO, int NT> struct CtaSolver
     __syncthreads();
     assemble(delta, rho);
     if (!factor()) return SFB_QP_FLAG_POLISH_FAILED;
-    for (int j = tid; j < n; j += NT) t1[j] = T(0);
+    for (int j = tid; j < np; j += NT) t1[j] = T(0);
     for (int i = tid; i < m; i += NT) rinv[i] = T(0);
     __syncthreads();
     for (unsigned it = 0; it < prm.polish_iter; ++it) {
-      // r = h - H t -> (t2, z):  r1 = -qb - sym(Pbar) t1 - Aa^T rinv,  r2 = bnd - Aa t1 on active rows
-      for (int j = tid; j < n; j += NT) t2[j] = -qb[j] - Psym_row_dot(j, t1) - At_col_dot(j, rinv);
+      // r = h - H t:  r1 = -qb - sym(Pbar) t1 - Aa^T rinv -> v,  r2 = bnd - Aa t1 on active rows -> z
+      for (int j = tid; j < np; j += NT) v[j] = -qb[j] - Psym_row_dot(j, t1) - At_col_dot(j, rinv);
       for (int i = tid; i < m; i += NT) z[i] = (w[i] != T(0)) ? yold[i] - A_row_dot(i, t1) : T(0);
       __syncthreads();
       // s = Hp^-1 r -> (sv, s2):  (..) s1 = r1 + Aa^T r2 / delta,  s2 = (Aa s1 - r2) / delta
-      for (int j = tid; j < n; j += NT) v[j] = t2[j] + dinv * At_col_dot(j, z);
+      for (int j = tid; j < np; j += NT) v[j] += dinv * At_col_dot(j, z);
       __syncthreads();
       solve();
       T dm[2] = {T(0), T(0)};
@@ -660,7 +842,7 @@ template <typename T, typename TIO, int NT> struct CtaSolver
         dm[1] = fmax(dm[1], fabs(tn));
         rinv[i] = tn;  // read by its own thread only in this loop
       }
-      for (int j = tid; j < n; j += NT) {
+      for (int j = tid; j < np; j += NT) {
         const T s1 = sv[j], tn = t1[j] + s1;
         dm[0] = fmax(dm[0], fabs(s1));
         dm[1] = fmax(dm[1], fabs(tn));
@@ -670,9 +852,9 @@ template <typename T, typename TIO, int NT> struct CtaSolver
       if (dm[0] <= T(1e-12) * dm[1]) break;  // see qp_sparse_tiled.cuh::polish
     }
     bool bad = false;
-    for (int j = tid; j < n; j += NT) bad = bad || !(fabs(t1[j]) < Num<T>::inf());
+    for (int j = tid; j < np; j += NT) bad = bad || !(fabs(t1[j]) < Num<T>::inf());
     if (bany(bad)) return SFB_QP_FLAG_POLISH_FAILED;
-    for (int j = tid; j < n; j += NT) x[j] = t1[j];  // :199
+    for (int j = tid; j < np; j += NT) x[j] = t1[j];  // :199
     for (int i = tid; i < m; i += NT)
       if (w[i] != T(0)) y[i] = rinv[i];  // :200-201
     __syncthreads();
@@ -691,9 +873,7 @@ template <typename T, typename TIO, int NT> struct CtaSolver
     if (prof != nullptr && tid == 0) tlast = clock64();
     {
       const TIO* gA = a.A + b * (long long)S.nnzA;
-      const TIO* gP = a.P + b * (long long)S.nnzP;
       for (int e = tid; e < S.nnzA; e += NT) A[e] = (T)__ldg(gA + e);
-      for (int e = tid; e < S.nnzP; e += NT) P[e] = (T)__ldg(gP + e);
       T qn = T(0);
       for (int j = tid; j < n; j += NT) qn = fmax(qn, fabs((T)__ldg(a.q + b * (long long)n + j)));
       qn_us = bmax(qn);
@@ -702,7 +882,7 @@ template <typename T, typename TIO, int NT> struct CtaSolver
     if (prm.scaling) scale();  // :347
     else {
       c = T(1);
-      for (int j = tid; j < n; j += NT) sx[j] = T(1);
+      for (int j = tid; j < np; j += NT) sx[j] = T(1);
       for (int i = tid; i < m; i += NT) sy[i] = T(1);
       __syncthreads();
     }
@@ -725,7 +905,7 @@ template <typename T, typename TIO, int NT> struct CtaSolver
     }
     if (bany(triv)) code = SFB_QP_PRIMAL_INFEASIBLE;
     // ---- scaled data: qb = c Sx q, Abar = Sy A Sx  (:401-403, :450)
-    for (int j = tid; j < n; j += NT) qb[j] = (c * sx[j]) * qg(j);
+    for (int j = tid; j < np; j += NT) qb[j] = (c * sx[j]) * qg(j);
     for (int i = tid; i < m; i += NT) {
       const T syi = sy[i];
       const int e1 = arp[i + 1];
@@ -742,20 +922,26 @@ template <typename T, typename TIO, int NT> struct CtaSolver
     }
     // ---- initial iterate  :436-445
     if (polish_only) {
-      for (int pj = tid; pj < n; pj += NT) x[pj] = (T(1) / sx[pj]) * (T)a.out_x[b * (long long)n + __ldg(S.perm + pj)];
+      for (int pj = tid; pj < np; pj += NT) {
+        const int jo = __ldg(S.perm + pj);
+        x[pj] = jo >= 0 ? (T(1) / sx[pj]) * (T)a.out_x[b * (long long)n + jo] : T(0);
+      }
       for (int i = tid; i < m; i += NT) {
         y[i] = c * ((T(1) / sy[i]) * (T)a.out_y[b * (long long)m + i]);
         z[i] = T(0);
       }
     } else if (a.warm_x != nullptr) {
-      for (int pj = tid; pj < n; pj += NT) x[pj] = (T(1) / sx[pj]) * (T)__ldg(a.warm_x + b * (long long)n + __ldg(S.perm + pj));
+      for (int pj = tid; pj < np; pj += NT) {
+        const int jo = __ldg(S.perm + pj);
+        x[pj] = jo >= 0 ? (T(1) / sx[pj]) * (T)__ldg(a.warm_x + b * (long long)n + jo) : T(0);
+      }
       __syncthreads();
       for (int i = tid; i < m; i += NT) {
         y[i] = c * ((T(1) / sy[i]) * (T)__ldg(a.warm_y + b * (long long)m + i));
         z[i] = A_row_dot(i, x);
       }
     } else {
-      for (int j = tid; j < n; j += NT) x[j] = T(0);
+      for (int j = tid; j < np; j += NT) x[j] = T(0);
       for (int i = tid; i < m; i += NT) { y[i] = T(0); z[i] = T(0); }
     }
     __syncthreads();
@@ -769,12 +955,13 @@ template <typename T, typename TIO, int NT> struct CtaSolver
     if (polish_only) { code = skip ? kStatusUnset - 1 : (int)SFB_QP_OPTIMAL; iter = a.out_iter[b]; }
     for (; iter != a.max_iter_eff && code == kStatusUnset; ++iter) {
       // rhs = sigma x - qb + Abar^T w   (reduced system)
-      At_gather(w, v, [&](int j, T sum) { return sigma * x[j] - qb[j] + sum; });
+      for (int j = tid; j < np; j += NT) v[j] = sigma * x[j] - qb[j] + At_col_dot(j, w);
+      __syncthreads();
       mark(kPhRhs);
       solve();
       mark(kPhSolve);
       const bool chk = (iter % sci == 1u);
-      for (int j = tid; j < n; j += NT) {
+      for (int j = tid; j < np; j += NT) {
         const T xi = x[j];
         if (chk) xold[j] = xi;  // :465-468
         x[j] = alpha * sv[j] + alpha_comp * xi;  // :470
@@ -796,7 +983,7 @@ template <typename T, typename TIO, int NT> struct CtaSolver
       __syncthreads();
       mark(kPhUpdate);
       if (chk) {
-        code = check_stopping(prm, a.dinf_guard != 0);  // :488 (clobbers w, v, t1, t2)
+        code = check_stopping(prm, a.dinf_guard != 0);  // :488 (clobbers w, v, sv, t1)
         if (code == kStatusUnset && prm.has_max_time) {
           const bool late = (long long)(global_timer_ns() - t0) > prm.max_time_ns;  // :504-508
           if (bany(late)) code = SFB_QP_MAX_TIME;
@@ -835,15 +1022,17 @@ template <typename T, typename TIO, int NT> struct CtaSolver
     mark(kPhPolish);
     if (skip) return;
     // ---- unscale + objective  :544-548
-    for (int j = tid; j < n; j += NT) t1[j] = sx[j] * x[j];
+    for (int j = tid; j < np; j += NT) t1[j] = sx[j] * x[j];
     __syncthreads();
     T obj = T(0);
-    for (int j = tid; j < n; j += NT) {
+    for (int j = tid; j < np; j += NT) {
+      const int jo = __ldg(S.perm + j);
+      if (jo < 0) continue;
       T px = T(0);
-      for (int e = S.PR_ptr[j]; e < S.PR_ptr[j + 1]; ++e) px += (T(0.5) * P[__ldg(S.PR_slot + e)]) * t1[__ldg(S.PR_col + e)];
+      for (int e = S.PR_ptr[j]; e < S.PR_ptr[j + 1]; ++e) px += (T(0.5) * Pg(__ldg(S.PR_slot + e))) * t1[__ldg(S.PR_col + e)];
       const T xv = t1[j];
-      a.out_x[b * (long long)n + __ldg(S.perm + j)] = (TIO)xv;
-      obj += xv * (px + qg(j));
+      a.out_x[b * (long long)n + jo] = (TIO)xv;
+      obj += xv * (px + (T)__ldg(a.q + b * (long long)n + jo));
     }
     obj = bsum(obj);
     for (int i = tid; i < m; i += NT) a.out_y[b * (long long)m + i] = (TIO)(sy[i] * y[i] / c);
@@ -857,10 +1046,11 @@ template <typename T, typename TIO, int NT> struct CtaSolver
   }
 };
 
-template <typename T, typename TIO> __global__ void __launch_bounds__(kCtaNT, 1) qp_sparse_cta_kernel(const CtaArgs<T, TIO> a)
+// GT: the two big index tables stay in global memory (fp32: the working set then fits twice per SM)
+template <typename T, typename TIO, bool GT> __global__ void __launch_bounds__(kCtaNT, GT ? 2 : 1) qp_sparse_cta_kernel(const CtaArgs<T, TIO> a)
 {
   __shared__ long long next_inst;
-  CtaSolver<T, TIO, kCtaNT> s(a);
+  CtaSolver<T, TIO, kCtaNT, GT> s(a);
   s.load_tables();
   for (;;) {
     if (threadIdx.x == 0) next_inst = (long long)atomicAdd(a.work_counter, 1ull);

@@ -32,50 +32,64 @@
 
 namespace sfb {
 
-constexpr int kCtaNT = 512;  // threads of the on-chip kernel's CTA
+constexpr int kCtaNT = 256;  // threads of the on-chip kernel's CTA
 
 enum CtaStageKind { kStageFwdDiag = 0, kStageFwdPush = 1, kStageBwdPull = 2, kStageBwdDiag = 3 };
+
+// offset of row i inside a packed lower-triangular diagonal block whose rows are padded to multiples of pad = 1 << lpad scalars:
+// row i holds the entries (i, 0 .. i) -- the diagonal included -- followed by zeros up to the next multiple of pad
+inline int cta_diag_off(int i, int lpad)
+{
+  if (i <= 0) return 0;
+  const int G = i >> lpad, pad = 1 << lpad;
+  return ((G * (G + 1) / 2) << (2 * lpad)) + (i & (pad - 1)) * ((G + 1) << lpad);
+}
 
 struct CtaSymbolic
 {
   int n = 0, m = 0, nnzP = 0, nnzA = 0;
-  int nW = 0;        // value slots of the factor: the supernodal blocks; D_k lives at slot nW + k, 1 / D_k at nW + n + k
+  int pad = 4, lpad = 2;  // block rows and supernode starts are multiples of pad scalars (16-byte vector loads: 4 fp32 / 2 fp64)
+  int np = 0;             // padded column ids (holes behind supernodes whose size is not a multiple of pad); all n-vectors have np entries
+  int nW = 0;             // value slots of the factor (D_k lives on the diagonal of its block during the factorisation); 1 / D_k at nW + k (k: padded id)
   int ns = 0, nlev = 0, smax = 0;
-  int ordering = 0;  // 0 = minimum degree, 1 = nested dissection
-  int nnzL_true = 0; // structural entries of L before padding
+  int ordering = 0;       // 0 = minimum degree, 1 = nested dissection
+  int nnzL_true = 0;      // structural entries of L before padding
   long long flops = 0;
-  std::vector<int> perm, iperm;  // perm[new] = old
-  // supernodes (columns c0 .. c0 + s - 1, t rows below): diagonal block at dbase (entry (i, j), j < i, at dbase + i (i - 1) / 2 + j),
-  // below block at bbase (row r, column j at bbase + r s + j), its row indices rlist[rbase .. rbase + t)
-  std::vector<int> sn_c0, sn_s, sn_t, sn_dbase, sn_bbase, sn_rbase, sn_level;
+  std::vector<int> perm, iperm;  // perm[padded id] = original column or -1 (hole); iperm[original] = padded id
+  // supernodes (padded ids c0 .. c0 + s - 1, sp = s rounded up to pad, t rows below): diagonal block at dbase (entry (i, j), j <= i,
+  // at dbase + cta_diag_off(i) + j), below block at bbase (row r, column j at bbase + r sp + j), row ids rlist[rbase .. rbase + t)
+  std::vector<int> sn_c0, sn_s, sn_sp, sn_t, sn_dbase, sn_bbase, sn_rbase, sn_level;
   std::vector<int> rlist;
-  std::vector<int> col_sn;
-  // P and A in permuted indices and their gather mirrors (same meaning as in SparseSymbolic)
+  std::vector<int> col_sn;  // per padded id, -1 for holes
+  // P and A in padded ids and their gather mirrors (same meaning as in SparseSymbolic; pointer arrays have np + 1 entries)
   std::vector<int> P_rowp, P_colp, P_tgt;
   std::vector<int> A_rowptr, A_col;
   std::vector<int> AT_ptr, AT_row, AT_slot, PR_ptr, PR_col, PR_slot, PS_ptr, PS_col, PS_slot, PC_ptr, PC_slot;
   // assembly of Abar^T diag(w) Abar: rows of A are coloured so that rows of one colour touch disjoint columns; the pairs
-  // (a <= b) of the entries of every row of one colour are contiguous:  W[tgt] += w_row A[ea] A[eb]
-  std::vector<int> asm_ptr;         // [ncolors + 1] into the pair list
-  std::vector<int> asm_ab, asm_tr;  // ea | eb << 16 (entry indices of A),  tgt | row << 16
-  // the same list dealt to the kCtaNT threads of the kernel: rounds of kCtaNT (ab, tr) descriptors, every colour padded to
-  // whole rounds (padding: tr == -1); asm_round_sync[r] != 0: colour boundary, a barrier follows the round
+  // (a <= b) of the entries of every row of one colour are contiguous:  W[tgt] += w_row A[ea] A[eb].
+  // Dealt to the kCtaNT threads of the kernel: rounds of kCtaNT (ea | eb << 16, tgt | row << 16) descriptors, every colour
+  // padded to whole rounds (padding: second word == -1); asm_round_sync[r] != 0: colour boundary, a barrier follows the round
   std::vector<int> asm_round_desc, asm_round_sync;
-  // numeric factorisation: per supernode the pairs (a <= b) of its below rows and the slot of entry (R[b], R[a])
-  std::vector<int> ext_ptr, ext_word;  // a | b << 8 | target << 16
+  // numeric factorisation: per supernode the pairs (a <= b) of its below rows and the slot of entry (R[b], R[a]): a | b << 8 | target << 16
+  std::vector<int> ext_ptr, ext_word;
   // rounds: supernodes of one level (at most kCtaNT / 32 per round) advance column by column together.  4 ints per round:
-  // longest supernode, supernodes | warps << 16, first entry in fac_ext, first entry in fac_warp; fac_warp: one word per warp of the round,
-  // supernode | rank << 16 | warps of the supernode << 24 (warps without an entry idle)
+  // longest supernode, supernodes | warps << 16, first entry in fac_ext, first entry in fac_warp; fac_warp: one word per warp of
+  // the round, supernode | rank << 16 | warps of the supernode << 24
   std::vector<int> fac_rounds, fac_ext, fac_warp;
-  std::vector<int> sn_tab;  // 8 ints per supernode: c0, s, t, dbase, bbase, rbase, level, 0
-  // triangular sweeps: stages separated by CTA barriers; 4 ints per stage: kind, first output, outputs, 0.  Outputs of the
-  // diagonal / pull stages are the columns lev_cols[first ..] (columns in level order); outputs of a push stage are
-  // push_out[first ..] = dst | first task << 16 (the next entry bounds the task list), push_task = supernode | below row << 16
-  std::vector<int> stages, lev_cols, push_out, push_task;
-  // 16-bit copies (two per int) of the index arrays the kernel keeps in shared memory
-  std::vector<int> A_col16, AT_row16, AT_slot16, A_rowptr16, AT_ptr16, lev_cols16, col_sn16, rlist16;
+  std::vector<int> sn_tab;  // 8 ints per supernode: c0, s, t, dbase, bbase, rbase, sp, prbase
+  std::vector<int> prow;    // slot of every row of a supernode's panel (s rows of the diagonal block, then the t rows below), from prbase
+  // triangular sweeps: stages separated by CTA barriers; 4 ints per stage: kind, first output, outputs, log2(lanes per output).
+  //   forward diagonal stage:  outputs fdiag_out[first ..] = row k | supernode << 16
+  //   forward push stage:      outputs push_out[first ..] = dst | first task << 16 (the next entry bounds the task list),
+  //                            push_task = supernode | below row << 16
+  //   backward stages:         outputs bwd_out[first ..] = first column k of a group of pad columns | supernode << 16
+  std::vector<int> stages, fdiag_out, bwd_out, push_out, push_task;
+  std::vector<int> diag_off;  // cta_diag_off(i) for i <= smax
+  // 16-bit copies (two per int) of index arrays, and the column mirror of A as one word per entry: slot | row << 16
+  std::vector<int> A_col16, A_rowptr16, AT_ptr16, rlist16, diag_off16, prow16, AT_word;
   // everything the kernel copies into shared memory, concatenated (each table 16-byte aligned); smem_off[CtaIntTable]
   std::vector<int> smem_ints, smem_off;
+  bool big_tables_global = false;
   std::string error;
 };
 
@@ -394,32 +408,36 @@ inline SnPlan plan_supernodes(const Adj& adj, const std::vector<int>& perm_in, i
 
 }  // namespace cta_detail
 
-// shared-memory scalars the on-chip kernel needs per instance (W block, Abar, P, 11 n-vectors, 11 m-vectors, reduction scratch)
-// shared-memory footprint of the on-chip kernel per CTA: scalars of type T (factor slots + D + 1/D, Abar, P, 7 n-vectors,
+// shared-memory footprint of the on-chip kernel per CTA: scalars of type T (factor slots + 1/D, Abar, 6 n-vectors,
 // 8 m-vectors, reduction scratch) followed by the integer tables (CtaSymbolic::smem_ints)
-constexpr int kCtaNV = 7;
+constexpr int kCtaNV = 6;
 constexpr int kCtaMV = 8;
 constexpr int kCtaRed = 128;
-enum CtaIntTable { kI_Acol = 0, kI_ATrow, kI_ATslot, kI_Arowptr, kI_ATptr, kI_levcols, kI_colsn, kI_rlist, kI_sntab, kI_stages,
-                   kI_pushout, kI_pushtask, kI_extptr, kI_extword, kI_facrounds, kI_facext, kI_facwarp, kI_count };
+enum CtaIntTable { kI_Acol = 0, kI_ATword, kI_Arowptr, kI_ATptr, kI_rlist, kI_diagoff, kI_prow, kI_sntab, kI_stages, kI_fdiag, kI_bwd, kI_pushout,
+                   kI_pushtask, kI_extptr, kI_extword, kI_facrounds, kI_facext, kI_facwarp, kI_count };
+inline size_t cta_round4(size_t v) { return (v + 3) / 4 * 4; }
 inline size_t cta_smem_scalars(const CtaSymbolic& S)
 {
-  const size_t k = (size_t)S.nW + 2 * (size_t)S.n + S.nnzA + S.nnzP + (size_t)kCtaNV * (S.n + 1) + (size_t)kCtaMV * (S.m + 1) + kCtaRed;
-  return (k + 3) / 4 * 4;
+  return cta_round4((size_t)S.nW + (size_t)S.np) + cta_round4(S.nnzA) + (size_t)kCtaNV * cta_round4(S.np) +
+         (size_t)kCtaMV * cta_round4(S.m) + kCtaRed;
 }
 inline size_t cta_smem_bytes(const CtaSymbolic& S, size_t scalar) { return cta_smem_scalars(S) * scalar + S.smem_ints.size() * sizeof(int); }
 
-// md_perm: the minimum-degree order already computed by sparse_analyze (perm[new] = old)
+// md_perm: the minimum-degree order already computed by sparse_analyze (perm[new] = old); lpad: log2 of the row padding
 inline bool cta_analyze(int n, int m, const int32_t* P_colptr, const int32_t* P_rowidx, const int32_t* A_rowptr,
-                        const int32_t* A_colidx, const std::vector<int>& md_perm, CtaSymbolic& S, int force_ordering = -1)
+                        const int32_t* A_colidx, const std::vector<int>& md_perm, CtaSymbolic& S, int lpad = 2, int force_ordering = -1,
+                        bool big_tables_global = false)
 {
   using namespace cta_detail;
   S = CtaSymbolic();
   S.n = n;
   S.m = m;
+  S.lpad = lpad;
+  S.pad = 1 << lpad;
+  const int pad = S.pad;
   S.nnzP = P_colptr[n];
   S.nnzA = m > 0 ? A_rowptr[m] : 0;
-  if (n >= 0xffff || m >= 0xffff || S.nnzA >= 0xffff) { S.error = "too large for 16-bit schedule fields"; return false; }
+  if (n >= 0x7fff || m >= 0xffff || S.nnzA >= 0xffff) { S.error = "too large for 16-bit schedule fields"; return false; }
   // ---- pattern of M (original indices), as in sparse_analyze
   Adj adj(n);
   for (int j = 0; j < n; ++j)
@@ -454,57 +472,62 @@ inline bool cta_analyze(int n, int m, const int32_t* P_colptr, const int32_t* P_
     SnPlan pl = plan_supernodes(adj, postorder(adj, p), kZabs, kZrel, kScap);
     if (!have || pl.cost < best.cost) { best = std::move(pl); S.ordering = ord; have = true; }
   }
-  const SnPlan& pl = best;
-  S.perm = pl.perm;
-  S.iperm.assign(n, -1);
-  for (int k = 0; k < n; ++k) S.iperm[S.perm[k]] = k;
+  const SnPlan& pl = best;  // compact permuted indices 0 .. n - 1 (pl.perm[compact] = original)
   S.ns = (int)pl.s.size();
-  S.nlev = pl.nlev;
-  S.nW = pl.nW;
   S.flops = pl.flops;
   S.nnzL_true = pl.nnzL_true;
-  if ((long long)S.nW + 2LL * n >= 0xffff) { S.error = "factor too large for 16-bit schedule fields"; return false; }
-  // ---- slot layout
-  S.col_sn.assign(n, -1);
-  int slot = 0;
-  for (int q = 0; q < S.ns; ++q) {
-    const int s = pl.s[q], t = (int)pl.below[q].size();
-    S.sn_c0.push_back(pl.c0[q]);
-    S.sn_s.push_back(s);
-    S.sn_t.push_back(t);
-    S.sn_level.push_back(pl.level[q]);
-    S.sn_dbase.push_back(slot);
-    slot += s * (s - 1) / 2;
-    S.sn_bbase.push_back(slot);
-    slot += s * t;
-    S.sn_rbase.push_back((int)S.rlist.size());
-    S.rlist.insert(S.rlist.end(), pl.below[q].begin(), pl.below[q].end());
-    for (int c = 0; c < s; ++c) S.col_sn[pl.c0[q] + c] = q;
-    S.smax = std::max(S.smax, s);
+  // ---- padded ids and slot layout
+  std::vector<int> pid(n, -1), csn(n, -1);  // compact -> padded id / supernode
+  {
+    int next = 0, slot = 0;
+    for (int q = 0; q < S.ns; ++q) {
+      const int s = pl.s[q], sp = (s + pad - 1) / pad * pad, t = (int)pl.below[q].size();
+      S.sn_c0.push_back(next);
+      S.sn_s.push_back(s);
+      S.sn_sp.push_back(sp);
+      S.sn_t.push_back(t);
+      for (int c = 0; c < s; ++c) { pid[pl.c0[q] + c] = next + c; csn[pl.c0[q] + c] = q; }
+      next += sp;
+      S.sn_dbase.push_back(slot);
+      slot += cta_diag_off(s, lpad);
+      S.sn_bbase.push_back(slot);
+      slot += sp * t;
+      S.smax = std::max(S.smax, s);
+    }
+    S.np = next;
+    S.nW = slot;
   }
-  std::vector<std::unordered_map<int, int>> rowpos(S.ns);
+  if ((long long)S.nW + (long long)S.np >= 0xffff) { S.error = "factor too large for 16-bit schedule fields"; return false; }
+  S.perm.assign(S.np, -1);
+  S.iperm.assign(n, -1);
+  S.col_sn.assign(S.np, -1);
+  for (int k = 0; k < n; ++k) {
+    S.perm[pid[k]] = pl.perm[k];
+    S.iperm[pl.perm[k]] = pid[k];
+    S.col_sn[pid[k]] = csn[k];
+  }
+  for (int q = 0; q < S.ns; ++q) {
+    S.sn_rbase.push_back((int)S.rlist.size());
+    for (int r : pl.below[q]) S.rlist.push_back(pid[r]);
+  }
+  std::vector<std::unordered_map<int, int>> rowpos(S.ns);  // padded row id -> position in the below block
   for (int q = 0; q < S.ns; ++q)
     for (int r = 0; r < S.sn_t[q]; ++r) rowpos[q][S.rlist[S.sn_rbase[q] + r]] = r;
-  auto target = [&](int pr, int pc) -> int {  // permuted indices, any order
-    if (pr == pc) return S.nW + pr;
+  auto target = [&](int pr, int pc) -> int {  // PADDED ids, any order
     const int lo = std::min(pr, pc), hi = std::max(pr, pc);
     const int q = S.col_sn[lo];
     const int j = lo - S.sn_c0[q];
-    if (hi < S.sn_c0[q] + S.sn_s[q]) {
-      const int i = hi - S.sn_c0[q];
-      return S.sn_dbase[q] + i * (i - 1) / 2 + j;
-    }
+    if (hi < S.sn_c0[q] + S.sn_s[q]) return S.sn_dbase[q] + cta_diag_off(hi - S.sn_c0[q], lpad) + j;
     const auto f = rowpos[q].find(hi);
-    return f == rowpos[q].end() ? -2 : S.sn_bbase[q] + f->second * S.sn_s[q] + j;
+    return f == rowpos[q].end() ? -2 : S.sn_bbase[q] + f->second * S.sn_sp[q] + j;
   };
-  // the padded structure must contain the true one and be closed under elimination
-  {
-    const auto st = symbolic(adj, S.perm);
+  {  // the padded structure must contain the true one
+    const auto st = symbolic(adj, pl.perm);
     for (int k = 0; k < n; ++k)
       for (int r : st[k])
-        if (target(r, k) == -2) { S.error = "internal: supernodal structure does not cover L"; return false; }
+        if (target(pid[r], pid[k]) == -2) { S.error = "internal: supernodal structure does not cover L"; return false; }
   }
-  // ---- P, A in permuted indices, assembly targets, mirrors
+  // ---- P, A in padded ids, assembly targets, mirrors
   S.P_tgt.assign(S.nnzP, -1);
   S.P_rowp.resize(S.nnzP);
   S.P_colp.resize(S.nnzP);
@@ -540,21 +563,21 @@ inline bool cta_analyze(int n, int m, const int32_t* P_colptr, const int32_t* P_
     std::vector<std::array<int, 3>> trip;
     for (int i = 0; i < m; ++i)
       for (int e = S.A_rowptr[i]; e < S.A_rowptr[i + 1]; ++e) trip.push_back({S.A_col[e], i, e});
-    build_rows(n, trip, S.AT_ptr, S.AT_row, S.AT_slot);
+    build_rows(S.np, trip, S.AT_ptr, S.AT_row, S.AT_slot);
     trip.clear();
     for (int e = 0; e < S.nnzP; ++e) trip.push_back({S.P_rowp[e], S.P_colp[e], e});
-    build_rows(n, trip, S.PR_ptr, S.PR_col, S.PR_slot);
+    build_rows(S.np, trip, S.PR_ptr, S.PR_col, S.PR_slot);
     trip.clear();
     for (int e = 0; e < S.nnzP; ++e) {
       if (S.P_tgt[e] < 0) continue;
       trip.push_back({S.P_rowp[e], S.P_colp[e], e});
       if (S.P_rowp[e] != S.P_colp[e]) trip.push_back({S.P_colp[e], S.P_rowp[e], e});
     }
-    build_rows(n, trip, S.PS_ptr, S.PS_col, S.PS_slot);
+    build_rows(S.np, trip, S.PS_ptr, S.PS_col, S.PS_slot);
     trip.clear();
     for (int e = 0; e < S.nnzP; ++e) trip.push_back({S.P_colp[e], S.P_rowp[e], e});
     std::vector<int> dummy;
-    build_rows(n, trip, S.PC_ptr, dummy, S.PC_slot);
+    build_rows(S.np, trip, S.PC_ptr, dummy, S.PC_slot);
   }
   // ---- assembly pairs, rows coloured greedily (a colour = rows with pairwise disjoint column sets)
   {
@@ -563,7 +586,7 @@ inline bool cta_analyze(int n, int m, const int32_t* P_colptr, const int32_t* P_
     for (int i = 0; i < m; ++i) {
       int c = 0;
       for (;; ++c) {
-        if (c == (int)used.size()) used.emplace_back(n, 0);
+        if (c == (int)used.size()) used.emplace_back(S.np, 0);
         bool clash = false;
         for (int e = S.A_rowptr[i]; e < S.A_rowptr[i + 1] && !clash; ++e) clash = used[c][S.A_col[e]] != 0;
         if (!clash) break;
@@ -572,8 +595,8 @@ inline bool cta_analyze(int n, int m, const int32_t* P_colptr, const int32_t* P_
       for (int e = S.A_rowptr[i]; e < S.A_rowptr[i + 1]; ++e) used[c][S.A_col[e]] = 1;
     }
     const int ncol = (int)used.size();
-    S.asm_ptr.assign(1, 0);
     for (int c = 0; c < ncol; ++c) {
+      std::vector<int> ab, tr;
       for (int i = 0; i < m; ++i) {
         if (color[i] != c) continue;
         for (int e1 = S.A_rowptr[i]; e1 < S.A_rowptr[i + 1]; ++e1)
@@ -581,19 +604,15 @@ inline bool cta_analyze(int n, int m, const int32_t* P_colptr, const int32_t* P_
             const int t = target(S.A_col[e1], S.A_col[e2]);
             if (t == -2) { S.error = "internal: A^T A entry outside the symbolic factor"; return false; }
             if (e1 != e2 && S.A_col[e1] == S.A_col[e2]) { S.error = "duplicate column index in a row of A"; return false; }
-            S.asm_ab.push_back((int)((uint32_t)e1 | ((uint32_t)e2 << 16)));
-            S.asm_tr.push_back((int)((uint32_t)t | ((uint32_t)i << 16)));
+            ab.push_back((int)((uint32_t)e1 | ((uint32_t)e2 << 16)));
+            tr.push_back((int)((uint32_t)t | ((uint32_t)i << 16)));
           }
       }
-      S.asm_ptr.push_back((int)S.asm_ab.size());
-    }
-    for (int c = 0; c < ncol; ++c) {
-      const int p0 = S.asm_ptr[c], p1 = S.asm_ptr[c + 1];
-      if (p0 == p1) continue;
-      for (int p = p0; p < p1; p += kCtaNT) {
+      const int p1 = (int)ab.size();
+      for (int p = 0; p < p1; p += kCtaNT) {
         for (int k = 0; k < kCtaNT; ++k) {
-          S.asm_round_desc.push_back(p + k < p1 ? S.asm_ab[p + k] : 0);
-          S.asm_round_desc.push_back(p + k < p1 ? S.asm_tr[p + k] : -1);
+          S.asm_round_desc.push_back(p + k < p1 ? ab[p + k] : 0);
+          S.asm_round_desc.push_back(p + k < p1 ? tr[p + k] : -1);
         }
         S.asm_round_sync.push_back(p + kCtaNT >= p1 ? 1 : 0);
       }
@@ -625,52 +644,69 @@ inline bool cta_analyze(int n, int m, const int32_t* P_colptr, const int32_t* P_
     S.nlev = 0;
     for (int q = 0; q < S.ns; ++q) S.nlev = std::max(S.nlev, lev[q] + 1);
   }
-  // supernode table, 8 ints each (two 16-byte loads on the device)
   for (int q = 0; q < S.ns; ++q) {
-    const int row[8] = {S.sn_c0[q], S.sn_s[q], S.sn_t[q], S.sn_dbase[q], S.sn_bbase[q], S.sn_rbase[q], S.sn_level[q], 0};
+    const int row[8] = {S.sn_c0[q], S.sn_s[q], S.sn_t[q], S.sn_dbase[q], S.sn_bbase[q], S.sn_rbase[q], S.sn_sp[q], (int)S.prow.size()};
     S.sn_tab.insert(S.sn_tab.end(), row, row + 8);
+    for (int i = 0; i < S.sn_s[q]; ++i) S.prow.push_back(S.sn_dbase[q] + cta_diag_off(i, lpad));
+    for (int r = 0; r < S.sn_t[q]; ++r) S.prow.push_back(S.sn_bbase[q] + r * S.sn_sp[q]);
   }
-  // ---- sweep stages: columns in level order, pushes grouped by destination row
-  std::vector<int> lev_first(S.nlev + 1, 0);
-  for (int L = 0; L < S.nlev; ++L) {
-    lev_first[L] = (int)S.lev_cols.size();
-    for (int q = 0; q < S.ns; ++q)
-      if (S.sn_level[q] == L)
-        for (int i = 0; i < S.sn_s[q]; ++i) S.lev_cols.push_back(S.sn_c0[q] + i);
-  }
-  lev_first[S.nlev] = (int)S.lev_cols.size();
-  auto add_stage = [&](int kind, int first, int count) {
+  for (int i = 0; i <= S.smax; ++i) S.diag_off.push_back(cta_diag_off(i, lpad));
+  // ---- sweep stages
+  auto add_stage = [&](int kind, int first, int count, int longest) {  // longest: the most vector loads one output needs
     if (count == 0) return;
+    int lg = 0;
+    while (lg < 5 && (2 << lg) * count <= kCtaNT && (1 << lg) < longest) ++lg;
     S.stages.push_back(kind);
     S.stages.push_back(first);
     S.stages.push_back(count);
-    S.stages.push_back(0);
+    S.stages.push_back(lg);
   };
+  std::vector<int> bfirst(S.nlev + 1, 0);
+  for (int L = 0; L < S.nlev; ++L) {
+    bfirst[L] = (int)S.bwd_out.size();
+    for (int q = 0; q < S.ns; ++q)
+      if (S.sn_level[q] == L)
+        for (int kc = 0; kc < S.sn_s[q]; kc += pad) S.bwd_out.push_back((int)((uint32_t)(S.sn_c0[q] + kc) | ((uint32_t)q << 16)));
+  }
+  bfirst[S.nlev] = (int)S.bwd_out.size();
   for (int L = 0; L < S.nlev; ++L) {  // forward: diagonal blocks of level L, then their pushes into the rows above
-    add_stage(kStageFwdDiag, lev_first[L], lev_first[L + 1] - lev_first[L]);
+    int first = (int)S.fdiag_out.size(), longest = 0;
+    for (int q = 0; q < S.ns; ++q)
+      if (S.sn_level[q] == L)
+        for (int i = 0; i < S.sn_s[q]; ++i) {
+          S.fdiag_out.push_back((int)((uint32_t)(S.sn_c0[q] + i) | ((uint32_t)q << 16)));
+          longest = std::max(longest, (i + pad - 1) / pad);
+        }
+    add_stage(kStageFwdDiag, first, (int)S.fdiag_out.size() - first, longest);
     std::vector<std::array<int, 3>> tasks;  // dst, supernode, row of its below block
     for (int q = 0; q < S.ns; ++q) {
       if (S.sn_level[q] != L) continue;
       for (int r = 0; r < S.sn_t[q]; ++r) tasks.push_back({S.rlist[S.sn_rbase[q] + r], q, r});
     }
     std::stable_sort(tasks.begin(), tasks.end(), [](const std::array<int, 3>& a, const std::array<int, 3>& b) { return a[0] < b[0]; });
-    const int first = (int)S.push_out.size();
+    first = (int)S.push_out.size();
     int count = 0;
+    longest = 0;
     for (size_t k = 0; k < tasks.size();) {
       size_t e = k;
-      while (e < tasks.size() && tasks[e][0] == tasks[k][0]) ++e;
+      int len = 0;
+      while (e < tasks.size() && tasks[e][0] == tasks[k][0]) { len += S.sn_sp[tasks[e][1]] / pad; ++e; }
       S.push_out.push_back((int)((uint32_t)tasks[k][0] | ((uint32_t)S.push_task.size() << 16)));
       for (size_t j = k; j < e; ++j) S.push_task.push_back((int)((uint32_t)tasks[j][1] | ((uint32_t)tasks[j][2] << 16)));
+      longest = std::max(longest, len);
       ++count;
       k = e;
     }
     if (count > 0) S.push_out.push_back((int)(0xffffu | ((uint32_t)S.push_task.size() << 16)));  // sentinel: end of the last output's tasks
     if (S.push_task.size() >= 0xffff) { S.error = "too many push tasks for 16-bit schedule fields"; return false; }
-    add_stage(kStageFwdPush, first, count);
+    add_stage(kStageFwdPush, first, count, longest);
   }
   for (int L = S.nlev - 1; L >= 0; --L) {  // backward: pull from the rows above, then the transposed diagonal blocks
-    add_stage(kStageBwdPull, lev_first[L], lev_first[L + 1] - lev_first[L]);
-    add_stage(kStageBwdDiag, lev_first[L], lev_first[L + 1] - lev_first[L]);
+    int tmax = 0, smaxL = 0;
+    for (int q = 0; q < S.ns; ++q)
+      if (S.sn_level[q] == L) { tmax = std::max(tmax, S.sn_t[q]); smaxL = std::max(smaxL, S.sn_s[q]); }
+    add_stage(kStageBwdPull, bfirst[L], bfirst[L + 1] - bfirst[L], std::max(tmax, 1));
+    add_stage(kStageBwdDiag, bfirst[L], bfirst[L + 1] - bfirst[L], std::max(smaxL - 1, 1));
   }
   // ---- factorisation rounds: supernodes of one level advance column by column together, each with its own warps
   {
@@ -686,17 +722,24 @@ inline bool cta_analyze(int n, int m, const int32_t* P_colptr, const int32_t* P_
       std::sort(sn.begin(), sn.end(), [](const std::pair<long long, int>& a, const std::pair<long long, int>& b) { return a.first > b.first; });
       for (size_t k0 = 0; k0 < sn.size(); k0 += NWARP) {
         const int cnt = (int)std::min<size_t>(NWARP, sn.size() - k0);
-        std::vector<int> nw(cnt, 1);
+        std::vector<int> nw(cnt, 1), cap(cnt, 1);
+        for (int k = 0; k < cnt; ++k) {  // no more warps than vector elements of the first trailing panel, one per lane
+          const int q = sn[k0 + k].second;
+          cap[k] = std::max(1, std::min(NWARP, ((S.sn_s[q] + S.sn_t[q]) * (S.sn_sp[q] / pad) + 31) / 32));
+        }
         for (int extra = NWARP - cnt; extra > 0; --extra) {
-          int bi = 0;
-          for (int k = 1; k < cnt; ++k)
-            if (sn[k0 + k].first * nw[bi] > sn[k0 + bi].first * nw[k]) bi = k;
+          int bi = -1;
+          for (int k = 0; k < cnt; ++k)
+            if (nw[k] < cap[k] && (bi < 0 || sn[k0 + k].first * nw[bi] > sn[k0 + bi].first * nw[k])) bi = k;
+          if (bi < 0) break;
           nw[bi]++;
         }
+        int totw = 0;
+        for (int k = 0; k < cnt; ++k) totw += nw[k];
         int maxs = 0;
         for (int k = 0; k < cnt; ++k) maxs = std::max(maxs, S.sn_s[sn[k0 + k].second]);
         S.fac_rounds.push_back(maxs);
-        S.fac_rounds.push_back(cnt | (NWARP << 16));  // supernodes | warps with an entry << 16 (every warp gets one: cnt <= NWARP)
+        S.fac_rounds.push_back(cnt | (totw << 16));  // supernodes | warps with an entry << 16
         S.fac_rounds.push_back((int)S.fac_ext.size());
         S.fac_rounds.push_back((int)S.fac_warp.size());
         for (int k = 0; k < cnt; ++k) {
@@ -706,25 +749,29 @@ inline bool cta_analyze(int n, int m, const int32_t* P_colptr, const int32_t* P_
       }
     }
   }
-  // ---- 16-bit copies of the index arrays of A for shared memory (pairs packed into ints)
+  // ---- tables for shared memory
   auto pack16 = [](const std::vector<int>& v, std::vector<int>& out) {
     out.assign((v.size() + 1) / 2, 0);
     for (size_t k = 0; k < v.size(); ++k) out[k / 2] |= (int)((uint32_t)(v[k] & 0xffff) << (16 * (k & 1)));
   };
   pack16(S.A_col, S.A_col16);
-  pack16(S.AT_row, S.AT_row16);
-  pack16(S.AT_slot, S.AT_slot16);
   pack16(S.A_rowptr, S.A_rowptr16);
   pack16(S.AT_ptr, S.AT_ptr16);
-  pack16(S.lev_cols, S.lev_cols16);
-  pack16(S.col_sn, S.col_sn16);
   pack16(S.rlist, S.rlist16);
+  pack16(S.diag_off, S.diag_off16);
+  pack16(S.prow, S.prow16);
+  S.AT_word.resize(S.nnzA);
+  for (int e = 0; e < S.nnzA; ++e) S.AT_word[e] = (int)((uint32_t)S.AT_slot[e] | ((uint32_t)S.AT_row[e] << 16));
   {
-    const std::vector<int>* tabs[kI_count] = {&S.A_col16, &S.AT_row16, &S.AT_slot16, &S.A_rowptr16, &S.AT_ptr16, &S.lev_cols16, &S.col_sn16,
-                                              &S.rlist16, &S.sn_tab, &S.stages, &S.push_out, &S.push_task, &S.ext_ptr, &S.ext_word,
-                                              &S.fac_rounds, &S.fac_ext, &S.fac_warp};
+    const std::vector<int>* tabs[kI_count] = {&S.A_col16, &S.AT_word, &S.A_rowptr16, &S.AT_ptr16, &S.rlist16, &S.diag_off16, &S.prow16, &S.sn_tab, &S.stages,
+                                              &S.fdiag_out, &S.bwd_out, &S.push_out, &S.push_task, &S.ext_ptr, &S.ext_word, &S.fac_rounds,
+                                              &S.fac_ext, &S.fac_warp};
+    // big_tables_global: the column mirror of A and the external-update pairs stay in global memory (read through L1), which
+    // brings the fp32 working set under half an SM's shared memory: two CTAs per SM
+    S.big_tables_global = big_tables_global;
     for (int k = 0; k < kI_count; ++k) {
       S.smem_off.push_back((int)S.smem_ints.size());
+      if (big_tables_global && (k == kI_ATword || k == kI_extword)) continue;
       S.smem_ints.insert(S.smem_ints.end(), tabs[k]->begin(), tabs[k]->end());
       while (S.smem_ints.size() % 4) S.smem_ints.push_back(0);
     }
@@ -736,20 +783,24 @@ inline int cta_lo16(int x) { return (int)((uint32_t)x & 0xffffu); }
 inline int cta_hi16(int x) { return (int)((uint32_t)x >> 16); }
 
 // Host execution of the schedules on one instance (double): assembles M = shift I + triu-mirrored Pbar + A^T diag(w) A from
-// the tables, factorises, inverts the diagonal blocks and runs the sweeps exactly as the device kernel does (stage by
-// stage, sequentially).  Test infrastructure for the CPU suite: validates every table without a GPU.
+// the tables, factorises, inverts the diagonal blocks and runs the sweeps as the device kernel does (stage by stage,
+// sequentially, vector padding included).  Test infrastructure for the CPU suite: validates every table without a GPU.
 struct CtaHostExec
 {
   const CtaSymbolic& S;
-  std::vector<double> W;  // nW + 2 n
-  explicit CtaHostExec(const CtaSymbolic& s) : S(s), W((size_t)s.nW + 2 * (size_t)s.n, 0.0) {}
+  std::vector<double> W;  // nW + np
+  explicit CtaHostExec(const CtaSymbolic& s) : S(s), W((size_t)s.nW + (size_t)s.np, 0.0) {}
   static int u16at(const std::vector<int>& packed, int k) { return (int)(((uint32_t)packed[k / 2] >> (16 * (k & 1))) & 0xffffu); }
+  int prow(int q, int p) const { return u16at(S.prow16, S.sn_tab[8 * q + 7] + p); }  // slot of panel row p of supernode q
 
   // Pv: values of P in pattern order (already scaled), Av: values of A in CSR order, w: row weights
   void assemble(double shift, const double* Pv, const double* Av, const double* w)
   {
     std::fill(W.begin(), W.end(), 0.0);
-    for (int k = 0; k < S.n; ++k) W[S.nW + k] = shift;
+    for (int e = 0; e < S.n; ++e) {  // the diagonal of every real column, through the table the kernel uses
+      const int k = cta_lo16(S.fdiag_out[e]), q = cta_hi16(S.fdiag_out[e]), i = k - S.sn_tab[8 * q];
+      W[prow(q, i) + i] = shift;
+    }
     for (int e = 0; e < S.nnzP; ++e)
       if (S.P_tgt[e] >= 0) W[S.P_tgt[e]] += Pv[e];
     for (size_t r = 0; r < S.asm_round_sync.size(); ++r)
@@ -762,7 +813,7 @@ struct CtaHostExec
   // the factorisation rounds, executed sequentially; false on a non-positive pivot or an inconsistent round table
   bool factor()
   {
-    const int n = S.n, nW = S.nW;
+    const int nW = S.nW, pad = S.pad;
     bool ok = true;
     std::vector<int> done(S.ns, 0);
     for (size_t r = 0; r < S.fac_rounds.size() / 4; ++r) {
@@ -770,7 +821,8 @@ struct CtaHostExec
       int nwarps = 0;
       for (int k = 0; k < cnt; ++k) {
         const int q = S.fac_ext[e0 + k];
-        const int c0 = S.sn_tab[8 * q], s = S.sn_tab[8 * q + 1], t = S.sn_tab[8 * q + 2], db = S.sn_tab[8 * q + 3], bb = S.sn_tab[8 * q + 4];
+        const int c0 = S.sn_tab[8 * q], s = S.sn_tab[8 * q + 1], t = S.sn_tab[8 * q + 2], db = S.sn_tab[8 * q + 3], bb = S.sn_tab[8 * q + 4],
+                  sp = S.sn_tab[8 * q + 6];
         if (s > S.fac_rounds[4 * r]) ok = false;
         done[q]++;
         const int nw = (int)((uint32_t)S.fac_warp[w0 + nwarps] >> 24);
@@ -779,67 +831,69 @@ struct CtaHostExec
           if ((int)(wd & 0xffff) != q || (int)((wd >> 16) & 0xff) != rr || (int)(wd >> 24) != nw) ok = false;
         }
         nwarps += nw;
-        for (int kc = 0; kc <= s; ++kc) {
-          if (kc > 0) {  // lazy scaling of the previous column
-            const double dinv = W[nW + n + c0 + kc - 1];
-            for (int i = kc; i < s; ++i) W[db + i * (i - 1) / 2 + kc - 1] *= dinv;
-            for (int rr = 0; rr < t; ++rr) W[bb + rr * s + kc - 1] *= dinv;
-          }
-          if (kc == s) break;
-          const double d = W[nW + c0 + kc];
+        for (int p = 0; p < s + t; ++p)
+          if (prow(q, p) != (p < s ? db + cta_diag_off(p, S.lpad) : bb + (p - s) * sp)) ok = false;
+        for (int kc = 0; kc < s; ++kc) {
+          const double d = W[prow(q, kc) + kc];
           if (!(d > 0)) ok = false;
           const double dinv = 1.0 / d;
-          W[nW + n + c0 + kc] = dinv;
-          for (int p = 0; p < s - kc - 1 + t; ++p) {
-            const bool diag = p < s - kc - 1;
-            const int i = kc + 1 + p;
-            const int rb = diag ? db + i * (i - 1) / 2 : bb + (p - (s - kc - 1)) * s;
-            const int jmax = diag ? i : s - 1;
-            const double vi = W[rb + kc];
-            for (int j = kc + 1; j <= jmax; ++j) {
-              const double vj = W[db + j * (j - 1) / 2 + kc];
-              const int tg = (diag && j == i) ? nW + c0 + j : rb + j;
-              W[tg] -= vi * (vj * dinv);
+          W[nW + c0 + kc] = dinv;
+          // the kernel's uniform update: every row p > kc, every whole vector of columns from the one holding kc + 1 on; columns
+          // <= kc and >= s see a zero multiplier, the padding of a row (columns > p) collects garbage that the cleanup removes
+          for (int p = kc + 1; p < s + t; ++p) {
+            const double vi = W[prow(q, p) + kc];
+            const int jend = (p < s) ? (p / pad + 1) * pad : sp;
+            for (int j = (kc + 1) / pad * pad; j < jend; ++j) {
+              const double vjs = (j > kc && j < s) ? W[prow(q, j) + kc] * dinv : 0.0;
+              if (j > kc) W[prow(q, p) + j] -= vi * vjs;
             }
           }
         }
       }
       if (nwarps != cta_hi16(S.fac_rounds[4 * r + 1]) || nwarps > kCtaNT / 32) ok = false;
-      for (int k = 0; k < cnt; ++k) {  // external updates with the scaled columns: L D L^T
+      for (int k = 0; k < cnt; ++k) {  // external updates with the unscaled columns: U D^-1 U^T
         const int q = S.fac_ext[e0 + k];
-        const int c0 = S.sn_tab[8 * q], s = S.sn_tab[8 * q + 1], bb = S.sn_tab[8 * q + 4];
+        const int c0 = S.sn_tab[8 * q], bb = S.sn_tab[8 * q + 4], sp = S.sn_tab[8 * q + 6];
         for (int p = S.ext_ptr[q]; p < S.ext_ptr[q + 1]; ++p) {
           const uint32_t wd = (uint32_t)S.ext_word[p];
           const int a = wd & 0xff, b = (wd >> 8) & 0xff, tg = wd >> 16;
           double acc = 0;
-          for (int c = 0; c < s; ++c) acc += (W[bb + a * s + c] * W[nW + c0 + c]) * W[bb + b * s + c];
+          for (int c = 0; c < sp; ++c) acc += (W[bb + a * sp + c] * W[nW + c0 + c]) * W[bb + b * sp + c];  // padding: zeros, 1 / D of a hole: zero
           W[tg] -= acc;
         }
       }
     }
     for (int q = 0; q < S.ns; ++q)
       if (done[q] != 1) ok = false;
-    // invert the unit-lower diagonal blocks in place; stored: X' = -(strict lower part of L_SS^-1)
-    for (int i = 1; i < S.smax; ++i) {
-      std::vector<std::pair<int, double>> writes;
-      for (int q = 0; q < S.ns; ++q) {
-        const int s = S.sn_s[q], db = S.sn_dbase[q];
-        if (i >= s) continue;
-        for (int c = 0; c < i; ++c) {
-          double acc = W[db + i * (i - 1) / 2 + c];
-          for (int j = c + 1; j < i; ++j) acc -= W[db + i * (i - 1) / 2 + j] * W[db + j * (j - 1) / 2 + c];
-          writes.push_back({db + i * (i - 1) / 2 + c, acc});
+    // scale the panels, L = (unscaled columns) D^-1, and clear the diagonal and the padding of every row of a diagonal block
+    for (int q = 0; q < S.ns; ++q) {
+      const int c0 = S.sn_c0[q], s = S.sn_s[q], t = S.sn_t[q], sp = S.sn_sp[q];
+      for (int p = 0; p < s + t; ++p) {
+        const int jend = (p < s) ? (p / pad + 1) * pad : sp;
+        for (int j = 0; j < jend; ++j) {
+          double& e = W[prow(q, p) + j];
+          e = (p < s && j >= p) ? 0.0 : e * W[nW + c0 + j];
         }
       }
-      for (auto& wv : writes) W[wv.first] = wv.second;
     }
+    // invert the unit-lower diagonal blocks in place, right-looking; stored: X' = -(strict lower part of L_SS^-1).
+    // Step k: X'(i, c) -= L(i, k) X'(k, c) for i > k over the whole vectors of row k
+    for (int k = 1; k + 1 < S.smax; ++k)
+      for (int q = 0; q < S.ns; ++q) {
+        const int s = S.sn_s[q];
+        for (int i = k + 1; i < s; ++i) {
+          const double lik = W[prow(q, i) + k];
+          for (int c = 0; c < (k + pad - 1) / pad * pad; ++c) W[prow(q, i) + c] -= lik * W[prow(q, k) + c];
+        }
+      }
     return ok;
   }
-  // v (permuted order, length n) <- (L D L^T)^-1 v
+  // v (padded ids, length np, holes zero) <- (L D L^T)^-1 v.  Every dot product runs over whole padded rows, as the vector
+  // loads of the kernel do: the padding must hold zeros.
   void solve(std::vector<double>& v) const
   {
-    const int n = S.n, nW = S.nW;
-    std::vector<double> y(n, 0.0);
+    const int np = S.np, nW = S.nW, pad = S.pad;
+    std::vector<double> y(np, 0.0);
     for (size_t st = 0; st < S.stages.size() / 4; ++st) {
       const int kind = S.stages[4 * st], first = S.stages[4 * st + 1], count = S.stages[4 * st + 2];
       std::vector<std::pair<int, double>> writes;
@@ -849,26 +903,31 @@ struct CtaHostExec
           double acc = 0;
           for (int k = t0; k < t1; ++k) {
             const int q = cta_lo16(S.push_task[k]), r = cta_hi16(S.push_task[k]);
-            const int c0 = S.sn_tab[8 * q], s = S.sn_tab[8 * q + 1], bb = S.sn_tab[8 * q + 4];
-            for (int c = 0; c < s; ++c) acc += W[bb + r * s + c] * y[c0 + c];
+            const int c0 = S.sn_tab[8 * q], bb = S.sn_tab[8 * q + 4], sp = S.sn_tab[8 * q + 6];
+            for (int c = 0; c < sp; ++c) acc += W[bb + r * sp + c] * y[c0 + c];
           }
           writes.push_back({dst, v[dst] - acc});
-          continue;
-        }
-        const int k = u16at(S.lev_cols16, o), q = u16at(S.col_sn16, k);
-        const int c0 = S.sn_tab[8 * q], s = S.sn_tab[8 * q + 1], t = S.sn_tab[8 * q + 2], db = S.sn_tab[8 * q + 3], bb = S.sn_tab[8 * q + 4],
-                  rb = S.sn_tab[8 * q + 5];
-        const int i = k - c0;
-        double acc = 0;
-        if (kind == kStageFwdDiag) {
-          for (int c = 0; c < i; ++c) acc += W[db + i * (i - 1) / 2 + c] * v[c0 + c];
+        } else if (kind == kStageFwdDiag) {
+          const int k = cta_lo16(S.fdiag_out[o]), q = cta_hi16(S.fdiag_out[o]);
+          const int c0 = S.sn_tab[8 * q], i = k - c0;
+          double acc = 0;
+          for (int c = 0; c < (i + pad - 1) / pad * pad; ++c) acc += W[prow(q, i) + c] * v[c0 + c];
           writes.push_back({k, v[k] - acc});
-        } else if (kind == kStageBwdPull) {
-          for (int r = 0; r < t; ++r) acc += W[bb + r * s + i] * y[u16at(S.rlist16, rb + r)];
-          writes.push_back({k, W[nW + n + k] * y[k] - acc});
         } else {
-          for (int ii = i + 1; ii < s; ++ii) acc += W[db + ii * (ii - 1) / 2 + i] * v[c0 + ii];
-          writes.push_back({k, v[k] - acc});
+          const int k0 = cta_lo16(S.bwd_out[o]), q = cta_hi16(S.bwd_out[o]);
+          const int c0 = S.sn_tab[8 * q], s = S.sn_tab[8 * q + 1], t = S.sn_tab[8 * q + 2], bb = S.sn_tab[8 * q + 4], rb = S.sn_tab[8 * q + 5],
+                    sp = S.sn_tab[8 * q + 6];
+          const int kc = k0 - c0;
+          for (int c = 0; c < pad; ++c) {  // whole vectors: the holes come out as zero
+            double acc = 0;
+            if (kind == kStageBwdPull) {
+              for (int r = 0; r < t; ++r) acc += W[bb + r * sp + kc + c] * y[u16at(S.rlist16, rb + r)];
+              writes.push_back({k0 + c, W[nW + k0 + c] * y[k0 + c] - acc});
+            } else {
+              for (int i = kc + 1; i < s; ++i) acc += W[prow(q, i) + kc + c] * v[c0 + i];  // columns >= i of row i: zeros
+              writes.push_back({k0 + c, v[k0 + c] - acc});
+            }
+          }
         }
       }
       std::vector<double>& out = (kind == kStageFwdDiag || kind == kStageBwdDiag) ? y : v;

@@ -22,10 +22,14 @@ struct sfb_qp_sparse_pattern
   std::vector<int> csc2csr;
   int* d_csc2csr = nullptr;
   // on-chip kernel (qp_sparse_cta.cuh): its own ordering / supernodal schedules; cta_ok == false: tiled kernel only
-  bool cta_ok = false;
-  sfb::CtaSymbolic cta;
-  int* cta_dev = nullptr;
-  sfb::CtaPattern cta_pat{};
+  struct Cta
+  {
+    bool ok = false;
+    sfb::CtaSymbolic sym;
+    int* dev = nullptr;
+    sfb::CtaPattern pat{};
+  } cta[2];  // [0]: fp32 layout (rows padded to 4 scalars), [1]: fp64 layout (2 scalars)
+  template <typename T> const Cta& cta_for() const { return cta[sizeof(T) == 4 ? 0 : 1]; }
 };
 
 namespace {
@@ -75,37 +79,38 @@ int sp_launch(sfb_context* h, const sfb_qp_sparse_pattern* pt, sfb::SpArgs<T, TI
 }
 
 // ---- on-chip kernel: one CTA per instance, working set in shared memory ----
-template <typename T> size_t cta_smem_bytes(const sfb_qp_sparse_pattern* pt) { return sfb::cta_smem_bytes(pt->cta, sizeof(T)); }
+template <typename T> size_t cta_smem_bytes(const sfb_qp_sparse_pattern* pt) { return sfb::cta_smem_bytes(pt->cta_for<T>().sym, sizeof(T)); }
 
 template <typename T> bool cta_fits(const sfb_context* h, const sfb_qp_sparse_pattern* pt)
 {
-  return pt->cta_ok && h->sparse_kernel != 1 && cta_smem_bytes<T>(pt) + 64 <= (size_t)h->prop.sharedMemPerBlockOptin;
+  return pt->cta_for<T>().ok && h->sparse_kernel != 1 && cta_smem_bytes<T>(pt) + 64 <= (size_t)h->prop.sharedMemPerBlockOptin;
 }
 
 // ws: device workspace for the launch (grid x (n + m) scalars of T), carved by the caller
 template <typename T, typename TIO> int cta_launch(sfb_context* h, const sfb_qp_sparse_pattern* pt, sfb::CtaArgs<T, TIO>& a)
 {
   const size_t smem = cta_smem_bytes<T>(pt);
-  auto* kern = sfb::qp_sparse_cta_kernel<T, TIO>;
+  constexpr bool GT = sizeof(T) == 4;  // matches the analysis of the fp32 layout (big tables in global memory)
+  auto* kern = sfb::qp_sparse_cta_kernel<T, TIO, GT>;
   SFB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 1;
   SFB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, sfb::kCtaNT, smem));
   if (occ < 1) return fail(h, SFB_ERR_UNSUPPORTED_SIZE, "on-chip sparse kernel does not fit on an SM");
   const unsigned grid = (unsigned)std::min<long long>(a.batch, (long long)h->prop.multiProcessorCount * occ);
-  int rc = ensure_scratch(h, h->sparse_cta_ws, (size_t)grid * (size_t)(pt->cta.n + pt->cta.m) * sizeof(T), h->stream);
+  int rc = ensure_scratch(h, h->sparse_cta_ws, (size_t)grid * (size_t)(pt->cta_for<T>().sym.np + pt->cta_for<T>().sym.m) * sizeof(T), h->stream);
   if (rc != SFB_OK) return rc;
   a.ws = static_cast<T*>(h->sparse_cta_ws.dev);
   a.work_counter = next_counter(h, kNumSlots);
   SFB_CUDA(h, cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), h->stream));
   static const bool prof_on = getenv("SFB_CTA_PROF") != nullptr;  // dev instrumentation: cycles per phase, printed after a blocking sync
   unsigned long long* prof = nullptr;
-  if (prof_on && cudaMalloc(&prof, sizeof(unsigned long long) * sfb::kPhCount) == cudaSuccess) cudaMemset(prof, 0, sizeof(unsigned long long) * sfb::kPhCount);
+  if (prof_on && cudaMalloc(&prof, sizeof(unsigned long long) * sfb::kPhTotal) == cudaSuccess) cudaMemset(prof, 0, sizeof(unsigned long long) * sfb::kPhTotal);
   a.prof = prof;
   kern<<<grid, sfb::kCtaNT, smem, h->stream>>>(a);
   SFB_CUDA(h, cudaGetLastError());
   h->launches += 1;
   if (prof) {
-    unsigned long long hp[sfb::kPhCount];
+    unsigned long long hp[sfb::kPhTotal];
     cudaStreamSynchronize(h->stream);
     cudaMemcpy(hp, prof, sizeof(hp), cudaMemcpyDeviceToHost);
     cudaFree(prof);
@@ -114,6 +119,16 @@ template <typename T, typename TIO> int cta_launch(sfb_context* h, const sfb_qp_
     for (int k = 0; k < sfb::kPhCount; ++k) tot += (double)hp[k];
     fprintf(stderr, "[cta prof] T=%d mode=%d batch=%lld grid=%u smem=%zu cycles/instance=%.0f:", (int)sizeof(T), a.mode, a.batch, grid, smem, tot / (double)a.batch);
     for (int k = 0; k < sfb::kPhCount; ++k) fprintf(stderr, " %s=%.0f(%.1f%%)", names[k], (double)hp[k] / (double)a.batch, 100.0 * hp[k] / tot);
+    fprintf(stderr, "\n[cta prof] sweep stages (kind:lgG:count cycles per solve call), %d stages:", pt->cta_for<T>().pat.nstages);
+    {
+      const sfb::CtaSymbolic& Cs = pt->cta_for<T>().sym;
+      double calls = 0;  // solve() calls per instance = stage-0 total / ... : normalise by the solve phase instead
+      double stot = 0;
+      for (int k = 0; k < 32; ++k) stot += (double)hp[sfb::kPhStage0 + k];
+      (void)calls;
+      for (size_t k = 0; k < Cs.stages.size() / 4 && k < 32; ++k)
+        fprintf(stderr, " [%d:%d:%d %.1f%%]", Cs.stages[4 * k], Cs.stages[4 * k + 3], Cs.stages[4 * k + 2], 100.0 * hp[sfb::kPhStage0 + k] / std::max(stot, 1.0));
+    }
     fprintf(stderr, "\n");
   }
   return SFB_OK;
@@ -177,7 +192,7 @@ int qp_sparse_solve_impl(sfb_context* h, const sfb_qp_sparse_pattern* pt, const 
     int rc2;
     if (use_cta) {
       sfb::CtaArgs<T, T> ca{};
-      ca.pat = pt->cta_pat; ca.batch = a.batch; ca.prm = a.prm; ca.max_iter_eff = a.max_iter_eff; ca.mode = 0; ca.dinf_guard = a.dinf_guard;
+      ca.pat = pt->cta_for<T>().pat; ca.batch = a.batch; ca.prm = a.prm; ca.max_iter_eff = a.max_iter_eff; ca.mode = 0; ca.dinf_guard = a.dinf_guard;
       ca.P = a.P; ca.q = a.q; ca.A = a.A; ca.l = a.l; ca.u = a.u; ca.warm_x = a.warm_x; ca.warm_y = a.warm_y;
       ca.out_x = a.out_x; ca.out_y = a.out_y; ca.out_obj = a.out_obj; ca.out_status = a.out_status; ca.out_iter = a.out_iter;
       ca.out_active = a.out_active; ca.out_flags = a.out_flags;
@@ -188,7 +203,7 @@ int qp_sparse_solve_impl(sfb_context* h, const sfb_qp_sparse_pattern* pt, const 
     if (rc2 != SFB_OK || !mixed) return rc2;
     if (polish_cta) {
       sfb::CtaArgs<double, T> ca{};
-      ca.pat = pt->cta_pat; ca.batch = a.batch; ca.prm = a.prm; ca.max_iter_eff = a.max_iter_eff; ca.mode = 2; ca.dinf_guard = a.dinf_guard;
+      ca.pat = pt->cta_for<double>().pat; ca.batch = a.batch; ca.prm = a.prm; ca.max_iter_eff = a.max_iter_eff; ca.mode = 2; ca.dinf_guard = a.dinf_guard;
       ca.P = a.P; ca.q = a.q; ca.A = a.A; ca.l = a.l; ca.u = a.u;
       ca.out_x = a.out_x; ca.out_y = a.out_y; ca.out_obj = a.out_obj; ca.out_status = a.out_status; ca.out_iter = a.out_iter;
       ca.out_active = a.out_active; ca.out_flags = a.out_flags;
@@ -323,36 +338,38 @@ int sfb_qp_sparse_analyze(sfb_handle_t h, int n, int m, const int32_t* P_colptr,
   d.nFS = (int)S.FS_meta.size(); d.nBS = (int)S.BS_meta.size();
   d.RP_col = base + off[38]; d.RP_slot = base + off[39]; d.ATP_row = base + off[40]; d.ATP_slot = base + off[41];
   d.WR = S.WR; d.WA = S.WA; d.m_pad = S.m_pad; d.n_pad = S.n_pad;
-  // ---- on-chip kernel: second analysis (ordering for a short supernodal elimination tree); failure only disables that path
-  {
-    sfb::CtaSymbolic& Cs = p->cta;
-    if (n <= 4 * sfb::kCtaNT && sfb::cta_analyze(n, m, P_colptr, P_rowidx, A_rowptr, A_colidx, S.perm, Cs)) {
-      const std::vector<int>* carr[] = {&Cs.smem_ints, &Cs.perm, &Cs.iperm, &Cs.P_rowp, &Cs.P_colp, &Cs.P_tgt, &Cs.PR_ptr, &Cs.PR_col, &Cs.PR_slot,
-                                        &Cs.PS_ptr, &Cs.PS_col, &Cs.PS_slot, &Cs.PC_ptr, &Cs.PC_slot, &Cs.asm_round_sync, &Cs.asm_round_desc};
-      size_t ctotal = 0;
-      std::vector<size_t> coff;
-      for (auto* v : carr) { coff.push_back(ctotal); ctotal += (v->size() + 31) / 32 * 32; }
-      std::vector<int> cflat(ctotal, 0);
-      for (size_t k = 0; k < coff.size(); ++k) std::copy(carr[k]->begin(), carr[k]->end(), cflat.begin() + coff[k]);
-      if (cudaMalloc(&p->cta_dev, ctotal * sizeof(int)) == cudaSuccess &&
-          cudaMemcpy(p->cta_dev, cflat.data(), ctotal * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess) {
-        sfb::CtaPattern& c = p->cta_pat;
-        const int* cb = p->cta_dev;
-        c.n = n; c.m = m; c.nnzP = Cs.nnzP; c.nnzA = Cs.nnzA; c.nW = Cs.nW; c.ns = Cs.ns; c.smax = Cs.smax;
-        c.nstages = (int)Cs.stages.size() / 4; c.nrounds = (int)Cs.asm_round_sync.size(); c.nfacrounds = (int)Cs.fac_rounds.size() / 4;
-        c.nints = (int)Cs.smem_ints.size();
-        c.tscalars = (unsigned)sfb::cta_smem_scalars(Cs);
-        for (int k = 0; k < sfb::kI_count; ++k) c.ioff[k] = Cs.smem_off[k];
-        c.ints = cb + coff[0]; c.perm = cb + coff[1]; c.iperm = cb + coff[2]; c.P_rowp = cb + coff[3]; c.P_colp = cb + coff[4];
-        c.P_tgt = cb + coff[5]; c.PR_ptr = cb + coff[6]; c.PR_col = cb + coff[7]; c.PR_slot = cb + coff[8];
-        c.PS_ptr = cb + coff[9]; c.PS_col = cb + coff[10]; c.PS_slot = cb + coff[11]; c.PC_ptr = cb + coff[12]; c.PC_slot = cb + coff[13];
-        c.asm_sync = cb + coff[14];
-        c.asm_desc = reinterpret_cast<const int2*>(cb + coff[15]);
-        p->cta_ok = true;
-      } else {
-        cudaGetLastError();
-        if (p->cta_dev) { cudaFree(p->cta_dev); p->cta_dev = nullptr; }
-      }
+  // ---- on-chip kernel: its own analyses (ordering for a short supernodal elimination tree; one layout per precision);
+  // a failure only disables that path
+  for (int which = 0; which < 2 && n <= 2 * sfb::kCtaNT; ++which) {
+    sfb_qp_sparse_pattern::Cta& C = p->cta[which];
+    sfb::CtaSymbolic& Cs = C.sym;
+    if (!sfb::cta_analyze(n, m, P_colptr, P_rowidx, A_rowptr, A_colidx, S.perm, Cs, which == 0 ? 2 : 1, -1, which == 0)) continue;
+    const std::vector<int>* carr[] = {&Cs.smem_ints, &Cs.perm, &Cs.iperm, &Cs.P_rowp, &Cs.P_colp, &Cs.P_tgt, &Cs.PR_ptr, &Cs.PR_col, &Cs.PR_slot,
+                                      &Cs.PS_ptr, &Cs.PS_col, &Cs.PS_slot, &Cs.PC_ptr, &Cs.PC_slot, &Cs.asm_round_sync, &Cs.asm_round_desc, &Cs.AT_word, &Cs.ext_word};
+    size_t ctotal = 0;
+    std::vector<size_t> coff;
+    for (auto* v : carr) { coff.push_back(ctotal); ctotal += (v->size() + 31) / 32 * 32; }
+    std::vector<int> cflat(ctotal, 0);
+    for (size_t k = 0; k < coff.size(); ++k) std::copy(carr[k]->begin(), carr[k]->end(), cflat.begin() + coff[k]);
+    if (cudaMalloc(&C.dev, ctotal * sizeof(int)) == cudaSuccess &&
+        cudaMemcpy(C.dev, cflat.data(), ctotal * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess) {
+      sfb::CtaPattern& c = C.pat;
+      const int* cb = C.dev;
+      c.n = n; c.m = m; c.np = Cs.np; c.nnzP = Cs.nnzP; c.nnzA = Cs.nnzA; c.nW = Cs.nW; c.ns = Cs.ns; c.smax = Cs.smax;
+      c.nstages = (int)Cs.stages.size() / 4; c.nrounds = (int)Cs.asm_round_sync.size(); c.nfacrounds = (int)Cs.fac_rounds.size() / 4;
+      c.nints = (int)Cs.smem_ints.size();
+      c.tscalars = (unsigned)sfb::cta_smem_scalars(Cs);
+      for (int k = 0; k < sfb::kI_count; ++k) c.ioff[k] = Cs.smem_off[k];
+      c.ints = cb + coff[0]; c.perm = cb + coff[1]; c.iperm = cb + coff[2]; c.P_rowp = cb + coff[3]; c.P_colp = cb + coff[4];
+      c.P_tgt = cb + coff[5]; c.PR_ptr = cb + coff[6]; c.PR_col = cb + coff[7]; c.PR_slot = cb + coff[8];
+      c.PS_ptr = cb + coff[9]; c.PS_col = cb + coff[10]; c.PS_slot = cb + coff[11]; c.PC_ptr = cb + coff[12]; c.PC_slot = cb + coff[13];
+      c.asm_sync = cb + coff[14];
+      c.asm_desc = reinterpret_cast<const int2*>(cb + coff[15]);
+      c.ATword_g = cb + coff[16]; c.extword_g = cb + coff[17];
+      C.ok = true;
+    } else {
+      cudaGetLastError();
+      if (C.dev) { cudaFree(C.dev); C.dev = nullptr; }
     }
   }
   *out = p;
@@ -383,69 +400,73 @@ int sfb_qp_sparse_cta_selfcheck(int n, int m, const int32_t* P_colptr, const int
   if (n <= 0 || m < 0 || !P_colptr || (m > 0 && !A_rowptr)) return SFB_ERR_INVALID_ARGUMENT;
   sfb::SparseSymbolic S0;
   if (!sfb::sparse_analyze(n, m, P_colptr, P_rowidx, A_rowptr, A_colidx, S0)) return fail(nullptr, SFB_ERR_INVALID_ARGUMENT, "sparse pattern rejected: %s", S0.error.c_str());
-  sfb::CtaSymbolic S;
-  if (!sfb::cta_analyze(n, m, P_colptr, P_rowidx, A_rowptr, A_colidx, S0.perm, S, ordering))
-    return fail(nullptr, SFB_ERR_UNSUPPORTED_SIZE, "on-chip sparse analysis failed: %s", S.error.c_str());
-  if (info_out) {
-    info_out[0] = S.ns; info_out[1] = S.nlev; info_out[2] = S.nW; info_out[3] = S.nnzL_true; info_out[4] = S.flops;
-    info_out[5] = S.smax; info_out[6] = (int64_t)S.stages.size() / 4; info_out[7] = S.ordering;
-  }
-  // seeded values (xorshift), M = shift I + mirrored triu(P) + A^T diag(w) A in the permuted order, dense reference
-  uint64_t st = 0x9e3779b97f4a7c15ull;
-  auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return (double)(st >> 11) / 9007199254740992.0 - 0.5; };
-  std::vector<double> Pv(S.nnzP), Av(S.nnzA), w(m), b(n);
-  for (auto& v : Av) v = rnd();
-  for (auto& v : w) v = (rnd() > -0.2) ? 0.1 + rnd() * 0.1 : 0.0;
-  for (auto& v : b) v = rnd();
-  std::vector<double> M((size_t)n * n, 0.0);
-  for (int j = 0; j < n; ++j)
-    for (int e = P_colptr[j]; e < P_colptr[j + 1]; ++e) {
-      const int r = P_rowidx[e];
-      Pv[e] = (r == j) ? 1.0 + rnd() : 0.05 * rnd();
-      if (j >= r) {
-        const int pr = S.iperm[r], pc = S.iperm[j];
-        M[(size_t)pr * n + pc] += Pv[e];
-        if (pr != pc) M[(size_t)pc * n + pr] += Pv[e];
+  double worst = 0;
+  for (int lpad = 1; lpad <= 2; ++lpad) {  // the fp64 (pad 2) and fp32 (pad 4) layouts
+    sfb::CtaSymbolic S;
+    if (!sfb::cta_analyze(n, m, P_colptr, P_rowidx, A_rowptr, A_colidx, S0.perm, S, lpad, ordering))
+      return fail(nullptr, SFB_ERR_UNSUPPORTED_SIZE, "on-chip sparse analysis failed: %s", S.error.c_str());
+    if (info_out && lpad == 2) {
+      info_out[0] = S.ns; info_out[1] = S.nlev; info_out[2] = S.nW; info_out[3] = S.nnzL_true; info_out[4] = S.flops;
+      info_out[5] = S.smax; info_out[6] = (int64_t)S.stages.size() / 4; info_out[7] = S.ordering;
+    }
+    const int np = S.np;
+    // seeded values (xorshift), M = shift I + mirrored triu(P) + A^T diag(w) A in the padded order (holes: shift I), dense reference
+    uint64_t st = 0x9e3779b97f4a7c15ull;
+    auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return (double)(st >> 11) / 9007199254740992.0 - 0.5; };
+    std::vector<double> Pv(S.nnzP), Av(S.nnzA), w(m), b(np, 0.0);
+    for (auto& v : Av) v = rnd();
+    for (auto& v : w) v = (rnd() > -0.2) ? 0.1 + rnd() * 0.1 : 0.0;
+    for (int j = 0; j < n; ++j) b[S.iperm[j]] = rnd();
+    std::vector<double> M((size_t)np * np, 0.0);
+    for (int j = 0; j < n; ++j)
+      for (int e = P_colptr[j]; e < P_colptr[j + 1]; ++e) {
+        const int r = P_rowidx[e];
+        Pv[e] = (r == j) ? 1.0 + rnd() : 0.05 * rnd();
+        if (j >= r) {
+          const int pr = S.iperm[r], pc = S.iperm[j];
+          M[(size_t)pr * np + pc] += Pv[e];
+          if (pr != pc) M[(size_t)pc * np + pr] += Pv[e];
+        }
+      }
+    const double shift = 1.0;  // keeps the random matrix positive definite (off-diagonal P entries are small)
+    for (int k = 0; k < np; ++k) M[(size_t)k * np + k] += shift;
+    for (int i = 0; i < m; ++i)
+      for (int e1 = A_rowptr[i]; e1 < A_rowptr[i + 1]; ++e1)
+        for (int e2 = A_rowptr[i]; e2 < A_rowptr[i + 1]; ++e2)
+          M[(size_t)S.iperm[A_colidx[e1]] * np + S.iperm[A_colidx[e2]]] += w[i] * Av[e1] * Av[e2];
+    sfb::CtaHostExec ex(S);
+    ex.assemble(shift, Pv.data(), Av.data(), w.data());
+    const bool ok = ex.factor();
+    std::vector<double> x = b;
+    ex.solve(x);
+    std::vector<double> ref = b;  // dense Cholesky of M (in place), solve
+    for (int k = 0; k < np; ++k) {
+      double d = M[(size_t)k * np + k];
+      for (int j = 0; j < k; ++j) d -= M[(size_t)k * np + j] * M[(size_t)k * np + j];
+      if (!(d > 0)) return fail(nullptr, SFB_ERR_INVALID_ARGUMENT, "selfcheck: random matrix not positive definite");
+      d = std::sqrt(d);
+      M[(size_t)k * np + k] = d;
+      for (int i = k + 1; i < np; ++i) {
+        double v = M[(size_t)i * np + k];
+        for (int j = 0; j < k; ++j) v -= M[(size_t)i * np + j] * M[(size_t)k * np + j];
+        M[(size_t)i * np + k] = v / d;
       }
     }
-  const double shift = 1.0;  // keeps the random matrix positive definite (Gershgorin: off-diagonal P entries are small)
-  for (int k = 0; k < n; ++k) M[(size_t)k * n + k] += shift;
-  for (int i = 0; i < m; ++i)
-    for (int e1 = A_rowptr[i]; e1 < A_rowptr[i + 1]; ++e1)
-      for (int e2 = A_rowptr[i]; e2 < A_rowptr[i + 1]; ++e2)
-        M[(size_t)S.iperm[A_colidx[e1]] * n + S.iperm[A_colidx[e2]]] += w[i] * Av[e1] * Av[e2];
-  sfb::CtaHostExec ex(S);
-  ex.assemble(shift, Pv.data(), Av.data(), w.data());
-  const bool ok = ex.factor();
-  std::vector<double> x = b;
-  ex.solve(x);
-  // dense Cholesky of M (in place), solve
-  std::vector<double> ref = b;
-  for (int k = 0; k < n; ++k) {
-    double d = M[(size_t)k * n + k];
-    for (int j = 0; j < k; ++j) d -= M[(size_t)k * n + j] * M[(size_t)k * n + j];
-    if (!(d > 0)) return fail(nullptr, SFB_ERR_INVALID_ARGUMENT, "selfcheck: random matrix not positive definite");
-    d = std::sqrt(d);
-    M[(size_t)k * n + k] = d;
-    for (int i = k + 1; i < n; ++i) {
-      double v = M[(size_t)i * n + k];
-      for (int j = 0; j < k; ++j) v -= M[(size_t)i * n + j] * M[(size_t)k * n + j];
-      M[(size_t)i * n + k] = v / d;
+    for (int i = 0; i < np; ++i) {
+      double v = ref[i];
+      for (int j = 0; j < i; ++j) v -= M[(size_t)i * np + j] * ref[j];
+      ref[i] = v / M[(size_t)i * np + i];
     }
+    for (int i = np - 1; i >= 0; --i) {
+      double v = ref[i];
+      for (int j = i + 1; j < np; ++j) v -= M[(size_t)j * np + i] * ref[j];
+      ref[i] = v / M[(size_t)i * np + i];
+    }
+    double err = 0, scale = 0;
+    for (int i = 0; i < np; ++i) { err = std::max(err, std::fabs(x[i] - ref[i])); scale = std::max(scale, std::fabs(ref[i])); }
+    worst = std::max(worst, ok ? err / std::max(scale, 1e-300) : 1e300);
   }
-  for (int i = 0; i < n; ++i) {
-    double v = ref[i];
-    for (int j = 0; j < i; ++j) v -= M[(size_t)i * n + j] * ref[j];
-    ref[i] = v / M[(size_t)i * n + i];
-  }
-  for (int i = n - 1; i >= 0; --i) {
-    double v = ref[i];
-    for (int j = i + 1; j < n; ++j) v -= M[(size_t)j * n + i] * ref[j];
-    ref[i] = v / M[(size_t)i * n + i];
-  }
-  double err = 0, scale = 0;
-  for (int i = 0; i < n; ++i) { err = std::max(err, std::fabs(x[i] - ref[i])); scale = std::max(scale, std::fabs(ref[i])); }
-  if (max_rel_err_out) *max_rel_err_out = ok ? err / std::max(scale, 1e-300) : 1e300;
+  if (max_rel_err_out) *max_rel_err_out = worst;
   return SFB_OK;
 }
 
@@ -455,9 +476,23 @@ int sfb_qp_sparse_pattern_destroy(sfb_qp_sparse_pattern_t p)
   cudaSetDevice(p->device);
   if (p->dev) cudaFree(p->dev);
   if (p->d_csc2csr) cudaFree(p->d_csc2csr);
-  if (p->cta_dev) cudaFree(p->cta_dev);
+  for (auto& C : p->cta)
+    if (C.dev) cudaFree(C.dev);
   delete p;
   return SFB_OK;
+}
+
+int sfb_qp_sparse_uses_onchip(sfb_handle_t h, sfb_qp_sparse_pattern_t p, int scalar_bytes, int64_t* info_out)
+{
+  if (!h || !p || (scalar_bytes != 4 && scalar_bytes != 8)) return 0;
+  const sfb_qp_sparse_pattern::Cta& C = p->cta[scalar_bytes == 4 ? 0 : 1];
+  if (info_out) {
+    const sfb::CtaSymbolic& S = C.sym;
+    info_out[0] = S.ns; info_out[1] = S.nlev; info_out[2] = S.nW; info_out[3] = S.nnzL_true; info_out[4] = S.flops;
+    info_out[5] = S.smax; info_out[6] = (int64_t)S.stages.size() / 4;
+    info_out[7] = C.ok ? (int64_t)sfb::cta_smem_bytes(S, (size_t)scalar_bytes) : 0;
+  }
+  return (scalar_bytes == 4 ? cta_fits<float>(h, p) : cta_fits<double>(h, p)) ? 1 : 0;
 }
 
 int sfb_qp_sparse_pattern_info(sfb_qp_sparse_pattern_t p, int64_t* nnz_L, int64_t* factor_flops, int32_t* perm_out)

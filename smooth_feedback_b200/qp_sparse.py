@@ -72,6 +72,14 @@ class SparsePattern:
     def raw(self):
         return self._p
 
+    def uses_onchip(self, scalar_bytes: int = 8):
+        """-> (bool, info dict): whether solves with this pattern run the on-chip kernel (one CTA per instance, working set in
+        shared memory; qp_sparse_cta.cuh) and its analysis (supernodes, levels, factor slots, sweep stages, smem bytes)."""
+        info = np.zeros(8, np.int64)
+        r = _lib.lib().sfb_qp_sparse_uses_onchip(self.handle.raw, self._p, int(scalar_bytes), info.ctypes.data_as(C.c_void_p))
+        keys = ("supernodes", "levels", "factor_slots", "nnzL", "factor_flops", "largest_supernode", "sweep_stages", "smem_bytes")
+        return bool(r), dict(zip(keys, info.tolist()))
+
     def bytes_per_iteration(self, scalar: int = 8) -> int:
         """Algorithmic bytes one ADMM iteration streams per instance: Abar twice, the L D L^T factor twice, and the
         vector traffic of the iterate updates."""
@@ -87,6 +95,21 @@ class SparsePattern:
                 self._p = C.c_void_p()
         except Exception:
             pass
+
+
+def sparse_onchip_selfcheck(n: int, m: int, P_colptr, P_rowidx, A_rowptr, A_colidx, ordering: int = -1):
+    """Host-only check of the on-chip kernel's schedules (sfb_qp_sparse_cta_selfcheck): analyses the pattern (ordering -1: cost
+    model, 0: minimum degree, 1: nested dissection), runs assembly / factorisation / inversion / staged sweeps on the host from the
+    very tables the kernel uses and compares with a dense solve.  -> (info dict, max relative error over both layouts)."""
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    pc, pr, ar, ac = i32(P_colptr), i32(P_rowidx), i32(A_rowptr), i32(A_colidx)
+    ip = lambda a: a.ctypes.data_as(C.c_void_p)
+    info = np.zeros(8, np.int64); err = C.c_double()
+    rc = _lib.lib().sfb_qp_sparse_cta_selfcheck(int(n), int(m), ip(pc), ip(pr), ip(ar), ip(ac), int(ordering), ip(info), C.byref(err))
+    if rc != 0:
+        raise _lib.SfbError(rc, _lib.lib().sfb_last_error_message(None).decode())
+    keys = ("supernodes", "levels", "factor_slots", "nnzL", "factor_flops", "largest_supernode", "sweep_stages", "ordering")
+    return dict(zip(keys, info.tolist())), float(err.value)
 
 
 def sparse_symbolic(n: int, m: int, P_colptr, P_rowidx, A_rowptr, A_colidx):

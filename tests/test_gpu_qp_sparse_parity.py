@@ -20,11 +20,43 @@ def sfb():
     return s
 
 
+_HANDLES = {}
+_KERNEL = "onchip"
+
+
+def _handle(sfb, kernel):
+    """One handle per sparse kernel: the on-chip kernel (qp_sparse_cta.cuh, default whenever the instance fits in shared memory)
+    and the HBM-tiled kernel (qp_sparse_tiled.cuh, the fallback), selected when the handle is created."""
+    import os
+
+    if kernel not in _HANDLES:
+        os.environ["SFB_SPARSE_KERNEL"] = "tiled" if kernel == "tiled" else "cta"
+        try:
+            _HANDLES[kernel] = sfb.Handle(0)
+        finally:
+            os.environ.pop("SFB_SPARSE_KERNEL", None)
+    return _HANDLES[kernel]
+
+
+@pytest.fixture(autouse=True, params=["onchip", "tiled"])
+def sparse_kernel(request):
+    """Every test of this module runs against both sparse kernels."""
+    global _KERNEL
+    _KERNEL = request.param
+    yield request.param
+    _KERNEL = "onchip"
+
+
+def _pattern(sfb, pat, **kw):
+    sp = sfb.SparsePattern(pat["n"], pat["m"], pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], pat["A_colidx"], handle=_handle(sfb, _KERNEL), **kw)
+    return sp
+
+
 def _solve_both(sfb, oracle, pat, Pv, q, Av, l, u, prm_kw=None, max_iter=4000, warm=None, dtype=np.float64):
     from smooth_feedback_b200.generators import sparse_to_dense
 
     prm_kw = dict(prm_kw or {})
-    sp = sfb.SparsePattern(pat["n"], pat["m"], pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], pat["A_colidx"])
+    sp = _pattern(sfb, pat)
     prm = sfb.QPSolverParams(max_iter=max_iter, **prm_kw)
     c = lambda t: None if t is None else np.ascontiguousarray(t, dtype=dtype)
     wx, wy = (None, None) if warm is None else warm
@@ -181,7 +213,7 @@ def test_device_path_equals_host_path_and_errors(sfb):
     from smooth_feedback_b200.generators import random_sparse_qp_numpy
 
     pat, Pv, q, Av, l, u = random_sparse_qp_numpy(70, 20, 30, density=0.2, seed=8)
-    sp = sfb.SparsePattern(pat["n"], pat["m"], pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], pat["A_colidx"])
+    sp = sfb.SparsePattern(pat["n"], pat["m"], pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], pat["A_colidx"], handle=_handle(sfb, _KERNEL))
     prm = sfb.QPSolverParams(max_iter=4000)
     rh = sfb.solve_sparse_batch(sp, Pv, q, Av, l, u, prm)
     t = lambda a: torch.from_numpy(a).cuda()
@@ -210,7 +242,7 @@ def test_full_size_properties_cfg3(sfb, oracle):
     pat, Pv, q, Av, l, u, _, _, _ = vehicle_mpc_batch(base, seed=9)
     rep = B // base
     t = lambda a, dt=torch.float64: torch.from_numpy(np.tile(a, (rep, 1))).to("cuda:0", dtype=dt).contiguous()
-    sp = sfb.SparsePattern(pat["n"], pat["m"], pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], pat["A_colidx"])
+    sp = sfb.SparsePattern(pat["n"], pat["m"], pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], pat["A_colidx"], handle=_handle(sfb, _KERNEL))
     prm = sfb.QPSolverParams(max_iter=4000)
     r = sfb.solve_sparse_batch(sp, t(Pv), t(q), t(Av), t(l), t(u), prm)
     torch.cuda.synchronize()
@@ -265,7 +297,7 @@ def test_csc_ingestion_matches_csr(sfb):
     pat, Pv, q, Av, l, u = random_sparse_qp_numpy(96, 30, 45, density=0.2, seed=21)
     n, m = pat["n"], pat["m"]
     prm = sfb.QPSolverParams(max_iter=4000)
-    sp = sfb.SparsePattern(n, m, pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], pat["A_colidx"])
+    sp = sfb.SparsePattern(n, m, pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], pat["A_colidx"], handle=_handle(sfb, _KERNEL))
     r = sfb.solve_sparse_batch(sp, Pv, q, Av, l, u, prm)
     _, A = sparse_to_dense(pat, Pv, Av)
     mask = np.zeros((m, n), bool)
@@ -273,7 +305,7 @@ def test_csc_ingestion_matches_csr(sfb):
     cc, cr = np.nonzero(mask.T)  # column-major order: (col, row)
     A_colptr = np.concatenate([[0], np.cumsum(np.bincount(cc, minlength=n))]).astype(np.int32)
     Av_csc = np.ascontiguousarray(A[:, cr, cc])
-    spc = sfb.SparsePattern(n, m, pat["P_colptr"], pat["P_rowidx"], A_colptr, cr.astype(np.int32), a_csc=True)
+    spc = sfb.SparsePattern(n, m, pat["P_colptr"], pat["P_rowidx"], A_colptr, cr.astype(np.int32), a_csc=True, handle=_handle(sfb, _KERNEL))
     rc = sfb.solve_sparse_batch(spc, Pv, q, Av_csc, l, u, prm)
     assert np.array_equal(r.x, rc.x) and np.array_equal(r.y, rc.y) and np.array_equal(r.status, rc.status) and np.array_equal(r.iter, rc.iter)
     t = lambda a: torch.from_numpy(a).cuda()
@@ -305,7 +337,7 @@ def test_known_answers_through_sparse_c_abi(sfb, case):
     # dense cases as sparse problems, cf. TwoDimensional :314-336 dense == sparse) against the sparse CUDA path, including
     # empty rows (Unconstrained: A = 0 has no stored entry) and the warm re-solve of every Optimal case
     pat, Pv, q, Av, l, u = _case_as_sparse(case)
-    sp = sfb.SparsePattern(pat["n"], pat["m"], pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], pat["A_colidx"])
+    sp = sfb.SparsePattern(pat["n"], pat["m"], pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], pat["A_colidx"], handle=_handle(sfb, _KERNEL))
     r = sfb.solve_sparse_batch(sp, Pv, q, Av, l, u)
     assert r.status[0] == case["status"]
     if case["x"] is not None:
@@ -323,7 +355,7 @@ def test_known_answers_sparse_match_oracle(sfb, oracle, case):
     from qp_cases import as_batch
 
     pat, Pv, q, Av, l, u = _case_as_sparse(case)
-    sp = sfb.SparsePattern(pat["n"], pat["m"], pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], pat["A_colidx"])
+    sp = sfb.SparsePattern(pat["n"], pat["m"], pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], pat["A_colidx"], handle=_handle(sfb, _KERNEL))
     r = sfb.solve_sparse_batch(sp, Pv, q, Av, l, u)
     P, q_, A, l_, u_ = as_batch(case)
     o = oracle.qp_solve_batch(P, q_, A, l_, u_)
@@ -344,7 +376,7 @@ def test_edge_patterns(sfb, oracle):
     pc, pr = np.nonzero(P[0].T)
     pat = dict(n=n, m=0, P_colptr=np.concatenate([[0], np.cumsum(np.bincount(pc, minlength=n))]).astype(np.int32),
                P_rowidx=pr.astype(np.int32), A_rowptr=np.zeros(1, np.int32), A_colidx=np.zeros(0, np.int32))
-    sp = sfb.SparsePattern(n, 0, pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], pat["A_colidx"])
+    sp = sfb.SparsePattern(n, 0, pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], pat["A_colidx"], handle=_handle(sfb, _KERNEL))
     z = np.zeros((B, 0))
     r = sfb.solve_sparse_batch(sp, np.ascontiguousarray(P[:, pr, pc]), q, z, z, z, sfb.QPSolverParams(max_iter=4000))
     o = oracle.qp_solve_batch(P, q, np.zeros((B, 0, n)), z, z, params=oracle.default_params(max_iter=4000))
@@ -354,8 +386,35 @@ def test_edge_patterns(sfb, oracle):
     P1 = 1.0 + rng.random((B, 1, 1)); q1 = rng.uniform(-1, 1, (B, 1))
     A1 = np.zeros((B, 3, 1)); A1[:, 0, 0] = 1.0; A1[:, 2, 0] = -2.0
     l1 = np.tile([-0.1, -np.inf, -0.3], (B, 1)); u1 = np.tile([0.1, np.inf, 0.3], (B, 1))
-    sp1 = sfb.SparsePattern(1, 3, np.array([0, 1], np.int32), np.array([0], np.int32), np.array([0, 1, 1, 2], np.int32), np.array([0, 0], np.int32))
+    sp1 = sfb.SparsePattern(1, 3, np.array([0, 1], np.int32), np.array([0], np.int32), np.array([0, 1, 1, 2], np.int32), np.array([0, 0], np.int32), handle=_handle(sfb, _KERNEL))
     r1 = sfb.solve_sparse_batch(sp1, P1[:, :, 0], q1, np.ascontiguousarray(A1[:, [0, 2], 0]), l1, u1, sfb.QPSolverParams(max_iter=4000))
     o1 = oracle.qp_solve_batch(P1, q1, A1, l1, u1, params=oracle.default_params(max_iter=4000))
     assert np.array_equal(r1.status, o1.status) and np.array_equal(r1.iter, o1.iter) and np.array_equal(r1.active, o1.active)
     assert np.abs(r1.x - o1.x).max() <= 1e-9
+
+
+
+def test_onchip_kernel_is_the_one_that_runs_and_agrees_with_the_tiled_kernel(sfb, sparse_kernel):
+    """The real vehicle MPC pattern (n = m = 422) fits in shared memory in both precisions: the default handle must run the
+    on-chip kernel (a silent fallback to the tiled kernel would hide it from every other test), a handle created with
+    SFB_SPARSE_KERNEL=tiled must not; both kernels return the same discrete outcomes and solutions to rounding."""
+    import torch
+    from workloads import vehicle_mpc_batch
+
+    pat, Pv, q, Av, l, u = vehicle_mpc_batch(24)[:6]
+    outs = {}
+    for kind in ("onchip", "tiled"):
+        sp = sfb.SparsePattern(pat["n"], pat["m"], pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], pat["A_colidx"], handle=_handle(sfb, kind))
+        for sb in (4, 8):
+            used, info = sp.uses_onchip(sb)
+            assert used == (kind == "onchip"), (kind, sb, info)
+            if kind == "onchip":
+                assert info["levels"] == 4 and info["sweep_stages"] == 15 and 0 < info["smem_bytes"] <= 227 * 1024, info
+        outs[kind] = sfb.solve_sparse_batch(sp, Pv, q, Av, l, u, sfb.QPSolverParams(max_iter=4000))
+    a, b = outs["onchip"], outs["tiled"]
+    assert np.array_equal(a.status, b.status) and np.array_equal(a.iter, b.iter) and np.array_equal(a.active, b.active)
+    assert (a.status == 0).all() and (a.flags & 1).all()
+    assert rel_err(a.x, b.x).max() <= 1e-9 and rel_err(a.y, b.y).max() <= 1e-9
+    # a default handle (no environment override) picks the on-chip kernel
+    sp0 = sfb.SparsePattern(pat["n"], pat["m"], pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], pat["A_colidx"])
+    assert sp0.uses_onchip(8)[0] and sp0.uses_onchip(4)[0]

@@ -127,3 +127,46 @@ def test_malformed_patterns_are_rejected_not_dereferenced():
     assert rc(2, 1, [0, 1, 2], [0, 1], [0, 2], [0, 2]) == 1                    # column index out of range
     assert rc(2, 1, [0, 1, 2], [0, 1], [0, 2], [1, 1]) == 1                    # duplicate column in a row
     assert rc(2, 0, [0, 0, 0], None, None, None) == 0                          # empty P, no rows
+
+
+# ---- on-chip kernel (qp_sparse_cta.cuh): its schedules are executed on the host, table by table, against a dense solve ----
+def _onchip_patterns():
+    pats = [("mpc63", mpc_structured_pattern(Nx=3, Nu=2, nivals=3, Ki=4)), ("mpc422", mpc_structured_pattern())]
+    for (n, m, dens, seed) in [(20, 30, 0.2, 3), (7, 5, 0.5, 4), (60, 30, 0.1, 5), (33, 80, 0.08, 6)]:
+        pats.append((f"rand{n}x{m}", random_sparse_qp_numpy(2, n, m, density=dens, seed=seed)[0]))
+    n = 5  # no constraints at all, diagonal P: every column its own supernode
+    pats.append(("m0", dict(n=n, m=0, P_colptr=np.arange(n + 1), P_rowidx=np.arange(n), A_rowptr=np.zeros(1, int), A_colidx=np.zeros(0, int))))
+    pats.append(("n1", dict(n=1, m=2, P_colptr=np.array([0, 1]), P_rowidx=np.array([0]), A_rowptr=np.array([0, 1, 2]), A_colidx=np.array([0, 0]))))
+    dn = 9  # dense P and A: one supernode
+    pats.append(("dense", dict(n=dn, m=4, P_colptr=np.arange(dn + 1) * dn, P_rowidx=np.tile(np.arange(dn), dn),
+                               A_rowptr=np.arange(5) * dn, A_colidx=np.tile(np.arange(dn), 4))))
+    return pats
+
+
+@pytest.mark.parametrize("ordering", [-1, 0, 1])
+def test_onchip_schedules_solve_the_reduced_system(ordering):
+    """sfb_qp_sparse_cta_selfcheck: assembly (coloured pairs), level-synchronous supernodal factorisation, in-place inversion
+    of the diagonal blocks and the staged sweeps -- run on the host from the kernel's own tables (fp32 and fp64 layouts) --
+    reproduce a dense Cholesky solve of the same random SPD matrix."""
+    for name, pat in _onchip_patterns():
+        info, err = sfb.sparse_onchip_selfcheck(pat["n"], pat["m"], pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], pat["A_colidx"], ordering)
+        assert err < 1e-10, (name, ordering, err, info)
+        assert info["nnzL"] <= info["factor_slots"] and info["supernodes"] >= 1 and info["levels"] >= 1, (name, info)
+        assert info["sweep_stages"] <= 4 * info["levels"], (name, info)
+
+
+def test_onchip_ordering_shortens_the_elimination_tree_of_the_mpc_problem():
+    """The point of the on-chip analysis: minimum degree orders the REAL K = 50 vehicle MPC problem (the pattern ocp_to_qp
+    produces, n = m = 422) along the time axis (a chain of 13 supernodes, 51 sweep stages); nested dissection + amalgamation
+    gives 4 levels / 15 stages, and the cost model picks it."""
+    from workloads import vehicle_mpc_batch
+
+    pat = vehicle_mpc_batch(1)[0]
+    args = (pat["n"], pat["m"], pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], pat["A_colidx"])
+    md, e0 = sfb.sparse_onchip_selfcheck(*args, 0)
+    nd, e1 = sfb.sparse_onchip_selfcheck(*args, 1)
+    auto, _ = sfb.sparse_onchip_selfcheck(*args, -1)
+    assert max(e0, e1) < 1e-10
+    assert md["levels"] == 13 and nd["levels"] == 4 and nd["sweep_stages"] == 15 and md["sweep_stages"] == 51
+    assert auto["ordering"] == 1 and auto["levels"] == nd["levels"]
+    assert nd["factor_slots"] < 1.3 * md["factor_slots"]  # the shorter tree costs some fill, not a multiple
