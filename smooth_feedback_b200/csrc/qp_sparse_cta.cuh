@@ -443,7 +443,7 @@ template <typename T, typename TIO, int NT, bool GT> struct CtaSolver
         }
         const bool pivot_group = j0 <= kc;                     // its columns <= kc are being read by everybody: not rewritten
         const int nextc = kc + 1 - j0;                          // 0 .. PAD - 1: this group holds the next pivot's diagonal
-        constexpr int U = 2;
+        constexpr int U = 2;  // rows in flight per thread (4 measured the same: the step is paced by its instruction count, not by load latency)
         for (int p0 = max(kc + 1, j0) + rc; p0 < nrows; p0 += U * RC) {  // rows of the diagonal block from j0 on (they hold the group), then the rows below
           T vi[U], old[U][PAD];
           int base[U];

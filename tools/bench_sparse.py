@@ -5,7 +5,7 @@ batch 8192 agents, on one GPU.
     python tools/bench_sparse.py [--batch 8192] [--dtype f64|f32] [--steps 3]
 
 Prints one JSON line: solves/s (CUDA events, data resident), mean iterations, status histogram, and the achieved
-HBM figure over the algorithmic bytes of the tiled solver: B_comp + iters * B_iter with
+HBM figure over the algorithmic bytes of the streaming model (what the tiled kernel really moves): B_comp + iters * B_iter with
     B_iter = s * (2 nnzA + 2 nnzL + n  [Abar twice, L twice, 1/D]  +  5 n + 10 m  [iterate vectors])
 (DESIGN.md section 4.3).  Data: the vehicle MPC QPs the engine's own fleet transcribes (sfb_mpc_fleet_to_qp); --small uses the LTV surrogate generator.
 """
@@ -74,7 +74,15 @@ def run(batch=8192, dtype="f64", steps=3, small=False, tw=0):
     if os.path.exists(pk):
         peak = float(json.load(open(pk))["hbm_gbs"])
     ach = batch * (bcomp + it * biter) / (mean_ms * 1e-3) / 1e9
+    onchip, info = sp.uses_onchip(s)
     return {
+        "kernel": ("qp_sparse_cta_kernel: one CTA per instance, factor / Abar / vectors / schedules in shared memory" if onchip
+                   else "qp_sparse_tiled_kernel: working set tiled in HBM"),
+        "onchip": info if onchip else None,
+        "achieved_compulsory_gbs": batch * bcomp / (mean_ms * 1e-3) / 1e9,
+        "bound": ("the on-chip kernel moves only the compulsory bytes through HBM (B_comp per solve); it is bound by the latency of one "
+                  "warp's dependent instruction stream between the barriers of its 15 sweep stages / 175 column steps, see DESIGN 4.3"
+                  if onchip else "HBM-streaming model, see DESIGN 4.3"),
         "source": source, "ms_min": min(ms), "ms_median": mean_ms,
         "workload": f"sparse QP (MPC structure) n={pat['n']} m={pat['m']} nnzA={sp.nnzA} nnzP={sp.nnzP} nnzL={sp.nnzL} batch={batch} {dtype} tw={tw or 'auto'}",
         "solves_per_s": batch / (mean_ms * 1e-3), "ms": mean_ms, "ms_all": ms, "mean_iter": it,

@@ -29,6 +29,16 @@ for tw in (4, 8, 32):
     sfb.solve_sparse_batch(sp, t(Pv), t(q), t(Av), t(l), t(u), prm)
     f = lambda a: t(a).float()
     sfb.solve_sparse_batch(sp, f(Pv), f(q), f(Av), f(l), f(u), prm)
+os.environ.pop("SFB_SPARSE_TW", None)
+# the on-chip sparse kernel (default handle): MPC structure (several supernode levels, fp64 + fp32 with its fp64 polish pass),
+# warm start, a random pattern, no constraints at all
+h = sfb.Handle(0)
+sp = sfb.SparsePattern(pat["n"], pat["m"], pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], pat["A_colidx"], handle=h)
+assert sp.uses_onchip(8)[0] and sp.uses_onchip(4)[0]
+r0 = sfb.solve_sparse_batch(sp, t(Pv), t(q), t(Av), t(l), t(u), prm)
+sfb.solve_sparse_batch(sp, t(Pv), t(q), t(Av), t(l), t(u), prm, warm_x=r0.x, warm_y=r0.y)
+f = lambda a: t(a).float()
+sfb.solve_sparse_batch(sp, f(Pv), f(q), f(Av), f(l), f(u), prm)
 pat2, Pv, q, Av, l, u = random_sparse_qp_numpy(9, 20, 30, density=0.2, seed=3)
 sp = sfb.SparsePattern(pat2["n"], pat2["m"], pat2["P_colptr"], pat2["P_rowidx"], pat2["A_rowptr"], pat2["A_colidx"], handle=h)
 sfb.solve_sparse_batch(sp, t(Pv), t(q), t(Av), t(l), t(u), prm)
