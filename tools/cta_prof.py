@@ -1,7 +1,15 @@
-"""Dev tool: per-phase cycle counts of the on-chip sparse kernel (SFB_CTA_PROF=1) on the real vehicle MPC workload."""
+"""Dev tool: the on-chip sparse kernel on the real vehicle MPC workload (fp64 solve, fp32 solve + its fp64 polish pass, twice
+each).  Default: per-phase cycle counts from the in-kernel clock64 accounting (SFB_CTA_PROF=1, printed by libsfb on stderr);
+--plain: no instrumentation (the target of `ncu -k regex:qp_sparse_cta_kernel -s 1 -c 3`).
+
+    python tools/cta_prof.py [batch] [--plain]
+"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ["SFB_CTA_PROF"] = "1"
+if "--plain" in sys.argv:
+    sys.argv.remove("--plain")
+else:
+    os.environ["SFB_CTA_PROF"] = "1"
 import numpy as np, torch
 import smooth_feedback_b200 as sfb
 from smooth_feedback_b200.generators import vehicle_fleet_numpy
