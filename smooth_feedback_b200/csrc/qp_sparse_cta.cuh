@@ -99,6 +99,7 @@ template <> struct VecOf<double>
 template <typename T, typename TIO, int NT, bool GT> struct CtaSolver
 {
   static constexpr int PAD = VecOf<T>::PAD, LPAD = VecOf<T>::LPAD;
+  static constexpr int BW = 4, LBW = 2;  // pivot columns per step of the blocked factorisation (one fp32 vector, two fp64 vectors)
   using VT = typename VecOf<T>::type;
   static constexpr int NW = NT / 32;
   using V = SV<T>;
@@ -108,7 +109,7 @@ template <typename T, typename TIO, int NT, bool GT> struct CtaSolver
   V W, A;                             // factor slots (+ 1/D), Abar (CSR order)
   V qb, x, v, sv, sx, t1;             // n-vectors over the padded ids (holes stay zero); v / sv: the two buffers of the sweeps, sv = result
   V sy, rho, rinv, z, y, w, lo, hi;   // m-vectors
-  V red;
+  V red, piv;                         // reduction scratch; parked pivot-block factorisations (2 x NW slots)
   T *xold, *yold;                     // global: iterate at the previous stop check
   unsigned ibase;                     // byte offset of the integer tables
   T c;
@@ -128,6 +129,7 @@ template <typename T, typename TIO, int NT, bool GT> struct CtaSolver
     qb = take(np); x = take(np); v = take(np); sv = take(np); sx = take(np); t1 = take(np);
     sy = take(m); rho = take(m); rinv = take(m); z = take(m); y = take(m); w = take(m); lo = take(m); hi = take(m);
     red = take(kCtaRed);
+    piv = take(2 * NW * kCtaPivot);
     ibase = S.tscalars * (unsigned)sizeof(T);
     xold = a.ws + (size_t)blockIdx.x * (size_t)(np + m);
     yold = xold + np;
@@ -388,13 +390,72 @@ template <typename T, typename TIO, int NT, bool GT> struct CtaSolver
     }
   }
 
+  // ---------------------------------------------------------------- pieces of the blocked factorisation
+  // The first nv (1 .. BW) of BW consecutive scalars from slot (a multiple of PAD), zeros behind them: only the vectors that hold
+  // one of the nv columns are read -- a below row ends with its supernode's last (padded) column
+  __device__ __forceinline__ void ldb(int slot, int nv, T (&o)[BW]) const
+  {
+#pragma unroll
+    for (int h = 0; h < BW / PAD; ++h) {
+      T part[PAD];
+      const bool in = h * PAD < nv;
+      if (in) ldv(W, slot + h * PAD, part);
+#pragma unroll
+      for (int cc = 0; cc < PAD; ++cc) o[h * PAD + cc] = (in && h * PAD + cc < nv) ? part[cc] : T(0);
+    }
+  }
+  // y = u L11^-T for the unit-lower pivot block L11 (multipliers lm[c][c'], c' < c): y[c] = u[c] - sum_{c' < c} y[c'] lm[c][c']
+  __device__ __forceinline__ void fwd_sub(const T (&u)[BW], const T (&lm)[BW][BW], T (&y)[BW]) const
+  {
+#pragma unroll
+    for (int cc = 0; cc < BW; ++cc) {
+      T acc = u[cc];
+#pragma unroll
+      for (int c2 = 0; c2 < cc; ++c2) acc -= y[c2] * lm[cc][c2];
+      y[cc] = acc;
+    }
+  }
+  // L D L^T of the BW x BW pivot block at (kb, kb) of a supernode's diagonal block, in registers: yd[i][c] (c <= i) the
+  // forward-substituted entries (yd[i][i] = D_i), lm the unit-lower multipliers, dinv = 1 / D (0 for columns >= s).  False on a
+  // non-positive pivot.  (A row shorter than the block is read past its end: those entries are never used.)
+  __device__ __forceinline__ bool pivot_block(const unsigned short* pr, int kb, int s, T (&lm)[BW][BW], T (&dinv)[BW], T (&yd)[BW][BW]) const
+  {
+    const T inf = Num<T>::inf();
+    T av[BW][BW];
+#pragma unroll
+    for (int i = 0; i < BW; ++i) {
+      const bool in = kb + i < s;
+      if (in) ldb(pr[kb + i] + kb, min(BW, s - kb), av[i]);
+#pragma unroll
+      for (int cc = 0; cc < BW; ++cc) av[i][cc] = in ? av[i][cc] : T(0);
+    }
+    bool good = true;
+#pragma unroll
+    for (int cc = 0; cc < BW; ++cc) {
+#pragma unroll
+      for (int i = cc; i < BW; ++i) {
+        T acc = av[i][cc];
+#pragma unroll
+        for (int c2 = 0; c2 < cc; ++c2) acc -= yd[i][c2] * lm[cc][c2];
+        yd[i][cc] = acc;
+      }
+      const bool valid = kb + cc < s;
+      const T d = yd[cc][cc];
+      if (valid && (!(d > T(0)) || !(d < inf))) good = false;
+      dinv[cc] = valid ? T(1) / d : T(0);
+#pragma unroll
+      for (int i = cc + 1; i < BW; ++i) lm[i][cc] = yd[i][cc] * dinv[cc];
+    }
+    return good;
+  }
+
   // ---------------------------------------------------------------- supernodal right-looking L D L^T in place
   // Afterwards: below blocks hold L, diagonal blocks hold X' = -(strict lower part of L_SS^-1) (diagonal and padding zero),
   // W[nW + k] = 1 / D_k.  False on a non-positive pivot.
-  // Rounds (qp_sparse_cta_host.hpp): the supernodes of a round advance column by column together, each with its own warps.
-  // The diagonal D_i lives IN row i of its block during the factorisation, so a column step is one uniform update of the
-  // trailing panel: a thread owns a group of PAD adjacent columns (their pivot-column entries are loaded once) and walks panel
-  // rows with 16-byte read-modify-writes; the padding of a row (columns > i) collects garbage that the scaling pass clears.
+  // Rounds (qp_sparse_cta_host.hpp): the supernodes of a round advance together, each with its own warps, PAD columns per step.
+  // The diagonal D_i lives IN row i of its block during the factorisation, so a step is one uniform update of the trailing
+  // panel: a thread owns a group of PAD adjacent columns and walks panel rows with 16-byte read-modify-writes; the padding of
+  // a row (columns > i) collects garbage that the scaling pass clears.
   __device__ bool factor()
   {
     const T inf = Num<T>::inf();
@@ -425,57 +486,106 @@ template <typename T, typename TIO, int NT, bool GT> struct CtaSolver
       const bool active = q >= 0 && cg < NCG && rc < RC;
       const int j0 = cg << LPAD;
       const int nrows = s + t;
-      __syncthreads();  // the external updates of the previous round are complete
-      if (q >= 0 && gtid == 0) {
-        const T d0 = W[pr[0]];
-        if (!(d0 > T(0)) || !(d0 < inf)) ok = false;
-        W[Di + c0] = T(1) / d0;
-      }
-      for (int kc = 0; kc + 1 < maxs; ++kc) {
+      // Blocked right-looking steps, BW = 4 pivot columns at a time.  In step kb a thread of a column group right of the block
+      // (A) factorises the BW x BW pivot block in registers (redundantly: a dozen loads and a few dozen flops instead of a
+      // barrier), forward-substitutes the pivot-column entries of its PAD group rows and of every panel row it owns
+      // (y = u L11^-T) and applies the rank-BW update to its vectors.  The pivot columns themselves are read by everybody during
+      // the step, so their final values y (and D on the diagonal, 1 / D beside it) are written back one step LATER, by the
+      // threads of the block's first column group (B), from the pivot factorisation that one otherwise idle thread of that group
+      // (P) parked in shared memory during the step -- nobody re-reads rows that are being overwritten.
+      const int nsteps = ((maxs + BW - 1) >> LBW) + 1;
+      const int pslot = (warp - rank) * kCtaPivot;  // this supernode's slot in the pivot scratch (double-buffered by step parity)
+      for (int b = 0; b < nsteps; ++b) {
+        const int kb = b << LBW;
         __syncthreads();
-        if (!active || kc + 1 >= s || j0 + PAD - 1 <= kc) continue;  // (a group entirely left of / at the pivot column has nothing to update)
-        const T dinv = W[Di + c0 + kc];
-        T vjs[PAD];
+        if (!active) continue;
+        const int kp = kb - BW;  // the previous block
+        if (j0 == kb && rc == 0 && kb < s) {  // (P) park this block's factorisation: yd (lower triangle, row-major), then 1 / D
+          T lm[BW][BW], dinv[BW], yd[BW][BW];
+          if (!pivot_block(pr, kb, s, lm, dinv, yd)) ok = false;
+          const int sl = (b & 1) * NW * kCtaPivot + pslot;
 #pragma unroll
-        for (int cc = 0; cc < PAD; ++cc) {
-          const int j = j0 + cc;
-          vjs[cc] = (j > kc && j < s) ? W[pr[j] + kc] * dinv : T(0);
+          for (int i = 0; i < BW; ++i) {
+#pragma unroll
+            for (int cc = 0; cc <= i; ++cc) piv[sl + i * (i + 1) / 2 + cc] = yd[i][cc];
+            piv[sl + BW * (BW + 1) / 2 + i] = dinv[i];
+          }
         }
-        const bool pivot_group = j0 <= kc;                     // its columns <= kc are being read by everybody: not rewritten
-        const int nextc = kc + 1 - j0;                          // 0 .. PAD - 1: this group holds the next pivot's diagonal
-        constexpr int U = 2;  // rows in flight per thread (4 measured the same: the step is paced by its instruction count, not by load latency)
-        for (int p0 = max(kc + 1, j0) + rc; p0 < nrows; p0 += U * RC) {  // rows of the diagonal block from j0 on (they hold the group), then the rows below
-          T vi[U], old[U][PAD];
-          int base[U];
+        if (kp >= 0 && j0 == kp && kp < s) {  // (B) write the previous block back: all its BW columns of the rows this thread owns
+          T lm[BW][BW], dinv[BW], yd[BW][BW];
+          const int sl = ((b - 1) & 1) * NW * kCtaPivot + pslot;
 #pragma unroll
-          for (int k = 0; k < U; ++k) {
-            const int p = p0 + k * RC;
-            base[k] = -1;
-            if (p < nrows) {
-              base[k] = pr[p];
-              vi[k] = W[base[k] + kc];
-              ldv(W, base[k] + j0, old[k]);
-            }
+          for (int i = 0; i < BW; ++i) {
+#pragma unroll
+            for (int cc = 0; cc <= i; ++cc) yd[i][cc] = piv[sl + i * (i + 1) / 2 + cc];
+            dinv[i] = piv[sl + BW * (BW + 1) / 2 + i];
           }
 #pragma unroll
-          for (int k = 0; k < U; ++k) {
-            if (base[k] < 0) continue;
-            T nv[PAD];
+          for (int i = 1; i < BW; ++i) {
 #pragma unroll
-            for (int cc = 0; cc < PAD; ++cc) nv[cc] = old[k][cc] - vi[k] * vjs[cc];
-            if (!pivot_group) stv(W, base[k] + j0, nv);
-            else {
+            for (int cc = 0; cc < i; ++cc) lm[i][cc] = yd[i][cc] * dinv[cc];
+          }
+          const int kend = min(kb, s), nvp = min(BW, s - kp);
+          for (int p = kp + rc; p < nrows; p += RC) {
+            T y[BW];
+            const int base = pr[p];
+            if (p < kend) {  // a row of the pivot block: multipliers left of the diagonal, D on it, zeros right of it
+              const int i = p - kp;
 #pragma unroll
-              for (int cc = 1; cc < PAD; ++cc)
-                if (j0 + cc > kc) W[base[k] + j0 + cc] = nv[cc];
+              for (int cc = 0; cc < BW; ++cc) {
+                T val = T(0);
+#pragma unroll
+                for (int ii = 0; ii < BW; ++ii) val = (ii == i && cc <= ii) ? yd[ii][cc] : val;
+                y[cc] = val;
+              }
+              T di = dinv[0];
+#pragma unroll
+              for (int ii = 1; ii < BW; ++ii) di = (ii == i) ? dinv[ii] : di;
+              W[Di + c0 + p] = di;
+            } else {
+              T u[BW];
+              ldb(base + kp, nvp, u);
+              fwd_sub(u, lm, y);
             }
-            if (p0 + k * RC == kc + 1 && nextc >= 0 && nextc < PAD) {  // the next pivot: its reciprocal, off everyone else's path
-              T dn = nv[0];
 #pragma unroll
-              for (int cc = 1; cc < PAD; ++cc) dn = (nextc == cc) ? nv[cc] : dn;
-              if (!(dn > T(0)) || !(dn < inf)) ok = false;
-              W[Di + c0 + kc + 1] = T(1) / dn;
+            for (int h = 0; h < BW / PAD; ++h) {
+              if (h * PAD < nvp && (p >= s || kp + h * PAD <= p)) {  // the vector exists: inside the supernode's columns, and a row of the diagonal block reaches that far
+                T out[PAD];
+#pragma unroll
+                for (int cc = 0; cc < PAD; ++cc) out[cc] = y[h * PAD + cc];
+                stv(W, base + kp + h * PAD, out);
+              }
             }
+          }
+        }
+        if (kb < s && j0 >= kb + BW && j0 < s) {  // (A) rank-BW update of this thread's column group
+          T lm[BW][BW], dinv[BW], yd[BW][BW];
+          pivot_block(pr, kb, s, lm, dinv, yd);
+          T ys[PAD][BW];  // ys[jj][c] = y(j0 + jj, c) / D_c for the rows of the diagonal block that carry this group's columns
+#pragma unroll
+          for (int jj = 0; jj < PAD; ++jj) {
+            T u[BW], y[BW];
+            const bool in = j0 + jj < s;
+            if (in) ldb(pr[j0 + jj] + kb, BW, u);
+#pragma unroll
+            for (int cc = 0; cc < BW; ++cc) u[cc] = in ? u[cc] : T(0);
+            fwd_sub(u, lm, y);
+#pragma unroll
+            for (int cc = 0; cc < BW; ++cc) ys[jj][cc] = y[cc] * dinv[cc];
+          }
+          for (int p = max(min(kb + BW, s), j0) + rc; p < nrows; p += RC) {  // rows below the pivot block that hold this group
+            T u[BW], y[BW], old[PAD];
+            const int base = pr[p];
+            ldb(base + kb, BW, u); ldv(W, base + j0, old);
+            fwd_sub(u, lm, y);
+#pragma unroll
+            for (int jj = 0; jj < PAD; ++jj) {
+              T acc = old[jj];
+#pragma unroll
+              for (int cc = 0; cc < BW; ++cc) acc -= y[cc] * ys[jj][cc];
+              old[jj] = acc;
+            }
+            stv(W, base + j0, old);
           }
         }
       }

@@ -413,13 +413,14 @@ inline SnPlan plan_supernodes(const Adj& adj, const std::vector<int>& perm_in, i
 constexpr int kCtaNV = 6;
 constexpr int kCtaMV = 8;
 constexpr int kCtaRed = 128;
+constexpr int kCtaPivot = 16;  // scalars of a parked 4 x 4 pivot-block factorisation (10 + 4, padded)
 enum CtaIntTable { kI_Acol = 0, kI_ATword, kI_Arowptr, kI_ATptr, kI_rlist, kI_diagoff, kI_prow, kI_sntab, kI_stages, kI_fdiag, kI_bwd, kI_pushout,
                    kI_pushtask, kI_extptr, kI_extword, kI_facrounds, kI_facext, kI_facwarp, kI_count };
 inline size_t cta_round4(size_t v) { return (v + 3) / 4 * 4; }
 inline size_t cta_smem_scalars(const CtaSymbolic& S)
 {
   return cta_round4((size_t)S.nW + (size_t)S.np) + cta_round4(S.nnzA) + (size_t)kCtaNV * cta_round4(S.np) +
-         (size_t)kCtaMV * cta_round4(S.m) + kCtaRed;
+         (size_t)kCtaMV * cta_round4(S.m) + kCtaRed + 2 * (kCtaNT / 32) * kCtaPivot;
 }
 inline size_t cta_smem_bytes(const CtaSymbolic& S, size_t scalar) { return cta_smem_scalars(S) * scalar + S.smem_ints.size() * sizeof(int); }
 
