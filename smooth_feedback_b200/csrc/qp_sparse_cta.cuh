@@ -417,7 +417,7 @@ template <typename T, typename TIO, int NT, bool GT> struct CtaSolver
   }
   // L D L^T of the BW x BW pivot block at (kb, kb) of a supernode's diagonal block, in registers: yd[i][c] (c <= i) the
   // forward-substituted entries (yd[i][i] = D_i), lm the unit-lower multipliers, dinv = 1 / D (0 for columns >= s).  False on a
-  // non-positive pivot.  (A row shorter than the block is read past its end: those entries are never used.)
+  // non-positive pivot.
   __device__ __forceinline__ bool pivot_block(const unsigned short* pr, int kb, int s, T (&lm)[BW][BW], T (&dinv)[BW], T (&yd)[BW][BW]) const
   {
     const T inf = Num<T>::inf();
@@ -425,7 +425,7 @@ template <typename T, typename TIO, int NT, bool GT> struct CtaSolver
 #pragma unroll
     for (int i = 0; i < BW; ++i) {
       const bool in = kb + i < s;
-      if (in) ldb(pr[kb + i] + kb, min(BW, s - kb), av[i]);
+      if (in) ldb(pr[kb + i] + kb, i + 1, av[i]);  // row i of the block holds its columns 0 .. i only (a longer read would touch the next row)
 #pragma unroll
       for (int cc = 0; cc < BW; ++cc) av[i][cc] = in ? av[i][cc] : T(0);
     }
