@@ -53,6 +53,7 @@ template <typename T, typename TIO = T> struct CtaArgs
   int8_t* out_active;
   uint32_t* out_flags;
   T* ws;  // per CTA: np + m scalars (x and y of the previous stop check)
+  TIO* scale_ws;  // [batch][n + m + 1] or nullptr: the scaling (Sx in the caller's column order, Sy, c) an fp32 solve hands to its fp64 polish pass
   unsigned long long* work_counter;
   long long batch;
   sfb_qp_params prm;
@@ -477,14 +478,14 @@ template <typename T, typename TIO, int NT, bool GT> struct CtaSolver
         const int4 h = *reinterpret_cast<const int4*>(sn + 8 * q);
         c0 = h.x; s = h.y; t = h.z; sp = sn[8 * q + 6]; pr = prow + sn[8 * q + 7];
       }
-      // thread -> (column group cg of NCG = sp / PAD, row chunk rc of RC); NCG rounded up to a power of two (<= 32 <= group size)
+      // thread -> (column group cg0 of NCG = sp / PAD, row chunk rc of RC); up to 32 column groups side by side (NCG rounded up to a
+      // power of two), a wider supernode is walked in strides of 32 groups
       const int gsize = nw * 32, gtid = rank * 32 + lane;
       const int NCG = sp >> LPAD;
       int lcg = 0;
-      while ((1 << lcg) < NCG) ++lcg;
-      const int cg = gtid & ((1 << lcg) - 1), rc = gtid >> lcg, RC = gsize >> lcg;
-      const bool active = q >= 0 && cg < NCG && rc < RC;
-      const int j0 = cg << LPAD;
+      while ((1 << lcg) < NCG && lcg < 5) ++lcg;
+      const int CGS = 1 << lcg, cg0 = gtid & (CGS - 1), rc = gtid >> lcg, RC = gsize >> lcg;
+      const bool active = q >= 0 && rc < RC;
       const int nrows = s + t;
       // Blocked right-looking steps, BW = 4 pivot columns at a time.  In step kb a thread of a column group right of the block
       // (A) factorises the BW x BW pivot block in registers (redundantly: a dozen loads and a few dozen flops instead of a
@@ -500,6 +501,8 @@ template <typename T, typename TIO, int NT, bool GT> struct CtaSolver
         __syncthreads();
         if (!active) continue;
         const int kp = kb - BW;  // the previous block
+        for (int cg = cg0; cg < NCG; cg += CGS) {
+        const int j0 = cg << LPAD;
         if (j0 == kb && rc == 0 && kb < s) {  // (P) park this block's factorisation: yd (lower triangle, row-major), then 1 / D
           T lm[BW][BW], dinv[BW], yd[BW][BW];
           if (!pivot_block(pr, kb, s, lm, dinv, yd)) ok = false;
@@ -588,6 +591,7 @@ template <typename T, typename TIO, int NT, bool GT> struct CtaSolver
             stv(W, base + j0, old);
           }
         }
+        }  // column groups of this thread
       }
       __syncthreads();
       mark(kPhFactorCols);
@@ -989,12 +993,31 @@ template <typename T, typename TIO, int NT, bool GT> struct CtaSolver
       qn_us = bmax(qn);
     }
     mark(kPhLoad);
-    if (prm.scaling) scale();  // :347
+    TIO* const sws = a.scale_ws != nullptr ? a.scale_ws + b * (long long)(n + m + 1) : nullptr;
+    if (a.mode == 2 && sws != nullptr) {
+      // polish pass of a lower-precision solve: reuse ITS equilibration (any positive scaling is a valid one for polish_qp, and the
+      // iterate to polish was computed in that scaling) instead of ten more passes over P and A
+      for (int pj = tid; pj < np; pj += NT) {
+        const int jo = __ldg(S.perm + pj);
+        sx[pj] = jo >= 0 ? (T)sws[jo] : T(1);
+      }
+      for (int i = tid; i < m; i += NT) sy[i] = (T)sws[n + i];
+      c = (T)sws[n + m];
+      __syncthreads();
+    } else if (prm.scaling) scale();  // :347
     else {
       c = T(1);
       for (int j = tid; j < np; j += NT) sx[j] = T(1);
       for (int i = tid; i < m; i += NT) sy[i] = T(1);
       __syncthreads();
+    }
+    if (a.mode != 2 && sws != nullptr) {
+      for (int pj = tid; pj < np; pj += NT) {
+        const int jo = __ldg(S.perm + pj);
+        if (jo >= 0) sws[jo] = (TIO)sx[pj];
+      }
+      for (int i = tid; i < m; i += NT) sws[n + i] = (TIO)sy[i];
+      if (tid == 0) sws[n + m] = (TIO)c;
     }
     mark(kPhScale);
     // ---- rho classes + trivially empty feasible set  :361-374

@@ -496,6 +496,7 @@ int sfb_destroy(sfb_handle_t h)
     if (sc.dev) cudaFree(sc.dev);
   if (h->sparse_ws.dev) cudaFree(h->sparse_ws.dev);
   if (h->sparse_cta_ws.dev) cudaFree(h->sparse_cta_ws.dev);
+  if (h->sparse_scale_ws.dev) cudaFree(h->sparse_scale_ws.dev);
   if (h->sparse_stage.dev) cudaFree(h->sparse_stage.dev);
   if (h->act_tmp.dev) cudaFree(h->act_tmp.dev);
   if (h->csc_tmp.dev) cudaFree(h->csc_tmp.dev);

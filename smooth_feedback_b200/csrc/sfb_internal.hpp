@@ -59,6 +59,7 @@ struct sfb_context
   int sparse_tw = 0;     // SFB_SPARSE_TW=4|8|32 overrides the tile-width heuristic of the sparse QP path (A/B measurements)
   int sparse_kernel = 0; // SFB_SPARSE_KERNEL=tiled (1) forces the HBM-tiled kernel, =cta (2) / unset: the on-chip kernel when the instance fits in shared memory
   sfbi::Scratch sparse_cta_ws; // per-CTA global vectors of the on-chip sparse kernel
+  sfbi::Scratch sparse_scale_ws; // equilibration of an fp32 on-chip solve, handed to its fp64 polish pass
   sfbi::Scratch sparse_ws;     // tiled working set of the sparse QP path
   sfbi::Scratch sparse_stage;  // device copies of host buffers (sparse path)
   sfbi::Scratch csc_tmp;       // CSC -> CSR permuted A values (sfb_qp_solve_sparse_batch_csc_f64)

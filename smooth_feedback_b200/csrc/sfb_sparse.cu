@@ -196,6 +196,12 @@ int qp_sparse_solve_impl(sfb_context* h, const sfb_qp_sparse_pattern* pt, const 
       ca.P = a.P; ca.q = a.q; ca.A = a.A; ca.l = a.l; ca.u = a.u; ca.warm_x = a.warm_x; ca.warm_y = a.warm_y;
       ca.out_x = a.out_x; ca.out_y = a.out_y; ca.out_obj = a.out_obj; ca.out_status = a.out_status; ca.out_iter = a.out_iter;
       ca.out_active = a.out_active; ca.out_flags = a.out_flags;
+      ca.scale_ws = nullptr;
+      if (mixed && polish_cta) {  // the fp64 polish pass reuses this solve's equilibration
+        rc2 = ensure_scratch(h, h->sparse_scale_ws, (size_t)a.batch * (size_t)(n + m + 1) * sizeof(T), h->stream);
+        if (rc2 != SFB_OK) return rc2;
+        ca.scale_ws = static_cast<T*>(h->sparse_scale_ws.dev);
+      }
       rc2 = cta_launch<T, T>(h, pt, ca);
     } else {
       rc2 = sp_launch<T, T>(h, pt, a, tw);
@@ -207,6 +213,7 @@ int qp_sparse_solve_impl(sfb_context* h, const sfb_qp_sparse_pattern* pt, const 
       ca.P = a.P; ca.q = a.q; ca.A = a.A; ca.l = a.l; ca.u = a.u;
       ca.out_x = a.out_x; ca.out_y = a.out_y; ca.out_obj = a.out_obj; ca.out_status = a.out_status; ca.out_iter = a.out_iter;
       ca.out_active = a.out_active; ca.out_flags = a.out_flags;
+      ca.scale_ws = use_cta ? static_cast<T*>(h->sparse_scale_ws.dev) : nullptr;
       return cta_launch<double, T>(h, pt, ca);
     }
     sfb::SpArgs<double, T> pa{};

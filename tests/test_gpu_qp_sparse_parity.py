@@ -418,3 +418,21 @@ def test_onchip_kernel_is_the_one_that_runs_and_agrees_with_the_tiled_kernel(sfb
     # a default handle (no environment override) picks the on-chip kernel
     sp0 = sfb.SparsePattern(pat["n"], pat["m"], pat["P_colptr"], pat["P_rowidx"], pat["A_rowptr"], pat["A_colidx"])
     assert sp0.uses_onchip(8)[0] and sp0.uses_onchip(4)[0]
+
+
+def test_parity_wide_supernodes(sfb, oracle, sparse_kernel):
+    """Nearly dense patterns: the factor collapses into one or two supernodes of 100+ columns (more than 32 vector column groups
+    per supernode: the on-chip factorisation walks them in strides; the sweeps run more outputs than threads per stage)."""
+    from smooth_feedback_b200.generators import random_sparse_qp_numpy
+
+    for (n, m, dens, seed) in [(140, 90, 0.5, 11), (100, 160, 0.9, 12)]:
+        pat, Pv, q, Av, l, u = random_sparse_qp_numpy(48, n, m, density=dens, seed=seed)
+        sp, r, o, wp = _solve_both(sfb, oracle, pat, Pv, q, Av, l, u)
+        if sparse_kernel == "onchip":  # (the second pattern's fp64 working set exceeds shared memory: that solve falls back to the tiled kernel)
+            used64, info = sp.uses_onchip(8)
+            used32, _ = sp.uses_onchip(4)
+            assert info["largest_supernode"] > 32 * 2 and used32 and (used64 or n == 100), (info, used32, used64)
+        _assert_parity(r, o, wp, REL_F64, min_well_posed=0.9)
+        r32 = sfb.solve_sparse_batch(sp, *(np.ascontiguousarray(a, dtype=np.float32) for a in (Pv, q, Av, l, u)), sfb.QPSolverParams(max_iter=4000))
+        same = (r32.status == o.status) & (o.status == 0)
+        assert same.mean() >= 0.9 and rel_err(r32.x[same].astype(np.float64), o.x[same]).max() <= 5e-2  # fp32 on |x| ~ 1e2 problems: sanity, not parity
