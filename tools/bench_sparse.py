@@ -81,7 +81,7 @@ def run(batch=8192, dtype="f64", steps=3, small=False, tw=0):
         "onchip": info if onchip else None,
         "achieved_compulsory_gbs": batch * bcomp / (mean_ms * 1e-3) / 1e9,
         "bound": ("the on-chip kernel moves only the compulsory bytes through HBM (B_comp per solve); it is bound by the latency of one "
-                  "warp's dependent instruction stream between the barriers of its 15 sweep stages / 175 column steps, see DESIGN 4.3"
+                  "warp's dependent instruction stream between the barriers of its 15 sweep stages / 46 four-column factorisation steps, see DESIGN 4.3"
                   if onchip else "HBM-streaming model, see DESIGN 4.3"),
         "source": source, "ms_min": min(ms), "ms_median": mean_ms,
         "workload": f"sparse QP (MPC structure) n={pat['n']} m={pat['m']} nnzA={sp.nnzA} nnzP={sp.nnzP} nnzL={sp.nnzL} batch={batch} {dtype} tw={tw or 'auto'}",
