@@ -436,3 +436,17 @@ def test_parity_wide_supernodes(sfb, oracle, sparse_kernel):
         r32 = sfb.solve_sparse_batch(sp, *(np.ascontiguousarray(a, dtype=np.float32) for a in (Pv, q, Av, l, u)), sfb.QPSolverParams(max_iter=4000))
         same = (r32.status == o.status) & (o.status == 0)
         assert same.mean() >= 0.9 and rel_err(r32.x[same].astype(np.float64), o.x[same]).max() <= 5e-2  # fp32 on |x| ~ 1e2 problems: sanity, not parity
+
+
+def test_max_time_and_iteration_budget(sfb, sparse_kernel):
+    """qp_solver.hpp:504-508 / :449: a time budget that is already spent ends the solve at the first stop check with MaxTime, an
+    iteration budget below the first successful check with MaxIterations; both return finite iterates (both sparse kernels)."""
+    from smooth_feedback_b200.generators import mpc_structured_batch, mpc_structured_pattern
+
+    pat = mpc_structured_pattern(Nx=3, Nu=2, nivals=3, Ki=4)
+    Pv, q, Av, l, u = mpc_structured_batch(pat, 40, seed=7)
+    sp = _pattern(sfb, pat)
+    r = sfb.solve_sparse_batch(sp, Pv, q, Av, l, u, sfb.QPSolverParams(max_time=1e-9))
+    assert (r.status == int(sfb.QPSolutionStatus.MaxTime)).all() and (r.iter == 2).all() and np.isfinite(r.x).all()
+    r = sfb.solve_sparse_batch(sp, Pv, q, Av, l, u, sfb.QPSolverParams(max_iter=20))
+    assert (r.status == int(sfb.QPSolutionStatus.MaxIterations)).all() and (r.iter == 20).all() and np.isfinite(r.x).all()
