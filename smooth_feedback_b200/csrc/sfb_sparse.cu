@@ -164,16 +164,22 @@ int qp_sparse_solve_impl(sfb_context* h, const sfb_qp_sparse_pattern* pt, const 
   const bool use_cta = cta_fits<T>(h, pt);
   const bool polish_cta = cta_fits<double>(h, pt);  // the fp64 second pass of an fp32 solve
   int tw = 4;
-  {
+  const bool mixed = std::is_same<T, float>::value && prm->polish;
+  const bool needs_tiled = !use_cta || (mixed && !polish_cta);  // only the tiled kernel has a per-instance HBM workspace
+  if (needs_tiled) {
     const size_t per_inst4 = (sfb::sp_a_len(pt->pat, 4) + pt->sym.nnzP + sfb::sp_w_len(pt->pat, 4) + (size_t)sfb::kSpNV * n +
                               (size_t)sfb::kSpMV * m) * sizeof(T);
-    size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = 0; }
-    if (h->sparse_ws.bytes < per_inst4 * (size_t)batch && per_inst4 * (size_t)batch > free_b / 2) tw = 32;
+    // cudaMemGetInfo goes through the resource manager (an ioctl that serialises with NVML / nvidia-smi polling: measured
+    // 10 - 70 ms stalls per call while nvidia-smi -lms ran, profiles/r02_host_stall_diag.txt), so it is asked only when the
+    // workspace really has to grow
+    if (h->sparse_ws.bytes < per_inst4 * (size_t)batch) {
+      size_t free_b = 0, total_b = 0;
+      if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = 0; }
+      if (per_inst4 * (size_t)batch > free_b / 2) tw = 32;
+    }
   }
   if (h->sparse_tw == 4 || h->sparse_tw == 8 || h->sparse_tw == 32) tw = h->sparse_tw;
   // fp32 + polish runs a second, fp64 pass over the same instances (mixed precision, see sp_polish_pass): size the workspace once
-  const bool mixed = std::is_same<T, float>::value && prm->polish;
   const long long tiles = (batch + tw - 1) / tw;
   const size_t ws_bytes = std::max(use_cta ? (size_t)0 : sp_tile_bytes<T>(pt, tw), (mixed && !polish_cta) ? sp_tile_bytes<double>(pt, tw) : (size_t)0) * (size_t)tiles;
   rc = ensure_scratch(h, h->sparse_ws, ws_bytes, h->stream);
