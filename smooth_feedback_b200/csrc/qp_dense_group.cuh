@@ -51,6 +51,24 @@ template <typename T> __device__ __forceinline__ typename Vec2T<T>::type ld2(con
 
 __device__ __forceinline__ double rcp(double x) { return __drcp_rn(x); }
 __device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
+// Branch-free reciprocal for the pivots of the register-blocked inverse: MUFU.RCP64H seed (20 bits) + Newton steps, <= 1 ulp
+// for normal inputs.  __drcp_rn carries a slow-path call (BSSY / CALL / BSYNC) that splits the basic block, so ptxas
+// could not overlap it with the rank-1 update; this one is plain DFMAs the scheduler interleaves with the update.
+__device__ __forceinline__ double rcp_inline(double x)
+{
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+__device__ __forceinline__ float rcp_inline(float x) { return __frcp_rn(x); }
+// the value is materialised at this point of the program (an empty asm the optimiser cannot move the definition across)
+__device__ __forceinline__ void keep_here(double& x) { asm volatile("" : "+d"(x)); }
+__device__ __forceinline__ void keep_here(float& x) { asm volatile("" : "+f"(x)); }
 
 template <typename T> struct Num;
 template <> struct Num<double>
@@ -467,6 +485,10 @@ template <typename T, int G, int NS, int MS> struct QpGroup
       for (int h = 0; h < TR / TC; ++h) {
         constexpr int Q = TR / TC;
         const int bk = ak * Q + h;
+        // 1 / pivot is computed by every thread on ITS slot (ak, bk) one step ahead, overlapped with the rank-1 update; the
+        // thread that owns the pivot publishes it in colk[k] (that entry of the pivot column is never read: the pivot row
+        // zeroes its own multiplier) -- the reciprocal is off the barrier -> update critical path of every step
+        T pn = rcp_inline(v[ak][bk]);
 #pragma unroll 1
         for (int t2 = 0; t2 < TC; ++t2) {
           const int t = h * TC + t2;
@@ -480,12 +502,12 @@ template <typename T, int G, int NS, int MS> struct QpGroup
           }
           if (tj == t2) {
 #pragma unroll
-            for (int a = 0; a < RB; ++a) colk[ti + TR * a] = v[a][bk];
+            for (int a = 0; a < RB; ++a) colk[ti + TR * a] = (ti == t && a == ak) ? pn : v[a][bk];
           }
           gsync();
           const T p = rowk[k];
+          const T pinv = colk[k];
           if (!(p > T(0)) || !(p < Num<T>::inf())) { ok = false; break; }
-          const T pinv = rcp(p);
           T ck[RB], rk[CB];
 #pragma unroll
           for (int a = 0; a < RB; ++a) ck[a] = colk[ti + TR * a];
@@ -503,10 +525,14 @@ template <typename T, int G, int NS, int MS> struct QpGroup
 #pragma unroll
             for (int b2 = 0; b2 < CB; ++b2) v[ak][b2] = rk[b2];
           }
+          v[ak][bk] -= ck[ak] * rk[bk];  // the next pivot's slot first: its reciprocal overlaps the rest of the update
+          pn = rcp_inline(v[ak][bk]);
 #pragma unroll
           for (int a = 0; a < RB; ++a)
 #pragma unroll
-            for (int b2 = 0; b2 < CB; ++b2) v[a][b2] -= ck[a] * rk[b2];
+            for (int b2 = 0; b2 < CB; ++b2)
+              if (a != ak || b2 != bk) v[a][b2] -= ck[a] * rk[b2];
+          keep_here(pn);  // the reciprocal stays in THIS iteration (not sunk to the top of the next one)
         }
       }
     }
