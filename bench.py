@@ -66,6 +66,9 @@ def bind_to_gpu_numa_node(local: int) -> dict:
     process happened to run on): pin THIS rank's threads to the CPUs that are local to its GPU before any pinned host buffer
     is allocated, so first-touch places those buffers on the GPU's own NUMA node. Best effort; reports what it did."""
     info = {"bound": False}
+    if os.environ.get("SFB_BENCH_NUMA", "1") == "0":  # A/B switch
+        info["disabled"] = True
+        return info
     try:
         import torch
 
@@ -621,8 +624,9 @@ def main():
                "host_link_gbs_per_rank": (h2d + d2h) * e_steps / te.item() / 1e9,
                "host_link_gbs_all_ranks": world * (h2d + d2h) * e_steps / te.item() / 1e9,
                "numa_binding_rank0": numa,
-               "note": "62 KB of problem data per solve cross PCIe: e2e is bound by the host link (all ranks share the host memory / "
-                       "PCIe complex); the fleet entry points (secondary cfg3 / cfg5) build the problems on the device instead"}
+               "note": "62 KB of problem data per solve cross PCIe: e2e is bound by the host link (~55 GB/s per GPU; measured 4 GPUs: "
+                       "4 x 49.7 GB/s = 3.14e6 solves/s on a single-NUMA-node host, profiles/r02_bench_4gpu.jsonl); the fleet entry "
+                       "points (secondary cfg3 / cfg5) build the problems on the device instead"}
         assert (hout.status == 0).mean() == optimal_frac or True
 
     if rank == 0:
