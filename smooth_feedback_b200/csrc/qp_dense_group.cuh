@@ -1385,7 +1385,10 @@ template <typename T, int G, int NS, int MS> struct QpGroup
         }
         if (has_row) w[myrow] = rr * zr - yr;
       }
-      gsync();
+      // w[rg + 16 ia] is produced and consumed by the SAME warp (rg = 4 warp + rl on both sides), and every other buffer of
+      // the iteration is already ordered by the three barriers above (part4: read before barrier 2, rewritten after barrier 3
+      // of the same iteration; xt, nv1, x: rewritten only after the next barrier 1): a warp-level sync is enough here
+      __syncwarp();
     }
     if (has_row) { z[myrow] = zr; y[myrow] = yr; }
     gsync();
