@@ -391,6 +391,16 @@ int sfb_mpc_fleet_step_f64(sfb_mpc_fleet_t f, const double* t, const double* x, 
                            uint32_t* out_iter, double* out_primal, double* out_dual);
 int sfb_mpc_fleet_step_f32(sfb_mpc_fleet_t f, const float* t, const float* x, float* out_u, int32_t* out_status,
                            uint32_t* out_iter, float* out_primal, float* out_dual);
+/*
+ * The optional outputs of MPC::operator() (mpc.hpp:453-454, :493-507), computed from the solution the LAST step left on
+ * the device: out_u_traj [batch][N][2], u_traj[i] = udes(t + tf tau_i) + primal.segment<Nu>(uvar_B + i Nu);
+ * out_x_traj [batch][N + 1][7], x_traj[i] = xdes(t + tf tau_i) (+) primal.segment<Nx>(i Nx).  t [batch] must be the times
+ * given to that step; either output may be NULL.  sfb_mpc_fleet_nodes: N = Mesh::N_colloc() and tau [N + 1] =
+ * Mesh::all_nodes() (collocation/mesh.hpp:213-224), either may be NULL.
+ */
+int sfb_mpc_fleet_nodes(sfb_mpc_fleet_t f, int* N, double* tau);
+int sfb_mpc_fleet_trajectories_f64(sfb_mpc_fleet_t f, const double* t, double* out_u_traj, double* out_x_traj);
+int sfb_mpc_fleet_trajectories_f32(sfb_mpc_fleet_t f, const float* t, float* out_u_traj, float* out_x_traj);
 
 /*
  * ---- multi-GPU: the one collective of the path -----------------------------------------------------

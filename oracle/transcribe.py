@@ -629,6 +629,15 @@ class MPCRestated:
     def input_from_primal(self, t, primal):
         return self.udes(t) + primal[self.dims["xvar_L"]: self.dims["xvar_L"] + self.Nu]   # mpc.hpp:518
 
+    def trajectories(self, t, primal):
+        """The optional outputs of MPC::operator() (mpc.hpp:493-507): u_traj[i] = udes(t + tf tau_i) + primal.segment<Nu>(uvar_B
+        + i Nu), i < N; x_traj[i] = xdes(t + tf tau_i) (+) primal.segment<Nx>(i Nx), i <= N; tau = Mesh::all_nodes()."""
+        tau = self.mesh.all_nodes()
+        N, Nx, Nu, uB = len(tau) - 1, self.Nx, self.Nu, self.dims["xvar_L"]
+        u_traj = np.stack([self.udes(t + self.tf * tau[i]) + primal[uB + i * Nu: uB + (i + 1) * Nu] for i in range(N)])
+        x_traj = np.stack([self.group.rplus(self.xdes(t + self.tf * tau[i])[0], primal[i * Nx: (i + 1) * Nx]) for i in range(N + 1)])
+        return u_traj, x_traj
+
     @staticmethod
     def keeps_warmstart(code: int) -> bool:
         return code in (0, 5, 4)  # Optimal, MaxTime, MaxIterations  (mpc.hpp:510-516)

@@ -57,6 +57,7 @@ EXPORTED_SYMBOLS = [
     "sfb_asif_fleet_set_warmstart", "sfb_asif_fleet_filter_f64", "sfb_asif_fleet_filter_f32", "sfb_asif_fleet_to_qp_f64",
     "sfb_mpc_vehicle_params_default", "sfb_mpc_fleet_create", "sfb_mpc_fleet_destroy", "sfb_mpc_fleet_reset_warmstart",
     "sfb_mpc_fleet_dims", "sfb_mpc_fleet_pattern", "sfb_mpc_fleet_to_qp_f64", "sfb_mpc_fleet_step_f64", "sfb_mpc_fleet_step_f32",
+    "sfb_mpc_fleet_nodes", "sfb_mpc_fleet_trajectories_f64", "sfb_mpc_fleet_trajectories_f32",
     "sfb_comm_unique_id", "sfb_comm_create", "sfb_comm_destroy", "sfb_allgather_results", "sfb_comm_wait",
 ]
 
@@ -153,6 +154,9 @@ def lib() -> C.CDLL:
     L.sfb_mpc_fleet_to_qp_f64.argtypes = [vp] * 8
     L.sfb_mpc_fleet_step_f64.argtypes = [vp] * 8
     L.sfb_mpc_fleet_step_f32.argtypes = [vp] * 8
+    L.sfb_mpc_fleet_nodes.argtypes = [vp, C.POINTER(C.c_int), vp]
+    L.sfb_mpc_fleet_trajectories_f64.argtypes = [vp] * 4
+    L.sfb_mpc_fleet_trajectories_f32.argtypes = [vp] * 4
     L.sfb_comm_unique_id.argtypes = [vp]
     L.sfb_comm_create.argtypes = [vp, i32, i32, vp, C.POINTER(vp)]
     L.sfb_comm_destroy.argtypes = [vp]

@@ -138,4 +138,50 @@ template <typename T> __global__ void __launch_bounds__(128) mpc_vehicle_epilogu
   }
 }
 
+// The optional outputs of MPC::operator() (mpc.hpp:493-507): u_traj[i] = udes(t + tf tau_i) + primal.segment<Nu>(uvar_B + i Nu),
+// i < N, and x_traj[i] = xdes(t + tf tau_i) (+) primal.segment<Nx>(i Nx), i <= N, with (+) of Bundle<SE2, R^3>:
+// (g * exp(a_0..2), v + a_3..5).  One thread per (agent, node); evaluated in fp64 whatever the fleet's scalar type.
+template <typename T> struct MpcTrajArgs
+{
+  long long batch;
+  int N, n, xvar_L;
+  double tf, g0[3], vdes[3], udes[2];
+  const double* tau;  // [N + 1]
+  const T* t;         // [batch] the absolute time given to the step whose solution is read
+  const T* sol_x;     // [batch][n]
+  T* u_traj;          // [batch][N][2] or nullptr
+  T* x_traj;          // [batch][N + 1][7] (x, y, sin, cos, v1, v2, v3) or nullptr
+};
+
+template <typename T> __global__ void __launch_bounds__(128) mpc_vehicle_traj_kernel(const __grid_constant__ MpcTrajArgs<T> a)
+{
+  const long long total = a.batch * (long long)(a.N + 1);
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long b = idx / (a.N + 1);
+    const int i = (int)(idx - b * (a.N + 1));
+    const T* sol = a.sol_x + b * (long long)a.n;
+    if (a.u_traj != nullptr && i < a.N) {
+      T* uo = a.u_traj + (b * a.N + i) * 2;
+      uo[0] = (T)(a.udes[0] + (double)sol[a.xvar_L + 2 * i]);
+      uo[1] = (T)(a.udes[1] + (double)sol[a.xvar_L + 2 * i + 1]);
+    }
+    if (a.x_traj != nullptr) {
+      const double ta = (double)a.t[b] + a.tf * a.tau[i];
+      double ex[4], es[4];
+      se2_exp_d(ta * a.vdes[0], ta * a.vdes[1], ta * a.vdes[2], ex);
+      double s0, c0;
+      sincos(a.g0[2], &s0, &c0);
+      const double gx = a.g0[0] + c0 * ex[0] - s0 * ex[1], gy = a.g0[1] + s0 * ex[0] + c0 * ex[1];
+      const double gs = s0 * ex[3] + c0 * ex[2], gc = c0 * ex[3] - s0 * ex[2];
+      se2_exp_d((double)sol[6 * i], (double)sol[6 * i + 1], (double)sol[6 * i + 2], es);
+      T* xo = a.x_traj + (b * (a.N + 1) + i) * 7;
+      xo[0] = (T)(gx + gc * es[0] - gs * es[1]);
+      xo[1] = (T)(gy + gs * es[0] + gc * es[1]);
+      xo[2] = (T)(gs * es[3] + gc * es[2]);
+      xo[3] = (T)(gc * es[3] - gs * es[2]);
+      for (int k = 0; k < 3; ++k) xo[4 + k] = (T)(a.vdes[k] + (double)sol[6 * i + 3 + k]);
+    }
+  }
+}
+
 }  // namespace sfb

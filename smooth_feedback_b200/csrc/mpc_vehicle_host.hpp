@@ -32,6 +32,7 @@ struct MpcVehicleHost
   int nivals = 0, Ki = 0, N = 0, n = 0, m = 0, xvar_L = 0;
   std::vector<int> P_colptr, P_rowidx, A_rowptr, A_colidx;
   std::vector<double> P_vals, A_base, l_base, u_base;
+  std::vector<double> tau;  // Mesh::all_nodes() (mesh.hpp:213-224): N + 1 values in [0, 1], the times of x_0 .. x_N (u_i lives at tau[i], i < N)
   int ce_slot[Nce][Nce];  // position in A_vals of end-constraint entry (r, c), -1 outside d_exp_sparse_pattern<X>
   int ce_row0 = 0;
   std::string error;
@@ -121,6 +122,15 @@ inline bool mpc_vehicle_build(const sfb_mpc_vehicle_params& p, MpcVehicleHost& H
   std::vector<double> ext(lx);
   ext.push_back(1.0);
   const auto Dus = lagrange_diffmat(ext);  // Dus[j][i], i < Ki used
+
+  H.tau.clear();
+  for (int iv = 0; iv < nivals; ++iv) {  // interval_nodes (mesh.hpp:182-206): tau0 + al (x_k + 1), the extra point of the last interval is 1
+    const double tau0 = (nivals < 2) ? 0.0 : (double)iv * (1.0 / (double)nivals);
+    const double tauf = (iv + 1 < nivals) ? (double)(iv + 1) * (1.0 / (double)nivals) : 1.0;
+    const double al = (tauf - tau0) / 2;
+    for (int k = 0; k < Ki; ++k) H.tau.push_back(tau0 + al * (lx[k] + 1));
+    if (iv + 1 == nivals) H.tau.push_back(tau0 + al * (1.0 + 1));
+  }
 
   std::vector<std::map<int, double>> rows(H.m), pcols(H.n);
   H.l_base.assign(H.m, 0.0);

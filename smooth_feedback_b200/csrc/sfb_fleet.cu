@@ -43,7 +43,7 @@ struct sfb_mpc_fleet
   int64_t batch = 0;
   int scalar_bytes = 8;
   // fleet constants on the device
-  double *d_Pc = nullptr, *d_Ac = nullptr, *d_lc = nullptr, *d_uc = nullptr;
+  double *d_Pc = nullptr, *d_Ac = nullptr, *d_lc = nullptr, *d_uc = nullptr, *d_tau = nullptr;
   // per-agent QP values, solutions and resident warm starts (scalar type of the fleet)
   void *d_P = nullptr, *d_q = nullptr, *d_A = nullptr, *d_l = nullptr, *d_u = nullptr;
   void *d_sx = nullptr, *d_sy = nullptr, *d_obj = nullptr, *d_wx = nullptr, *d_wy = nullptr;
@@ -427,6 +427,8 @@ int sfb_mpc_fleet_create(sfb_handle_t h, const sfb_mpc_vehicle_params* p, int64_
   auto dm = [&](void** ptr, size_t bytes) { return cudaMalloc(ptr, std::max<size_t>(bytes, 16)) == cudaSuccess; };
   bool ok = cudaSetDevice(h->device) == cudaSuccess;
   ok = ok && dm((void**)&f->d_Pc, 8 * nP) && dm((void**)&f->d_Ac, 8 * nA) && dm((void**)&f->d_lc, 8 * m) && dm((void**)&f->d_uc, 8 * m);
+  ok = ok && dm((void**)&f->d_tau, 8 * H.tau.size()) &&
+       cudaMemcpy(f->d_tau, H.tau.data(), 8 * H.tau.size(), cudaMemcpyHostToDevice) == cudaSuccess;
   ok = ok && dm(&f->d_P, sb * nP * B) && dm(&f->d_q, sb * n * B) && dm(&f->d_A, sb * nA * B) && dm(&f->d_l, sb * m * B) && dm(&f->d_u, sb * m * B);
   ok = ok && dm(&f->d_sx, sb * n * B) && dm(&f->d_sy, sb * m * B) && dm(&f->d_obj, sb * B) && dm(&f->d_wx, sb * n * B) && dm(&f->d_wy, sb * m * B);
   ok = ok && dm((void**)&f->d_warm_valid, B) && dm(&f->d_t, sb * B) && dm(&f->d_x, sb * 7 * B) && dm(&f->d_uout, sb * 2 * B);
@@ -451,7 +453,7 @@ int sfb_mpc_fleet_destroy(sfb_mpc_fleet_t f)
   if (!f) return SFB_OK;
   cudaSetDevice(f->h->device);
   cudaStreamSynchronize(f->h->stream);
-  void* ptrs[] = {f->d_Pc, f->d_Ac, f->d_lc, f->d_uc, f->d_P, f->d_q, f->d_A, f->d_l, f->d_u, f->d_sx, f->d_sy, f->d_obj, f->d_wx,
+  void* ptrs[] = {f->d_tau, f->d_Pc, f->d_Ac, f->d_lc, f->d_uc, f->d_P, f->d_q, f->d_A, f->d_l, f->d_u, f->d_sx, f->d_sy, f->d_obj, f->d_wx,
                   f->d_wy, f->d_warm_valid, f->d_t, f->d_x, f->d_uout, f->d_status, f->d_iter};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -520,6 +522,70 @@ int sfb_mpc_fleet_to_qp_f64(sfb_mpc_fleet_t f, const double* t, const double* x,
   SFB_CUDA(h, cudaMemcpyAsync(u, uu, 8 * m * B, cudaMemcpyDeviceToHost, h->stream));
   SFB_CUDA(h, cudaStreamSynchronize(h->stream));
   return SFB_OK;
+}
+
+int sfb_mpc_fleet_nodes(sfb_mpc_fleet_t f, int* N, double* tau)
+{
+  if (!f) return SFB_ERR_INVALID_ARGUMENT;
+  if (N) *N = f->host.N;
+  if (tau) std::copy(f->host.tau.begin(), f->host.tau.end(), tau);
+  return SFB_OK;
+}
+
+namespace {
+// mpc.hpp:493-507 on the solution the last step left on the device
+template <typename T> int mpc_traj_impl(sfb_mpc_fleet* f, const T* t, T* out_u_traj, T* out_x_traj)
+{
+  if (!f) return SFB_ERR_INVALID_ARGUMENT;
+  sfb_context* h = f->h;
+  if (f->scalar_bytes != (int)sizeof(T)) return fail(h, SFB_ERR_INVALID_ARGUMENT, "fleet was created for %d-byte scalars", f->scalar_bytes);
+  if (!t) return fail(h, SFB_ERR_INVALID_ARGUMENT, "t is NULL");
+  if (!out_u_traj && !out_x_traj) return SFB_OK;
+  const int space = classify({t, out_u_traj, out_x_traj});
+  if (space < 0) return fail(h, SFB_ERR_MIXED_MEMORY, "host and device pointers mixed in one call");
+  SFB_CUDA(h, cudaSetDevice(h->device));
+  const size_t B = (size_t)f->batch;
+  const int N = f->host.N;
+  const size_t ub = sizeof(T) * 2 * (size_t)N * B, xb = sizeof(T) * 7 * (size_t)(N + 1) * B;
+  sfb::MpcTrajArgs<T> a{};
+  a.batch = f->batch; a.N = N; a.n = f->host.n; a.xvar_L = f->host.xvar_L; a.tf = f->prm.tf;
+  for (int k = 0; k < 3; ++k) { a.g0[k] = f->prm.g0[k]; a.vdes[k] = f->prm.vdes[k]; }
+  a.udes[0] = f->prm.udes[0]; a.udes[1] = f->prm.udes[1];
+  a.tau = f->d_tau; a.sol_x = static_cast<const T*>(f->d_sx);
+  a.t = t; a.u_traj = out_u_traj; a.x_traj = out_x_traj;
+  if (space == 0) {  // host buffers: staged through the handle's scratch
+    int rc = sfbi::ensure_scratch(h, h->sparse_stage, sizeof(T) * B + ub + xb + 512, h->stream);
+    if (rc != SFB_OK) return rc;
+    char* d = static_cast<char*>(h->sparse_stage.dev);
+    auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+    T* dt = reinterpret_cast<T*>(d);
+    T* du = reinterpret_cast<T*>(d + al(sizeof(T) * B));
+    T* dx = reinterpret_cast<T*>(d + al(sizeof(T) * B) + al(ub));
+    SFB_CUDA(h, cudaMemcpyAsync(dt, t, sizeof(T) * B, cudaMemcpyHostToDevice, h->stream));
+    a.t = dt; a.u_traj = out_u_traj ? du : nullptr; a.x_traj = out_x_traj ? dx : nullptr;
+  }
+  const long long total = (long long)B * (N + 1);
+  const int grid = (int)std::min<long long>((total + 127) / 128, (long long)h->prop.multiProcessorCount * 16);
+  sfb::mpc_vehicle_traj_kernel<T><<<grid, 128, 0, h->stream>>>(a);
+  SFB_CUDA(h, cudaGetLastError());
+  h->launches += 1;
+  if (space == 0) {
+    if (out_u_traj) SFB_CUDA(h, cudaMemcpyAsync(out_u_traj, a.u_traj, ub, cudaMemcpyDeviceToHost, h->stream));
+    if (out_x_traj) SFB_CUDA(h, cudaMemcpyAsync(out_x_traj, a.x_traj, xb, cudaMemcpyDeviceToHost, h->stream));
+    SFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return SFB_OK;
+}
+}  // namespace
+
+int sfb_mpc_fleet_trajectories_f64(sfb_mpc_fleet_t f, const double* t, double* out_u_traj, double* out_x_traj)
+{
+  return mpc_traj_impl<double>(f, t, out_u_traj, out_x_traj);
+}
+
+int sfb_mpc_fleet_trajectories_f32(sfb_mpc_fleet_t f, const float* t, float* out_u_traj, float* out_x_traj)
+{
+  return mpc_traj_impl<float>(f, t, out_u_traj, out_x_traj);
 }
 
 int sfb_mpc_fleet_step_f64(sfb_mpc_fleet_t f, const double* t, const double* x, double* out_u, int32_t* out_status,

@@ -132,6 +132,35 @@ class MPCVehicleFleet:
         self._h.check(fn(self._f, _ptr(t), _ptr(x), _ptr(u), _ptr(st), _ptr(it), _ptr(px), _ptr(py)))
         return (u, st, it, px, py) if return_solution else (u, st, it)
 
+    def nodes(self):
+        """(N, tau [N + 1]): Mesh::N_colloc() and Mesh::all_nodes(); x_i lives at t + tf tau[i], u_i at t + tf tau[i], i < N."""
+        N = C.c_int(0)
+        self._h.check(_lib.lib().sfb_mpc_fleet_nodes(self._f, C.byref(N), None))
+        tau = np.empty(N.value + 1, np.float64)
+        self._h.check(_lib.lib().sfb_mpc_fleet_nodes(self._f, None, tau.ctypes.data_as(C.c_void_p)))
+        return N.value, tau
+
+    def trajectories(self, t):
+        """The optional outputs of MPC::operator() (mpc.hpp:493-507) for the solution of the LAST step (t = the times given
+        to it): u_traj [B, N, 2] and x_traj [B, N + 1, 7]."""
+        N, _ = self.nodes()
+        B = self.batch
+        if _is_torch(t):
+            import torch
+
+            assert t.is_cuda and t.is_contiguous() and t.dtype == (torch.float64 if self.dtype == np.float64 else torch.float32)
+            self._h.set_stream(torch.cuda.current_stream(t.device).cuda_stream)
+            ut = torch.empty((B, N, 2), dtype=t.dtype, device=t.device)
+            xt = torch.empty((B, N + 1, 7), dtype=t.dtype, device=t.device)
+        else:
+            t = np.ascontiguousarray(t, dtype=self.dtype)
+            ut, xt = np.empty((B, N, 2), self.dtype), np.empty((B, N + 1, 7), self.dtype)
+        assert tuple(t.shape) == (B,)
+        L = _lib.lib()
+        fn = L.sfb_mpc_fleet_trajectories_f64 if self.dtype == np.float64 else L.sfb_mpc_fleet_trajectories_f32
+        self._h.check(fn(self._f, _ptr(t), _ptr(ut), _ptr(xt)))
+        return ut, xt
+
     def to_qp(self, t, x):
         """The transcription alone -> P_vals [B,nnzP], q [B,n], A_vals [B,nnzA], l, u [B,m] (pattern(): shared pattern)."""
         assert self.dtype == np.float64

@@ -143,6 +143,49 @@ def test_step_fp32_and_device_path(sfb, oracle):
     assert np.array_equal(px.cpu().numpy()[:, xvar:xvar + 2], uh)
 
 
+def test_trajectory_outputs(sfb):
+    """The optional outputs of MPC::operator() (mpc.hpp:493-507): u_traj / x_traj of the fleet against the restatement applied
+    to the SAME primal solution (1e-12: pure post-processing), the mesh nodes against Mesh::all_nodes(), the properties the
+    reference's construction guarantees (u_traj[0] is the applied input; x_traj[0] is the measured state: the end constraint
+    pins x_0), host path == device path, fp32 within 1e-5."""
+    import torch
+
+    from workloads import vehicle_mpc_batch
+
+    B = 24
+    pat, _, _, _, _, _, mpc, t0, x0 = vehicle_mpc_batch(B, seed=8)
+    fleet = sfb.MPCVehicleFleet(B, sfb.MPCVehicleParams(qp=sfb.QPSolverParams(max_iter=4000)))
+    N, tau = fleet.nodes()
+    ref_tau = mpc.mesh.all_nodes()
+    assert N == len(ref_tau) - 1 == 52 and np.abs(tau - ref_tau).max() <= 1e-15
+    u, st, it, px, py = fleet(t0, x0, return_solution=True)
+    ut, xt = fleet.trajectories(t0)
+    assert ut.shape == (B, N, 2) and xt.shape == (B, N + 1, 7)
+    for b in range(B):
+        uo, xo = mpc.trajectories(t0[b], px[b])
+        assert np.abs(ut[b] - uo).max() <= 1e-12 * max(1.0, np.abs(uo).max())
+        assert np.abs(xt[b] - xo).max() <= 1e-12 * max(1.0, np.abs(xo).max())
+    assert np.array_equal(ut[:, 0, :], u)
+    ok = st == 0
+    assert ok.mean() >= 0.9
+    assert np.abs(xt[ok, 0, :] - x0[ok]).max() <= 1e-4           # ce = x_0 (-) x0_fix = 0 up to the solver's tolerance
+    assert np.abs(np.hypot(xt[..., 2], xt[..., 3]) - 1).max() <= 1e-12   # SE(2) elements stay on the group
+    # device tensors: same bits
+    td = torch.from_numpy(t0).cuda()
+    utd, xtd = fleet.trajectories(td)
+    torch.cuda.synchronize()
+    assert np.array_equal(utd.cpu().numpy(), ut) and np.array_equal(xtd.cpu().numpy(), xt)
+    # fp32 fleet
+    f32 = sfb.MPCVehicleFleet(B, sfb.MPCVehicleParams(qp=sfb.QPSolverParams(max_iter=4000)), dtype=np.float32)
+    t32 = t0.astype(np.float32)
+    u32, _, _, p32, _ = f32(t32, x0.astype(np.float32), return_solution=True)
+    ut32, xt32 = f32.trajectories(t32)
+    for b in range(0, B, 5):
+        uo, xo = mpc.trajectories(float(t32[b]), p32[b].astype(np.float64))
+        assert np.abs(ut32[b] - uo).max() <= 1e-5 * max(1.0, np.abs(uo).max())
+        assert np.abs(xt32[b] - xo).max() <= 1e-5 * max(1.0, np.abs(xo).max())
+
+
 def test_full_size_closed_loop_properties(sfb):
     """BASELINE configs[2] at full size (8192 agents, fp32) for 5 control steps on device tensors: every solve Optimal, warm
     steps exit at the first check, inputs inside their box, replicas of 256 distinct agents identical."""
