@@ -387,6 +387,50 @@ int mpc_step_impl(sfb_mpc_fleet* f, const T* t, const T* x, T* out_u, int32_t* o
   return SFB_OK;
 }
 
+// mpc.hpp:493-507 on the solution the last step left on the device
+template <typename T> int mpc_traj_impl(sfb_mpc_fleet* f, const T* t, T* out_u_traj, T* out_x_traj)
+{
+  if (!f) return SFB_ERR_INVALID_ARGUMENT;
+  sfb_context* h = f->h;
+  if (f->scalar_bytes != (int)sizeof(T)) return fail(h, SFB_ERR_INVALID_ARGUMENT, "fleet was created for %d-byte scalars", f->scalar_bytes);
+  if (!t) return fail(h, SFB_ERR_INVALID_ARGUMENT, "t is NULL");
+  if (!out_u_traj && !out_x_traj) return SFB_OK;
+  const int space = classify({t, out_u_traj, out_x_traj});
+  if (space < 0) return fail(h, SFB_ERR_MIXED_MEMORY, "host and device pointers mixed in one call");
+  SFB_CUDA(h, cudaSetDevice(h->device));
+  const size_t B = (size_t)f->batch;
+  const int N = f->host.N;
+  const size_t ub = sizeof(T) * 2 * (size_t)N * B, xb = sizeof(T) * 7 * (size_t)(N + 1) * B;
+  sfb::MpcTrajArgs<T> a{};
+  a.batch = f->batch; a.N = N; a.n = f->host.n; a.xvar_L = f->host.xvar_L; a.tf = f->prm.tf;
+  for (int k = 0; k < 3; ++k) { a.g0[k] = f->prm.g0[k]; a.vdes[k] = f->prm.vdes[k]; }
+  a.udes[0] = f->prm.udes[0]; a.udes[1] = f->prm.udes[1];
+  a.tau = f->d_tau; a.sol_x = static_cast<const T*>(f->d_sx);
+  a.t = t; a.u_traj = out_u_traj; a.x_traj = out_x_traj;
+  if (space == 0) {  // host buffers: staged through the handle's scratch
+    int rc = sfbi::ensure_scratch(h, h->sparse_stage, sizeof(T) * B + ub + xb + 512, h->stream);
+    if (rc != SFB_OK) return rc;
+    char* d = static_cast<char*>(h->sparse_stage.dev);
+    auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+    T* dt = reinterpret_cast<T*>(d);
+    T* du = reinterpret_cast<T*>(d + al(sizeof(T) * B));
+    T* dx = reinterpret_cast<T*>(d + al(sizeof(T) * B) + al(ub));
+    SFB_CUDA(h, cudaMemcpyAsync(dt, t, sizeof(T) * B, cudaMemcpyHostToDevice, h->stream));
+    a.t = dt; a.u_traj = out_u_traj ? du : nullptr; a.x_traj = out_x_traj ? dx : nullptr;
+  }
+  const long long total = (long long)B * (N + 1);
+  const int grid = (int)std::min<long long>((total + 127) / 128, (long long)h->prop.multiProcessorCount * 16);
+  sfb::mpc_vehicle_traj_kernel<T><<<grid, 128, 0, h->stream>>>(a);
+  SFB_CUDA(h, cudaGetLastError());
+  h->launches += 1;
+  if (space == 0) {
+    if (out_u_traj) SFB_CUDA(h, cudaMemcpyAsync(out_u_traj, a.u_traj, ub, cudaMemcpyDeviceToHost, h->stream));
+    if (out_x_traj) SFB_CUDA(h, cudaMemcpyAsync(out_x_traj, a.x_traj, xb, cudaMemcpyDeviceToHost, h->stream));
+    SFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return SFB_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -531,52 +575,6 @@ int sfb_mpc_fleet_nodes(sfb_mpc_fleet_t f, int* N, double* tau)
   if (tau) std::copy(f->host.tau.begin(), f->host.tau.end(), tau);
   return SFB_OK;
 }
-
-namespace {
-// mpc.hpp:493-507 on the solution the last step left on the device
-template <typename T> int mpc_traj_impl(sfb_mpc_fleet* f, const T* t, T* out_u_traj, T* out_x_traj)
-{
-  if (!f) return SFB_ERR_INVALID_ARGUMENT;
-  sfb_context* h = f->h;
-  if (f->scalar_bytes != (int)sizeof(T)) return fail(h, SFB_ERR_INVALID_ARGUMENT, "fleet was created for %d-byte scalars", f->scalar_bytes);
-  if (!t) return fail(h, SFB_ERR_INVALID_ARGUMENT, "t is NULL");
-  if (!out_u_traj && !out_x_traj) return SFB_OK;
-  const int space = classify({t, out_u_traj, out_x_traj});
-  if (space < 0) return fail(h, SFB_ERR_MIXED_MEMORY, "host and device pointers mixed in one call");
-  SFB_CUDA(h, cudaSetDevice(h->device));
-  const size_t B = (size_t)f->batch;
-  const int N = f->host.N;
-  const size_t ub = sizeof(T) * 2 * (size_t)N * B, xb = sizeof(T) * 7 * (size_t)(N + 1) * B;
-  sfb::MpcTrajArgs<T> a{};
-  a.batch = f->batch; a.N = N; a.n = f->host.n; a.xvar_L = f->host.xvar_L; a.tf = f->prm.tf;
-  for (int k = 0; k < 3; ++k) { a.g0[k] = f->prm.g0[k]; a.vdes[k] = f->prm.vdes[k]; }
-  a.udes[0] = f->prm.udes[0]; a.udes[1] = f->prm.udes[1];
-  a.tau = f->d_tau; a.sol_x = static_cast<const T*>(f->d_sx);
-  a.t = t; a.u_traj = out_u_traj; a.x_traj = out_x_traj;
-  if (space == 0) {  // host buffers: staged through the handle's scratch
-    int rc = sfbi::ensure_scratch(h, h->sparse_stage, sizeof(T) * B + ub + xb + 512, h->stream);
-    if (rc != SFB_OK) return rc;
-    char* d = static_cast<char*>(h->sparse_stage.dev);
-    auto al = [](size_t v) { return (v + 255) / 256 * 256; };
-    T* dt = reinterpret_cast<T*>(d);
-    T* du = reinterpret_cast<T*>(d + al(sizeof(T) * B));
-    T* dx = reinterpret_cast<T*>(d + al(sizeof(T) * B) + al(ub));
-    SFB_CUDA(h, cudaMemcpyAsync(dt, t, sizeof(T) * B, cudaMemcpyHostToDevice, h->stream));
-    a.t = dt; a.u_traj = out_u_traj ? du : nullptr; a.x_traj = out_x_traj ? dx : nullptr;
-  }
-  const long long total = (long long)B * (N + 1);
-  const int grid = (int)std::min<long long>((total + 127) / 128, (long long)h->prop.multiProcessorCount * 16);
-  sfb::mpc_vehicle_traj_kernel<T><<<grid, 128, 0, h->stream>>>(a);
-  SFB_CUDA(h, cudaGetLastError());
-  h->launches += 1;
-  if (space == 0) {
-    if (out_u_traj) SFB_CUDA(h, cudaMemcpyAsync(out_u_traj, a.u_traj, ub, cudaMemcpyDeviceToHost, h->stream));
-    if (out_x_traj) SFB_CUDA(h, cudaMemcpyAsync(out_x_traj, a.x_traj, xb, cudaMemcpyDeviceToHost, h->stream));
-    SFB_CUDA(h, cudaStreamSynchronize(h->stream));
-  }
-  return SFB_OK;
-}
-}  // namespace
 
 int sfb_mpc_fleet_trajectories_f64(sfb_mpc_fleet_t f, const double* t, double* out_u_traj, double* out_x_traj)
 {

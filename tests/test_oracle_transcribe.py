@@ -212,3 +212,28 @@ def test_vehicle_mpc_cfg3(oracle):
     cp, ri, pv = qp.csc_P()
     assert rp[-1] == 312 * 12 + 104 * 8 + 10 and cp[-1] == 6 * 52 + 2 * 52  # nnz(A), nnz(P)
     assert np.abs(np.array(us)).max() <= 0.5 + 1e-9
+
+
+def test_mpc_trajectory_outputs(oracle):
+    # mpc.hpp:493-507: u_traj[i] = udes(t + tf tau_i) + u-segment i, x_traj[i] = xdes(t + tf tau_i) (+) x-segment i.  The
+    # reference's tests never read them; pinned here by what the construction guarantees: u_traj[0] is the applied input
+    # (:518), x_traj[0] is the measured state (end constraint ce = x_0 (-) x0_fix = 0), the trajectory satisfies the input
+    # box, and a zero primal returns the desired trajectory itself.
+    mpc = tr.vehicle_mpc()
+    t0, x0 = tr.sample_vehicle_states(2, seed=3)
+    tau = mpc.mesh.all_nodes()
+    assert len(tau) == 53 and tau[0] == 0.0 and tau[-1] == 1.0 and (np.diff(tau) > 0).all()
+    for b in range(2):
+        o = _solve_triplet(oracle, mpc.transcribe(t0[b], x0[b]))
+        assert o.status[0] == 0
+        ut, xt = mpc.trajectories(t0[b], o.x[0])
+        assert ut.shape == (52, 2) and xt.shape == (53, 7)
+        assert np.array_equal(ut[0], mpc.input_from_primal(t0[b], o.x[0]))
+        assert np.abs(xt[0] - x0[b]).max() < 1e-6
+        assert np.abs(ut).max() <= 0.5 + 1e-6
+        assert np.abs(np.hypot(xt[:, 2], xt[:, 3]) - 1).max() < 1e-12
+    ut, xt = mpc.trajectories(1.5, np.zeros(mpc.dims["Nvar"]))
+    assert not ut.any()
+    for i in (0, 17, 52):
+        assert np.allclose(xt[i], tr.vehicle_xdes(1.5 + mpc.tf * tau[i])[0], rtol=0, atol=1e-15)
+
