@@ -102,6 +102,7 @@ typedef struct {
                                          which is also what the reference returns when its polish fails */
 #define SFB_QP_FLAG_POLISH_FAILED 4u  /* non-positive / non-finite pivot in the polish systems */
 #define SFB_QP_FLAG_POLISH_SCRATCH 8u /* (with POLISHED) the polish Schur block lived in the global workspace, not on chip */
+#define SFB_QP_FLAG_POLISH_REDUCED 16u /* (with POLISHED, dense kernels) the polish system was solved in its reduced n x n form */
 
 int sfb_version(void);
 const char* sfb_error_string(int err);
@@ -127,6 +128,12 @@ int sfb_synchronize(sfb_handle_t h);
 /*   SFB_OPT_FORCE_POLISH_SCRATCH (default 0, debug / tests): dense polish keeps its Schur block in the global workspace even
  *     when it fits in shared memory, so that both placements can be compared on the same problems. */
 #define SFB_OPT_FORCE_POLISH_SCRATCH 2
+/*   SFB_OPT_POLISH_FORM (default 0): how the dense kernel eliminates the regularised polish system of polish_qp
+ *     (qp_solver.hpp:160-195).  0: duals first (one n x n inverse of Pbar + delta I + Aa^T Aa / delta), refined with literal
+ *     residual sweeps until the correction is below 1e-8 of the solution, and redone in the Schur form if polish_iter sweeps
+ *     do not get there; 1: always the Schur form (primal block first, Eigen's pivot order; the round-1 / early round-2
+ *     behaviour); 2: always the reduced form (A/B measurements). */
+#define SFB_OPT_POLISH_FORM 3
 int sfb_set_option(sfb_handle_t h, int option, int value);
 /* number of kernels of this library launched through the handle since creation */
 int sfb_kernel_launch_count(sfb_handle_t h, uint64_t* out);

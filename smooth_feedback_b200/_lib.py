@@ -89,6 +89,7 @@ def _preload_cudart() -> None:
 
 OPT_DUAL_INF_DX_GUARD = 1
 OPT_FORCE_POLISH_SCRATCH = 2
+OPT_POLISH_FORM = 3
 
 _lib = None
 

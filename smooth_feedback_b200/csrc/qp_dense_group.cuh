@@ -132,6 +132,7 @@ template <typename T, typename TIO = T> struct QpArgs
   sfb_qp_params prm;
   unsigned max_iter_eff;
   int force_polish_scratch;  // debug (SFB_OPT_FORCE_POLISH_SCRATCH): keep the polish Schur block in the global workspace even when it fits on chip
+  int polish_form;  // SFB_OPT_POLISH_FORM: 0 reduced form with accuracy check and schur fallback (default), 1 schur always, 2 reduced always
   int dinf_guard;  // 1: the dual-infeasibility certificate needs dx != 0 (SFB_OPT_DUAL_INF_DX_GUARD, default); 0: literal reference rule
   unsigned long long* work_counter;
 };
@@ -825,16 +826,26 @@ template <typename T, int G, int NS, int MS> struct QpGroup
     // reference returns when its polish fails (unpolished solution, code Optimal).
     if (sizeof(T) == 4) return SFB_QP_FLAG_POLISH_SKIPPED;
     const T delta = T(a.prm.delta);
-    const bool woodbury = na > n;  // more active rows than variables: S would be na x na and singular-ish
+    const T dinv = T(1) / delta;
+    // Two block eliminations of the same regularised system Hp = [K Aa^T; Aa -delta I], K = Pbar + delta I:
+    //   schur    primal block first (the order Eigen's diagonal pivoting takes): Kinv, S = delta I + Aa Kinv Aa^T (na x na), Sinv;
+    //   reduced  duals first: N = K + Aa^T Aa / delta (n x n), ONE inverse, no S -- 40 % less work at the headline shape, but
+    //            1 / delta sits inside N, so one application of the computed inverse is only good to cond(N) eps.
+    // a.polish_form 0 (default): reduced, refined with literal residual sweeps until the correction is below 1e-8 of the
+    // solution; an instance that does not get there within polish_iter sweeps is redone in the schur form.  1: schur always.  2: reduced always.
+    // na > n has no schur form (S would be singular-ish).  A CTA owns one instance: the choice is CTA-uniform.
     T* S = nullptr;
     int ldS = 0;
     bool s_shared = false;  // NOT derivable from ldS == ldA: with every row of an m == ldA problem active, na == ldA too (the
                             // root cause of the round-1 "2 x 2" polish failures: S in the workspace was addressed as if on chip)
-    if (!woodbury && na > 0) {
+    if (na > 0 && na <= n) {
       if (2 * na <= ldA && !a.force_polish_scratch) { S = As + na; ldS = ldA; s_shared = true; }  // below the compacted rows
       else if (gscratch != nullptr && (long long)na * na <= a.scratch_per_cta) { S = gscratch; ldS = na; }
-      else return SFB_QP_FLAG_POLISH_SKIPPED;
     }
+    const bool schur_possible = (na == 0) || (S != nullptr);
+    bool woodbury = (na > n) || (na > 0 && a.polish_form != 1);
+    if (!woodbury && !schur_possible) return SFB_QP_FLAG_POLISH_SKIPPED;
+    const bool may_fall_back = woodbury && na <= n && a.polish_form == 0 && schur_possible;
 
     // compact the active rows of Abar to the top of every column (idx ascending => in-place safe)
 #pragma unroll 1
@@ -845,82 +856,6 @@ template <typename T, int G, int NS, int MS> struct QpGroup
     }
     gsync();
 
-    // K = Pbar + delta I  (+ Aa^T Aa / delta in the Woodbury form)   :161,175
-    // one coalesced sweep over the unscaled P: every upper-triangle entry is scaled and written to both (i,j), (j,i)
-    {
-      int i = tid % n, j = tid / n;
-      const int di = NT % n, dj = NT / n;
-#pragma unroll 1
-      for (int e = tid; e < n * n; e += NT) {
-        if (i <= j) {
-          T h = ((c * sx[i]) * (T)__ldg(gP + e)) * sx[j];
-          if (i == j) h += delta;
-          Ms[i + ldN * j] = h;
-          Ms[j + ldN * i] = h;
-        }
-        i += di; j += dj;
-        if (i >= n) { i -= n; ++j; }
-      }
-    }
-    gsync();
-    if (woodbury) {
-      const T dinv = T(1) / delta;
-      int i = tid % n, j = tid / n;
-      const int di = NT % n, dj = NT / n;
-#pragma unroll 1
-      for (int e = tid; e < n * n; e += NT) {
-        const T* ci = As + ldA * i;
-        const T* cj = As + ldA * j;
-        T acc = T(0);
-#pragma unroll 1
-        for (int r = 0; r < na; ++r) acc += ci[r] * cj[r];
-        Ms[i + ldN * j] += dinv * acc;
-        i += di; j += dj;
-        if (i >= n) { i -= n; ++j; }
-      }
-      gsync();
-    }
-    if (!gj_invert_at(0, n)) return SFB_QP_FLAG_POLISH_FAILED;
-
-    if (S != nullptr) {
-      // S = delta I + Aa Kinv Aa^T, four columns at a time: T4 = Kinv Aa[s0..s0+3,:]^T (n x 4 in xt,xold,nv1,nv2; stride npad),
-      // then S[:, s0..s0+3] = Aa T4
-#pragma unroll 1
-      for (int s0 = 0; s0 < na; s0 += 4) {
-        const int ns = min(4, na - s0);
-#pragma unroll 1
-        for (int e = tid; e < n * ns; e += NT) {
-          const int i = e % n, sc = e / n;
-          const T* p = Ms + i;
-          const T* arow = As + (s0 + sc);
-          T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0);
-          int j = 0;
-#pragma unroll 2
-          for (; j + 3 < n; j += 4) {
-            a0 += p[ldN * j] * arow[ldA * j];
-            a1 += p[ldN * (j + 1)] * arow[ldA * (j + 1)];
-            a2 += p[ldN * (j + 2)] * arow[ldA * (j + 2)];
-            a3 += p[ldN * (j + 3)] * arow[ldA * (j + 3)];
-          }
-#pragma unroll 1
-          for (; j < n; ++j) a0 += p[ldN * j] * arow[ldA * j];
-          xt[sc * npad + i] = (a0 + a1) + (a2 + a3);
-        }
-        gsync();
-#pragma unroll 1
-        for (int e = tid; e < na * ns; e += NT) {
-          const int r = e % na, sc = e / na;
-          T acc = rowdot(As, ldA, r, n, xt + sc * npad);
-          if (r == s0 + sc) acc += delta;
-          if (s_shared) As[na + r + ldA * (s0 + sc)] = acc; else S[r + ldS * (s0 + sc)] = acc;
-        }
-        gsync();
-      }
-      const bool s_ok = s_shared ? gj_invert_at(1, na) : qp_stage_gj_generic<T, G, NS, MS>(n, m, S, ldS, na);
-      if (!s_ok) return SFB_QP_FLAG_POLISH_FAILED;
-    }
-
-    // iterative refinement  t += Hp^-1 (h - H t)   :192-195
     T* tx = xt;    // n
     T* ty = z;     // na
     T* rx = nv1;   // n
@@ -928,120 +863,205 @@ template <typename T, int G, int NS, int MS> struct QpGroup
     T* ry = yold;  // na
     T* sv = rho;   // na
     T* dy = rinv;  // na
-    const T dinv = T(1) / delta;
+    bool used_scratch = false;
 #pragma unroll 1
-    for (int j = tid; j < n; j += NT) tx[j] = T(0);
-#pragma unroll 1
-    for (int r = tid; r < na; r += NT) ty[r] = T(0);
-    gsync();
-    // The reference iterates t <- t + Hp^-1 (h - H t) with H = Hp - D, D = diag(delta I_n, -delta I_na).  Since
-    // h - H t = (h + D t) - Hp t, the same sequence is t <- Hp^-1 (h + D t): no product with H (whose Pbar block lives
-    // in HBM) is needed.  Only the last sweep uses the literal residual form, so that rounding errors of the explicit
-    // inverses are corrected once, exactly like iterative refinement does.
-    bool converged = false;
-#pragma unroll 1
-    for (uint32_t it = 0; it != a.prm.polish_iter; ++it) {
-      // Once t stops changing (to a few ulp) further sweeps of the fixed-point form are no-ops up to rounding: jump to
-      // the closing literal sweep.  Well-conditioned systems contract by delta / lambda_min ~ 1e-6 per sweep.
-      const bool literal = ((it + 1 == a.prm.polish_iter) || converged) && (it > 0);
-      if (literal) {
-        // residual r = h - sym(H) t,  H = [Pbar Aa^T; Aa 0]
-#pragma unroll 1
-        for (int i = tid; i < n; i += NT) {
-          T acc = T(0);
-#pragma unroll 10
-          for (int j = 0; j < n; ++j) acc += pbar(gP, i, j) * tx[j];
-          rx[i] = -c * (sx[i] * q[i]) - (acc + vecdot(As + ldA * i, ty, na));  // :180
-        }
-#pragma unroll 1
-        for (int r = tid; r < na; r += NT) ry[r] = bnd[r] - rowdot(As, ldA, r, n, tx);  // :181-182
-      } else {
-        // rhs = h + D t ; the solve below then yields the new t directly
-#pragma unroll 1
-        for (int i = tid; i < n; i += NT) rx[i] = -c * (sx[i] * q[i]) + delta * tx[i];
-#pragma unroll 1
-        for (int r = tid; r < na; r += NT) ry[r] = bnd[r] - delta * ty[r];
-      }
-      gsync();
-      T diff = T(0), mag = T(0);
-      if (!woodbury) {
-        // [K Aa^T; Aa -delta I] [dx; dy] = [rx; ry]:  dy = Sinv (Aa Kinv rx - ry),  dx = Kinv (rx - Aa^T dy)
-#pragma unroll 1
-        for (int i = tid; i < n; i += NT) ux[i] = rowdot(Ms, ldN, i, n, rx);
-        gsync();
-#pragma unroll 1
-        for (int r = tid; r < na; r += NT) sv[r] = rowdot(As, ldA, r, n, ux) - ry[r];
-        gsync();
-#pragma unroll 1
-        for (int r = tid; r < na; r += NT)
-          dy[r] = s_shared ? rowdot(As + na, ldA, r, na, sv) : rowdot(S, ldS, r, na, sv);  // keep LDS on the common path
-        gsync();
-#pragma unroll 1
-        for (int i = tid; i < n; i += NT) ux[i] = rx[i] - vecdot(As + ldA * i, dy, na);
-        gsync();
-#pragma unroll 1
-        for (int i = tid; i < n; i += NT) {
-          const T d = rowdot(Ms, ldN, i, n, ux);
-          if (literal) {
-            tx[i] += d;
-          } else {
-            diff = fmax(diff, fabs(d - tx[i]));
-            mag = fmax(mag, fabs(d));
-            tx[i] = d;
-          }
-        }
-#pragma unroll 1
-        for (int r = tid; r < na; r += NT) {
-          const T d = dy[r];
-          if (literal) {
-            ty[r] += d;
-          } else {
-            diff = fmax(diff, fabs(d - ty[r]));
-            mag = fmax(mag, fabs(d));
-            ty[r] = d;
-          }
-        }
-      } else {
-        // same system, duals eliminated first:  (K + Aa^T Aa / delta) dx = rx + Aa^T ry / delta,  dy = (Aa dx - ry) / delta
-#pragma unroll 1
-        for (int i = tid; i < n; i += NT) ux[i] = rx[i] + dinv * vecdot(As + ldA * i, ry, na);
-        gsync();
-#pragma unroll 1
-        for (int i = tid; i < n; i += NT) rx[i] = rowdot(Ms, ldN, i, n, ux);  // rx now holds dx
-        gsync();
-#pragma unroll 1
-        for (int r = tid; r < na; r += NT) {
-          const T d = (rowdot(As, ldA, r, n, rx) - ry[r]) * dinv;
-          if (literal) {
-            ty[r] += d;
-          } else {
-            diff = fmax(diff, fabs(d - ty[r]));
-            mag = fmax(mag, fabs(d));
-            ty[r] = d;
-          }
-        }
-#pragma unroll 1
-        for (int i = tid; i < n; i += NT) {
-          const T d = rx[i];
-          if (literal) {
-            tx[i] += d;
-          } else {
-            diff = fmax(diff, fabs(d - tx[i]));
-            mag = fmax(mag, fabs(d));
-            tx[i] = d;
-          }
-        }
-      }
-      if (literal) {
-        gsync();
-        break;
-      }
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      // K = Pbar + delta I  (+ Aa^T Aa / delta in the reduced form)   :161,175
+      // one coalesced sweep over the unscaled P: every upper-triangle entry is scaled and written to both (i,j), (j,i)
       {
-        T mx[2] = {diff, mag}, sm[1] = {T(0)};
-        greduce<2, 1>(mx, sm);
-        converged = mx[0] <= T(8) * Num<T>::eps() * mx[1];
+        int i = tid % n, j = tid / n;
+        const int di = NT % n, dj = NT / n;
+#pragma unroll 1
+        for (int e = tid; e < n * n; e += NT) {
+          if (i <= j) {
+            T h = ((c * sx[i]) * (T)__ldg(gP + e)) * sx[j];
+            if (i == j) h += delta;
+            Ms[i + ldN * j] = h;
+            Ms[j + ldN * i] = h;
+          }
+          i += di; j += dj;
+          if (i >= n) { i -= n; ++j; }
+        }
       }
       gsync();
+      if (woodbury) form_weighted_gram(T(0), na, nullptr, dinv);
+      bool ok = gj_invert_at(0, n);
+
+      if (ok && !woodbury && S != nullptr) {
+        // S = delta I + Aa Kinv Aa^T, four columns at a time: T4 = Kinv Aa[s0..s0+3,:]^T (n x 4 in xt,xold,nv1,nv2; stride npad),
+        // then S[:, s0..s0+3] = Aa T4
+#pragma unroll 1
+        for (int s0 = 0; s0 < na; s0 += 4) {
+          const int ns = min(4, na - s0);
+#pragma unroll 1
+          for (int e = tid; e < n * ns; e += NT) {
+            const int i = e % n, sc = e / n;
+            const T* p = Ms + i;
+            const T* arow = As + (s0 + sc);
+            T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0);
+            int j = 0;
+#pragma unroll 2
+            for (; j + 3 < n; j += 4) {
+              a0 += p[ldN * j] * arow[ldA * j];
+              a1 += p[ldN * (j + 1)] * arow[ldA * (j + 1)];
+              a2 += p[ldN * (j + 2)] * arow[ldA * (j + 2)];
+              a3 += p[ldN * (j + 3)] * arow[ldA * (j + 3)];
+            }
+#pragma unroll 1
+            for (; j < n; ++j) a0 += p[ldN * j] * arow[ldA * j];
+            xt[sc * npad + i] = (a0 + a1) + (a2 + a3);
+          }
+          gsync();
+#pragma unroll 1
+          for (int e = tid; e < na * ns; e += NT) {
+            const int r = e % na, sc = e / na;
+            T acc = rowdot(As, ldA, r, n, xt + sc * npad);
+            if (r == s0 + sc) acc += delta;
+            if (s_shared) As[na + r + ldA * (s0 + sc)] = acc; else S[r + ldS * (s0 + sc)] = acc;
+          }
+          gsync();
+        }
+        ok = s_shared ? gj_invert_at(1, na) : qp_stage_gj_generic<T, G, NS, MS>(n, m, S, ldS, na);
+        used_scratch = !s_shared;
+      }
+
+      bool accurate = true;
+      if (ok) {
+        // iterative refinement  t += Hp^-1 (h - H t)   :192-195
+#pragma unroll 1
+        for (int j = tid; j < n; j += NT) tx[j] = T(0);
+#pragma unroll 1
+        for (int r = tid; r < na; r += NT) ty[r] = T(0);
+        gsync();
+        // The reference iterates t <- t + Hp^-1 (h - H t) with H = Hp - D, D = diag(delta I_n, -delta I_na).  Since
+        // h - H t = (h + D t) - Hp t, the same sequence is t <- Hp^-1 (h + D t): no product with H (whose Pbar block lives
+        // in HBM) is needed.  The closing sweep(s) use the literal residual form, so that rounding errors of the explicit
+        // inverses are corrected, exactly like iterative refinement does.
+        bool converged = false;
+#pragma unroll 1
+        for (uint32_t it = 0; it != a.prm.polish_iter; ++it) {
+          // schur: once t stops changing (to a few ulp) further sweeps of the fixed-point form are no-ops up to rounding: jump
+          // to ONE closing literal sweep.  Well-conditioned systems contract by delta / lambda_min ~ 1e-6 per sweep.
+          // reduced: two fixed-point sweeps reach the fixed point of the COMPUTED inverse to 1e-12; accuracy beyond
+          // cond(N) eps only comes from literal sweeps, repeated until the correction is negligible.
+          const bool literal = (it > 0) && (woodbury ? (it >= 2 || it + 1 == a.prm.polish_iter) : ((it + 1 == a.prm.polish_iter) || converged));
+          if (literal) {
+            // residual r = h - sym(H) t,  H = [Pbar Aa^T; Aa 0]
+#pragma unroll 1
+            for (int i = tid; i < n; i += NT) {
+              T acc = T(0);
+#pragma unroll 10
+              for (int j = 0; j < n; ++j) acc += pbar(gP, i, j) * tx[j];
+              rx[i] = -c * (sx[i] * q[i]) - (acc + vecdot(As + ldA * i, ty, na));  // :180
+            }
+#pragma unroll 1
+            for (int r = tid; r < na; r += NT) ry[r] = bnd[r] - rowdot(As, ldA, r, n, tx);  // :181-182
+          } else {
+            // rhs = h + D t ; the solve below then yields the new t directly
+#pragma unroll 1
+            for (int i = tid; i < n; i += NT) rx[i] = -c * (sx[i] * q[i]) + delta * tx[i];
+#pragma unroll 1
+            for (int r = tid; r < na; r += NT) ry[r] = bnd[r] - delta * ty[r];
+          }
+          gsync();
+          T diff = T(0), mag = T(0), diffy = T(0), magy = T(0);  // literal sweeps: x and y blocks apart (their scales differ)
+          if (!woodbury) {
+            // [K Aa^T; Aa -delta I] [dx; dy] = [rx; ry]:  dy = Sinv (Aa Kinv rx - ry),  dx = Kinv (rx - Aa^T dy)
+#pragma unroll 1
+            for (int i = tid; i < n; i += NT) ux[i] = rowdot(Ms, ldN, i, n, rx);
+            gsync();
+#pragma unroll 1
+            for (int r = tid; r < na; r += NT) sv[r] = rowdot(As, ldA, r, n, ux) - ry[r];
+            gsync();
+#pragma unroll 1
+            for (int r = tid; r < na; r += NT)
+              dy[r] = s_shared ? rowdot(As + na, ldA, r, na, sv) : rowdot(S, ldS, r, na, sv);  // keep LDS on the common path
+            gsync();
+#pragma unroll 1
+            for (int i = tid; i < n; i += NT) ux[i] = rx[i] - vecdot(As + ldA * i, dy, na);
+            gsync();
+#pragma unroll 1
+            for (int i = tid; i < n; i += NT) {
+              const T d = rowdot(Ms, ldN, i, n, ux);
+              if (literal) {
+                tx[i] += d;
+              } else {
+                diff = fmax(diff, fabs(d - tx[i]));
+                mag = fmax(mag, fabs(d));
+                tx[i] = d;
+              }
+            }
+#pragma unroll 1
+            for (int r = tid; r < na; r += NT) {
+              const T d = dy[r];
+              if (literal) {
+                ty[r] += d;
+              } else {
+                diff = fmax(diff, fabs(d - ty[r]));
+                mag = fmax(mag, fabs(d));
+                ty[r] = d;
+              }
+            }
+          } else {
+            // same system, duals eliminated first:  (K + Aa^T Aa / delta) dx = rx + Aa^T ry / delta,  dy = (Aa dx - ry) / delta
+#pragma unroll 1
+            for (int i = tid; i < n; i += NT) ux[i] = rx[i] + dinv * vecdot(As + ldA * i, ry, na);
+            gsync();
+#pragma unroll 1
+            for (int i = tid; i < n; i += NT) rx[i] = rowdot(Ms, ldN, i, n, ux);  // rx now holds dx
+            gsync();
+#pragma unroll 1
+            for (int r = tid; r < na; r += NT) {
+              const T d = (rowdot(As, ldA, r, n, rx) - ry[r]) * dinv;
+              if (literal) {
+                const T tn = ty[r] + d;
+                diffy = fmax(diffy, fabs(d));
+                magy = fmax(magy, fabs(tn));
+                ty[r] = tn;
+              } else {
+                diff = fmax(diff, fabs(d - ty[r]));
+                mag = fmax(mag, fabs(d));
+                ty[r] = d;
+              }
+            }
+#pragma unroll 1
+            for (int i = tid; i < n; i += NT) {
+              const T d = rx[i];
+              if (literal) {
+                const T tn = tx[i] + d;
+                diff = fmax(diff, fabs(d));
+                mag = fmax(mag, fabs(tn));
+                tx[i] = tn;
+              } else {
+                diff = fmax(diff, fabs(d - tx[i]));
+                mag = fmax(mag, fabs(d));
+                tx[i] = d;
+              }
+            }
+          }
+          if (literal && !woodbury) {
+            gsync();
+            break;
+          }
+          {
+            T mx[4] = {diff, mag, diffy, magy}, sm[1] = {T(0)};
+            greduce<4, 1>(mx, sm);
+            // a literal sweep's correction is the error BEFORE it (relative, per block); what is left after it is smaller, but
+            // by a factor that is anything between 1e-7 (first sweep) and 0.5 (measured) -- so only the correction itself is
+            // trusted: 1e-8 of the solution, two orders inside the 1e-6 parity bar
+            if (literal) accurate = (mx[0] <= T(1e-8) * mx[1]) && (mx[2] <= T(1e-8) * mx[3]);
+            else converged = mx[0] <= T(8) * Num<T>::eps() * mx[1];
+          }
+          gsync();
+          if (literal && accurate) break;
+        }
+      }
+      if (ok && accurate) break;
+      if (!may_fall_back || !woodbury) {
+        if (!ok) return SFB_QP_FLAG_POLISH_FAILED;
+        break;  // refined as far as polish_iter sweeps go; there is no other form to try
+      }
+      woodbury = false;  // redo this instance in the schur form
     }
     // :199-201
 #pragma unroll 1
@@ -1050,13 +1070,15 @@ template <typename T, int G, int NS, int MS> struct QpGroup
 #pragma unroll 1
     for (int r = tid; r < na; r += NT) y[idx[r]] = ty[r];
     gsync();
-    return SFB_QP_FLAG_POLISHED | ((S != nullptr && !s_shared) ? SFB_QP_FLAG_POLISH_SCRATCH : 0u);
+    return SFB_QP_FLAG_POLISHED | (used_scratch ? SFB_QP_FLAG_POLISH_SCRATCH : 0u) | (woodbury ? SFB_QP_FLAG_POLISH_REDUCED : 0u);
   }
 
   // ---------------------------------------------------------------- M = Pbar + sigma I + Abar^T R Abar
   // 4x4 register tiles over the upper triangle; each thread walks the m rows in a rotated order so that the
   // threads of a warp hit different shared-memory banks.
-  __device__ void form_reduced_kkt(T sigma)
+  __device__ void form_reduced_kkt(T sigma) { form_weighted_gram(sigma, m, rho, T(0)); }
+  // Ms += diag + As[0..rows)^T W As[0..rows), W = diag(wts) or wconst I (wts == nullptr)
+  __device__ void form_weighted_gram(T sigma, int rows, const T* wts, T wconst)
   {
     const int nb = (n + 3) / 4;
     const int ntiles = nb * (nb + 1) / 2;
@@ -1077,10 +1099,10 @@ template <typename T, int G, int NS, int MS> struct QpGroup
       for (int p = 0; p < 4; ++p)
 #pragma unroll
         for (int s = 0; s < 4; ++s) acc[p][s] = T(0);
-      int r = (m > 0) ? (tid % m) : 0;
+      int r = (rows > 0) ? (tid % rows) : 0;
 #pragma unroll 1
-      for (int k = 0; k < m; ++k) {
-        const T rr = rho[r];
+      for (int k = 0; k < rows; ++k) {
+        const T rr = wts != nullptr ? wts[r] : wconst;
         T av[4], bv[4];
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
@@ -1091,7 +1113,7 @@ template <typename T, int G, int NS, int MS> struct QpGroup
         for (int p = 0; p < 4; ++p)
 #pragma unroll
           for (int s = 0; s < 4; ++s) acc[p][s] += av[p] * bv[s];
-        if (++r == m) r = 0;
+        if (++r == rows) r = 0;
       }
 #pragma unroll
       for (int p = 0; p < 4; ++p)

@@ -235,7 +235,7 @@ int qp_launch(sfb_context* h, cudaStream_t st, int scratch_slot, const sfb::QpAr
       pa.P = args.P; pa.q = args.q; pa.A = args.A; pa.l = args.l; pa.u = args.u;
       pa.out_x = args.out_x; pa.out_y = args.out_y; pa.out_obj = args.out_obj; pa.out_status = args.out_status;
       pa.out_iter = args.out_iter; pa.out_active = args.out_active; pa.out_flags = args.out_flags;
-      pa.batch = args.batch; pa.n = args.n; pa.m = args.m; pa.mode = 2; pa.prm = args.prm; pa.max_iter_eff = args.max_iter_eff; pa.dinf_guard = args.dinf_guard; pa.force_polish_scratch = args.force_polish_scratch;
+      pa.batch = args.batch; pa.n = args.n; pa.m = args.m; pa.mode = 2; pa.prm = args.prm; pa.max_iter_eff = args.max_iter_eff; pa.dinf_guard = args.dinf_guard; pa.force_polish_scratch = args.force_polish_scratch; pa.polish_form = args.polish_form;
       rc = qp_launch_group<double, T>(h, st, scratch_slot, pa);
       if (rc != SFB_OK) return rc;
     }
@@ -317,6 +317,7 @@ int qp_solve_impl(sfb_context* h, const sfb_qp_params* prm, int64_t batch, int n
   a.max_iter_eff = prm->has_max_iter ? prm->max_iter : SFB_QP_DEVICE_ITER_CAP;
   a.dinf_guard = h->dinf_guard;
   a.force_polish_scratch = h->force_polish_scratch;
+  a.polish_form = h->polish_form;
 
   if (space == 1) {
     a.P = P; a.q = q; a.A = A; a.l = l; a.u = u; a.warm_x = warm_x; a.warm_y = warm_y;
@@ -526,6 +527,10 @@ int sfb_set_option(sfb_handle_t h, int option, int value)
   switch (option) {
     case SFB_OPT_DUAL_INF_DX_GUARD: h->dinf_guard = value ? 1 : 0; return SFB_OK;
     case SFB_OPT_FORCE_POLISH_SCRATCH: h->force_polish_scratch = value ? 1 : 0; return SFB_OK;
+    case SFB_OPT_POLISH_FORM:
+      if (value < 0 || value > 2) return fail(h, SFB_ERR_INVALID_ARGUMENT, "SFB_OPT_POLISH_FORM takes 0, 1 or 2");
+      h->polish_form = value;
+      return SFB_OK;
     default: return fail(h, SFB_ERR_INVALID_ARGUMENT, "unknown option %d", option);
   }
 }

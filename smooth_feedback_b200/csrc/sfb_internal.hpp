@@ -54,6 +54,7 @@ struct sfb_context
   cudaEvent_t ev_order = nullptr;  // orders the handle's workspaces across a change of stream (sfb_set_stream)
   int dinf_guard = 1;  // SFB_OPT_DUAL_INF_DX_GUARD
   int force_polish_scratch = 0;  // SFB_OPT_FORCE_POLISH_SCRATCH
+  int polish_form = 0;           // SFB_OPT_POLISH_FORM
   bool ekf_force_generic = false;
   bool dense_force_generic = false;  // SFB_DENSE_FORCE_GENERIC=1: bypass the tall-skinny register kernel (A/B measurements)
   int sparse_tw = 0;     // SFB_SPARSE_TW=4|8|32 overrides the tile-width heuristic of the sparse QP path (A/B measurements)

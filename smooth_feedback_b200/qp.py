@@ -42,6 +42,7 @@ FLAG_POLISHED = 1
 FLAG_POLISH_SKIPPED = 2
 FLAG_POLISH_FAILED = 4
 FLAG_POLISH_SCRATCH = 8
+FLAG_POLISH_REDUCED = 16
 
 
 @dataclass
