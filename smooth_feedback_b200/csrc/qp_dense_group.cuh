@@ -942,9 +942,9 @@ template <typename T, int G, int NS, int MS> struct QpGroup
         for (uint32_t it = 0; it != a.prm.polish_iter; ++it) {
           // schur: once t stops changing (to a few ulp) further sweeps of the fixed-point form are no-ops up to rounding: jump
           // to ONE closing literal sweep.  Well-conditioned systems contract by delta / lambda_min ~ 1e-6 per sweep.
-          // reduced: two fixed-point sweeps reach the fixed point of the COMPUTED inverse to 1e-12; accuracy beyond
-          // cond(N) eps only comes from literal sweeps, repeated until the correction is negligible.
-          const bool literal = (it > 0) && (woodbury ? (it >= 2 || it + 1 == a.prm.polish_iter) : ((it + 1 == a.prm.polish_iter) || converged));
+          // reduced: the fixed point of the COMPUTED inverse is only good to cond(N) eps (y: 1e-2), so every sweep after the
+          // first is a literal one, repeated until the correction is negligible (typically two: 1e-2 -> 1e-9 -> accepted).
+          const bool literal = (it > 0) && (woodbury || (it + 1 == a.prm.polish_iter) || converged);
           if (literal) {
             // residual r = h - sym(H) t,  H = [Pbar Aa^T; Aa 0]
 #pragma unroll 1
