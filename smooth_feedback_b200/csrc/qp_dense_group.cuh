@@ -821,9 +821,9 @@ template <typename T, int G, int NS, int MS> struct QpGroup
   // `na` active rows (ascending) are listed in idx[], their scaled bounds in bnd[].  Returns SFB_QP_FLAG_* bits.
   template <typename TIO> __device__ unsigned polish(const QpArgs<T, TIO>& a, const TIO* gP, int na, const int* idx, const T* bnd, T* gscratch)
   {
-    // fp32: the delta = 1e-6 regularised polish systems are not resolvable in single precision (8 ulp); until the
-    // mixed-precision refinement lands the f32 entry point reports the polish as skipped, which is also what the
-    // reference returns when its polish fails (unpolished solution, code Optimal).
+    // fp32: the delta = 1e-6 regularised polish systems are not resolvable in single precision (8 ulp): an fp32 solve flags
+    // the polish as skipped here and the host launches this kernel again in fp64 on the fp32 iterate and active set (mode 2,
+    // sfb_api.cu), which is where the _f32 entry points get SFB_QP_FLAG_POLISHED from.
     if (sizeof(T) == 4) return SFB_QP_FLAG_POLISH_SKIPPED;
     const T delta = T(a.prm.delta);
     const T dinv = T(1) / delta;

@@ -963,7 +963,9 @@ template <typename T, typename TIO, int NT, bool GT> struct CtaSolver
         t1[j] = tn;
       }
       reduce<2, 0x3u>(dm);
-      if (dm[0] <= T(1e-12) * dm[1]) break;  // see qp_sparse_tiled.cuh::polish
+      // see qp_sparse_tiled.cuh::polish.  A sweep's correction is the error BEFORE it; the fp64 polish pass of an fp32 solve
+      // (TIO = float: parity bar 1e-3, the inputs themselves carry 6e-8) stops at 1e-8 instead of 1e-12
+      if (dm[0] <= T(sizeof(TIO) == 4 ? 1e-8 : 1e-12) * dm[1]) break;
     }
     bool bad = false;
     for (int j = tid; j < np; j += NT) bad = bad || !(fabs(t1[j]) < Num<T>::inf());
